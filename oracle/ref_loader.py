@@ -1,0 +1,156 @@
+"""Load the REAL reference hot-path modules from /root/reference, in place, unmodified.
+
+TEST INFRASTRUCTURE ONLY.  Works only in the build container (the GPU box has no
+/root/reference).  Used by `tests/golden/make_golden.py` to generate the committed
+golden vectors and by `tests/test_oracle_vs_reference.py` (skipped when the
+reference tree is absent) to pin `oracle/` against the reference itself.
+
+`import sleap_nn` fails here (sleap_io / omegaconf / lightning are absent), so the
+eight hot-path files are exec'd individually under empty namespace packages and
+stub modules for the names they import but never touch on this path
+(SURVEY.md section 8c).  No reference source is copied: files are read where they
+lie.
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("SLEAPNN_REFERENCE_ROOT", "/root/reference")
+
+# (module name, path relative to REF_ROOT) in dependency order.
+_HOT_FILES = [
+    ("sleap_nn.data.instance_cropping", "sleap_nn/data/instance_cropping.py"),
+    ("sleap_nn.data.utils", "sleap_nn/data/utils.py"),
+    ("sleap_nn.data.confidence_maps", "sleap_nn/data/confidence_maps.py"),
+    ("sleap_nn.data.edge_maps", "sleap_nn/data/edge_maps.py"),
+    ("sleap_nn.inference.utils", "sleap_nn/inference/utils.py"),
+    ("sleap_nn.inference.ops.crops", "sleap_nn/inference/ops/crops.py"),
+    ("sleap_nn.inference.ops.peaks", "sleap_nn/inference/ops/peaks.py"),
+    ("sleap_nn.inference.ops.paf", "sleap_nn/inference/ops/paf.py"),
+]
+
+_NAMESPACE_PKGS = [
+    "sleap_nn",
+    "sleap_nn.inference",
+    "sleap_nn.inference.ops",
+    "sleap_nn.data",
+    "sleap_nn.config",
+]
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "sleap_nn/inference/ops/peaks.py"))
+
+
+class _Anything:
+    """Attribute sink: any attribute access / call returns another sink."""
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        return _Anything()
+
+    def __call__(self, *a, **k):
+        return _Anything()
+
+
+def _stub(name: str, **attrs) -> types.ModuleType:
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+
+    def _module_getattr(attr):
+        if attr.startswith("__"):  # keep inspect / importlib machinery honest
+            raise AttributeError(attr)
+        return _Anything
+
+    mod.__getattr__ = _module_getattr  # type: ignore[attr-defined]
+    return mod
+
+
+def load(prefix: str = "_sleapnn_ref") -> dict:
+    """Return {short name: module} for the eight reference hot-path files.
+
+    The modules are registered under their real dotted names while they are being
+    exec'd (they import one another), then the `sleap_nn*` entries are moved out of
+    `sys.modules` so the reference never shadows `sleap_nn_b200.compat.install()`.
+    """
+    if not available():
+        raise FileNotFoundError(f"reference tree not found under {REF_ROOT}")
+    import attrs, networkx, numpy, scipy.optimize, torch  # noqa: F401  real deps, import before stubbing
+
+    saved = {k: v for k, v in sys.modules.items() if k == "sleap_nn" or k.startswith("sleap_nn.")}
+    for k in saved:
+        del sys.modules[k]
+    stub_names = []
+    try:
+        for pkg in _NAMESPACE_PKGS:
+            m = types.ModuleType(pkg)
+            m.__path__ = []  # namespace package marker
+            sys.modules[pkg] = m
+        for name, attrs in [
+            ("omegaconf", dict(OmegaConf=_Anything, DictConfig=_Anything)),
+            ("sleap_io", {}),
+            ("sleap_io.io", {}),
+            ("sleap_io.io.skeleton", dict(SkeletonYAMLDecoder=_Anything)),
+            ("sleap_nn.data.skia_augmentation", {}),
+            ("sleap_nn.config.utils", {}),
+            ("sleap_nn.data.providers", {}),
+        ]:
+            if name not in sys.modules:
+                sys.modules[name] = _stub(name, **attrs)
+                stub_names.append(name)
+        # psutil / loguru etc. are importable here; anything else missing gets a stub lazily.
+        out = {}
+        for modname, rel in _HOT_FILES:
+            path = os.path.join(REF_ROOT, rel)
+            spec = importlib.util.spec_from_file_location(modname, path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[modname] = mod
+            while True:
+                try:
+                    spec.loader.exec_module(mod)
+                    break
+                except ModuleNotFoundError as e:  # stub whatever else is absent
+                    missing = e.name
+                    if missing in sys.modules:
+                        raise
+                    sys.modules[missing] = _stub(missing)
+                    stub_names.append(missing)
+            out[modname.rsplit(".", 1)[-1]] = mod
+        return out
+    finally:
+        for k in [k for k in sys.modules if k == "sleap_nn" or k.startswith("sleap_nn.")]:
+            mod = sys.modules.pop(k)
+            sys.modules[f"{prefix}.{k}"] = mod
+        for k in stub_names:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
+_CACHE = None
+
+
+def ref() -> types.SimpleNamespace:
+    """Cached namespace: ref().peaks, .crops, .paf, .utils (inference), .confidence_maps,
+    .edge_maps, .data_utils, .instance_cropping."""
+    global _CACHE
+    if _CACHE is None:
+        mods = load()
+        # two files are called utils.py; disambiguate
+        full = {name: sys.modules[f"_sleapnn_ref.{name}"] for name, _ in _HOT_FILES}
+        _CACHE = types.SimpleNamespace(
+            peaks=mods["peaks"],
+            crops=mods["crops"],
+            paf=mods["paf"],
+            interp=full["sleap_nn.inference.utils"],
+            confidence_maps=mods["confidence_maps"],
+            edge_maps=mods["edge_maps"],
+            data_utils=full["sleap_nn.data.utils"],
+            instance_cropping=mods["instance_cropping"],
+        )
+    return _CACHE

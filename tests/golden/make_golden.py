@@ -1,0 +1,286 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every array under tests/golden/*.npz is an input fed to, or an output produced by,
+the reference's own functions loaded in place by oracle/ref_loader.py.  The GPU box
+has no reference tree, so these files are what pins both the oracle and the CUDA
+path there.  Inputs are stored next to the outputs (never re-synthesised on the box:
+libm / SLEEF differences between hosts could move an input by an ulp).
+"""
+
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_loader, synth  # noqa: E402
+
+REF_ASSETS = os.path.join(ref_loader.REF_ROOT, "tests/assets/inference")
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **{k: npy(v) for k, v in arrays.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB, {len(arrays)} arrays")
+
+
+def ragged(prefix, tensors, out):
+    """Store a list of per-sample arrays as prefix_0, prefix_1, ... plus prefix_n."""
+    out[f"{prefix}_n"] = np.int64(len(tensors))
+    for i, t in enumerate(tensors):
+        out[f"{prefix}_{i}"] = npy(t)
+
+
+def peaks_minimal(R):
+    cms = torch.load(os.path.join(REF_ASSETS, "minimal_cms.pt")).unsqueeze(0)
+    bboxes = torch.load(os.path.join(REF_ASSETS, "minimal_bboxes.pt"))
+    out = dict(cms=cms, bboxes=bboxes)
+    lr = R.peaks.find_local_peaks_rough(cms)
+    out.update(lr_pts=lr[0], lr_vals=lr[1], lr_s=lr[2], lr_c=lr[3])
+    li = R.peaks.find_local_peaks(cms, refinement="integral")
+    out.update(li_pts=li[0], li_vals=li[1])
+    gr = R.peaks.find_global_peaks_rough(cms, threshold=0.1)
+    out.update(gr_pts=gr[0], gr_vals=gr[1])
+    gi = R.peaks.find_global_peaks(cms, threshold=0.2, refinement="integral")
+    out.update(gi_pts=gi[0], gi_vals=gi[1])
+    planes = cms.reshape(13, 1, 80, 80)
+    crops = R.crops.crop_bboxes(planes, bboxes, torch.arange(13))
+    gv = torch.arange(5, dtype=torch.float32) - 2
+    dx, dy = R.peaks.integral_regression(crops, gv, gv)
+    out.update(crops=crops, ir_dx=dx, ir_dy=dy, dil=R.peaks.morphological_dilation(planes, None))
+    save("ref_peaks_minimal.npz", **out)
+
+
+def peaks_random(R):
+    g = torch.Generator().manual_seed(1234)
+    cms = torch.rand((3, 4, 24, 20), generator=g)
+    cms[1, 2, 5, 7] = float("nan")  # NaN neighbours suppress peaks, NaN itself is never one
+    cms[2, 0] = 0.05  # an all-below-threshold plane -> NaN global peak
+    out = dict(cms=cms)
+    for tag, thr in (("t02", 0.2), ("t09", 0.9)):
+        r = R.peaks.find_local_peaks_rough(cms, threshold=thr)
+        out.update({f"lr_{tag}_pts": r[0], f"lr_{tag}_vals": r[1], f"lr_{tag}_s": r[2], f"lr_{tag}_c": r[3]})
+    for size in (3, 4, 5, 7):
+        r = R.peaks.find_local_peaks(cms, threshold=0.9, refinement="integral", integral_patch_size=size)
+        out[f"li_t09_p{size}_pts"] = r[0]
+    clean = torch.nan_to_num(cms, nan=0.3)
+    for tag, thr in (("t01", 0.1), ("t0999", 0.999)):
+        r = R.peaks.find_global_peaks_rough(clean, threshold=thr)
+        out.update({f"gr_{tag}_pts": r[0], f"gr_{tag}_vals": r[1]})
+    for size in (3, 4, 5):
+        r = R.peaks.find_global_peaks(clean, threshold=0.2, refinement="integral", integral_patch_size=size)
+        out[f"gi_p{size}_pts"] = r[0]
+        out[f"gi_p{size}_vals"] = r[1]
+    out["clean"] = clean
+    # crop_bboxes on fractional / negative / far-out-of-bounds centroids, even size, 2 channels
+    imgs = torch.rand((2, 2, 30, 26), generator=g)
+    cents = torch.tensor([[20.3, 18.7], [2.4, 2.4], [0.6, 3.0], [10.0, 10.0], [1.4, 1.4], [1000.0, 1000.0],
+                          [-1000.0, -3.0], [25.0, 29.0]])
+    sidx = torch.tensor([0, 1, 0, 1, 1, 0, 1, 0])
+    for (bh, bw) in ((6, 6), (5, 7)):
+        bb = R.instance_cropping.make_centered_bboxes(cents, bh, bw)
+        out[f"bb_{bh}x{bw}"] = bb
+        out[f"crops_{bh}x{bw}"] = R.crops.crop_bboxes(imgs, bb, sidx)
+    out.update(imgs=imgs, cents=cents, sidx=sidx)
+    save("ref_peaks_random.npz", **out)
+
+
+def paf_units(R):
+    P = R.paf
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    # line subscripts: random sub-pixel peaks, several (stride, n_points)
+    peaks = torch.rand((60, 2), generator=g) * torch.tensor([300.0, 200.0])
+    epi = torch.randint(0, 60, (400, 2), generator=g)
+    ei = torch.randint(0, 5, (400,), generator=g).to(torch.int32)
+    out.update(ls_peaks=peaks, ls_epi=epi, ls_ei=ei)
+    for stride, n in ((2, 10), (4, 10), (8, 5), (3, 7), (1, 3)):
+        hw = (200 // stride, 300 // stride)
+        out[f"ls_s{stride}_n{n}"] = P.make_line_subs(peaks, epi, ei, n, stride, hw)
+    # the reference's own unit-test vectors (tests/inference/test_paf_grouping.py)
+    pafs = torch.arange(6 * 4 * 2).view(6, 4, 2).float()
+    pk = torch.tensor([[0, 0], [4, 8]], dtype=torch.float32)
+    e1 = torch.tensor([[0, 1]], dtype=torch.int32)
+    z = torch.tensor([0], dtype=torch.int32)
+    lines = P.get_paf_lines(pafs, pk, e1, z, 3, 2)
+    out.update(ut_lines=lines, ut_score=P.score_paf_lines(lines, pk, e1, max_edge_length=2))
+    out["ut_pen"] = P.compute_distance_penalty(torch.tensor([1, 2, 3, 4.0]), 2, dist_penalty_weight=2)
+    # scoring on a random field
+    field = torch.randn((40, 50, 10), generator=g)
+    ch = torch.randint(0, 6, (30,), generator=g).to(torch.int32)
+    pk2 = torch.rand((30, 2), generator=g) * torch.tensor([98.0, 78.0])
+    edges = [(0, 1), (1, 2), (2, 3), (1, 4), (4, 5)]
+    r = P.score_paf_lines_batch(field[None], [pk2], [ch], torch.tensor(edges, dtype=torch.int32), 10, 2, 0.25, 1.0, 6)
+    out.update(sc_field=field, sc_ch=ch, sc_peaks=pk2, sc_edges=np.asarray(edges), sc_ei=r[0][0], sc_epi=r[1][0], sc_scores=r[2][0])
+    m = P.match_candidates_sample(r[0][0], r[1][0], r[2][0], 5)
+    out.update(mt_e=m[0], mt_s=m[1], mt_d=m[2], mt_sc=m[3])
+    save("ref_paf_units.npz", **out)
+
+
+def paf_pipeline(R, name, seed, n_frames, n_inst, n_nodes, img_hw, edges, step, min_instance_peaks=0):
+    P = R.paf
+    stride = 2
+    poses = synth.make_poses(seed, n_frames, n_inst, n_nodes, img_hw, margin=40.0, step=step, edges=edges)
+    cms, pafs = synth.render(poses, img_hw, stride, edges, seed=seed)
+    good = synth.certify(cms, pafs, edges, n_nodes, stride)
+    out = dict(poses=poses, cms=cms, pafs=pafs, edges=np.asarray(edges), certified=good,
+               stride=np.int64(stride), n_nodes=np.int64(n_nodes), min_instance_peaks=np.float64(min_instance_peaks))
+    pts, vals, si, ci = R.peaks.find_local_peaks(cms, threshold=0.2, refinement="integral")
+    out.update(pk_pts=pts, pk_vals=vals, pk_s=si, pk_c=ci)
+    pts = pts * stride
+    peaks = synth.split_by_sample(pts, si, n_frames)
+    pvals = synth.split_by_sample(vals, si, n_frames)
+    pch = synth.split_by_sample(ci, si, n_frames)
+    names = [str(i) for i in range(n_nodes)]
+    scorer = P.PAFScorer(part_names=names, edges=[(str(a), str(b)) for a, b in edges], pafs_stride=stride,
+                         min_instance_peaks=min_instance_peaks)
+    out["sorted_edge_inds"] = np.asarray(scorer.sorted_edge_inds)
+    res = scorer.predict(pafs.permute(0, 2, 3, 1), peaks, pvals, pch)
+    ragged("inst", res[0], out)
+    ragged("inst_pv", res[1], out)
+    ragged("inst_sc", res[2], out)
+    ragged("cand_e", res[3], out)
+    ragged("cand_p", res[4], out)
+    ragged("cand_s", res[5], out)
+    m = scorer.match_candidates(res[3], res[4], res[5])
+    ragged("m_e", m[0], out)
+    ragged("m_s", m[1], out)
+    ragged("m_d", m[2], out)
+    ragged("m_sc", m[3], out)
+    print(name, "certified frames:", good.tolist(), "instances/frame:", [len(x) for x in res[0]])
+    save(name, **out)
+
+
+def assembly_cases(R):
+    """Hand-made match lists that hit every branch of the greedy assembly."""
+    P = R.paf
+    out = {}
+    g = np.random.default_rng(5)
+    n_cases = 0
+    for case in range(24):
+        n_nodes = int(g.integers(3, 7))
+        edges = synth.star_chain_edges(n_nodes, fan=2) if case % 2 else synth.chain_edges(n_nodes)
+        if case % 5 == 0:
+            edges = edges[::-1]
+        n_per = g.integers(1, 4, n_nodes)
+        ch = np.concatenate([np.full(n, k) for k, n in enumerate(n_per)]).astype(np.int32)
+        perm = g.permutation(len(ch))
+        ch = ch[perm]
+        pk = g.uniform(0, 100, (len(ch), 2)).astype(np.float32)
+        pv = g.uniform(0.2, 1, len(ch)).astype(np.float32)
+        me, ms, md, msc = [], [], [], []
+        for k, (a, b) in enumerate(edges):
+            # random partial matchings, occasionally re-using a peak twice (case-3 branch)
+            for _ in range(int(g.integers(0, 4))):
+                me.append(k)
+                ms.append(int(g.integers(0, n_per[a])))
+                md.append(int(g.integers(0, n_per[b])))
+                msc.append(float(g.uniform(0.0, 1.0)))
+        order = g.permutation(len(me))
+        me, ms, md, msc = (np.asarray(x)[order] for x in (me, ms, md, msc))
+        et = [P.EdgeType(a, b) for a, b in edges]
+        sorted_inds = P.toposort_edges(et)
+        mip = [0, 2, 0.5][case % 3]
+        res = P.group_instances_sample(
+            torch.from_numpy(pk), torch.from_numpy(pv), torch.from_numpy(ch),
+            torch.as_tensor(me, dtype=torch.int32), torch.as_tensor(ms, dtype=torch.int32),
+            torch.as_tensor(md, dtype=torch.int32), torch.as_tensor(msc, dtype=torch.float32),
+            n_nodes, sorted_inds, et, mip, 0.25)
+        pre = f"c{case}_"
+        out.update({pre + "edges": np.asarray(edges), pre + "ch": ch, pre + "pk": pk, pre + "pv": pv,
+                    pre + "me": me.astype(np.int32), pre + "ms": ms.astype(np.int32), pre + "md": md.astype(np.int32),
+                    pre + "msc": msc.astype(np.float32), pre + "sorted": np.asarray(sorted_inds, dtype=np.int64),
+                    pre + "mip": np.float64(mip), pre + "mip_is_float": np.bool_(isinstance(mip, float)),
+                    pre + "inst": res[0], pre + "inst_pv": res[1], pre + "inst_sc": res[2]})
+        n_cases += 1
+    out["n_cases"] = np.int64(n_cases)
+    # toposort on the reference's two test skeletons + a forest + a DAG with a cross edge
+    skels = [
+        [(5, 7), (5, 8), (5, 9), (5, 6), (5, 11), (5, 12), (1, 0), (1, 3), (1, 2), (1, 10), (1, 13), (1, 14), (4, 5), (4, 1)],
+        [(1, 4), (1, 5), (6, 8), (6, 7), (6, 9), (9, 10), (1, 0), (1, 3), (1, 2), (6, 1)],
+        [(0, 1), (2, 3)],
+        [(0, 1), (0, 2), (1, 2)],
+        [(2, 1), (1, 0)],
+    ]
+    for i, sk in enumerate(skels):
+        out[f"topo{i}_edges"] = np.asarray(sk)
+        out[f"topo{i}_order"] = np.asarray(P.toposort_edges([P.EdgeType(a, b) for a, b in sk]), dtype=np.int64)
+    out["n_topo"] = np.int64(len(skels))
+    save("ref_assembly.npz", **out)
+
+
+def targets(R):
+    C, E, U = R.confidence_maps, R.edge_maps, R.data_utils
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    hw, stride, sigma = (48, 64), 2, 1.5
+    xv, yv = U.make_grid_vectors(hw[0], hw[1], stride)
+    pts = torch.rand((2, 5, 2), generator=g) * torch.tensor([64.0, 48.0])
+    pts[0, 1] = float("nan")
+    pts[1, 3, 0] = float("nan")
+    out.update(xv=xv, yv=yv, cm_pts=pts, cm=C.make_confmaps(pts, xv, yv, sigma * stride))
+    inst = torch.rand((1, 4, 5, 2), generator=g) * torch.tensor([64.0, 48.0])
+    inst[0, 2, 1] = float("nan")
+    inst[0, 3] = float("nan")
+    out.update(mc_pts=inst, mc=C.make_multi_confmaps(inst, xv, yv, sigma * stride))
+    out["gmc"] = C.generate_multiconfmaps(inst, hw, 3, sigma, stride)
+    out["gmc_centroids"] = C.generate_multiconfmaps(inst[:, :, 0], hw, 4, sigma, stride, is_centroids=True)
+    out["gc"] = C.generate_confmaps(inst[:, 0], hw, sigma, stride)
+    # wide-range confmaps: far tails reach the denormal band and exact zero
+    xv2, yv2 = U.make_grid_vectors(256, 256, 1)
+    far = torch.tensor([[[3.25, 7.5], [250.0, 128.75]]])
+    out.update(xv2=xv2, yv2=yv2, far_pts=far, far_cm=C.make_confmaps(far, xv2, yv2, 5.0))
+    # the reference's 3x3 known-answer vectors (tests/data/test_edge_maps.py)
+    xv3, yv3 = U.make_grid_vectors(3, 3, 1)
+    s3 = torch.tensor([[1, 0.5], [0, 0]], dtype=torch.float32)
+    d3 = torch.tensor([[1, 1.5], [2, 2]], dtype=torch.float32)
+    yy, xx = torch.meshgrid(yv3, xv3, indexing="ij")
+    out.update(k_src=s3, k_dst=d3, k_dist=E.distance_to_edge(torch.stack((xx, yy), -1), s3, d3),
+               k_em=E.make_edge_maps(xv3, yv3, s3, d3, 1.0), k_paf=E.make_pafs(xv3, yv3, s3, d3, 1.0),
+               k_mpaf=E.make_multi_pafs(xv3, yv3, torch.stack([s3, s3]), torch.stack([d3, d3]), 1.0))
+    # random edges incl. a degenerate (src == dst) edge, a sub-unit-length edge and a NaN edge
+    edges = torch.tensor([[0, 1], [1, 2], [2, 3], [1, 4]])
+    inst2 = inst.clone()[0]
+    inst2[1, 2] = inst2[1, 1]  # degenerate edge (1,2) in instance 1
+    inst2[0, 4] = inst2[0, 1] + torch.tensor([0.3, 0.4])  # |v| < 1 -> edge_length clamps to 1
+    src, dst = E.get_edge_points(inst2, edges)
+    out.update(pf_inst=inst2, pf_edges=edges, pf_src=src, pf_dst=dst,
+               pf_single=E.make_pafs(xv, yv, src[0], dst[0], sigma),
+               pf_degenerate=E.make_pafs(xv, yv, src[1], dst[1], sigma),
+               pf_multi=E.make_multi_pafs(xv, yv, src, dst, sigma),
+               pf_em=E.make_edge_maps(xv, yv, src[0], dst[0], sigma))
+    inst3 = inst2.clone()[None]
+    inst3[0, 1] = inst3[0, 1] + 500.0  # wholly outside the image -> filtered by generate_pafs
+    out.update(gp_inst=inst3, gp=E.generate_pafs(inst3, hw, sigma, stride, edges, flatten_channels=True))
+    save("ref_targets.npz", **out)
+
+
+def main():
+    R = ref_loader.ref()
+    torch.set_num_threads(1)  # reductions are then run-to-run reproducible
+    peaks_minimal(R)
+    peaks_random(R)
+    paf_units(R)
+    paf_pipeline(R, "ref_pipeline_mice.npz", seed=11, n_frames=3, n_inst=2, n_nodes=5, img_hw=(128, 160),
+                 edges=synth.chain_edges(5), step=24.0)
+    paf_pipeline(R, "ref_pipeline_tree.npz", seed=23, n_frames=3, n_inst=4, n_nodes=8, img_hw=(192, 192),
+                 edges=synth.star_chain_edges(8, fan=2), step=26.0, min_instance_peaks=2)
+    assembly_cases(R)
+    targets(R)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+"""Shared helpers for the test-suite: golden loading and keyed comparisons."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FLT_MIN = 1.1754944e-38
+
+
+def golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name))
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def ragged(d, prefix):
+    return [T(d[f"{prefix}_{i}"]) for i in range(int(d[f"{prefix}_n"]))]
+
+
+def eq(a, b):
+    """Bit-exact equality, NaN == NaN."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    np.testing.assert_array_equal(a, b)
+
+
+def close(a, b, rtol=0.0, atol=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def candidate_table(edge_inds, edge_peak_inds, scores):
+    """{(edge, src peak, dst peak): score} - candidate order inside an edge is
+    implementation-defined in the reference (unstable argsort)."""
+    e, p, s = npy(edge_inds), npy(edge_peak_inds), npy(scores)
+    out = {}
+    for i in range(len(e)):
+        out[(int(e[i]), int(p[i, 0]), int(p[i, 1]))] = float(s[i])
+    assert len(out) == len(e), "duplicate candidates"
+    return out
