@@ -1,0 +1,98 @@
+"""ctypes binding of libsleapnn_b200.so (the C ABI declared in include/sleapnn_b200.h).
+
+There is NO fallback: if the shared library is missing or a symbol is absent, importing
+this module raises.  torch is used only for device memory, streams and dtype plumbing.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SLEAPNN_B200_LIB", os.path.join(_HERE, "lib", "libsleapnn_b200.so"))
+
+OK = 0
+ERRORS = {-1: "bad argument", -2: "unsupported configuration", -3: "CUDA launch failed"}
+
+STATUS_PEAK_OVERFLOW = 1
+STATUS_CAND_OVERFLOW = 2
+STATUS_LSAP_INFEASIBLE = 4
+STATUS_LSAP_TOO_LARGE = 8
+STATUS_INSTANCE_OVERFLOW = 16
+STATUS_BAD_INDEX = 32
+STATUS_MATCH_OVERFLOW = 64
+
+_i, _ll, _f, _p = C.c_int, C.c_longlong, C.c_float, C.c_void_p
+_ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+
+# name -> argtypes; every function returns int.  Keep in the order of include/sleapnn_b200.h.
+SIGNATURES = {
+    "snb_abi_version": [],
+    "snb_local_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
+    "snb_pack_peaks": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_global_peaks_workspace": [_i, _i, _i, _i, _ip, _ip, _llp],
+    "snb_global_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p],
+    "snb_crop_bboxes": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p, _p, _p],
+    "snb_centered_bboxes": [_p, _ll, _f, _f, _p, _p],
+    "snb_integral_regression": [_p, _ll, _i, _i, _p, _p, _p, _p, _p],
+    "snb_dilate8": [_p, _ll, _i, _i, _p, _p],
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.isfile(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or sleap_nn_b200/csrc/build.sh. There is no CPU / PyTorch fallback for this path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    return lib
+
+
+lib = _load()
+ABI_VERSION = lib.snb_abi_version()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise RuntimeError(f"{what}: {ERRORS.get(rc, f'error {rc}')}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def compute_device(*tensors) -> torch.device:
+    """The CUDA device kernels run on: the first CUDA input's device, else the current device.
+
+    CPU tensors are accepted by the public API (the reference's own tests pass them) and are
+    staged to this device; compute never happens on the host.
+    """
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise NativeLibraryError(
+            "sleap_nn_b200 needs a CUDA device: every op runs in hand-written sm_100a kernels and there is no CPU fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,81 @@
+// Shared device helpers for the sm_100a heat-map path kernels.
+//
+// Arithmetic rule for everything that feeds an integer decision (line subscripts, crop
+// corners, thresholds): every fp32 product / sum / quotient is a SEPARATE IEEE rounding
+// (__fmul_rn / __fadd_rn / __fdiv_rn), never contracted into FMA, because the reference
+// is a chain of individually rounded ATen CPU ops.  The library is
+// built WITHOUT --use_fast_math and with -ftz=false -prec-div=true -prec-sqrt=true.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/sleapnn_b200.h"
+
+#define SNB_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    cudaError_t e__ = cudaGetLastError();                    \
+    if (e__ != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;      \
+  } while (0)
+
+namespace snb {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  // 128-bit read-only streaming load; the confidence maps are read exactly once.
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Integral-regression offsets on a size x size patch whose centre tap is the integer
+// peak (px, py) of plane `plane` (row stride sh, col stride sw, in elements).
+// Patch top-left follows crop_bboxes (ops/crops.py:85-90): trunc((p - s/2 + 0.5) + s//2) - s//2;
+// taps outside the image read 0 (ops/crops.py:97-99).  Grid = arange(s) - (s-1)/2
+// (ops/peaks.py:174).  Sums are accumulated in fp64 and rounded once to fp32 before the
+// fp32 division that the reference performs (ops/peaks.py:84-85); 0/0 -> NaN as there.
+__device__ __forceinline__ void integral_refine(const float* __restrict__ plane, int H, int W, long long sh,
+                                                long long sw, float px, float py, int size, float* ox,
+                                                float* oy) {
+  const float half_f = 0.5f * (float)size;           // box / 2 (python float, exact in fp32 for int size)
+  const int half_i = size / 2;                       // box // 2
+  // make_centered_bboxes: (x - half) + 0.5, each rounded in fp32 (instance_cropping.py:151-171)
+  const float tlx_f = __fadd_rn(__fadd_rn(__fsub_rn(px, half_f), 0.5f), (float)half_i);
+  const float tly_f = __fadd_rn(__fadd_rn(__fsub_rn(py, half_f), 0.5f), (float)half_i);
+  const int x0 = (int)truncf(tlx_f) - half_i;
+  const int y0 = (int)truncf(tly_f) - half_i;
+  const float g0 = -0.5f * (float)(size - 1);        // (size-1)/2 exact in fp32
+  double z = 0.0, sx = 0.0, sy = 0.0;
+  for (int j = 0; j < size; ++j) {
+    const int yy = y0 + j;
+    const bool yin = (yy >= 0) && (yy < H);
+    const float gy = g0 + (float)j;
+    for (int i = 0; i < size; ++i) {
+      const int xx = x0 + i;
+      float p = 0.f;
+      if (yin && xx >= 0 && xx < W) p = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+      const float gx = g0 + (float)i;
+      z += (double)p;
+      sx += (double)__fmul_rn(gx, p);
+      sy += (double)__fmul_rn(gy, p);
+    }
+  }
+  const float zf = (float)z;
+  *ox = __fdiv_rn((float)sx, zf);
+  *oy = __fdiv_rn((float)sy, zf);
+}
+
+}  // namespace snb

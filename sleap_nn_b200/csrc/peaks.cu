@@ -1,0 +1,621 @@
+// Peak finding on confidence maps: sm_100a kernels + C-ABI entry points.
+//
+//   K1  snb_local_peaks        fused 3x3 NMS + threshold + peak emission (streaming read of the
+//                              maps, 128-bit loads) -> per-frame key sort -> integral refinement
+//                              (replaces ops/peaks.py:184-259 + ops/crops.py:31-124)
+//   K2  snb_global_peaks       per-(sample,channel) arg-max with the reference's two independent
+//                              arg-max semantics + threshold + refinement (ops/peaks.py:89-181)
+//   K3  snb_crop_bboxes        integer-aligned zero-padded patch gather (ops/crops.py:31-124)
+//       snb_integral_regression, snb_dilate8, snb_pack_peaks
+//
+// Bound: HBM read bandwidth.  K1 reads every map element exactly once (4*C*H*W bytes per
+// frame); everything after the streaming pass touches O(#peaks) data.
+#include "common.cuh"
+
+namespace snb {
+
+// ----------------------------------------------------------------------------------------
+// K1a: streaming detect.  One warp owns one map row at a time (grid-stride over B*C*H rows);
+// lanes stride over the row in float4s.  A lane only leaves the streaming path when one of
+// its four values exceeds the threshold (a few pixels per thousand on real maps); it then
+// re-reads the 8 neighbours through L1/L2 and applies the reference's test
+//     v > threshold  &&  v > every in-image neighbour        (ops/peaks.py:47-63, 209)
+// "v > each neighbour" equals "v > max(neighbours)" including NaN behaviour (a NaN neighbour
+// makes torch's max NaN and the comparison false) and the -inf padding (out-of-image
+// neighbours are skipped: v > -inf holds for every v that passed v > threshold).
+// Peaks are appended to the frame's key list; key = (y*W + x)*C + c orders them the way
+// torch.where over (B,H,W,C) does (ops/peaks.py:211-217).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_strict_max(const float* __restrict__ plane, int H, int W, long long sh,
+                                              long long sw, int y, int x, float v) {
+  bool ok = true;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if ((dy == 0 && dx == 0) || xx < 0 || xx >= W) continue;
+      const float nb = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+      ok = ok && (v > nb);
+    }
+  }
+  return ok;
+}
+
+__device__ __forceinline__ void emit_peak(int* __restrict__ frame_count, uint32_t* __restrict__ keys, int cap,
+                                          int b, int C, int W, int c, int y, int x) {
+  const int pos = atomicAdd(frame_count + b, 1);
+  if (pos < cap) keys[(long long)b * cap + pos] = (uint32_t)((y * W + x) * C + c);
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+local_peaks_detect_vec4(const float* __restrict__ cms, int B, int C, int H, int W, long long sb, long long sc,
+                        long long sh, float thr, int cap, int* __restrict__ frame_count,
+                        uint32_t* __restrict__ keys) {
+  const int lane = lane_id();
+  const int warps_per_block = blockDim.x >> 5;
+  const long long n_rows = (long long)B * C * H;
+  const int W4 = W >> 2;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
+       row += (long long)gridDim.x * warps_per_block) {
+    const int y = (int)(row % H);
+    const long long pc = row / H;
+    const int c = (int)(pc % C);
+    const int b = (int)(pc / C);
+    const float* plane = cms + (long long)b * sb + (long long)c * sc;
+    const float* rowp = plane + (long long)y * sh;
+    for (int x4 = lane; x4 < W4; x4 += 32 * UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xx4 = x4 + 32 * u;
+        if (xx4 < W4) v[u] = ldg_stream4(rowp + 4 * xx4);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xx4 = x4 + 32 * u;
+        if (xx4 >= W4) continue;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        if (!((e[0] > thr) || (e[1] > thr) || (e[2] > thr) || (e[3] > thr))) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (e[k] > thr) {
+            const int x = 4 * xx4 + k;
+            if (is_strict_max(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Generic-stride scalar variant (non-contiguous views, W % 4 != 0, unaligned base).
+__global__ void __launch_bounds__(256)
+local_peaks_detect_scalar(const float* __restrict__ cms, int B, int C, int H, int W, long long sb, long long sc,
+                          long long sh, long long sw, float thr, int cap, int* __restrict__ frame_count,
+                          uint32_t* __restrict__ keys) {
+  const long long n = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H);
+    r /= H;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const float* plane = cms + (long long)b * sb + (long long)c * sc;
+    const float v = __ldg(plane + (long long)y * sh + (long long)x * sw);
+    if (v > thr && is_strict_max(plane, H, W, sh, sw, y, x, v)) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K1b: per-frame finalize.  One CTA per frame: bitonic-sort the frame's keys in shared
+// memory (ascending key == (y, x, c) order), then one thread per peak decodes the key,
+// re-reads the value, runs integral refinement on the size x size patch and writes the
+// frame's slot of the padded peak table.  `n_sort` = power of two >= cap.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_smem(uint32_t* s, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = s[i], b = s[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+                     long long sw, int refine_size, float xy_scale, int cap, int keys_presorted,
+                     const int* __restrict__ frame_count, uint32_t* __restrict__ keys, float* __restrict__ out_xy,
+                     float* __restrict__ out_val, int* __restrict__ out_chan, int* __restrict__ status) {
+  extern __shared__ uint32_t skeys[];
+  const int b = blockIdx.x;
+  const int total = frame_count[b];
+  if (total > cap && threadIdx.x == 0) atomicOr(status, SNB_STATUS_PEAK_OVERFLOW);
+  const int n = min(total, cap);
+  if (n == 0) return;
+  uint32_t* gk = keys + (long long)b * cap;
+  const uint32_t* sorted = gk;
+  if (!keys_presorted) {
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) skeys[i] = (i < n) ? gk[i] : 0xffffffffu;
+    __syncthreads();
+    bitonic_sort_smem(skeys, n2);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) gk[i] = skeys[i];  // keep sorted keys for callers
+    sorted = skeys;
+  }
+  const float* frame = cms + (long long)b * sb;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t key = sorted[i];
+    const int c = (int)(key % (uint32_t)C);
+    const uint32_t yx = key / (uint32_t)C;
+    const int x = (int)(yx % (uint32_t)W);
+    const int y = (int)(yx / (uint32_t)W);
+    const float* plane = frame + (long long)c * sc;
+    const float v = __ldg(plane + (long long)y * sh + (long long)x * sw);
+    float fx = (float)x, fy = (float)y;
+    if (refine_size > 0) {
+      float ox, oy;
+      integral_refine(plane, H, W, sh, sw, fx, fy, refine_size, &ox, &oy);
+      fx = __fadd_rn(fx, ox);  // ops/peaks.py:258
+      fy = __fadd_rn(fy, oy);
+    }
+    if (xy_scale != 1.0f) {  // layers/bottomup.py:111  peaks * cms_output_stride
+      fx = __fmul_rn(fx, xy_scale);
+      fy = __fmul_rn(fy, xy_scale);
+    }
+    const long long o = (long long)b * cap + i;
+    out_xy[2 * o] = fx;
+    out_xy[2 * o + 1] = fy;
+    out_val[o] = v;
+    out_chan[o] = c;
+  }
+}
+
+// Global-memory bitonic step for frames whose key list does not fit in shared memory
+// (pathological inputs such as pure noise).  Segments are `cap` (power of two) long.
+__global__ void pad_keys_global(uint32_t* keys, const int* frame_count, int cap, int B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * cap) return;
+  const int b = (int)(i / cap);
+  if ((int)(i % cap) >= min(frame_count[b], cap)) keys[i] = 0xffffffffu;
+}
+__global__ void bitonic_step_global(uint32_t* keys, int cap, long long total, int j, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int li = (int)(i % cap);
+  const int lx = li ^ j;
+  if (lx > li) {
+    uint32_t* seg = keys + (i - li);
+    const uint32_t a = seg[li], b = seg[lx];
+    const bool up = ((li & k) == 0);
+    if ((a > b) == up) {
+      seg[li] = b;
+      seg[lx] = a;
+    }
+  }
+}
+
+// Padded per-frame peak table -> the reference's concatenated layout (points, vals,
+// sample_inds, channel_inds), frame order preserved (ops/peaks.py:213-217).
+__global__ void pack_peaks(const int* __restrict__ frame_count, int B, int cap, const float* __restrict__ xy,
+                           const float* __restrict__ val, const int* __restrict__ chan, float* __restrict__ o_xy,
+                           float* __restrict__ o_val, int* __restrict__ o_sample, int* __restrict__ o_chan) {
+  const int b = blockIdx.x;
+  __shared__ int s_off;
+  if (threadIdx.x < 32) {
+    int acc = 0;
+    for (int i = threadIdx.x; i < b; i += 32) acc += min(frame_count[i], cap);
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+    if (threadIdx.x == 0) s_off = acc;
+  }
+  __syncthreads();
+  const int n = min(frame_count[b], cap);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long s = (long long)b * cap + i, d = s_off + i;
+    o_xy[2 * d] = xy[2 * s];
+    o_xy[2 * d + 1] = xy[2 * s + 1];
+    o_val[d] = val[s];
+    o_sample[d] = b;
+    o_chan[d] = chan[s];
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K2: global peaks.  Reference semantics (ops/peaks.py:103-111): x = first column whose
+// column-max equals the plane max, y = first row whose row-max equals it; NaN propagates as
+// the greatest value.  That is the associative reduction of (v, x, y) with
+//     a beats b  if a.v is NaN and b.v is not, or a.v > b.v;   on equality (or both NaN)
+//     x = min(x), y = min(y)
+// so any tree order gives the reference's answer.  Planes are split into row chunks; the
+// last CTA to finish a plane combines the partials, applies the threshold (NaN coords, 0
+// value when max < thr, ops/peaks.py:121-129) and the integral refinement.
+// ----------------------------------------------------------------------------------------
+struct Best {
+  float v;
+  int x, y;
+};
+__device__ __forceinline__ Best best_merge(Best a, Best b) {
+  const bool an = isnan(a.v), bn = isnan(b.v);
+  if ((an && bn) || a.v == b.v) return Best{a.v, min(a.x, b.x), min(a.y, b.y)};
+  if (an) return a;
+  if (bn) return b;
+  return (a.v > b.v) ? a : b;
+}
+__device__ __forceinline__ Best best_warp(Best a) {
+  for (int d = 16; d > 0; d >>= 1) {
+    Best o{__shfl_xor_sync(FULL, a.v, d), __shfl_xor_sync(FULL, a.x, d), __shfl_xor_sync(FULL, a.y, d)};
+    a = best_merge(a, o);
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+                    long long sw, int vec_ok, int rows_per_chunk, int n_chunks, float thr, int refine_size,
+                    float* __restrict__ part_v, int* __restrict__ part_xy, unsigned* __restrict__ tickets,
+                    float* __restrict__ out_xy, float* __restrict__ out_val) {
+  const int plane_id = blockIdx.x / n_chunks;
+  const int chunk = blockIdx.x % n_chunks;
+  const int b = plane_id / C, c = plane_id % C;
+  const float* plane = cms + (long long)b * sb + (long long)c * sc;
+  const int y0 = chunk * rows_per_chunk;
+  const int y1 = min(H, y0 + rows_per_chunk);
+  Best acc{-INFINITY, 0x7fffffff, 0x7fffffff};
+  bool any = false;
+  auto take = [&](float v, int x, int y) {
+    Best o{v, x, y};
+    acc = any ? best_merge(acc, o) : o;
+    any = true;
+  };
+  if (vec_ok) {
+    const int W4 = W >> 2;
+    const int n4 = (y1 - y0) * W4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int y = y0 + i / W4, x4 = i % W4;
+      const float4 v = ldg_stream4(plane + (long long)y * sh + 4 * x4);
+      take(v.x, 4 * x4, y);
+      take(v.y, 4 * x4 + 1, y);
+      take(v.z, 4 * x4 + 2, y);
+      take(v.w, 4 * x4 + 3, y);
+    }
+  } else {
+    const int n = (y1 - y0) * W;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int y = y0 + i / W, x = i % W;
+      take(__ldg(plane + (long long)y * sh + (long long)x * sw), x, y);
+    }
+  }
+  if (!any) acc = Best{-INFINITY, 0x7fffffff, 0x7fffffff};  // -inf loses to every real element
+  __shared__ Best s_best[8];
+  __shared__ bool s_last;
+  acc = best_warp(acc);
+  if (lane_id() == 0) s_best[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best r = s_best[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = best_merge(r, s_best[w]);
+    if (n_chunks > 1) {
+      const long long slot = (long long)plane_id * n_chunks + chunk;
+      part_v[slot] = r.v;
+      part_xy[2 * slot] = r.x;
+      part_xy[2 * slot + 1] = r.y;
+      __threadfence();
+      const unsigned t = atomicAdd(tickets + plane_id, 1u);
+      s_last = (t == (unsigned)(n_chunks - 1));
+      if (s_last) {
+        __threadfence();
+        tickets[plane_id] = 0;  // self-reset so the workspace can be reused without a memset
+        r = Best{__ldcg(part_v + (long long)plane_id * n_chunks), __ldcg(part_xy + 2LL * plane_id * n_chunks),
+                 __ldcg(part_xy + 2LL * plane_id * n_chunks + 1)};
+        for (int k = 1; k < n_chunks; ++k) {
+          const long long s2 = (long long)plane_id * n_chunks + k;
+          r = best_merge(r, Best{__ldcg(part_v + s2), __ldcg(part_xy + 2 * s2), __ldcg(part_xy + 2 * s2 + 1)});
+        }
+      }
+    } else {
+      s_last = true;
+    }
+    if (s_last) {
+      // An empty plane (H*W == 0) cannot occur: the host rejects it.
+      const bool low = r.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
+      float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
+      if (!low && refine_size > 0) {
+        float ox, oy;
+        integral_refine(plane, H, W, sh, sw, fx, fy, refine_size, &ox, &oy);
+        fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
+        fy = __fadd_rn(fy, oy);
+      }
+      out_xy[2 * plane_id] = fx;
+      out_xy[2 * plane_id + 1] = fy;
+      out_val[plane_id] = low ? 0.f : r.v;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K3: crop_bboxes.  One thread per output element; top-left = trunc(tl + size//2) - size//2
+// in fp32 exactly as ops/crops.py:85-90; taps outside the image are 0.
+// ----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void crop_bboxes_kernel(const T* __restrict__ img, int S, int C, int H, int W, long long sb, long long sc,
+                                   long long sh, long long sw, const float* __restrict__ bboxes,
+                                   const long long* __restrict__ sample_inds, long long n, int ch, int cw,
+                                   T* __restrict__ out, int* __restrict__ status) {
+  const long long total = n * C * ch * cw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int xi = (int)(i % cw);
+    long long r = i / cw;
+    const int yi = (int)(r % ch);
+    r /= ch;
+    const int c = (int)(r % C);
+    const long long k = r / C;
+    const float tlx = __fadd_rn(__ldg(bboxes + k * 8 + 0), (float)(cw / 2));
+    const float tly = __fadd_rn(__ldg(bboxes + k * 8 + 1), (float)(ch / 2));
+    // float -> int64 truncation; far-out-of-range values saturate, which still lands outside the image
+    const long long x = (long long)truncf(fminf(fmaxf(tlx, -1e15f), 1e15f)) - (cw / 2) + xi;
+    const long long y = (long long)truncf(fminf(fmaxf(tly, -1e15f), 1e15f)) - (ch / 2) + yi;
+    long long s = sample_inds[k];
+    if (s < 0) s += S;  // python-style negative index
+    T v = T(0);
+    if (s < 0 || s >= S) {
+      atomicOr(status, SNB_STATUS_BAD_INDEX);
+    } else if (x >= 0 && x < W && y >= 0 && y < H) {
+      v = img[s * sb + (long long)c * sc + y * sh + x * sw];
+    }
+    out[i] = v;
+  }
+}
+
+// integral_regression(cms, xv, yv) on arbitrary patches (ops/peaks.py:66-86): one warp per (n, c).
+__global__ void integral_regression_kernel(const float* __restrict__ p, long long n_planes, int h, int w,
+                                           const float* __restrict__ xv, const float* __restrict__ yv,
+                                           float* __restrict__ ox, float* __restrict__ oy) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= n_planes) return;
+  const float* q = p + wid * h * w;
+  double z = 0, sx = 0, sy = 0;
+  for (int i = lane_id(); i < h * w; i += 32) {
+    const float v = q[i];
+    z += v;
+    sx += (double)__fmul_rn(__ldg(xv + i % w), v);
+    sy += (double)__fmul_rn(__ldg(yv + i / w), v);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    z += __shfl_xor_sync(FULL, z, d);
+    sx += __shfl_xor_sync(FULL, sx, d);
+    sy += __shfl_xor_sync(FULL, sy, d);
+  }
+  if (lane_id() == 0) {
+    ox[wid] = __fdiv_rn((float)sx, (float)z);
+    oy[wid] = __fdiv_rn((float)sy, (float)z);
+  }
+}
+
+// morphological_dilation (ops/peaks.py:26-63): max of the 8 neighbours, -inf outside, NaN propagates.
+__global__ void dilate8_kernel(const float* __restrict__ img, long long P, int H, int W, float* __restrict__ out) {
+  const long long total = P * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const float* plane = img + (r / H) * H * W;
+    float m = -INFINITY;
+    bool nan = false;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if ((dy == 0 && dx == 0) || xx < 0 || xx >= W) continue;
+        const float v = __ldg(plane + (long long)yy * W + xx);
+        nan = nan || isnan(v);
+        m = fmaxf(m, v);
+      }
+    }
+    out[i] = nan ? NAN : m;
+  }
+}
+
+// make_centered_bboxes (data/instance_cropping.py:129-171): corners TL,TR,BR,BL = centre -/+ half,
+// then +/- 0.5 inset; two separately rounded fp32 ops per coordinate.
+__global__ void centered_bboxes_kernel(const float* __restrict__ c, long long n, float half_h, float half_w,
+                                       float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = c[2 * i], y = c[2 * i + 1];
+  const float xl = __fadd_rn(__fsub_rn(x, half_w), 0.5f), xr = __fadd_rn(__fadd_rn(x, half_w), -0.5f);
+  const float yt = __fadd_rn(__fsub_rn(y, half_h), 0.5f), yb = __fadd_rn(__fadd_rn(y, half_h), -0.5f);
+  float* o = out + 8 * i;
+  o[0] = xl; o[1] = yt;
+  o[2] = xr; o[3] = yt;
+  o[4] = xr; o[5] = yb;
+  o[6] = xl; o[7] = yb;
+}
+
+static inline int grid_for(long long work_items, int per_block, int max_blocks) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
+      g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+extern "C" int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                               long long sw, float threshold, int refine_size, float xy_scale, int cap,
+                               int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
+                               int* status, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || refine_size < 0) return SNB_ERR_BAD_ARG;
+  if ((double)H * W * C >= 4294967295.0) return SNB_ERR_UNSUPPORTED;
+  if (B == 0) return SNB_OK;
+  if (cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+  const bool vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
+                   (((uintptr_t)cms) % 16 == 0);
+  const long long rows = (long long)B * C * H;
+  if (vec) {
+    // 8 warps per CTA, one row per warp at a time; cap the grid at 8 CTAs per SM (persistent, grid-stride)
+    const int grid = grid_for(rows, 8, sm_count() * 8);
+    if (W >= 512)
+      local_peaks_detect_vec4<4><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
+    else if (W >= 256)
+      local_peaks_detect_vec4<2><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
+    else
+      local_peaks_detect_vec4<1><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
+  } else {
+    const int grid = grid_for(rows * W, 256 * 4, sm_count() * 16);
+    local_peaks_detect_scalar<<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys);
+  }
+  SNB_LAUNCH_CHECK();
+  int n2 = 1;
+  while (n2 < cap) n2 <<= 1;
+  const size_t smem = sizeof(uint32_t) * (size_t)n2;
+  int presorted = 0;
+  if (smem > 200 * 1024) {
+    // Pathological key counts: sort in global memory. Requires cap to be a power of two.
+    if (n2 != cap) return SNB_ERR_BAD_ARG;
+    const long long total = (long long)B * cap;
+    const int g = (int)((total + 255) / 256);
+    pad_keys_global<<<g, 256, 0, st>>>(keys, frame_count, cap, B);
+    for (int k = 2; k <= cap; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) bitonic_step_global<<<g, 256, 0, st>>>(keys, cap, total, j, k);
+    SNB_LAUNCH_CHECK();
+    presorted = 1;
+  } else if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(local_peaks_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return SNB_ERR_CUDA_LAUNCH;
+  }
+  local_peaks_finalize<<<B, 256, presorted ? 0 : smem, st>>>(cms, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap,
+                                                            presorted, frame_count, keys, out_xy, out_val, out_chan,
+                                                            status);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val,
+                              const int* chan, float* o_xy, float* o_val, int* o_sample, int* o_chan, void* stream_) {
+  if (B <= 0) return SNB_OK;
+  pack_peaks<<<B, 128, 0, (cudaStream_t)stream_>>>(frame_count, B, cap, xy, val, chan, o_xy, o_val, o_sample, o_chan);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_global_peaks_workspace(int B, int C, int H, int W, int* rows_per_chunk, int* n_chunks,
+                                          long long* n_bytes) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return SNB_ERR_BAD_ARG;
+  int rpc = (int)((8192 + (long long)W - 1) / W);  // ~8K elements (32 KB) per CTA
+  if (rpc < 1) rpc = 1;
+  if (rpc > H) rpc = H;
+  const int nc = (H + rpc - 1) / rpc;
+  *rows_per_chunk = rpc;
+  *n_chunks = nc;
+  const long long planes = (long long)B * C;
+  // part_v (f32) + part_xy (2 x i32) per (plane, chunk) + one ticket per plane
+  *n_bytes = planes * nc * 12 + planes * 4 + 16;
+  return SNB_OK;
+}
+
+extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                                long long sw, float threshold, int refine_size, void* workspace, float* out_xy,
+                                float* out_val, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rpc, nc;
+  long long nbytes;
+  const int rc = snb_global_peaks_workspace(B, C, H, W, &rpc, &nc, &nbytes);
+  if (rc != SNB_OK) return rc;
+  if (B == 0) return SNB_OK;
+  const long long planes = (long long)B * C;
+  if (planes * nc > 0x7fffffffLL) return SNB_ERR_UNSUPPORTED;
+  // workspace layout: tickets (zero on first use, self-resetting) | part_v | part_xy
+  unsigned* tickets = (unsigned*)workspace;
+  float* part_v = (float*)(tickets + planes);
+  int* part_xy = (int*)(part_v + planes * nc);
+  const int vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
+                  (((uintptr_t)cms) % 16 == 0);
+  global_peaks_kernel<<<(unsigned)(planes * nc), 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold,
+                                                               refine_size, part_v, part_xy, tickets, out_xy, out_val);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_crop_bboxes(const void* images, int elem_size, int S, int C, int H, int W, long long sb,
+                               long long sc, long long sh, long long sw, const float* bboxes,
+                               const long long* sample_inds, long long n, int crop_h, int crop_w, void* out,
+                               int* status, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || C < 0 || crop_h < 0 || crop_w < 0) return SNB_ERR_BAD_ARG;
+  const long long total = n * C * crop_h * crop_w;
+  if (total == 0) return SNB_OK;
+  const int grid = grid_for(total, 256, sm_count() * 16);
+#define SNB_CROP(T)                                                                                              \
+  crop_bboxes_kernel<T><<<grid, 256, 0, st>>>((const T*)images, S, C, H, W, sb, sc, sh, sw, bboxes, sample_inds, \
+                                              n, crop_h, crop_w, (T*)out, status)
+  switch (elem_size) {
+    case 1: SNB_CROP(uint8_t); break;
+    case 2: SNB_CROP(uint16_t); break;
+    case 4: SNB_CROP(uint32_t); break;
+    case 8: SNB_CROP(unsigned long long); break;
+    default: return SNB_ERR_UNSUPPORTED;
+  }
+#undef SNB_CROP
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_integral_regression(const float* patches, long long n_planes, int h, int w, const float* xv,
+                                       const float* yv, float* out_x, float* out_y, void* stream_) {
+  if (n_planes <= 0) return SNB_OK;
+  const long long threads = n_planes * 32;
+  integral_regression_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      patches, n_planes, h, w, xv, yv, out_x, out_y);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_dilate8(const float* image, long long n_planes, int H, int W, float* out, void* stream_) {
+  const long long total = n_planes * H * W;
+  if (total <= 0) return SNB_OK;
+  dilate8_kernel<<<grid_for(total, 256, sm_count() * 16), 256, 0, (cudaStream_t)stream_>>>(image, n_planes, H, W, out);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_centered_bboxes(const float* centers, long long n, float half_h, float half_w, float* out,
+                                   void* stream_) {
+  if (n <= 0) return SNB_OK;
+  centered_bboxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(centers, n, half_h, half_w,
+                                                                                         out);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
