@@ -93,6 +93,124 @@ int snb_integral_regression(const float* patches, long long n_planes, int h, int
 /* morphological_dilation (ops/peaks.py:26-63) on contiguous (n_planes,H,W). */
 int snb_dilate8(const float* image, long long n_planes, int H, int W, float* out, void* stream);
 
+/* ------------------------------------------------------- PAF grouping (inference/ops/paf.py)
+ *
+ * Tables.  Per-frame variable-length data lives either in a PADDED table (start == NULL: frame b
+ * begins at b*stride, counts are clamped to stride) or a CSR table (start[b] given, count[b]
+ * exact).  Peak tables: peak_xy (2 floats, image scale), peak_val, peak_chan (node index).
+ *
+ * snb_paf_prepare: per-frame grouping of peaks by node and per-edge candidate / match offsets.
+ *   Replaces the argsort / meshgrid bookkeeping of get_connection_candidates (paf.py:84-130).
+ *   edges: (n_edges,2) int32 node ids.  Outputs: node_start (B,N+1), node_peaks (same addressing
+ *   as the peak table), edge_off (B,E+1) exclusive prefix of n_src*n_dst, match_off (B,E+1)
+ *   exclusive prefix of min(n_src,n_dst).  Canonical candidate order: edge-major, source peak
+ *   ascending, destination peak ascending (= a stable argsort; the reference's argsort is
+ *   unstable for n >= 17). */
+int snb_paf_prepare(const int* peak_chan, const int* frame_start, int frame_stride, const int* frame_count, int B,
+                    const int* edges, int n_nodes, int n_edges, int* node_start, int* node_peaks, int* edge_off,
+                    int* match_off, void* stream);
+
+/* snb_paf_score: candidate enumeration + line sampling + gather + score, one thread per candidate.
+ *   Replaces get_connection_candidates, make_line_subs (paf.py:133-234 with inference/utils.py:29-130),
+ *   get_paf_lines (:237-287), compute_distance_penalty (:290-332), score_paf_lines (:335-410) and
+ *   the per-sample loop of score_paf_lines_batch (:413-497).
+ *   pafs: the (B,H,W,2E) VIEW with element strides (pb,py,px,pc), read in place; NULL = enumerate
+ *   candidates only.  t_table: torch.linspace(0,1,n_points) computed on the HOST (bit-exactness).
+ *   stride = float(pafs_stride); max_edge_length = ratio*max(H,W,2E)*stride (paf.py:457-461).
+ *   Output candidate table (padded by cand_stride, or CSR via cand_start): cand_edge i32,
+ *   cand_epi (2 x int64 peak indices local to the frame), cand_score f32.
+ *   max_cand_per_frame only sizes the grid. */
+int snb_paf_score(const float* pafs, long long pb, long long py, long long px, long long pc, int H, int W,
+                  const float* t_table, int n_points, float stride, float max_edge_length, float penalty_weight,
+                  const float* peak_xy, const int* frame_start, int frame_stride, int B, const int* edges,
+                  int n_nodes, int n_edges, const int* node_start, const int* node_peaks, const int* edge_off,
+                  const int* cand_start, int cand_stride, int max_cand_per_frame, int* cand_edge,
+                  long long* cand_epi, float* cand_score, int* status, void* stream);
+
+/* make_line_subs (paf.py:133-234): out (M,n_points,2,3) int32 [row,col,channel]. */
+int snb_line_subs(const float* peaks, long long n_peaks, const long long* epi, const int* edge_inds, long long M,
+                  const float* t_table, int n_points, float stride, int H, int W, int* out, int* status,
+                  void* stream);
+/* The gather of get_paf_lines (paf.py:282-287): subs (n_sub,3) int32 into an (H,W,Cn) strided view. */
+int snb_paf_gather(const float* pafs, long long py, long long px, long long pc, int H, int W, int Cn,
+                   const int* subs, long long n_sub, float* out, int* status, void* stream);
+/* score_paf_lines on pre-gathered lines (paf.py:335-410): lines (M,n_points,2). */
+int snb_score_lines(const float* lines, const float* peaks, long long n_peaks, const long long* epi, long long M,
+                    int n_points, float max_edge_length, float weight, float* out, int* status, void* stream);
+/* compute_distance_penalty (paf.py:290-332). */
+int snb_distance_penalty(const float* lengths, long long n, float max_edge_length, float weight, float* out,
+                         void* stream);
+
+/* Matching = scipy.optimize.linear_sum_assignment semantics on cost = -score, NaN -> +inf
+ * (match_candidates_sample, paf.py:500-619).  Matches of frame b / edge k are written at
+ * match_off[b][k] inside the frame's slot, rows ascending; m_src / m_dst are RANKS within the
+ * node's peaks (paf.py:596-599).
+ *   snb_match_structured: candidates are the full cross product written by snb_paf_score.
+ *     ws: B*n_edges*snb_lsap_workspace_bytes(ws_max_dim) bytes, used when an edge has more than
+ *     32 peaks per node (NULL/0 -> such edges raise SNB_STATUS_LSAP_TOO_LARGE).
+ *   snb_match_generic: arbitrary candidate lists (CSR).  phase 0 writes dims (B,E,2) = distinct
+ *     (src,dst) counts; phase 1 needs cost_off (B*E) offsets into cost / cell_src scratch
+ *     (n_src*n_dst each), match_start (B*E) output offsets and ws as above. */
+long long snb_lsap_workspace_bytes(int max_dim);
+int snb_match_structured(const float* cand_score, const int* cand_start, int cand_stride, const int* edges,
+                         int n_nodes, int n_edges, const int* node_start, const int* edge_off, const int* match_off,
+                         const int* match_start, int match_stride, void* ws, int ws_max_dim, int B, int* m_edge,
+                         int* m_src, int* m_dst, float* m_score, int* m_count, int* status, void* stream);
+int snb_match_generic(int phase, const int* cand_edge, const long long* cand_epi, const float* cand_score,
+                      const int* cand_start, const int* cand_count, int B, int n_edges, int max_peak_id, int* dims,
+                      const long long* cost_off, double* cost, int* cell_src, const int* match_start, void* ws,
+                      int ws_max_dim, int* m_edge, int* m_src, int* m_dst, float* m_score, int* status,
+                      void* stream);
+
+/* snb_assemble: min_line_scores filter + assign_connections_to_instances (paf.py:705-820) +
+ * make_predicted_instances (:823-887) + the per-sample loop of group_instances_batch (:1041-1149).
+ *   sorted_edges: toposort_edges() order (host, paf.py:890-912).  min_instance_peaks is already
+ *   an int (the caller applies int(frac*n_nodes), paf.py:802).  ws: B*4*ws_stride int32.
+ *   Outputs (NaN-filled): inst_xy (B,inst_cap,N,2), inst_val (B,inst_cap,N), inst_score
+ *   (B,inst_cap), n_inst (B). */
+int snb_assemble(const float* peak_xy, const float* peak_val, const int* peak_chan, const int* frame_start,
+                 int frame_stride, const int* frame_count, int B, const int* node_start, const int* node_peaks,
+                 int n_nodes, const int* edges, const int* sorted_edges, int n_sorted, const int* m_edge,
+                 const int* m_src, const int* m_dst, const float* m_score, const int* match_start, int match_stride,
+                 const int* m_count, int min_instance_peaks, float min_line_scores, int* ws, int ws_stride,
+                 int inst_cap, float* inst_xy, float* inst_val, float* inst_score, int* n_inst, int* status,
+                 void* stream);
+
+/* make_predicted_instances (paf.py:823-887), dict-API form: n_assign assignments in insertion order
+ * (xy, val, compacted instance index, node), n_conn connections in visiting order (instance index of
+ * the source peak or -1, score).  Outputs NaN-filled (n_inst,N,2), (n_inst,N) and (n_inst,). */
+int snb_scatter_instances(const float* xy, const float* val, const int* inst, const int* node, int n_assign,
+                          const int* conn_inst, const float* conn_score, int n_conn, int n_inst, int n_nodes,
+                          float* o_xy, float* o_val, float* o_score, void* stream);
+
+/* interp1d (inference/utils.py:29-130): x (x_rows,n), y (y_rows,n), xnew (xn_rows,p), *_rows in {1, rows};
+ * out (rows,p). */
+int snb_interp1d(const float* x, int x_rows, const float* y, int y_rows, const float* xnew, int xn_rows, int n, int p,
+                 long long rows, float* out, void* stream);
+
+/* ------------------------------------- training targets (data/confidence_maps.py, data/edge_maps.py)
+ *
+ * snb_confmaps: make_confmaps (confidence_maps.py:94-129, I = 1) and make_multi_confmaps (:132-166).
+ *   points (G,I,N,2) fp32 (NaN = missing), xv (w), yv (h), den = fl32(2*sigma^2).
+ *   out (G,N,h,w) fp32 or bf16 = max over I of nan_to_num(exp(-((xv-x)^2+(yv-y)^2)/den)). */
+int snb_confmaps(const float* points, int G, int I, int N, const float* xv, const float* yv, int h, int w, float den,
+                 int out_bf16, void* out, void* stream);
+
+/* snb_pafs: make_pafs (edge_maps.py:120-164; accumulate = 0, I = 1, NaNs kept) and make_multi_pafs
+ *   (:167-220; accumulate = 1: per-instance NaN -> 0, summed in instance order).
+ *   srcs/dsts (I,E,2); out (E,2,h,w) fp32 or bf16.  The weight is exp(-(d2*d2)/den) on the SQUARED
+ *   point-segment distance d2, exactly as distance_to_edge + gaussian_pdf compose in the reference. */
+int snb_pafs(const float* srcs, const float* dsts, int I, int E, const float* xv, const float* yv, int h, int w,
+             float den, int accumulate, int out_bf16, void* out, void* stream);
+
+/* distance_to_edge (edge_maps.py:15-78; apply_pdf = 0) and make_edge_maps (:81-117; apply_pdf = 1).
+ *   points (n_pts,2) or NULL for the (yv, xv) meshgrid with n_pts = h*w; out (n_pts,E). */
+int snb_edge_distance(const float* points, const float* xv, const float* yv, int w, long long n_pts,
+                      const float* src, const float* dst, int E, int apply_pdf, float den, float* out, void* stream);
+
+/* gaussian_pdf (data/utils.py:114-125): out = exp(-(x*x)/den). */
+int snb_gaussian_pdf(const float* x, long long n, float den, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

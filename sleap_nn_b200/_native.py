@@ -40,7 +40,25 @@ SIGNATURES = {
     "snb_centered_bboxes": [_p, _ll, _f, _f, _p, _p],
     "snb_integral_regression": [_p, _ll, _i, _i, _p, _p, _p, _p, _p],
     "snb_dilate8": [_p, _ll, _i, _i, _p, _p],
+    "snb_paf_prepare": [_p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p],
+    "snb_paf_score": [_p, _ll, _ll, _ll, _ll, _i, _i, _p, _i, _f, _f, _f, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p,
+                      _i, _i, _p, _p, _p, _p, _p],
+    "snb_line_subs": [_p, _ll, _p, _p, _ll, _p, _i, _f, _i, _i, _p, _p, _p],
+    "snb_paf_gather": [_p, _ll, _ll, _ll, _i, _i, _i, _p, _ll, _p, _p, _p],
+    "snb_score_lines": [_p, _p, _ll, _p, _ll, _i, _f, _f, _p, _p, _p],
+    "snb_distance_penalty": [_p, _ll, _f, _f, _p, _p],
+    "snb_match_structured": [_p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "snb_match_generic": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
+    "snb_assemble": [_p, _p, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p, _i, _p, _i, _f, _p, _i,
+                     _i, _p, _p, _p, _p, _p, _p],
+    "snb_scatter_instances": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p],
+    "snb_interp1d": [_p, _i, _p, _i, _p, _i, _i, _i, _ll, _p, _p],
+    "snb_confmaps": [_p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _p, _p],
+    "snb_pafs": [_p, _p, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
+    "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
+    "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
 }
+RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i]}
 
 
 class NativeLibraryError(RuntimeError):
@@ -61,6 +79,10 @@ def _load() -> C.CDLL:
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    for name, argtypes in RETURNS_LONGLONG.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_longlong
     return lib
 
 
