@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Benchmark of the bottom-up post-processing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (`config.workload`): BASELINE cfg3 "bottom-up mice" - 1024x1024 frames, 5 nodes /
+4 edges, stride-2 confidence maps (64,5,512,512) + PAFs (64,8,512,512), batch 64, full peak +
+PAF grouping.  One STEP = one pass of the whole hot path (K1 peaks + refinement -> K4 line
+scores -> K5 assignment -> K6 assembly) over one batch of 64 synthetic frames.
+
+  value   frames/s with the maps already resident in HBM (as they are after the backbone),
+          batches pipelined over `--streams` CUDA streams, inputs rotated over several distinct
+          batches (each 872 MB > 126 MB L2, so nothing is served from cache);
+  e2e     the same metric through the public API with HOST buffers: per step a pinned-host ->
+          device copy of the maps and a device -> host read of the grouped instances;
+  roofline  the dominant kernel (streaming NMS detect) timed in situ with CUDA events recorded
+          around it inside the timed region; algorithmic bytes = 4*C*H*W*B per launch;
+  cpu_baseline  the CPU oracle (a port of the reference's op chain, torch CPU ops, all host
+          threads) on a bounded sample of the same frames.  N=1, rank 0 only.
+
+`--impl reference` times that CPU port alone (the reference is pure Python / ATen and cannot
+travel to the GPU box).  Multi-GPU: frames shard, no collective on the hot path;
+one process per GPU (torchrun), barrier + synchronize around the timed region, max over ranks.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(
+    workload="cfg3 bottom-up mice: 1024x1024 frames, 5 nodes/4 edges, stride-2 cms (64,5,512,512) + pafs (64,8,512,512), "
+             "batch 64, peaks+integral refine+PAF score+match+group",
+    batch=64, n_nodes=5, n_edges=4, n_instances=2, img_hw=[1024, 1024], stride=2, maps_hw=[512, 512],
+)
+B, N_NODES, N_INST, IMG_HW, STRIDE = 64, 5, 2, (1024, 1024), 2
+ALGO_BYTES_PER_FRAME = 4 * N_NODES * 512 * 512  # K1 reads every confidence-map element once
+METRIC, UNIT = "bottom-up post-proc frames/s", "frames/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"  # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------- CPU port (oracle)
+def oracle_postproc(cms_cpu, pafs_cpu, edges):
+    """The reference's bottom-up post-processing chain, as restated by oracle/ (CPU, torch ops)."""
+    from oracle import paf as opaf
+    from oracle import peaks as opeaks
+    from oracle.synth import split_by_sample
+
+    nb = cms_cpu.shape[0]
+    pts, vals, si, ci = opeaks.local_peaks(cms_cpu, 0.2, "integral")
+    peaks, pvs, pcs = (split_by_sample(x, si, nb) for x in (pts * STRIDE, vals, ci))
+    return opaf.predict(pafs_cpu.permute(0, 2, 3, 1), peaks, pvs, pcs, edges, N_NODES, STRIDE)
+
+
+def time_cpu_port(cms_cpu, pafs_cpu, edges, frames_per_call: int, calls: int, warm: int = 1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    c, p = cms_cpu[:frames_per_call], pafs_cpu[:frames_per_call]
+    for _ in range(warm):
+        oracle_postproc(c, p, edges)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        oracle_postproc(c, p, edges)
+    dt = time.perf_counter() - t0
+    return frames_per_call * calls / dt, dt / calls
+
+
+def make_inputs(dev, n_batches: int, seed0: int):
+    from sleap_nn_b200 import synthetic
+
+    edges = synthetic.chain_edges(N_NODES)
+    out = []
+    for i in range(n_batches):
+        poses = synthetic.random_poses(seed0 + i, B, N_INST, N_NODES, IMG_HW, edges)
+        out.append(synthetic.render_batch(poses, IMG_HW, STRIDE, edges, dev, seed=seed0 + i))
+    return edges, out
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    from sleap_nn_b200 import synthetic
+
+    frames_per_step = 16  # bounded sample of the workload: 16 of the batch's 64 frames per step
+    edges = synthetic.chain_edges(N_NODES)
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+        poses = synthetic.random_poses(1000, frames_per_step, N_INST, N_NODES, IMG_HW, edges)
+        cms, pafs = synthetic.render_batch(poses, IMG_HW, STRIDE, edges, dev, seed=1000)
+        cms_cpu, pafs_cpu = cms.cpu(), pafs.cpu()
+        del cms, pafs
+    else:  # CPU-only box: render with the oracle's own target code
+        from oracle import synth as osynth
+
+        poses = osynth.make_poses(1000, frames_per_step, N_INST, N_NODES, IMG_HW, edges=edges)
+        cms_cpu, pafs_cpu = osynth.render(poses, IMG_HW, STRIDE, edges, seed=1000)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(args.warmup):
+        oracle_postproc(cms_cpu, pafs_cpu, edges)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_postproc(cms_cpu, pafs_cpu, edges)
+    dt = time.perf_counter() - t0
+    fps = frames_per_step * args.steps / dt
+    sample = f"{frames_per_step} frames/step of the cfg3 batch, {args.steps} steps, torch CPU ops, {torch.get_num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, frames_per_step=frames_per_step),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python/ATen with no native path and cannot be installed offline (needs sleap-io, "
+                "lightning, omegaconf): this arm times oracle/, the CPU port of its op chain, on the host cores",
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, rank: int, world: int):
+    import torch.distributed as dist
+
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_bufs, n_streams = args.buffers, args.streams
+    edges, inputs = make_inputs(dev, n_bufs, seed0=100 * (rank + 1))
+    pipes = [BottomUpPostproc(N_NODES, edges, B, (512, 512), cms_stride=STRIDE, pafs_stride=STRIDE, device=dev)
+             for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    main = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_steps(n, events=None):
+        for i in range(n):
+            s = i % n_streams
+            with torch.cuda.stream(streams[s]):
+                cms, pafs = inputs[i % n_bufs]
+                pipes[s](cms, pafs, detect_events=None if events is None else events[i])
+
+    # ---- correctness guard: the timed configuration must produce the planted animals
+    res = pipes[0](*inputs[0])
+    inst, _, _ = res.to_lists()
+    assert sum(len(x) for x in inst) == B * N_INST, "pipeline did not recover the planted instances"
+
+    # ---- device-resident timed region (value)
+    run_steps(max(args.warmup, 3))
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_begin.record(main)
+        for s in streams:
+            s.wait_event(t_begin)
+        run_steps(args.steps, ev)
+        for s in streams:
+            done = torch.cuda.Event()
+            done.record(s)
+            main.wait_event(done)
+        t_end.record(main)
+        barrier()
+        # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
+        if t_begin.elapsed_time(t_end) < 600 and rank == 0:
+            t_fill = time.perf_counter()
+            while time.perf_counter() - t_fill < 0.8:
+                run_steps(n_streams * 8)
+                torch.cuda.synchronize(dev)
+    ms_total = t_begin.elapsed_time(t_end)
+    detect_ms = [a.elapsed_time(b) for a, b in ev]
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end timed region (host buffers in, host results out), same steps
+    host = [(c.cpu().pin_memory(), p.cpu().pin_memory()) for c, p in inputs[: min(2, n_bufs)]]
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+    pipe0 = pipes[0]
+    for i in range(2):
+        pipe0.run_host(*host[i % len(host)])
+    barrier()
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d2h = 0
+    e_begin.record(main)
+    t0 = time.perf_counter()
+    e2e_steps = min(args.steps, args.e2e_steps)
+    for i in range(e2e_steps):
+        out = pipe0.run_host(*host[i % len(host)])
+        d2h = pipe0.buf["inst_xy"].numel() * 4 + pipe0.buf["inst_val"].numel() * 4 + pipe0.buf["inst_score"].numel() * 4 + B * 4 + 4
+    e_end.record(main)
+    barrier()
+    e2e_ms = max(e_begin.elapsed_time(e_end), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, which = measured_peaks()
+        avg_detect_ms = sum(detect_ms) / len(detect_ms)
+        achieved = ALGO_BYTES_PER_FRAME * B / (avg_detect_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(WORKLOAD, parallelism=f"frame-sharded x{world}, no collective", streams=n_streams,
+                           input_batches=n_bufs, l2="inputs larger than L2: each batch is 872 MB and batches rotate"),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": pipes[0].launches_per_call * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "local_peaks_detect_vec4<4>", "peak_source": which,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "avg_launch_ms": avg_detect_ms,
+                         "whole_step_frac": (ALGO_BYTES_PER_FRAME * B / (ms_total / args.steps / 1e3) / 1e9) / peak},
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cms_cpu, pafs_cpu = inputs[0][0][:16].cpu(), inputs[0][1][:16].cpu()
+            fps, per_call = time_cpu_port(cms_cpu, pafs_cpu, edges, 16, args.cpu_calls)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{args.cpu_calls} x 16 frames of the same cfg3 batch ({per_call:.2f} s/call), "
+                                              "oracle/ torch-CPU port of the reference chain"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--buffers", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-calls", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU port)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,13 @@ int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, 
                     long long sw, float threshold, int refine_size, float xy_scale, int cap, int* frame_count,
                     uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* stream);
 
+/* Same as snb_local_peaks; ev_begin / ev_end are optional cudaEvent_t handles recorded right before /
+ * after the streaming detect kernel so a benchmark can time the dominant kernel in situ. */
+int snb_local_peaks_ev(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                       long long sw, float threshold, int refine_size, float xy_scale, int cap, int* frame_count,
+                       uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* ev_begin,
+                       void* ev_end, void* stream);
+
 /* Padded table -> the reference's concatenated (points, vals, sample_inds, channel_inds). */
 int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val, const int* chan,
                    float* o_xy, float* o_val, int* o_sample, int* o_chan, void* stream);
@@ -210,6 +217,73 @@ int snb_edge_distance(const float* points, const float* xv, const float* yv, int
 
 /* gaussian_pdf (data/utils.py:114-125): out = exp(-(x*x)/den). */
 int snb_gaussian_pdf(const float* x, long long n, float den, float* out, void* stream);
+
+/* ------------------------------------------------------------ fused bottom-up post-processing
+ *
+ * snb_bottomup_postproc enqueues K1 -> K4 -> K5 -> K6 on `stream` with padded tables: no host
+ * sync, no allocation.  Replaces the sequence find_local_peaks -> "peaks * stride" -> per-sample
+ * split -> PAFScorer.predict in BottomUpLayer (inference/layers/bottomup.py:95-236) and
+ * group_scored_batch (inference/streaming.py:147-255).  n_nodes == C.  All pointers are caller
+ * allocated device buffers:
+ *   frame_count B | keys B*peak_cap | peak_xy B*peak_cap*2 | peak_val, peak_chan, node_peaks B*peak_cap
+ *   node_start B*(C+1) | edge_off, match_off B*(n_edges+1)
+ *   cand_edge, cand_score B*cand_cap | cand_epi B*cand_cap*2 (int64)
+ *   m_edge, m_src, m_dst, m_score B*match_cap | m_count B
+ *   lsap_ws B*n_edges*snb_lsap_workspace_bytes(lsap_max_dim) bytes (may be NULL when lsap_max_dim <= 32)
+ *   asm_ws B*4*peak_cap int32 | inst_xy B*inst_cap*C*2 | inst_val B*inst_cap*C | inst_score B*inst_cap
+ *   n_inst B | status 1 (zeroed by the caller). */
+typedef struct snb_bottomup_args {
+  const float* cms;
+  int B, C, H, W;
+  long long cms_sb, cms_sc, cms_sh, cms_sw;
+  const float* pafs; /* (B, paf_H, paf_W, 2*n_edges) view, element strides below */
+  int paf_H, paf_W;
+  long long paf_sb, paf_sy, paf_sx, paf_sc;
+  const int* edges; /* (n_edges, 2) node ids */
+  int n_edges;
+  const int* sorted_edges; /* toposort_edges() order */
+  int n_sorted;
+  const float* t_table; /* torch.linspace(0, 1, n_points), host-computed */
+  int n_points;
+  float peak_threshold;
+  int refine_size;   /* 0 = rough peaks, else integral patch size */
+  float cms_stride;  /* peaks are multiplied by this (layers/bottomup.py:111) */
+  float pafs_stride;
+  float max_edge_length; /* ratio * max(paf_H, paf_W, 2*n_edges) * pafs_stride (paf.py:457-461) */
+  float dist_penalty_weight;
+  int min_instance_peaks;
+  float min_line_scores;
+  int peak_cap, cand_cap, match_cap, inst_cap, lsap_max_dim;
+  int* frame_count;
+  uint32_t* keys;
+  float* peak_xy;
+  float* peak_val;
+  int* peak_chan;
+  int* node_start;
+  int* node_peaks;
+  int* edge_off;
+  int* match_off;
+  int* cand_edge;
+  long long* cand_epi;
+  float* cand_score;
+  int* m_edge;
+  int* m_src;
+  int* m_dst;
+  float* m_score;
+  int* m_count;
+  void* lsap_ws;
+  int* asm_ws;
+  float* inst_xy;
+  float* inst_val;
+  float* inst_score;
+  int* n_inst;
+  int* status;
+  void* ev_detect_begin; /* optional cudaEvent_t around the streaming detect kernel */
+  void* ev_detect_end;
+} snb_bottomup_args;
+
+int snb_bottomup_postproc(const snb_bottomup_args* args, void* stream);
+int snb_bottomup_launches_per_call(void);
 
 #ifdef __cplusplus
 }

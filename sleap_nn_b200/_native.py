@@ -33,6 +33,7 @@ _ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
 SIGNATURES = {
     "snb_abi_version": [],
     "snb_local_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
+    "snb_local_peaks_ev": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_pack_peaks": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_global_peaks_workspace": [_i, _i, _i, _i, _ip, _ip, _llp],
     "snb_global_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p],
@@ -57,8 +58,33 @@ SIGNATURES = {
     "snb_pafs": [_p, _p, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
+    "snb_bottomup_postproc": [_p, _p],
+    "snb_bottomup_launches_per_call": [],
 }
 RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i]}
+
+
+class BottomUpArgs(C.Structure):
+    """Mirror of `snb_bottomup_args` (include/sleapnn_b200.h); field order must match."""
+
+    _fields_ = [
+        ("cms", _p), ("B", _i), ("C", _i), ("H", _i), ("W", _i),
+        ("cms_sb", _ll), ("cms_sc", _ll), ("cms_sh", _ll), ("cms_sw", _ll),
+        ("pafs", _p), ("paf_H", _i), ("paf_W", _i),
+        ("paf_sb", _ll), ("paf_sy", _ll), ("paf_sx", _ll), ("paf_sc", _ll),
+        ("edges", _p), ("n_edges", _i), ("sorted_edges", _p), ("n_sorted", _i),
+        ("t_table", _p), ("n_points", _i),
+        ("peak_threshold", _f), ("refine_size", _i), ("cms_stride", _f), ("pafs_stride", _f),
+        ("max_edge_length", _f), ("dist_penalty_weight", _f), ("min_instance_peaks", _i), ("min_line_scores", _f),
+        ("peak_cap", _i), ("cand_cap", _i), ("match_cap", _i), ("inst_cap", _i), ("lsap_max_dim", _i),
+        ("frame_count", _p), ("keys", _p), ("peak_xy", _p), ("peak_val", _p), ("peak_chan", _p),
+        ("node_start", _p), ("node_peaks", _p), ("edge_off", _p), ("match_off", _p),
+        ("cand_edge", _p), ("cand_epi", _p), ("cand_score", _p),
+        ("m_edge", _p), ("m_src", _p), ("m_dst", _p), ("m_score", _p), ("m_count", _p),
+        ("lsap_ws", _p), ("asm_ws", _p),
+        ("inst_xy", _p), ("inst_val", _p), ("inst_score", _p), ("n_inst", _p), ("status", _p),
+        ("ev_detect_begin", _p), ("ev_detect_end", _p),
+    ]
 
 
 class NativeLibraryError(RuntimeError):

@@ -287,7 +287,7 @@ __global__ void distance_penalty_kernel(const float* __restrict__ len, long long
 // path[nc] col4row[nr] row4col[nc] free_[nc] ints, in_sr[nr] in_sc[nc] bytes.
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t lsap_ws_bytes(int max_dim) {
-  return (size_t)max_dim * (3 * 8 + 4 * 4 + 2) + 16;
+  return (((size_t)max_dim * (3 * 8 + 4 * 4 + 2) + 16) + 15) & ~(size_t)15;  // keeps every problem 16B-aligned
 }
 
 template <typename CostFn>
@@ -371,7 +371,7 @@ match_structured_kernel(const float* __restrict__ cand_score, const int* __restr
                         int ws_max_dim, int B, int* __restrict__ m_edge, int* __restrict__ m_src,
                         int* __restrict__ m_dst, float* __restrict__ m_score, int* __restrict__ m_count,
                         int* __restrict__ status) {
-  __shared__ __align__(16) unsigned char s_ws[MATCH_WARPS][LSAP_SMEM_DIM * 42 + 16];
+  __shared__ __align__(16) unsigned char s_ws[MATCH_WARPS][((LSAP_SMEM_DIM * 42 + 16) + 15) / 16 * 16];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long prob = (long long)blockIdx.x * MATCH_WARPS + warp;
   if (prob >= (long long)B * n_edges) return;

@@ -1,0 +1,182 @@
+"""Fused bottom-up post-processing: confidence maps + PAFs -> grouped instances, one C call per batch.
+
+`BottomUpPostproc` owns fixed-capacity device tables for one batch shape and enqueues the whole
+kernel chain (peaks + refinement -> candidates + line scores -> per-edge assignment -> assembly)
+on the current CUDA stream through `snb_bottomup_postproc`, with no host synchronisation and no
+allocation, so several instances can pipeline batches over separate streams.  It is the
+device-resident replacement for the reference call sequence in
+`BottomUpLayer._score_pafs_on_gpu` + `group_scored_batch`
+(sleap_nn/inference/layers/bottomup.py:95-236, sleap_nn/inference/streaming.py:147-255).
+Knob names and defaults follow `PAFScorer` (sleap_nn/inference/ops/paf.py:1208-1218).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from sleap_nn_b200 import _native as N
+from sleap_nn_b200.inference.ops.paf import EdgeType, _t_table, toposort_edges
+
+
+@dataclass
+class BottomUpResult:
+    """Padded device tensors of one batch (valid prefix given by the count tensors)."""
+
+    n_instances: torch.Tensor     # (B,) i32
+    instances: torch.Tensor       # (B, inst_cap, N, 2) f32, NaN = missing node
+    peak_scores: torch.Tensor     # (B, inst_cap, N) f32
+    instance_scores: torch.Tensor  # (B, inst_cap) f32
+    n_peaks: torch.Tensor         # (B,) i32 (true count; may exceed peak_cap -> status bit)
+    peaks: torch.Tensor           # (B, peak_cap, 2) f32 image-scale (x, y), (y, x, channel)-ordered
+    peak_vals: torch.Tensor       # (B, peak_cap)
+    peak_channels: torch.Tensor   # (B, peak_cap) i32
+    status: torch.Tensor          # (1,) i32, SNB_STATUS_* bits
+
+    def to_lists(self):
+        """One host sync: per-sample CPU tensors shaped like `PAFScorer.predict`'s first three outputs."""
+        n = self.n_instances.cpu().tolist()
+        status = int(self.status.item())
+        if status:
+            self.status.zero_()  # sticky bits are reported once
+        if status & N.STATUS_LSAP_INFEASIBLE:
+            raise ValueError("cost matrix is infeasible")
+        if status:
+            raise RuntimeError(f"bottom-up post-processing overflowed a fixed-capacity table (status 0x{status:x}); "
+                               "raise peak_cap / cand_cap / match_cap / inst_cap")
+        xy, pv, sc = self.instances.cpu(), self.peak_scores.cpu(), self.instance_scores.cpu()
+        B = len(n)
+        return ([xy[b, : n[b]] for b in range(B)], [pv[b, : n[b]] for b in range(B)], [sc[b, : n[b]] for b in range(B)])
+
+
+class BottomUpPostproc:
+    """Device-resident bottom-up post-processing for batches of a fixed shape.
+
+    Args:
+        n_nodes, edge_inds: skeleton (edge_inds = [(src_node, dst_node), ...]).
+        batch, cms_hw: confidence maps are (batch, n_nodes, H, W); PAFs are (batch, 2E, Hp, Wp) or
+            the permuted (batch, Hp, Wp, 2E) view - either is read in place through its strides.
+        cms_stride / pafs_stride: output strides of the two heads.
+        peak_threshold, refinement, integral_patch_size: as `find_local_peaks`.
+        max_edge_length_ratio, dist_penalty_weight, n_points, min_instance_peaks, min_line_scores:
+            as `PAFScorer`.
+        peak_cap, cand_cap, match_cap, inst_cap: per-frame table capacities; overflow sets a status
+            bit (reported by `BottomUpResult.to_lists`), it never corrupts memory.
+    """
+
+    def __init__(self, n_nodes: int, edge_inds: Sequence[Tuple[int, int]], batch: int, cms_hw: Tuple[int, int],
+                 cms_stride: int = 2, pafs_stride: int = 2, peak_threshold: float = 0.2,
+                 refinement: Optional[str] = "integral", integral_patch_size: int = 5,
+                 max_edge_length_ratio: float = 0.25, dist_penalty_weight: float = 1.0, n_points: int = 10,
+                 min_instance_peaks: Union[int, float] = 0, min_line_scores: float = 0.25, peak_cap: int = 256,
+                 cand_cap: int = 4096, match_cap: int = 512, inst_cap: int = 64, lsap_max_dim: int = 32,
+                 device: Optional[torch.device] = None):
+        self.device = torch.device(device) if device is not None else N.compute_device()
+        self.n_nodes, self.batch = int(n_nodes), int(batch)
+        self.edge_inds = [(int(a), int(b)) for a, b in edge_inds]
+        self.n_edges = len(self.edge_inds)
+        self.cms_hw = (int(cms_hw[0]), int(cms_hw[1]))
+        self.cms_stride, self.pafs_stride = cms_stride, pafs_stride
+        self.peak_threshold = float(peak_threshold)
+        self.refine_size = int(integral_patch_size) if refinement == "integral" else 0
+        self.max_edge_length_ratio = float(max_edge_length_ratio)
+        self.dist_penalty_weight = float(dist_penalty_weight)
+        self.n_points = int(n_points)
+        if isinstance(min_instance_peaks, float):
+            min_instance_peaks = int(min_instance_peaks * n_nodes) if min_instance_peaks > 0 else 0  # paf.py:791-802
+        self.min_instance_peaks = int(min_instance_peaks)
+        self.min_line_scores = float(min_line_scores)
+        self.caps = dict(peak_cap=int(peak_cap), cand_cap=int(cand_cap), match_cap=int(match_cap),
+                         inst_cap=int(inst_cap), lsap_max_dim=int(lsap_max_dim))
+        self.sorted_edge_inds = toposort_edges([EdgeType(a, b) for a, b in self.edge_inds]) if self.n_edges else ()
+        dev, B, Nn, E = self.device, self.batch, self.n_nodes, self.n_edges
+        i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            self._edges = torch.tensor(self.edge_inds, dtype=torch.int32, device=dev).reshape(-1, 2)
+            self._sorted = torch.tensor(list(self.sorted_edge_inds), dtype=torch.int32, device=dev)
+            self._t = _t_table(self.n_points, dev)
+            pc, cc, mc, ic = peak_cap, cand_cap, match_cap, inst_cap
+            self.buf = dict(
+                frame_count=i32(B), keys=i32(B * pc), peak_xy=f32(B, pc, 2), peak_val=f32(B, pc), peak_chan=i32(B, pc),
+                node_start=i32(B, Nn + 1), node_peaks=i32(B * pc), edge_off=i32(B, E + 1), match_off=i32(B, E + 1),
+                cand_edge=i32(B * cc), cand_epi=torch.empty((B * cc, 2), dtype=torch.int64, device=dev),
+                cand_score=f32(B * cc), m_edge=i32(B * mc), m_src=i32(B * mc), m_dst=i32(B * mc), m_score=f32(B * mc),
+                m_count=i32(B), asm_ws=i32(B * 4 * pc), inst_xy=f32(B, ic, Nn, 2), inst_val=f32(B, ic, Nn),
+                inst_score=f32(B, ic), n_inst=i32(B), status=torch.zeros((1,), dtype=torch.int32, device=dev),
+            )
+            ws_bytes = N.lib.snb_lsap_workspace_bytes(int(lsap_max_dim)) * B * max(E, 1) if lsap_max_dim > 32 else 0
+            self.buf["lsap_ws"] = torch.empty((max(ws_bytes // 8, 1),), dtype=torch.int64, device=dev)
+        self._args = N.BottomUpArgs()
+        a = self._args
+        a.B, a.C, a.H, a.W = B, Nn, self.cms_hw[0], self.cms_hw[1]
+        a.edges, a.n_edges = N.ptr(self._edges), E
+        a.sorted_edges, a.n_sorted = N.ptr(self._sorted), len(self.sorted_edge_inds)
+        a.t_table, a.n_points = N.ptr(self._t), self.n_points
+        a.peak_threshold, a.refine_size = self.peak_threshold, self.refine_size
+        a.cms_stride, a.pafs_stride = float(cms_stride), float(pafs_stride)
+        a.dist_penalty_weight = self.dist_penalty_weight
+        a.min_instance_peaks, a.min_line_scores = self.min_instance_peaks, self.min_line_scores
+        for k, v in self.caps.items():
+            setattr(a, k, v)
+        for k, t in self.buf.items():
+            setattr(a, k, N.ptr(t))
+        if lsap_max_dim <= 32:
+            a.lsap_ws = None
+        a.ev_detect_begin = a.ev_detect_end = None
+
+    # ------------------------------------------------------------------ device-resident path
+    def __call__(self, cms: torch.Tensor, pafs: torch.Tensor, detect_events=None) -> BottomUpResult:
+        """Enqueue the chain on the current stream of `self.device`; returns padded device tensors.
+
+        cms (B, N, H, W) fp32 CUDA; pafs (B, 2E, Hp, Wp) or (B, Hp, Wp, 2E) fp32 CUDA, any strides.
+        `detect_events` = (torch.cuda.Event, torch.cuda.Event) recorded around the streaming
+        detect kernel (for the benchmark's roofline figure).
+        """
+        if not (cms.is_cuda and pafs.is_cuda) or cms.dtype != torch.float32 or pafs.dtype != torch.float32:
+            raise TypeError("BottomUpPostproc expects fp32 CUDA tensors; use .run_host() for host buffers")
+        if tuple(cms.shape) != (self.batch, self.n_nodes) + self.cms_hw:
+            raise ValueError(f"cms shape {tuple(cms.shape)} does not match the pipeline's batch shape")
+        if pafs.dim() != 4 or pafs.shape[0] != self.batch:
+            raise ValueError("pafs must be (B, 2E, H, W) or its (B, H, W, 2E) view")
+        if pafs.shape[1] == 2 * self.n_edges and pafs.shape[-1] != 2 * self.n_edges:
+            pafs = pafs.permute(0, 2, 3, 1)  # channels-first tensor -> the channels-last VIEW (no copy)
+        elif pafs.shape[-1] != 2 * self.n_edges:
+            raise ValueError("pafs channel count must be 2 * n_edges")
+        a = self._args
+        a.cms = N.ptr(cms)
+        a.cms_sb, a.cms_sc, a.cms_sh, a.cms_sw = cms.stride()
+        a.pafs = N.ptr(pafs)
+        a.paf_H, a.paf_W = int(pafs.shape[1]), int(pafs.shape[2])
+        a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc = pafs.stride()
+        # max(H, W, 2E) really includes the channel dim (paf.py:457-461)
+        a.max_edge_length = self.max_edge_length_ratio * max(pafs.shape[-1], pafs.shape[-2], pafs.shape[-3]) * self.pafs_stride
+        if detect_events is not None:
+            a.ev_detect_begin, a.ev_detect_end = detect_events[0].cuda_event, detect_events[1].cuda_event
+        else:
+            a.ev_detect_begin = a.ev_detect_end = None
+        N.check(N.lib.snb_bottomup_postproc(C.byref(a), N.stream_ptr(self.device)), "snb_bottomup_postproc")
+        b = self.buf
+        return BottomUpResult(b["n_inst"], b["inst_xy"], b["inst_val"], b["inst_score"], b["frame_count"],
+                              b["peak_xy"], b["peak_val"], b["peak_chan"], b["status"])
+
+    @property
+    def launches_per_call(self) -> int:
+        return int(N.lib.snb_bottomup_launches_per_call())
+
+    # ------------------------------------------------------------------ host-buffer path
+    def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor):
+        """Host (ideally pinned) buffers in, per-sample CPU tensors out: H2D + chain + D2H.
+
+        Returns (instances, peak_scores, instance_scores) lists like `PAFScorer.predict`.
+        """
+        with torch.cuda.device(self.device):
+            if not hasattr(self, "_stage_cms") or self._stage_cms.shape != cms_host.shape:
+                self._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
+                self._stage_pafs = torch.empty(pafs_host.shape, dtype=torch.float32, device=self.device)
+            self._stage_cms.copy_(cms_host, non_blocking=True)
+            self._stage_pafs.copy_(pafs_host, non_blocking=True)
+            return self(self._stage_cms, self._stage_pafs).to_lists()

@@ -1,0 +1,88 @@
+"""GPU parity of the fused bottom-up pipeline (one C call per batch) vs reference goldens and,
+at BASELINE cfg3 map size, vs the CPU oracle run on the same device-rendered frames."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import T, close, eq, golden, npy, ragged
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ref_pipeline_mice.npz", "ref_pipeline_tree.npz"])
+def test_fused_pipeline_matches_reference_golden(name):
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    d = golden(name)
+    cms, pafs = T(d["cms"]).cuda(), T(d["pafs"]).cuda()
+    B, Nn, H, W = cms.shape
+    mip = float(d["min_instance_peaks"])
+    mip = int(mip) if mip == int(mip) else mip
+    pipe = BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), cms_stride=int(d["stride"]), pafs_stride=int(d["stride"]),
+                            min_instance_peaks=mip)
+    assert list(pipe.sorted_edge_inds) == d["sorted_edge_inds"].tolist()
+    for layout in ("nchw", "view"):
+        res = pipe(cms, pafs if layout == "nchw" else pafs.permute(0, 2, 3, 1))
+        inst, pv, sc = res.to_lists()
+        eq(npy(res.n_peaks), np.bincount(d["pk_s"], minlength=B).astype(np.int32))
+        want_inst, want_pv, want_sc = ragged(d, "inst"), ragged(d, "inst_pv"), ragged(d, "inst_sc")
+        for b in range(B):
+            assert inst[b].shape == want_inst[b].shape
+            eq(np.isnan(npy(inst[b])), np.isnan(npy(want_inst[b])))
+            close(npy(inst[b]), npy(want_inst[b]), atol=1e-4)
+            eq(npy(pv[b]), npy(want_pv[b]))
+            close(npy(sc[b]), npy(want_sc[b]), rtol=1e-5, atol=1e-5)
+
+
+def test_fused_pipeline_full_size_vs_oracle():
+    """cfg3 geometry (5 nodes / 4 edges, 1024^2 frames, stride 2 -> 512^2 maps), 6 frames."""
+    from oracle import paf as opaf
+    from oracle import peaks as opeaks
+    from oracle.synth import split_by_sample
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    B, n_inst, Nn, hw, stride = 6, 2, 5, (1024, 1024), 2
+    edges = synthetic.chain_edges(Nn)
+    poses = synthetic.random_poses(3, B, n_inst, Nn, hw, edges)
+    dev = torch.device("cuda")
+    cms, pafs = synthetic.render_batch(poses, hw, stride, edges, dev, seed=3)
+    assert cms.shape == (B, Nn, 512, 512) and pafs.shape == (B, 8, 512, 512)
+    pipe = BottomUpPostproc(Nn, edges, B, (512, 512), cms_stride=stride, pafs_stride=stride)
+    res = pipe(cms, pafs)
+    inst, pv, sc = res.to_lists()
+    # oracle on the very same maps
+    c_cpu, p_cpu = cms.cpu(), pafs.cpu()
+    pts, vals, si, ci = opeaks.local_peaks(c_cpu, 0.2, "integral")
+    eq(npy(res.n_peaks), np.bincount(npy(si), minlength=B).astype(np.int32))
+    pts = pts * stride
+    peaks, pvs, pcs = (split_by_sample(x, si, B) for x in (pts, vals, ci))
+    want = opaf.predict(p_cpu.permute(0, 2, 3, 1), peaks, pvs, pcs, edges, Nn, stride)
+    for b in range(B):
+        n = int(res.n_peaks[b])
+        close(npy(res.peaks[b, :n]), npy(peaks[b]), atol=1e-4)
+        eq(npy(res.peak_vals[b, :n]), npy(pvs[b])); eq(npy(res.peak_channels[b, :n]), npy(pcs[b]))
+        assert inst[b].shape == want[0][b].shape == (n_inst, Nn, 2)
+        eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
+        close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
+        eq(npy(pv[b]), npy(want[1][b]))
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-5)
+        # every planted animal is recovered within a pixel
+        got = npy(inst[b])
+        for a in range(n_inst):
+            dmin = min(np.nanmax(np.abs(got[k] - npy(poses[b, a]))) for k in range(n_inst))
+            assert dmin < 1.5
+
+
+def test_capacity_overflow_is_reported_not_silent():
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    g = torch.Generator().manual_seed(0)
+    cms = torch.rand((2, 3, 64, 64), generator=g).cuda()  # noise: hundreds of peaks per frame
+    pafs = torch.zeros((2, 4, 64, 64)).cuda()
+    pipe = BottomUpPostproc(3, [(0, 1), (1, 2)], 2, (64, 64), peak_cap=16, cand_cap=64, match_cap=16, inst_cap=4)
+    res = pipe(cms, pafs)
+    assert int(res.n_peaks.max()) > 16
+    with pytest.raises(RuntimeError, match="overflowed"):
+        res.to_lists()
