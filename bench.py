@@ -212,6 +212,10 @@ def run_ours(args, rank: int, world: int):
     run_steps(max(args.warmup, 3))
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a_, b_ in ev:  # torch creates the cudaEvent lazily on first record; the C side re-records them in situ
+        a_.record(main)
+        b_.record(main)
+    torch.cuda.synchronize(dev)
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
