@@ -63,12 +63,17 @@ int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, 
                     long long sw, float threshold, int refine_size, float xy_scale, int cap, int* frame_count,
                     uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* stream);
 
-/* Same as snb_local_peaks; ev_begin / ev_end are optional cudaEvent_t handles recorded right before /
- * after the streaming detect kernel so a benchmark can time the dominant kernel in situ. */
-int snb_local_peaks_ev(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
-                       long long sw, float threshold, int refine_size, float xy_scale, int cap, int* frame_count,
-                       uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* ev_begin,
-                       void* ev_end, void* stream);
+/* The two halves of snb_local_peaks, exposed so that a pipeline can put them on different streams.
+ * snb_local_peaks_detect zeroes frame_count and runs the streaming NMS kernel (the only kernel that
+ * moves real bytes); ev_begin / ev_end are optional cudaEvent_t handles recorded right around it so
+ * a benchmark can time the dominant kernel in situ.  snb_local_peaks_finalize sorts each frame's
+ * keys, reads the values, refines and fills the padded table. */
+int snb_local_peaks_detect(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                           long long sw, float threshold, int cap, int* frame_count, uint32_t* keys, void* ev_begin,
+                           void* ev_end, void* stream);
+int snb_local_peaks_finalize(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                             long long sw, int refine_size, float xy_scale, int cap, const int* frame_count,
+                             uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* stream);
 
 /* Padded table -> the reference's concatenated (points, vals, sample_inds, channel_inds). */
 int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val, const int* chan,
@@ -280,10 +285,26 @@ typedef struct snb_bottomup_args {
   int* status;
   void* ev_detect_begin; /* optional cudaEvent_t around the streaming detect kernel */
   void* ev_detect_end;
+  /* Optional two-stream mode: detect runs on `stream`, the per-frame tail on tail_stream (ideally a
+   * high-priority stream) after ev_handoff; ev_tail_done is recorded when the tail is enqueued and
+   * waited on by the next call that reuses these buffers.  All three NULL = single stream. */
+  void* tail_stream;
+  void* ev_handoff;
+  void* ev_tail_done;
+  int flags; /* SNB_FLAG_* */
 } snb_bottomup_args;
 
+#define SNB_FLAG_UNFUSED_TAIL 1 /* chain the stand-alone kernels instead of the fused per-frame tail */
+
+/* The tail (everything after the streaming detect kernel) runs as ONE CTA per frame with all tables
+ * in shared memory when snb_bottomup_tail_smem_bytes(...) <= 200 KB; the intermediate tables
+ * (node_start, node_peaks, edge_off, match_off, cand_*, m_*) are then optional outputs (NULL = skip).
+ * Otherwise, or with SNB_FLAG_UNFUSED_TAIL, the stand-alone kernels are chained and those tables
+ * are required. */
 int snb_bottomup_postproc(const snb_bottomup_args* args, void* stream);
-int snb_bottomup_launches_per_call(void);
+long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
+                                       int n_sorted, int n_points);
+int snb_bottomup_launches_per_call(const snb_bottomup_args* args);
 
 #ifdef __cplusplus
 }

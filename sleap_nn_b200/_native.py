@@ -33,7 +33,8 @@ _ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
 SIGNATURES = {
     "snb_abi_version": [],
     "snb_local_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
-    "snb_local_peaks_ev": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_local_peaks_detect": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
+    "snb_local_peaks_finalize": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_pack_peaks": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_global_peaks_workspace": [_i, _i, _i, _i, _ip, _ip, _llp],
     "snb_global_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p],
@@ -59,9 +60,10 @@ SIGNATURES = {
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
-    "snb_bottomup_launches_per_call": [],
+    "snb_bottomup_launches_per_call": [_p],
 }
-RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i]}
+RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
+FLAG_UNFUSED_TAIL = 1
 
 
 class BottomUpArgs(C.Structure):
@@ -84,6 +86,7 @@ class BottomUpArgs(C.Structure):
         ("lsap_ws", _p), ("asm_ws", _p),
         ("inst_xy", _p), ("inst_val", _p), ("inst_score", _p), ("n_inst", _p), ("status", _p),
         ("ev_detect_begin", _p), ("ev_detect_end", _p),
+        ("tail_stream", _p), ("ev_handoff", _p), ("ev_tail_done", _p), ("flags", _i),
     ]
 
 

@@ -78,4 +78,64 @@ __device__ __forceinline__ void integral_refine(const float* __restrict__ plane,
   *oy = __fdiv_rn((float)sy, zf);
 }
 
+// Warp-cooperative variant: the size x size taps are spread over the 32 lanes (one DRAM/L2 round
+// trip instead of size^2 serial ones); fp64 partial sums are combined by shuffles.  All lanes
+// return the same offsets.
+__device__ __forceinline__ void integral_refine_warp(const float* __restrict__ plane, int H, int W, long long sh,
+                                                     long long sw, float px, float py, int size, int lane, float* ox,
+                                                     float* oy) {
+  const float half_f = 0.5f * (float)size;
+  const int half_i = size / 2;
+  const float tlx_f = __fadd_rn(__fadd_rn(__fsub_rn(px, half_f), 0.5f), (float)half_i);
+  const float tly_f = __fadd_rn(__fadd_rn(__fsub_rn(py, half_f), 0.5f), (float)half_i);
+  const int x0 = (int)truncf(tlx_f) - half_i;
+  const int y0 = (int)truncf(tly_f) - half_i;
+  const float g0 = -0.5f * (float)(size - 1);
+  double z = 0.0, sx = 0.0, sy = 0.0;
+  for (int t = lane; t < size * size; t += 32) {
+    const int j = t / size, i = t - j * size;
+    const int yy = y0 + j, xx = x0 + i;
+    float p = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) p = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+    z += (double)p;
+    sx += (double)__fmul_rn(g0 + (float)i, p);
+    sy += (double)__fmul_rn(g0 + (float)j, p);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    z += __shfl_xor_sync(FULL, z, d);
+    sx += __shfl_xor_sync(FULL, sx, d);
+    sy += __shfl_xor_sync(FULL, sy, d);
+  }
+  const float zf = (float)z;
+  *ox = __fdiv_rn((float)sx, zf);
+  *oy = __fdiv_rn((float)sy, zf);
+}
+
+// ---- mbarrier + bulk async copy (cp.async.bulk, the 1-D TMA path; SASS: UBLKCP) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 }  // namespace snb

@@ -11,21 +11,9 @@
 // All of these touch O(#peaks) data; they are latency-bound, not bandwidth-bound.  The PAF
 // tensor is never streamed: each candidate reads n_points x 2 scalars through its strides
 // (the caller's (B,H,W,2E) permuted VIEW of a (B,2E,H,W) tensor is read in place).
-#include "common.cuh"
+#include "paf_device.cuh"
 
 namespace snb {
-
-// ------------------------------------------------------------------------------------------
-// Frame addressing: a "table" is either padded (frame b starts at b*stride) or CSR (explicit
-// start array).  Counts are clamped to the stride for padded tables.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long tbl_start(const int* start, int stride, int b) {
-  return start ? (long long)start[b] : (long long)b * stride;
-}
-__device__ __forceinline__ int tbl_count(const int* count, const int* start, int stride, int b) {
-  const int n = count[b];
-  return start ? n : min(n, stride);
-}
 
 // ------------------------------------------------------------------------------------------
 // K4a: per-frame preparation.  One warp per frame.
@@ -46,119 +34,11 @@ paf_prepare_kernel(const int* __restrict__ peak_chan, const int* __restrict__ fr
   const int b = blockIdx.x, lane = threadIdx.x;
   const long long base = tbl_start(frame_start, frame_stride, b);
   const int P = tbl_count(frame_count, frame_start, frame_stride, b);
-  const int* chan = peak_chan + base;
-  for (int k = lane; k <= n_nodes; k += 32) s_cnt[k] = 0;
-  __syncwarp();
-  for (int i = lane; i < P; i += 32) {
-    const int c = chan[i];
-    if (c >= 0 && c < n_nodes) atomicAdd(&s_cnt[c], 1);
-  }
-  __syncwarp();
-  if (lane == 0) {  // exclusive scan over nodes (N is small)
-    int acc = 0;
-    for (int k = 0; k < n_nodes; ++k) {
-      const int c = s_cnt[k];
-      s_cnt[k] = acc;
-      acc += c;
-    }
-    s_cnt[n_nodes] = acc;
-  }
-  __syncwarp();
   int* ns = node_start + (long long)b * (n_nodes + 1);
-  for (int k = lane; k <= n_nodes; k += 32) ns[k] = s_cnt[k];
-  __syncwarp();
-  // stable placement, 32 peaks at a time: rank among equal-channel lanes with a lower lane id
-  int* np_ = node_peaks + base;
-  for (int i0 = 0; i0 < P; i0 += 32) {
-    const int i = i0 + lane;
-    const int c = (i < P) ? chan[i] : -1;
-    const bool valid = (c >= 0 && c < n_nodes);
-    const unsigned peers = __match_any_sync(FULL, valid ? c : -1 - lane);
-    if (valid) {
-      const int before = __popc(peers & ((1u << lane) - 1));
-      np_[s_cnt[c] + before] = i;
-    }
-    __syncwarp();
-    if (valid && (__ffs(peers) - 1) == lane) s_cnt[c] += __popc(peers);
-    __syncwarp();
-  }
-  if (lane == 0) {
-    int* eo = edge_off + (long long)b * (n_edges + 1);
-    int* mo = match_off + (long long)b * (n_edges + 1);
-    int acc_c = 0, acc_m = 0;
-    for (int k = 0; k < n_edges; ++k) {
-      const int s = edges[2 * k], d = edges[2 * k + 1];
-      const int cs = (s >= 0 && s < n_nodes) ? ns[s + 1] - ns[s] : 0;
-      const int cd = (d >= 0 && d < n_nodes) ? ns[d + 1] - ns[d] : 0;
-      eo[k] = acc_c;
-      mo[k] = acc_m;
-      acc_c += cs * cd;
-      acc_m += min(cs, cd);
-    }
-    eo[n_edges] = acc_c;
-    mo[n_edges] = acc_m;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Line sampling arithmetic shared by make_line_subs / get_paf_lines / the fused scorer.
-// Bit-exact restatement: slope = (dst - src) / fl32(1 + eps); val = src + slope*t;
-// q = rint(val / stride) (half-to-even); clip.  `t` comes from torch.linspace on the host.
-// ------------------------------------------------------------------------------------------
-#define SNB_ONE_PLUS_EPS 1.00000011920928955078125f
-
-__device__ __forceinline__ int line_coord(float src, float dst, float t, float stride, int hi) {
-  const float slope = __fdiv_rn(__fsub_rn(dst, src), SNB_ONE_PLUS_EPS);
-  const float val = __fadd_rn(src, __fmul_rn(slope, t));
-  const float q = rintf(__fdiv_rn(val, stride));
-  // float -> int32 like ATen's CPU cast, then clip (paf.py:192-208); NaN / out-of-range end up clipped
-  int qi;
-  if (!(q >= -2147483648.f)) qi = INT_MIN;  // NaN or below range
-  else if (q >= 2147483648.f) qi = INT_MIN;  // x86 cvttss2si overflow value, clipped to 0 like the reference
-  else qi = (int)q;
-  return min(max(qi, 0), hi);
-}
-
-struct ScoreArgs {
-  const float* pafs;        // may be null: enumerate candidates only
-  long long pb, py, px, pc; // element strides of the (B, H, W, 2E) view
-  int H, W;
-  const float* t;           // n_points linspace table
-  int n_points;
-  float stride;
-  float max_edge_length;
-  float penalty_weight;
-};
-
-__device__ __forceinline__ float score_candidate(const ScoreArgs& a, int b, int k, float sx, float sy, float dx,
-                                                 float dy) {
-  // spatial vector, its length and unit direction (paf.py:381-388)
-  const float vx = __fsub_rn(dx, sx), vy = __fsub_rn(dy, sy);
-  const float len = sqrtf(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
-  const float ux = __fdiv_rn(vx, len), uy = __fdiv_rn(vy, len);
-  const float* fb = a.pafs + (long long)b * a.pb + (long long)(2 * k) * a.pc;
-  double acc = 0.0;
-  for (int p0 = 0; p0 < a.n_points; p0 += 8) {  // 16 independent gathers in flight
-    float fx[8], fy[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int p = p0 + u;
-      if (p < a.n_points) {
-        const float t = __ldg(a.t + p);
-        const int col = line_coord(sx, dx, t, a.stride, a.W - 1);
-        const int row = line_coord(sy, dy, t, a.stride, a.H - 1);
-        const float* q = fb + (long long)row * a.py + (long long)col * a.px;
-        fx[u] = __ldg(q);
-        fy[u] = __ldg(q + a.pc);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (p0 + u < a.n_points) acc += (double)__fadd_rn(__fmul_rn(fx[u], ux), __fmul_rn(fy[u], uy));  // paf.py:392
-  }
-  const float mean = (float)(acc / (double)a.n_points);                                   // paf.py:407
-  const float pen = __fmul_rn(fminf(__fsub_rn(__fdiv_rn(a.max_edge_length, len), 1.f), 0.f), a.penalty_weight);
-  return __fadd_rn(mean, pen);                                                            // paf.py:408
+  group_by_node_warp(peak_chan + base, P, n_nodes, ns, s_cnt, node_peaks + base, lane);
+  if (lane == 0)
+    edge_offsets(edges, n_nodes, n_edges, ns, edge_off + (long long)b * (n_edges + 1),
+                 match_off + (long long)b * (n_edges + 1));
 }
 
 // K4b: one thread per candidate.  Candidate m of frame b: edge k by search in edge_off, then
@@ -177,19 +57,10 @@ paf_score_kernel(ScoreArgs a, const float* __restrict__ peak_xy, const int* __re
   if (M > limit && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, SNB_STATUS_CAND_OVERFLOW);
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= limit) return;
-  int lo = 0, hi = n_edges;  // largest k with eo[k] <= m
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (eo[mid] <= m) lo = mid; else hi = mid;
-  }
-  const int k = lo;
   const int* ns = node_start + (long long)b * (n_nodes + 1);
-  const int s = edges[2 * k], d = edges[2 * k + 1];
-  const int nd = ns[d + 1] - ns[d];
-  const int r = m - eo[k];
   const long long base = tbl_start(frame_start, frame_stride, b);
-  const int ps = node_peaks[base + ns[s] + r / nd];
-  const int pd = node_peaks[base + ns[d] + r % nd];
+  int k, ps, pd;
+  decode_candidate(m, eo, n_edges, ns, edges, node_peaks + base, &k, &ps, &pd);
   const long long o = tbl_start(cand_start, cand_stride, b) + m;
   cand_edge[o] = k;
   cand_epi[2 * o] = ps;
@@ -274,87 +145,6 @@ __global__ void distance_penalty_kernel(const float* __restrict__ len, long long
                                         float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __fmul_rn(fminf(__fsub_rn(__fdiv_rn(max_len, len[i]), 1.f), 0.f), weight);
-}
-
-// ------------------------------------------------------------------------------------------
-// K5: rectangular linear-sum assignment with scipy's exact semantics (Crouse 2016 shortest
-// augmenting path, float64 duals).  Sequential per problem so that tie handling is identical to
-// scipy's: free columns are kept in a list filled in reverse, the scan prefers, among equal
-// reduced costs, the LAST unassigned column met (else the first minimum); a tall matrix is
-// solved transposed and reported rows-ascending.  `cost(i, j)` is an accessor in the ORIGINAL
-// orientation.  Returns false when infeasible (scipy raises ValueError).
-// Workspace (nr <= nc after the transpose, D = nc): u[nr] v[nc] spc[nc] doubles,
-// path[nc] col4row[nr] row4col[nc] free_[nc] ints, in_sr[nr] in_sc[nc] bytes.
-// ------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t lsap_ws_bytes(int max_dim) {
-  return (((size_t)max_dim * (3 * 8 + 4 * 4 + 2) + 16) + 15) & ~(size_t)15;  // keeps every problem 16B-aligned
-}
-
-template <typename CostFn>
-__device__ bool lsap_solve(int n_rows, int n_cols, CostFn cost, void* ws, int* out_row, int* out_col) {
-  const bool transposed = n_cols < n_rows;
-  const int nr = transposed ? n_cols : n_rows;
-  const int nc = transposed ? n_rows : n_cols;
-  if (nr == 0) return true;
-  double* u = (double*)ws;
-  double* v = u + nr;
-  double* spc = v + nc;
-  int* path = (int*)(spc + nc);
-  int* col4row = path + nc;
-  int* row4col = col4row + nr;
-  int* free_ = row4col + nc;
-  unsigned char* in_sr = (unsigned char*)(free_ + nc);
-  unsigned char* in_sc = in_sr + nr;
-  auto c_at = [&](int i, int j) -> double { return transposed ? cost(j, i) : cost(i, j); };
-  for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
-  for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
-  for (int cur = 0; cur < nr; ++cur) {
-    for (int j = 0; j < nc; ++j) { spc[j] = INFINITY; in_sc[j] = 0; free_[j] = nc - 1 - j; }
-    for (int i = 0; i < nr; ++i) in_sr[i] = 0;
-    int n_free = nc, i = cur, sink = -1;
-    double min_val = 0.0;
-    while (sink == -1) {
-      in_sr[i] = 1;
-      double lowest = INFINITY;
-      int pick = -1;
-      const double ui = u[i];
-      for (int it = 0; it < n_free; ++it) {
-        const int j = free_[it];
-        const double r = min_val + c_at(i, j) - ui - v[j];
-        if (r < spc[j]) { path[j] = i; spc[j] = r; }
-        if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; pick = it; }
-      }
-      min_val = lowest;
-      if (min_val == INFINITY) return false;
-      const int j = free_[pick];
-      if (row4col[j] == -1) sink = j; else i = row4col[j];
-      in_sc[j] = 1;
-      free_[pick] = free_[--n_free];
-    }
-    u[cur] += min_val;
-    for (int r_ = 0; r_ < nr; ++r_)
-      if (in_sr[r_] && r_ != cur) u[r_] += min_val - spc[col4row[r_]];
-    for (int j = 0; j < nc; ++j)
-      if (in_sc[j]) v[j] -= min_val - spc[j];
-    int j = sink;
-    while (true) {
-      const int ii = path[j];
-      row4col[j] = ii;
-      const int prev = col4row[ii];
-      col4row[ii] = j;
-      j = prev;
-      if (ii == cur) break;
-    }
-  }
-  if (!transposed) {
-    for (int i = 0; i < nr; ++i) { out_row[i] = i; out_col[i] = col4row[i]; }
-  } else {
-    // original rows = our columns: report ascending original row, i.e. ascending col4row value
-    int k = 0;
-    for (int j = 0; j < nc; ++j)
-      if (row4col[j] >= 0) { out_row[k] = j; out_col[k] = row4col[j]; ++k; }
-  }
-  return true;
 }
 
 constexpr int LSAP_SMEM_DIM = 32;
@@ -499,18 +289,7 @@ match_generic_kernel(int phase, const int* __restrict__ cand_edge, const long lo
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// K6: greedy instance assembly, one warp per frame, faithful to the reference's dict logic:
-//   - edges visited in `sorted_edges` order, connections in list order, only score >= min_line_scores
-//   - neither peak owned -> new id = max(current ids) + 1;  src owned -> dst joins;  both owned ->
-//     dst is MOVED first, then the two instances merge iff their node sets are disjoint;
-//     "src free, dst owned" does nothing (paf.py:754-789)
-//   - min_instance_peaks filter (:791-818), ids compacted in ascending order (:845-850)
-//   - instance score: fp32 running sum in connection order (:853-865)
-//   - scatter in first-assignment order, later entries overwrite (:879-885), NaN fill
-// A peak is addressed as (node, rank within node) -> node_peaks[node_start[node] + rank].
-// Workspace per frame: 4 * peak_stride ints (owner, order, id_count, id_rank) + n_nodes flags.
-// ------------------------------------------------------------------------------------------
+// K6 stand-alone kernel: one warp per frame, scratch in global memory (see assemble_frame_warp).
 struct AsmArgs {
   const float* peak_xy;
   const float* peak_val;
@@ -545,128 +324,30 @@ struct AsmArgs {
 
 __global__ void __launch_bounds__(32) assemble_kernel(AsmArgs a) {
   extern __shared__ unsigned char s_flags[];  // 2 * n_nodes
-  unsigned char* fa = s_flags;
-  unsigned char* fb = s_flags + a.n_nodes;
   const int b = blockIdx.x, lane = threadIdx.x;
   const long long base = tbl_start(a.frame_start, a.frame_stride, b);
   const int P = tbl_count(a.frame_count, a.frame_start, a.frame_stride, b);
-  const int* chan = a.peak_chan + base;
-  const int* ns = a.node_start + (long long)b * (a.n_nodes + 1);
-  const int* np_ = a.node_peaks + base;
   const long long m0 = tbl_start(a.match_start, a.match_stride, b);
-  const int K = a.match_start ? a.m_count[b] : min(a.m_count[b], a.match_stride);
-  int* owner = a.ws + (long long)b * 4 * a.ws_stride;
-  int* order = owner + a.ws_stride;
-  int* id_count = order + a.ws_stride;
-  int* id_rank = id_count + a.ws_stride;
   if (P > a.ws_stride) {
     if (lane == 0) { atomicOr(a.status, SNB_STATUS_PEAK_OVERFLOW); a.n_inst[b] = 0; }
     return;
   }
-  for (int i = lane; i < P; i += 32) { owner[i] = -1; id_count[i] = 0; }
-  __syncwarp();
-  int n_order = 0;
-  for (int se = 0; se < a.n_sorted; ++se) {
-    const int e = a.sorted_edges[se];
-    const int sn = a.edges[2 * e], dn = a.edges[2 * e + 1];
-    for (int m = 0; m < K; ++m) {
-      if (a.m_edge[m0 + m] != e) continue;
-      if (!(a.m_score[m0 + m] >= a.min_line_scores)) continue;  // paf.py:993
-      const int sp = a.m_src[m0 + m], dp = a.m_dst[m0 + m];
-      if (sn < 0 || sn >= a.n_nodes || dn < 0 || dn >= a.n_nodes || sp < 0 || dp < 0 ||
-          sp >= ns[sn + 1] - ns[sn] || dp >= ns[dn + 1] - ns[dn]) {
-        if (lane == 0) atomicOr(a.status, SNB_STATUS_BAD_INDEX);
-        continue;
-      }
-      const int pa = np_[ns[sn] + sp], pb = np_[ns[dn] + dp];
-      const int ia = owner[pa], ib = owner[pb];
-      if (ia < 0 && ib < 0) {
-        int mx = -1;
-        for (int i = lane; i < P; i += 32) mx = max(mx, owner[i]);
-        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
-        __syncwarp();
-        if (lane == 0) {
-          owner[pa] = mx + 1;
-          owner[pb] = mx + 1;
-          order[n_order] = pa;
-          if (pb != pa) order[n_order + 1] = pb;
-        }
-        n_order += (pb != pa) ? 2 : 1;
-      } else if (ia >= 0 && ib < 0) {
-        if (lane == 0) { owner[pb] = ia; order[n_order] = pb; }
-        n_order += 1;
-      } else if (ia >= 0 && ib >= 0) {
-        if (lane == 0) owner[pb] = ia;
-        __syncwarp();
-        if (ia != ib) {
-          for (int k = lane; k < a.n_nodes; k += 32) { fa[k] = 0; fb[k] = 0; }
-          __syncwarp();
-          for (int i = lane; i < P; i += 32) {
-            const int o = owner[i];
-            if (o == ia) fa[chan[i]] = 1;
-            if (o == ib) fb[chan[i]] = 1;
-          }
-          __syncwarp();
-          int hit = 0;
-          for (int k = lane; k < a.n_nodes; k += 32) hit |= (fa[k] & fb[k]);
-          hit = __any_sync(FULL, hit);
-          if (!hit)
-            for (int i = lane; i < P; i += 32)
-              if (owner[i] == ib) owner[i] = ia;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  // instance sizes, min_instance_peaks filter, ascending-id compaction
-  for (int i = lane; i < P; i += 32)
-    if (owner[i] >= 0) atomicAdd(&id_count[owner[i]], 1);
-  __syncwarp();
-  int n_inst = 0;
-  if (lane == 0) {
-    for (int id = 0; id < P; ++id) {
-      const bool keep = id_count[id] > 0 && (a.min_instance_peaks <= 0 || id_count[id] >= a.min_instance_peaks);
-      id_rank[id] = keep ? n_inst++ : -1;
-    }
-  }
-  n_inst = __shfl_sync(FULL, n_inst, 0);
-  __syncwarp();
-  if (n_inst > a.inst_cap) {
-    if (lane == 0) { atomicOr(a.status, SNB_STATUS_INSTANCE_OVERFLOW); a.n_inst[b] = n_inst; }
-    return;
-  }
-  float* oxy = a.inst_xy + (long long)b * a.inst_cap * a.n_nodes * 2;
-  float* oval = a.inst_val + (long long)b * a.inst_cap * a.n_nodes;
-  float* osc = a.inst_score + (long long)b * a.inst_cap;
-  for (int i = lane; i < n_inst * a.n_nodes; i += 32) { oxy[2 * i] = NAN; oxy[2 * i + 1] = NAN; oval[i] = NAN; }
-  for (int i = lane; i < n_inst; i += 32) osc[i] = 0.f;
-  __syncwarp();
-  if (lane == 0) {
-    a.n_inst[b] = n_inst;
-    for (int se = 0; se < a.n_sorted; ++se) {
-      const int e = a.sorted_edges[se];
-      const int sn = a.edges[2 * e];
-      if (sn < 0 || sn >= a.n_nodes) continue;
-      for (int m = 0; m < K; ++m) {
-        if (a.m_edge[m0 + m] != e || !(a.m_score[m0 + m] >= a.min_line_scores)) continue;
-        const int sp = a.m_src[m0 + m];
-        if (sp < 0 || sp >= ns[sn + 1] - ns[sn]) continue;
-        const int o = owner[np_[ns[sn] + sp]];
-        if (o >= 0 && id_rank[o] >= 0) osc[id_rank[o]] = __fadd_rn(osc[id_rank[o]], a.m_score[m0 + m]);
-      }
-    }
-    const float* xy = a.peak_xy + 2 * base;
-    const float* val = a.peak_val + base;
-    for (int t = 0; t < n_order; ++t) {
-      const int i = order[t];
-      const int r = id_rank[owner[i]];
-      if (r < 0) continue;
-      const long long slot = (long long)r * a.n_nodes + chan[i];
-      oxy[2 * slot] = xy[2 * i];
-      oxy[2 * slot + 1] = xy[2 * i + 1];
-      oval[slot] = val[i];
-    }
-  }
+  int* owner = a.ws + (long long)b * 4 * a.ws_stride;
+  AsmFrame f;
+  f.xy = a.peak_xy + 2 * base; f.val = a.peak_val + base; f.chan = a.peak_chan + base; f.P = P;
+  f.ns = a.node_start + (long long)b * (a.n_nodes + 1); f.np_ = a.node_peaks + base; f.n_nodes = a.n_nodes;
+  f.edges = a.edges; f.sorted = a.sorted_edges; f.n_sorted = a.n_sorted;
+  f.m_edge = a.m_edge + m0; f.m_src = a.m_src + m0; f.m_dst = a.m_dst + m0; f.m_score = a.m_score + m0;
+  f.K = a.match_start ? a.m_count[b] : min(a.m_count[b], a.match_stride);
+  f.min_instance_peaks = a.min_instance_peaks; f.min_line_scores = a.min_line_scores;
+  f.owner = owner; f.order = owner + a.ws_stride; f.id_count = owner + 2 * a.ws_stride; f.id_rank = owner + 3 * a.ws_stride;
+  f.fa = s_flags; f.fb = s_flags + a.n_nodes;
+  f.inst_cap = a.inst_cap;
+  f.oxy = a.inst_xy + (long long)b * a.inst_cap * a.n_nodes * 2;
+  f.oval = a.inst_val + (long long)b * a.inst_cap * a.n_nodes;
+  f.osc = a.inst_score + (long long)b * a.inst_cap;
+  f.n_inst_out = a.n_inst + b; f.status = a.status;
+  assemble_frame_warp(f, lane);
 }
 
 // make_predicted_instances (paf.py:823-887) for the dict API: assignments arrive in insertion order

@@ -1,0 +1,368 @@
+// Device-side building blocks of the PAF grouping path, shared by the stand-alone kernels
+// (paf.cu) and the fused per-frame tail kernel (pipeline.cu).  Citations paf.py:NN are into
+// sleap_nn/inference/ops/paf.py.
+#pragma once
+
+#include "common.cuh"
+
+namespace snb {
+
+// ------------------------------------------------------------------------------------------
+// Frame addressing: a "table" is either padded (frame b starts at b*stride) or CSR (explicit
+// start array).  Counts are clamped to the stride for padded tables.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long tbl_start(const int* start, int stride, int b) {
+  return start ? (long long)start[b] : (long long)b * stride;
+}
+__device__ __forceinline__ int tbl_count(const int* count, const int* start, int stride, int b) {
+  const int n = count[b];
+  return start ? n : min(n, stride);
+}
+
+// ------------------------------------------------------------------------------------------
+// Line sampling arithmetic shared by make_line_subs / get_paf_lines / the fused scorer.
+// Bit-exact restatement: slope = (dst - src) / fl32(1 + eps); val = src + slope*t;
+// q = rint(val / stride) (half-to-even); clip.  `t` comes from torch.linspace on the host.
+// ------------------------------------------------------------------------------------------
+#define SNB_ONE_PLUS_EPS 1.00000011920928955078125f
+
+__device__ __forceinline__ int line_coord(float src, float dst, float t, float stride, int hi) {
+  const float slope = __fdiv_rn(__fsub_rn(dst, src), SNB_ONE_PLUS_EPS);
+  const float val = __fadd_rn(src, __fmul_rn(slope, t));
+  const float q = rintf(__fdiv_rn(val, stride));
+  // float -> int32 like ATen's CPU cast, then clip (paf.py:192-208); NaN / out-of-range end up clipped
+  int qi;
+  if (!(q >= -2147483648.f)) qi = INT_MIN;  // NaN or below range
+  else if (q >= 2147483648.f) qi = INT_MIN;  // x86 cvttss2si overflow value, clipped to 0 like the reference
+  else qi = (int)q;
+  return min(max(qi, 0), hi);
+}
+
+struct ScoreArgs {
+  const float* pafs;        // may be null: enumerate candidates only
+  long long pb, py, px, pc; // element strides of the (B, H, W, 2E) view
+  int H, W;
+  const float* t;           // n_points linspace table
+  int n_points;
+  float stride;
+  float max_edge_length;
+  float penalty_weight;
+};
+
+__device__ __forceinline__ float score_candidate(const ScoreArgs& a, int b, int k, float sx, float sy, float dx,
+                                                 float dy) {
+  // spatial vector, its length and unit direction (paf.py:381-388)
+  const float vx = __fsub_rn(dx, sx), vy = __fsub_rn(dy, sy);
+  const float len = sqrtf(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+  const float ux = __fdiv_rn(vx, len), uy = __fdiv_rn(vy, len);
+  const float* fb = a.pafs + (long long)b * a.pb + (long long)(2 * k) * a.pc;
+  double acc = 0.0;
+  for (int p0 = 0; p0 < a.n_points; p0 += 8) {  // 16 independent gathers in flight
+    float fx[8], fy[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = p0 + u;
+      if (p < a.n_points) {
+        const float t = a.t[p];  // global or shared memory
+        const int col = line_coord(sx, dx, t, a.stride, a.W - 1);
+        const int row = line_coord(sy, dy, t, a.stride, a.H - 1);
+        const float* q = fb + (long long)row * a.py + (long long)col * a.px;
+        fx[u] = __ldg(q);
+        fy[u] = __ldg(q + a.pc);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (p0 + u < a.n_points) acc += (double)__fadd_rn(__fmul_rn(fx[u], ux), __fmul_rn(fy[u], uy));  // paf.py:392
+  }
+  const float mean = (float)(acc / (double)a.n_points);                                   // paf.py:407
+  const float pen = __fmul_rn(fminf(__fsub_rn(__fdiv_rn(a.max_edge_length, len), 1.f), 0.f), a.penalty_weight);
+  return __fadd_rn(mean, pen);                                                            // paf.py:408
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: rectangular linear-sum assignment with scipy's exact semantics (Crouse 2016 shortest
+// augmenting path, float64 duals).  Sequential per problem so that tie handling is identical to
+// scipy's: free columns are kept in a list filled in reverse, the scan prefers, among equal
+// reduced costs, the LAST unassigned column met (else the first minimum); a tall matrix is
+// solved transposed and reported rows-ascending.  `cost(i, j)` is an accessor in the ORIGINAL
+// orientation.  Returns false when infeasible (scipy raises ValueError).
+// Workspace (nr <= nc after the transpose, D = nc): u[nr] v[nc] spc[nc] doubles,
+// path[nc] col4row[nr] row4col[nc] free_[nc] ints, in_sr[nr] in_sc[nc] bytes.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t lsap_ws_bytes(int max_dim) {
+  return (((size_t)max_dim * (3 * 8 + 4 * 4 + 2) + 16) + 15) & ~(size_t)15;  // keeps every problem 16B-aligned
+}
+
+template <typename CostFn>
+__device__ bool lsap_solve(int n_rows, int n_cols, CostFn cost, void* ws, int* out_row, int* out_col) {
+  const bool transposed = n_cols < n_rows;
+  const int nr = transposed ? n_cols : n_rows;
+  const int nc = transposed ? n_rows : n_cols;
+  if (nr == 0) return true;
+  double* u = (double*)ws;
+  double* v = u + nr;
+  double* spc = v + nc;
+  int* path = (int*)(spc + nc);
+  int* col4row = path + nc;
+  int* row4col = col4row + nr;
+  int* free_ = row4col + nc;
+  unsigned char* in_sr = (unsigned char*)(free_ + nc);
+  unsigned char* in_sc = in_sr + nr;
+  auto c_at = [&](int i, int j) -> double { return transposed ? cost(j, i) : cost(i, j); };
+  for (int i = 0; i < nr; ++i) { u[i] = 0.0; col4row[i] = -1; }
+  for (int j = 0; j < nc; ++j) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
+  for (int cur = 0; cur < nr; ++cur) {
+    for (int j = 0; j < nc; ++j) { spc[j] = INFINITY; in_sc[j] = 0; free_[j] = nc - 1 - j; }
+    for (int i = 0; i < nr; ++i) in_sr[i] = 0;
+    int n_free = nc, i = cur, sink = -1;
+    double min_val = 0.0;
+    while (sink == -1) {
+      in_sr[i] = 1;
+      double lowest = INFINITY;
+      int pick = -1;
+      const double ui = u[i];
+      for (int it = 0; it < n_free; ++it) {
+        const int j = free_[it];
+        const double r = min_val + c_at(i, j) - ui - v[j];
+        if (r < spc[j]) { path[j] = i; spc[j] = r; }
+        if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; pick = it; }
+      }
+      min_val = lowest;
+      if (min_val == INFINITY) return false;
+      const int j = free_[pick];
+      if (row4col[j] == -1) sink = j; else i = row4col[j];
+      in_sc[j] = 1;
+      free_[pick] = free_[--n_free];
+    }
+    u[cur] += min_val;
+    for (int r_ = 0; r_ < nr; ++r_)
+      if (in_sr[r_] && r_ != cur) u[r_] += min_val - spc[col4row[r_]];
+    for (int j = 0; j < nc; ++j)
+      if (in_sc[j]) v[j] -= min_val - spc[j];
+    int j = sink;
+    while (true) {
+      const int ii = path[j];
+      row4col[j] = ii;
+      const int prev = col4row[ii];
+      col4row[ii] = j;
+      j = prev;
+      if (ii == cur) break;
+    }
+  }
+  if (!transposed) {
+    for (int i = 0; i < nr; ++i) { out_row[i] = i; out_col[i] = col4row[i]; }
+  } else {
+    // original rows = our columns: report ascending original row, i.e. ascending col4row value
+    int k = 0;
+    for (int j = 0; j < nc; ++j)
+      if (row4col[j] >= 0) { out_row[k] = j; out_col[k] = row4col[j]; ++k; }
+  }
+  return true;
+}
+
+
+
+// ------------------------------------------------------------------------------------------
+// Per-frame grouping of peaks by node (one warp).  ns[0..N] = exclusive prefix of peaks per node,
+// node_peaks = peak indices grouped by node, ascending inside a node (a STABLE grouping: the
+// reference's torch.argsort is stable only for n <= 16; this is the canonical
+// order).  Peaks whose channel is outside [0, N) belong to no node (paf.py:110-112).
+// `cursor` is an (N+1)-int scratch; all pointers may be shared or global memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void group_by_node_warp(const int* chan, int P, int n_nodes, int* ns, int* cursor,
+                                                   int* node_peaks, int lane) {
+  for (int k = lane; k <= n_nodes; k += 32) cursor[k] = 0;
+  __syncwarp();
+  for (int i = lane; i < P; i += 32) {
+    const int c = chan[i];
+    if (c >= 0 && c < n_nodes) atomicAdd(&cursor[c], 1);
+  }
+  __syncwarp();
+  if (lane == 0) {  // exclusive scan over nodes (N is small)
+    int acc = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+      const int c = cursor[k];
+      cursor[k] = acc;
+      acc += c;
+    }
+    cursor[n_nodes] = acc;
+  }
+  __syncwarp();
+  for (int k = lane; k <= n_nodes; k += 32) ns[k] = cursor[k];
+  __syncwarp();
+  for (int i0 = 0; i0 < P; i0 += 32) {  // stable placement, 32 peaks at a time
+    const int i = i0 + lane;
+    const int c = (i < P) ? chan[i] : -1;
+    const bool valid = (c >= 0 && c < n_nodes);
+    const unsigned peers = __match_any_sync(FULL, valid ? c : -1 - lane);
+    if (valid) node_peaks[cursor[c] + __popc(peers & ((1u << lane) - 1))] = i;
+    __syncwarp();
+    if (valid && (__ffs(peers) - 1) == lane) cursor[c] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// eo[0..E] = exclusive prefix of candidates per edge (n_src * n_dst), mo[0..E] = of matches
+// per edge (min(n_src, n_dst)).  Single thread.
+__device__ __forceinline__ void edge_offsets(const int* edges, int n_nodes, int n_edges, const int* ns, int* eo,
+                                             int* mo) {
+  int acc_c = 0, acc_m = 0;
+  for (int k = 0; k < n_edges; ++k) {
+    const int s = edges[2 * k], d = edges[2 * k + 1];
+    const int cs = (s >= 0 && s < n_nodes) ? ns[s + 1] - ns[s] : 0;
+    const int cd = (d >= 0 && d < n_nodes) ? ns[d + 1] - ns[d] : 0;
+    eo[k] = acc_c;
+    mo[k] = acc_m;
+    acc_c += cs * cd;
+    acc_m += min(cs, cd);
+  }
+  eo[n_edges] = acc_c;
+  mo[n_edges] = acc_m;
+}
+
+// Candidate m of a frame -> (edge k, source peak, destination peak): edge-major, source-major.
+__device__ __forceinline__ void decode_candidate(int m, const int* eo, int n_edges, const int* ns, const int* edges,
+                                                 const int* node_peaks, int* k_out, int* ps, int* pd) {
+  int lo = 0, hi = n_edges;  // largest k with eo[k] <= m
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (eo[mid] <= m) lo = mid; else hi = mid;
+  }
+  const int s = edges[2 * lo], d = edges[2 * lo + 1];
+  const int nd = ns[d + 1] - ns[d];
+  const int r = m - eo[lo];
+  *k_out = lo;
+  *ps = node_peaks[ns[s] + r / nd];
+  *pd = node_peaks[ns[d] + r % nd];
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: greedy instance assembly of ONE frame by ONE warp, faithful to the reference's dict logic:
+//   - edges visited in `sorted` order, connections in list order, only score >= min_line_scores
+//   - neither peak owned -> new id = max(current ids) + 1;  src owned -> dst joins;  both owned ->
+//     dst is MOVED first, then the two instances merge iff their node sets are disjoint;
+//     "src free, dst owned" does nothing (paf.py:754-789)
+//   - min_instance_peaks filter (:791-818), ids compacted in ascending order (:845-850)
+//   - instance score: fp32 running sum in connection order (:853-865)
+//   - scatter in first-assignment order, later entries overwrite (:879-885), NaN fill
+// A peak is addressed as (node, rank within node) -> np_[ns[node] + rank].
+// Scratch: owner / order / id_count / id_rank (P ints each), fa / fb (n_nodes bytes each).
+// ------------------------------------------------------------------------------------------
+struct AsmFrame {
+  const float* xy; const float* val; const int* chan; int P;
+  const int* ns; const int* np_; int n_nodes;
+  const int* edges; const int* sorted; int n_sorted;
+  const int* m_edge; const int* m_src; const int* m_dst; const float* m_score; int K;
+  int min_instance_peaks; float min_line_scores;
+  int* owner; int* order; int* id_count; int* id_rank; unsigned char* fa; unsigned char* fb;
+  int inst_cap; float* oxy; float* oval; float* osc; int* n_inst_out; int* status;
+};
+
+__device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane) {
+  const int P = f.P, K = f.K;
+  for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
+  __syncwarp();
+  int n_order = 0;
+  for (int se = 0; se < f.n_sorted; ++se) {
+    const int e = f.sorted[se];
+    const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+    for (int m = 0; m < K; ++m) {
+      if (f.m_edge[m] != e) continue;
+      if (!(f.m_score[m] >= f.min_line_scores)) continue;  // paf.py:993
+      const int sp = f.m_src[m], dp = f.m_dst[m];
+      if (sn < 0 || sn >= f.n_nodes || dn < 0 || dn >= f.n_nodes || sp < 0 || dp < 0 ||
+          sp >= f.ns[sn + 1] - f.ns[sn] || dp >= f.ns[dn + 1] - f.ns[dn]) {
+        if (lane == 0) atomicOr(f.status, SNB_STATUS_BAD_INDEX);
+        continue;
+      }
+      const int pa = f.np_[f.ns[sn] + sp], pb = f.np_[f.ns[dn] + dp];
+      const int ia = f.owner[pa], ib = f.owner[pb];
+      if (ia < 0 && ib < 0) {
+        int mx = -1;
+        for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+        __syncwarp();
+        if (lane == 0) {
+          f.owner[pa] = mx + 1;
+          f.owner[pb] = mx + 1;
+          f.order[n_order] = pa;
+          if (pb != pa) f.order[n_order + 1] = pb;
+        }
+        n_order += (pb != pa) ? 2 : 1;
+      } else if (ia >= 0 && ib < 0) {
+        if (lane == 0) { f.owner[pb] = ia; f.order[n_order] = pb; }
+        n_order += 1;
+      } else if (ia >= 0 && ib >= 0) {
+        if (lane == 0) f.owner[pb] = ia;
+        __syncwarp();
+        if (ia != ib) {
+          for (int k = lane; k < f.n_nodes; k += 32) { f.fa[k] = 0; f.fb[k] = 0; }
+          __syncwarp();
+          for (int i = lane; i < P; i += 32) {
+            const int o = f.owner[i];
+            const int c = f.chan[i];
+            if (c >= 0 && c < f.n_nodes) {
+              if (o == ia) f.fa[c] = 1;
+              if (o == ib) f.fb[c] = 1;
+            }
+          }
+          __syncwarp();
+          int hit = 0;
+          for (int k = lane; k < f.n_nodes; k += 32) hit |= (f.fa[k] & f.fb[k]);
+          hit = __any_sync(FULL, hit);
+          if (!hit)
+            for (int i = lane; i < P; i += 32)
+              if (f.owner[i] == ib) f.owner[i] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // instance sizes, min_instance_peaks filter, ascending-id compaction
+  for (int i = lane; i < P; i += 32)
+    if (f.owner[i] >= 0) atomicAdd(&f.id_count[f.owner[i]], 1);
+  __syncwarp();
+  int n_inst = 0;
+  if (lane == 0) {
+    for (int id = 0; id < P; ++id) {
+      const bool keep = f.id_count[id] > 0 && (f.min_instance_peaks <= 0 || f.id_count[id] >= f.min_instance_peaks);
+      f.id_rank[id] = keep ? n_inst++ : -1;
+    }
+  }
+  n_inst = __shfl_sync(FULL, n_inst, 0);
+  __syncwarp();
+  if (n_inst > f.inst_cap) {
+    if (lane == 0) { atomicOr(f.status, SNB_STATUS_INSTANCE_OVERFLOW); *f.n_inst_out = n_inst; }
+    return;
+  }
+  for (int i = lane; i < n_inst * f.n_nodes; i += 32) { f.oxy[2 * i] = NAN; f.oxy[2 * i + 1] = NAN; f.oval[i] = NAN; }
+  for (int i = lane; i < n_inst; i += 32) f.osc[i] = 0.f;
+  __syncwarp();
+  if (lane == 0) {
+    *f.n_inst_out = n_inst;
+    for (int se = 0; se < f.n_sorted; ++se) {
+      const int e = f.sorted[se];
+      const int sn = f.edges[2 * e];
+      if (sn < 0 || sn >= f.n_nodes) continue;
+      for (int m = 0; m < K; ++m) {
+        if (f.m_edge[m] != e || !(f.m_score[m] >= f.min_line_scores)) continue;
+        const int sp = f.m_src[m];
+        if (sp < 0 || sp >= f.ns[sn + 1] - f.ns[sn]) continue;
+        const int o = f.owner[f.np_[f.ns[sn] + sp]];
+        if (o >= 0 && f.id_rank[o] >= 0) f.osc[f.id_rank[o]] = __fadd_rn(f.osc[f.id_rank[o]], f.m_score[m]);
+      }
+    }
+    for (int t = 0; t < n_order; ++t) {
+      const int i = f.order[t];
+      const int r = f.id_rank[f.owner[i]];
+      if (r < 0) continue;
+      const long long slot = (long long)r * f.n_nodes + f.chan[i];
+      f.oxy[2 * slot] = f.xy[2 * i];
+      f.oxy[2 * slot + 1] = f.xy[2 * i + 1];
+      f.oval[slot] = f.val[i];
+    }
+  }
+}
+
+}  // namespace snb

@@ -10,6 +10,9 @@
 //
 // Bound: HBM read bandwidth.  K1 reads every map element exactly once (4*C*H*W bytes per
 // frame); everything after the streaming pass touches O(#peaks) data.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace snb {
@@ -50,41 +53,54 @@ __device__ __forceinline__ void emit_peak(int* __restrict__ frame_count, uint32_
   if (pos < cap) keys[(long long)b * cap + pos] = (uint32_t)((y * W + x) * C + c);
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(256)
-local_peaks_detect_vec4(const float* __restrict__ cms, int B, int C, int H, int W, long long sb, long long sc,
+template <int UNROLL, int ROWS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
+local_peaks_detect_vec4(const float* __restrict__ cms, int n_rows, int C, int H, int W, long long sb, long long sc,
                         long long sh, float thr, int cap, int* __restrict__ frame_count,
                         uint32_t* __restrict__ keys) {
+  // One warp owns ROWS consecutive map rows per iteration and issues all of their 128-bit loads
+  // (ROWS * UNROLL per lane) before looking at any value: that is the memory-level parallelism
+  // that keeps HBM busy.  32-bit index math (the host guarantees n_rows < 2^31).
   const int lane = lane_id();
   const int warps_per_block = blockDim.x >> 5;
-  const long long n_rows = (long long)B * C * H;
   const int W4 = W >> 2;
-  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < n_rows;
-       row += (long long)gridDim.x * warps_per_block) {
-    const int y = (int)(row % H);
-    const long long pc = row / H;
-    const int c = (int)(pc % C);
-    const int b = (int)(pc / C);
-    const float* plane = cms + (long long)b * sb + (long long)c * sc;
-    const float* rowp = plane + (long long)y * sh;
+  const int stride_rows = gridDim.x * warps_per_block * ROWS;
+  for (int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * ROWS; row0 < n_rows; row0 += stride_rows) {
+    const float* rowp[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int row = min(row0 + r, n_rows - 1);
+      const int y = row % H, pc = row / H;
+      rowp[r] = cms + (long long)(pc / C) * sb + (long long)(pc % C) * sc + (long long)y * sh;
+    }
     for (int x4 = lane; x4 < W4; x4 += 32 * UNROLL) {
-      float4 v[UNROLL];
+      float4 v[ROWS][UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int xx4 = x4 + 32 * u;
-        if (xx4 < W4) v[u] = ldg_stream4(rowp + 4 * xx4);
-      }
+      for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int xx4 = x4 + 32 * u;
-        if (xx4 >= W4) continue;
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        if (!((e[0] > thr) || (e[1] > thr) || (e[2] > thr) || (e[3] > thr))) continue;
+        for (int u = 0; u < UNROLL; ++u) {
+          const int xx4 = x4 + 32 * u;
+          if (xx4 < W4) v[r][u] = ldg_stream4(rowp[r] + 4 * xx4);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (e[k] > thr) {
-            const int x = 4 * xx4 + k;
-            if (is_strict_max(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r >= n_rows) break;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int xx4 = x4 + 32 * u;
+          if (xx4 >= W4) continue;
+          const float e[4] = {v[r][u].x, v[r][u].y, v[r][u].z, v[r][u].w};
+          if (!((e[0] > thr) || (e[1] > thr) || (e[2] > thr) || (e[3] > thr))) continue;
+          const int row = row0 + r;  // rare path: recover (b, c, y) for this row
+          const int y = row % H, pc = row / H;
+          const int c = pc % C, b = pc / C;
+          const float* plane = cms + (long long)b * sb + (long long)c * sc;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (e[k] > thr) {
+              const int x = 4 * xx4 + k;
+              if (is_strict_max(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+            }
           }
         }
       }
@@ -108,6 +124,77 @@ local_peaks_detect_scalar(const float* __restrict__ cms, int B, int C, int H, in
     const float* plane = cms + (long long)b * sb + (long long)c * sc;
     const float v = __ldg(plane + (long long)y * sh + (long long)x * sw);
     if (v > thr && is_strict_max(plane, H, W, sh, sw, y, x, v)) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// K1a, contiguous tensors: bulk-async streaming detect.  The maps are one flat array; each
+// persistent CTA walks it in 16 KB chunks through a ring of shared-memory stages filled by
+// cp.async.bulk (1-D TMA) and signalled by mbarriers, so ~64 KB per CTA are in flight with no
+// registers tied up and a few instructions per 16 bytes (LDS.128 + 4 compares).  Only a value
+// above the threshold leaves the streaming path (neighbour test through L2, see is_strict_max).
+// ----------------------------------------------------------------------------------------
+constexpr int BULK_STAGE_FLOATS = 4096;  // 16 KB
+constexpr int BULK_STAGES = 4;
+constexpr int BULK_THREADS = 128;
+
+__global__ void __launch_bounds__(BULK_THREADS)
+local_peaks_detect_bulk(const float* __restrict__ cms, long long n_elems, int C, int H, int W, float thr, int cap,
+                        int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  float* stage_buf = reinterpret_cast<float*>(bulk_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(bulk_smem + (size_t)BULK_STAGES * BULK_STAGE_FLOATS * 4);
+  const int tid = threadIdx.x;
+  const long long n_chunks = (n_elems + BULK_STAGE_FLOATS - 1) / BULK_STAGE_FLOATS;
+  if (tid == 0) {
+    for (int s = 0; s < BULK_STAGES; ++s) mbar_init(full + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long chunk, int s) {
+    const long long e0 = chunk * BULK_STAGE_FLOATS;
+    const uint32_t bytes = (uint32_t)(min((long long)BULK_STAGE_FLOATS, n_elems - e0) * 4);
+    mbar_expect_tx(full + s, bytes);
+    bulk_g2s(stage_buf + (size_t)s * BULK_STAGE_FLOATS, cms + e0, bytes, full + s);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < BULK_STAGES; ++s) {
+      const long long chunk = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (chunk < n_chunks) issue(chunk, s);
+    }
+  }
+  const long long plane_elems = (long long)H * W;
+  int it = 0;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int s = it % BULK_STAGES;
+    mbar_wait(full + s, (uint32_t)((it / BULK_STAGES) & 1));
+    const long long e0 = chunk * BULK_STAGE_FLOATS;
+    const int n4 = (int)(min((long long)BULK_STAGE_FLOATS, n_elems - e0) >> 2);
+    const float4* buf = reinterpret_cast<const float4*>(stage_buf + (size_t)s * BULK_STAGE_FLOATS);
+#pragma unroll
+    for (int u = 0; u < BULK_STAGE_FLOATS / 4 / BULK_THREADS; ++u) {
+      const int i4 = tid + u * BULK_THREADS;
+      if (i4 >= n4) break;
+      const float4 v = buf[i4];
+      if ((v.x > thr) || (v.y > thr) || (v.z > thr) || (v.w > thr)) {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        const long long ebase = e0 + 4LL * i4;  // W % 4 == 0: the four values share one row
+        const long long pc = ebase / plane_elems;
+        const int rem = (int)(ebase - pc * plane_elems);
+        const int y = rem / W, x0 = rem - y * W;
+        const int c = (int)(pc % C), b = (int)(pc / C);
+        const float* plane = cms + pc * plane_elems;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (e[k] > thr && is_strict_max(plane, H, W, W, 1, y, x0 + k, e[k]))
+            emit_peak(frame_count, keys, cap, b, C, W, c, y, x0 + k);
+      }
+    }
+    __syncthreads();  // every thread is done with stage s: refill it
+    if (tid == 0) {
+      const long long next = chunk + (long long)BULK_STAGES * gridDim.x;
+      if (next < n_chunks) issue(next, s);
+    }
   }
 }
 
@@ -159,18 +246,18 @@ local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long lo
     sorted = skeys;
   }
   const float* frame = cms + (long long)b * sb;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int i = warp; i < n; i += n_warps) {  // one warp per peak: the patch taps are fetched in parallel
     const uint32_t key = sorted[i];
     const int c = (int)(key % (uint32_t)C);
     const uint32_t yx = key / (uint32_t)C;
     const int x = (int)(yx % (uint32_t)W);
     const int y = (int)(yx / (uint32_t)W);
     const float* plane = frame + (long long)c * sc;
-    const float v = __ldg(plane + (long long)y * sh + (long long)x * sw);
     float fx = (float)x, fy = (float)y;
     if (refine_size > 0) {
       float ox, oy;
-      integral_refine(plane, H, W, sh, sw, fx, fy, refine_size, &ox, &oy);
+      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, lane, &ox, &oy);
       fx = __fadd_rn(fx, ox);  // ops/peaks.py:258
       fy = __fadd_rn(fy, oy);
     }
@@ -178,11 +265,13 @@ local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long lo
       fx = __fmul_rn(fx, xy_scale);
       fy = __fmul_rn(fy, xy_scale);
     }
-    const long long o = (long long)b * cap + i;
-    out_xy[2 * o] = fx;
-    out_xy[2 * o + 1] = fy;
-    out_val[o] = v;
-    out_chan[o] = c;
+    if (lane == 0) {
+      const long long o = (long long)b * cap + i;
+      out_xy[2 * o] = fx;
+      out_xy[2 * o + 1] = fy;
+      out_val[o] = __ldg(plane + (long long)y * sh + (long long)x * sw);
+      out_chan[o] = c;
+    }
   }
 }
 
@@ -330,16 +419,21 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
     } else {
       s_last = true;
     }
-    if (s_last) {
-      // An empty plane (H*W == 0) cannot occur: the host rejects it.
-      const bool low = r.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
-      float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
-      if (!low && refine_size > 0) {
-        float ox, oy;
-        integral_refine(plane, H, W, sh, sw, fx, fy, refine_size, &ox, &oy);
-        fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
-        fy = __fadd_rn(fy, oy);
-      }
+    if (s_last) s_best[0] = r;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {  // warp 0 of the plane's last CTA: threshold + refinement
+    const Best r = s_best[0];
+    // An empty plane (H*W == 0) cannot occur: the host rejects it.
+    const bool low = r.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
+    float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
+    if (!low && refine_size > 0) {
+      float ox, oy;
+      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, threadIdx.x, &ox, &oy);
+      fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
+      fy = __fadd_rn(fy, oy);
+    }
+    if (threadIdx.x == 0) {
       out_xy[2 * plane_id] = fx;
       out_xy[2 * plane_id + 1] = fy;
       out_val[plane_id] = low ? 0.f : r.v;
@@ -471,49 +565,76 @@ static int sm_count() {
   return g_sm_count;
 }
 
-extern "C" int snb_local_peaks_ev(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
-                                  long long sh, long long sw, float threshold, int refine_size, float xy_scale, int cap,
-                                  int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
-                                  int* status, void* ev_begin, void* ev_end, void* stream_);
-
-extern "C" int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
-                               long long sw, float threshold, int refine_size, float xy_scale, int cap,
-                               int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
-                               int* status, void* stream_) {
-  return snb_local_peaks_ev(cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, xy_scale, cap, frame_count, keys,
-                            out_xy, out_val, out_chan, status, nullptr, nullptr, stream_);
-}
-
-// Same, with optional cudaEvent_t handles recorded immediately before / after the streaming detect
-// kernel (the dominant kernel) so a benchmark can time it inside its own timed region.
-extern "C" int snb_local_peaks_ev(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
-                                  long long sh, long long sw, float threshold, int refine_size, float xy_scale, int cap,
-                                  int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
-                                  int* status, void* ev_begin, void* ev_end, void* stream_) {
+// K1a: zero the per-frame counters and run the streaming detect kernel.  ev_begin / ev_end are
+// optional cudaEvent_t handles recorded right around the kernel (in-situ timing for benchmarks).
+extern "C" int snb_local_peaks_detect(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
+                                      long long sh, long long sw, float threshold, int cap, int* frame_count,
+                                      uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || refine_size < 0) return SNB_ERR_BAD_ARG;
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0) return SNB_ERR_BAD_ARG;
   if ((double)H * W * C >= 4294967295.0) return SNB_ERR_UNSUPPORTED;
   if (B == 0) return SNB_OK;
   if (cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
   const bool vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
                    (((uintptr_t)cms) % 16 == 0);
   const long long rows = (long long)B * C * H;
+  const bool contiguous = vec && sh == W && sc == (long long)H * W && sb == (long long)C * H * W;
+  // The cp.async.bulk ring is opt-in: on B200 it reaches only ~2.4 TB/s here (bulk copies issued
+  // from one SM are served with little overlap), the LDG.128 grid-stride kernel ~5.6 TB/s alone.
+  static const bool use_bulk = getenv("SNB_DETECT_BULK") != nullptr;
   if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, st);
-  if (vec) {
-    // 8 warps per CTA, one row per warp at a time; cap the grid at 8 CTAs per SM (persistent, grid-stride)
-    const int grid = grid_for(rows, 8, sm_count() * 8);
-    if (W >= 512)
-      local_peaks_detect_vec4<4><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
-    else if (W >= 256)
-      local_peaks_detect_vec4<2><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
-    else
-      local_peaks_detect_vec4<1><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys);
+  if (contiguous && use_bulk) {
+    const size_t smem = (size_t)BULK_STAGES * BULK_STAGE_FLOATS * 4 + BULK_STAGES * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(local_peaks_detect_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      attr_set = true;
+    }
+    const long long n_elems = rows * W;
+    const long long n_chunks = (n_elems + BULK_STAGE_FLOATS - 1) / BULK_STAGE_FLOATS;
+    const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 3);  // 3 CTAs x 64 KB per SM
+    local_peaks_detect_bulk<<<grid, BULK_THREADS, smem, st>>>(cms, n_elems, C, H, W, threshold, cap, frame_count, keys);
+  } else if (vec && rows < 0x7fffffffLL) {
+    // grid-stride kernel, 8 warps per CTA; the variant (loads in flight per lane, CTAs per SM) is
+    // picked by row length.  SNB_DETECT_VARIANT overrides it for A/B profiling.
+    static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
+    const int n_rows = (int)rows;
+    int variant = (W >= 512) ? 0 : (W >= 256 ? 1 : 2);
+    if (forced >= 0) variant = forced;
+    // One row per warp (4 x 128-bit loads per lane for W = 512), 40 registers -> 6 CTAs = 48 warps per
+    // SM, and a NON-persistent grid so the hardware CTA scheduler balances the SMs: measured on B200,
+    // cfg3 batch: 53.1 us = 6.3 TB/s.  Persistent / deeper-unrolled variants were slower (57-95 us).
+#define SNB_DETECT(U, R, MB, CTAS)                                                                             \
+  local_peaks_detect_vec4<U, R, MB><<<grid_for((rows + R - 1) / R, 8, sm_count() * CTAS), 256, 0, st>>>(        \
+      cms, n_rows, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys)
+    switch (variant) {
+      case 0: SNB_DETECT(4, 1, 6, 100000); break;  // default for W >= 512
+      case 1: SNB_DETECT(2, 1, 8, 100000); break;  // W in [256, 512)
+      case 2: SNB_DETECT(1, 4, 6, 100000); break;  // narrow maps: four rows of one load each
+      case 3: SNB_DETECT(4, 1, 4, 4); break;       // A/B: persistent single wave, 60 registers (57.1 us)
+      case 4: SNB_DETECT(4, 2, 4, 4); break;       // A/B: 8 loads per lane (66.6 us)
+      default: SNB_DETECT(4, 4, 2, 2); break;      // A/B: 16 loads per lane, 2 CTAs / SM (95.1 us)
+    }
+#undef SNB_DETECT
   } else {
     const int grid = grid_for(rows * W, 256 * 4, sm_count() * 16);
     local_peaks_detect_scalar<<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys);
   }
   if (ev_end) cudaEventRecord((cudaEvent_t)ev_end, st);
   SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+// K1b: per-frame key sort + value + integral refinement -> padded peak table.
+extern "C" int snb_local_peaks_finalize(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
+                                        long long sh, long long sw, int refine_size, float xy_scale, int cap,
+                                        const int* frame_count, uint32_t* keys, float* out_xy, float* out_val,
+                                        int* out_chan, int* status, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || refine_size < 0) return SNB_ERR_BAD_ARG;
+  if (B == 0) return SNB_OK;
   int n2 = 1;
   while (n2 < cap) n2 <<= 1;
   const size_t smem = sizeof(uint32_t) * (size_t)n2;
@@ -538,6 +659,18 @@ extern "C" int snb_local_peaks_ev(const float* cms, int B, int C, int H, int W, 
                                                             status);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
+}
+
+extern "C" int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                               long long sw, float threshold, int refine_size, float xy_scale, int cap,
+                               int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
+                               int* status, void* stream_) {
+  if (refine_size < 0) return SNB_ERR_BAD_ARG;
+  const int rc = snb_local_peaks_detect(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, nullptr,
+                                        nullptr, stream_);
+  if (rc != SNB_OK) return rc;
+  return snb_local_peaks_finalize(cms, B, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap, frame_count, keys,
+                                  out_xy, out_val, out_chan, status, stream_);
 }
 
 extern "C" int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val,

@@ -1,22 +1,300 @@
 // Fused bottom-up post-processing: one C call enqueues the whole chain
-//   K1 local peaks (+ integral refinement, x confmap stride)  ->  K4 candidates + PAF line scores
-//   ->  K5 per-edge assignment  ->  K6 instance assembly
-// on one stream with fixed-capacity tables, no host synchronisation and no allocation, so
-// batches can be pipelined across streams (and captured into a CUDA graph).  It replaces the
-// call sequence find_local_peaks -> peaks * stride -> per-sample split -> PAFScorer.predict of
+//   K1 streaming detect  ->  per-frame TAIL (key sort + integral refinement + node grouping +
+//   candidate enumeration + PAF line scores + per-edge assignment + instance assembly)
+// with fixed-capacity tables, no host synchronisation and no allocation.  It replaces the call
+// sequence find_local_peaks -> peaks * stride -> per-sample split -> PAFScorer.predict of
 // BottomUpLayer (layers/bottomup.py:95-236) + group_scored_batch (inference/streaming.py:147-255).
-#include "common.cuh"
+//
+// The tail touches O(#peaks) data per frame and is latency-bound, so it runs as ONE CTA per frame
+// with every table in shared memory (a handful of dependent memory round trips instead of five
+// kernel launches with global-memory tables).  When a second (high-priority) stream is given the
+// tail of batch i overlaps the detect pass of batch i+1: the detect kernel is the only part that
+// moves real bytes, so the step time tends to the HBM time of the confidence maps.
+// If the capacities do not fit in shared memory the stand-alone kernels are chained instead.
+#include "paf_device.cuh"
 
-extern "C" int snb_local_peaks_ev(const float*, int, int, int, int, long long, long long, long long, long long, float,
-                                  int, float, int, int*, uint32_t*, float*, float*, int*, int*, void*, void*, void*);
+namespace snb {
+
+struct TailLayout {
+  int keys, xy, val, chan, ns, cursor, np, eo, mo, score, m_edge, m_src, m_dst, m_score, lsap, owner, order, idc, idr,
+      flags, edges, sorted, ttab, total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline TailLayout tail_layout(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
+                                                  int n_warps, int n_sorted, int n_points) {
+  TailLayout L;
+  int p2 = 1;
+  while (p2 < peak_cap) p2 <<= 1;
+  int o = 0;
+  auto take = [&](int bytes) { const int at = o; o += align16(bytes); return at; };
+  L.keys = take(4 * p2);
+  L.xy = take(8 * peak_cap);
+  L.val = take(4 * peak_cap);
+  L.chan = take(4 * peak_cap);
+  L.ns = take(4 * (n_nodes + 1));
+  L.cursor = take(4 * (n_nodes + 1));
+  L.np = take(4 * peak_cap);
+  L.eo = take(4 * (n_edges + 1));
+  L.mo = take(4 * (n_edges + 1));
+  L.score = take(4 * cand_cap);
+  L.m_edge = take(4 * match_cap);
+  L.m_src = take(4 * match_cap);
+  L.m_dst = take(4 * match_cap);
+  L.m_score = take(4 * match_cap);
+  L.lsap = take(n_warps * (int)lsap_ws_bytes(32));
+  L.owner = take(4 * peak_cap);
+  L.order = take(4 * peak_cap);
+  L.idc = take(4 * peak_cap);
+  L.idr = take(4 * peak_cap);
+  L.flags = take(2 * n_nodes);
+  L.edges = take(8 * (n_edges > 0 ? n_edges : 1));
+  L.sorted = take(4 * (n_sorted > 0 ? n_sorted : 1));
+  L.ttab = take(4 * (n_points > 0 ? n_points : 1));
+  L.total = o;
+  return L;
+}
+
+constexpr int TAIL_THREADS = 256;
+
+__global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomup_args a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n_warps = TAIL_THREADS / 32;
+  const TailLayout L = tail_layout(a.peak_cap, a.C, a.n_edges, a.cand_cap, a.match_cap, n_warps, a.n_sorted, a.n_points);
+  uint32_t* s_keys = (uint32_t*)(smem + L.keys);
+  float* s_xy = (float*)(smem + L.xy);
+  float* s_val = (float*)(smem + L.val);
+  int* s_chan = (int*)(smem + L.chan);
+  int* s_ns = (int*)(smem + L.ns);
+  int* s_cursor = (int*)(smem + L.cursor);
+  int* s_np = (int*)(smem + L.np);
+  int* s_eo = (int*)(smem + L.eo);
+  int* s_mo = (int*)(smem + L.mo);
+  float* s_score = (float*)(smem + L.score);
+  int* s_m_edge = (int*)(smem + L.m_edge);
+  int* s_m_src = (int*)(smem + L.m_src);
+  int* s_m_dst = (int*)(smem + L.m_dst);
+  float* s_m_score = (float*)(smem + L.m_score);
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_nodes = a.C, E = a.n_edges;
+  // small read-only tables -> shared memory once (the sequential phases would otherwise pay an L2
+  // round trip per dependent access)
+  int* s_edges = (int*)(smem + L.edges);
+  int* s_sorted = (int*)(smem + L.sorted);
+  float* s_t = (float*)(smem + L.ttab);
+  for (int i = tid; i < 2 * E; i += TAIL_THREADS) s_edges[i] = a.edges[i];
+  for (int i = tid; i < a.n_sorted; i += TAIL_THREADS) s_sorted[i] = a.sorted_edges[i];
+  for (int i = tid; i < a.n_points; i += TAIL_THREADS) s_t[i] = a.t_table[i];
+  const int total = a.frame_count[b];
+  if (total > a.peak_cap && tid == 0) atomicOr(a.status, SNB_STATUS_PEAK_OVERFLOW);
+  const int n = min(total, a.peak_cap);
+
+  // ---- 1. order the frame's keys: ascending key == (y, x, channel) == torch.where order
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  const uint32_t* gk = a.keys + (long long)b * a.peak_cap;
+  for (int i = tid; i < n2; i += TAIL_THREADS) s_keys[i] = (i < n) ? gk[i] : 0xffffffffu;
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += TAIL_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t x = s_keys[i], y = s_keys[ixj];
+          if ((x > y) == ((i & k) == 0)) { s_keys[i] = y; s_keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 2. value + integral refinement, one warp per peak (taps fetched in parallel)
+  const float* frame = a.cms + (long long)b * a.cms_sb;
+  for (int i = warp; i < n; i += n_warps) {
+    const uint32_t key = s_keys[i];
+    const int c = (int)(key % (uint32_t)a.C);
+    const uint32_t yx = key / (uint32_t)a.C;
+    const int x = (int)(yx % (uint32_t)a.W), y = (int)(yx / (uint32_t)a.W);
+    const float* plane = frame + (long long)c * a.cms_sc;
+    float fx = (float)x, fy = (float)y;
+    if (a.refine_size > 0) {
+      float ox, oy;
+      integral_refine_warp(plane, a.H, a.W, a.cms_sh, a.cms_sw, fx, fy, a.refine_size, lane, &ox, &oy);
+      fx = __fadd_rn(fx, ox);
+      fy = __fadd_rn(fy, oy);
+    }
+    if (a.cms_stride != 1.0f) {
+      fx = __fmul_rn(fx, a.cms_stride);
+      fy = __fmul_rn(fy, a.cms_stride);
+    }
+    if (lane == 0) {
+      const float v = __ldg(plane + (long long)y * a.cms_sh + (long long)x * a.cms_sw);
+      s_xy[2 * i] = fx; s_xy[2 * i + 1] = fy; s_val[i] = v; s_chan[i] = c;
+      const long long o = (long long)b * a.peak_cap + i;
+      a.peak_xy[2 * o] = fx; a.peak_xy[2 * o + 1] = fy; a.peak_val[o] = v; a.peak_chan[o] = c;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. group peaks by node, candidate / match offsets
+  if (warp == 0) {
+    group_by_node_warp(s_chan, n, n_nodes, s_ns, s_cursor, s_np, lane);
+    if (lane == 0) edge_offsets(s_edges, n_nodes, E, s_ns, s_eo, s_mo);
+  }
+  __syncthreads();
+  const int M = s_eo[E];
+  const bool cand_ok = M <= a.cand_cap;
+  if (!cand_ok && tid == 0) atomicOr(a.status, SNB_STATUS_CAND_OVERFLOW);
+  const int K = s_mo[E];
+  const int klimit = min(K, a.match_cap);
+  if (K > klimit && tid == 0) atomicOr(a.status, SNB_STATUS_MATCH_OVERFLOW);
+  if (a.node_start) {  // optional copies of the intermediate tables (the API-level 6-tuple)
+    for (int i = tid; i <= n_nodes; i += TAIL_THREADS) a.node_start[(long long)b * (n_nodes + 1) + i] = s_ns[i];
+    for (int i = tid; i < n; i += TAIL_THREADS) a.node_peaks[(long long)b * a.peak_cap + i] = s_np[i];
+    for (int i = tid; i <= E; i += TAIL_THREADS) {
+      a.edge_off[(long long)b * (E + 1) + i] = s_eo[i];
+      a.match_off[(long long)b * (E + 1) + i] = s_mo[i];
+    }
+  }
+
+  // ---- 4. PAF line scores, one thread per candidate
+  if (cand_ok) {
+    ScoreArgs sa{a.pafs, a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc, a.paf_H, a.paf_W, s_t, a.n_points,
+                 a.pafs_stride, a.max_edge_length, a.dist_penalty_weight};
+    for (int m = tid; m < M; m += TAIL_THREADS) {
+      int k, ps, pd;
+      decode_candidate(m, s_eo, E, s_ns, s_edges, s_np, &k, &ps, &pd);
+      const float sc = score_candidate(sa, b, k, s_xy[2 * ps], s_xy[2 * ps + 1], s_xy[2 * pd], s_xy[2 * pd + 1]);
+      s_score[m] = sc;
+      if (a.cand_edge) {
+        const long long o = (long long)b * a.cand_cap + m;
+        a.cand_edge[o] = k; a.cand_epi[2 * o] = ps; a.cand_epi[2 * o + 1] = pd; a.cand_score[o] = sc;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. per-edge optimal assignment, one warp per edge (lane 0 runs scipy's algorithm)
+  if (cand_ok && lane == 0) {
+    for (int k = warp; k < E; k += n_warps) {
+      const int s = s_edges[2 * k], d = s_edges[2 * k + 1];
+      if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) continue;
+      const int n_src = s_ns[s + 1] - s_ns[s], n_dst = s_ns[d + 1] - s_ns[d];
+      const int n_match = min(n_src, n_dst);
+      if (n_match == 0 || s_mo[k] + n_match > klimit) continue;
+      const int dim = max(n_src, n_dst);
+      void* ws;
+      if (dim <= 32) ws = smem + L.lsap + warp * (int)lsap_ws_bytes(32);
+      else if (dim <= a.lsap_max_dim && a.lsap_ws)
+        ws = (unsigned char*)a.lsap_ws + ((size_t)b * E + k) * lsap_ws_bytes(a.lsap_max_dim);
+      else { atomicOr(a.status, SNB_STATUS_LSAP_TOO_LARGE); continue; }
+      const float* sc = s_score + s_eo[k];
+      auto cost = [&](int i, int j) -> double {
+        const float x = sc[i * n_dst + j];
+        return isnan(x) ? (double)INFINITY : -(double)x;
+      };
+      const int o = s_mo[k];
+      if (!lsap_solve(n_src, n_dst, cost, ws, s_m_src + o, s_m_dst + o)) {
+        atomicOr(a.status, SNB_STATUS_LSAP_INFEASIBLE);
+        for (int r = 0; r < n_match; ++r) { s_m_edge[o + r] = k; s_m_src[o + r] = -1; s_m_dst[o + r] = -1; s_m_score[o + r] = NAN; }
+        continue;
+      }
+      for (int r = 0; r < n_match; ++r) {
+        s_m_edge[o + r] = k;
+        s_m_score[o + r] = sc[s_m_src[o + r] * n_dst + s_m_dst[o + r]];
+      }
+    }
+  }
+  __syncthreads();
+  const int n_matches = cand_ok ? klimit : 0;
+  if (a.m_edge) {
+    for (int i = tid; i < n_matches; i += TAIL_THREADS) {
+      const long long o = (long long)b * a.match_cap + i;
+      a.m_edge[o] = s_m_edge[i]; a.m_src[o] = s_m_src[i]; a.m_dst[o] = s_m_dst[i]; a.m_score[o] = s_m_score[i];
+    }
+    if (tid == 0) a.m_count[b] = n_matches;
+  }
+
+  // ---- 6. greedy assembly by warp 0
+  if (warp == 0) {
+    AsmFrame f;
+    f.xy = s_xy; f.val = s_val; f.chan = s_chan; f.P = n;
+    f.ns = s_ns; f.np_ = s_np; f.n_nodes = n_nodes;
+    f.edges = s_edges; f.sorted = s_sorted; f.n_sorted = a.n_sorted;
+    f.m_edge = s_m_edge; f.m_src = s_m_src; f.m_dst = s_m_dst; f.m_score = s_m_score; f.K = n_matches;
+    f.min_instance_peaks = a.min_instance_peaks; f.min_line_scores = a.min_line_scores;
+    f.owner = (int*)(smem + L.owner); f.order = (int*)(smem + L.order);
+    f.id_count = (int*)(smem + L.idc); f.id_rank = (int*)(smem + L.idr);
+    f.fa = smem + L.flags; f.fb = smem + L.flags + n_nodes;
+    f.inst_cap = a.inst_cap;
+    f.oxy = a.inst_xy + (long long)b * a.inst_cap * n_nodes * 2;
+    f.oval = a.inst_val + (long long)b * a.inst_cap * n_nodes;
+    f.osc = a.inst_score + (long long)b * a.inst_cap;
+    f.n_inst_out = a.n_inst + b; f.status = a.status;
+    assemble_frame_warp(f, lane);
+  }
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+extern "C" int snb_local_peaks_detect(const float*, int, int, int, int, long long, long long, long long, long long,
+                                      float, int, int*, uint32_t*, void*, void*, void*);
+
+extern "C" long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
+                                                  int n_sorted, int n_points) {
+  return tail_layout(peak_cap, n_nodes, n_edges, cand_cap, match_cap, TAIL_THREADS / 32, n_sorted, n_points).total;
+}
+
+static int unfused_tail(const snb_bottomup_args* a, void* stream);
 
 extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
   if (!a) return SNB_ERR_BAD_ARG;
+  if (a->B < 0 || a->C <= 0 || a->peak_cap <= 0 || a->cand_cap <= 0 || a->match_cap <= 0 || a->inst_cap <= 0)
+    return SNB_ERR_BAD_ARG;
+  if (a->B == 0) return SNB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t tail_st = a->tail_stream ? (cudaStream_t)a->tail_stream : st;
+  // buffers of this pipeline instance may still be read by its previous tail
+  if (a->tail_stream && a->ev_tail_done) cudaStreamWaitEvent(st, (cudaEvent_t)a->ev_tail_done, 0);
+  int rc = snb_local_peaks_detect(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
+                                  a->peak_threshold, a->peak_cap, a->frame_count, a->keys, a->ev_detect_begin,
+                                  a->ev_detect_end, stream);
+  if (rc != SNB_OK) return rc;
+  if (a->tail_stream) {
+    if (!a->ev_handoff) return SNB_ERR_BAD_ARG;
+    cudaEventRecord((cudaEvent_t)a->ev_handoff, st);
+    cudaStreamWaitEvent(tail_st, (cudaEvent_t)a->ev_handoff, 0);
+  }
+  const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
+                                                      a->n_points);
+  if (!(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024) {
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(bottomup_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return SNB_ERR_CUDA_LAUNCH;
+    bottomup_tail_kernel<<<a->B, TAIL_THREADS, (size_t)smem, tail_st>>>(*a);
+    SNB_LAUNCH_CHECK();
+  } else {
+    rc = unfused_tail(a, (void*)tail_st);
+    if (rc != SNB_OK) return rc;
+  }
+  if (a->tail_stream && a->ev_tail_done) cudaEventRecord((cudaEvent_t)a->ev_tail_done, tail_st);
+  return SNB_OK;
+}
+
+// Stand-alone kernels chained on one stream (large capacities, or SNB_FLAG_UNFUSED_TAIL for tests).
+extern "C" int snb_local_peaks_finalize(const float*, int, int, int, int, long long, long long, long long, long long,
+                                        int, float, int, const int*, uint32_t*, float*, float*, int*, int*, void*);
+
+static int unfused_tail(const snb_bottomup_args* a, void* stream) {
   const int n_nodes = a->C;
-  int rc = snb_local_peaks_ev(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
-                              a->peak_threshold, a->refine_size, a->cms_stride, a->peak_cap, a->frame_count, a->keys,
-                              a->peak_xy, a->peak_val, a->peak_chan, a->status, a->ev_detect_begin, a->ev_detect_end,
-                              stream);
+  if (!a->node_start || !a->cand_edge || !a->m_edge) return SNB_ERR_BAD_ARG;  // needs the global tables
+  int rc = snb_local_peaks_finalize(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
+                                    a->refine_size, a->cms_stride, a->peak_cap, a->frame_count, a->keys, a->peak_xy,
+                                    a->peak_val, a->peak_chan, a->status, stream);
   if (rc != SNB_OK) return rc;
   rc = snb_paf_prepare(a->peak_chan, nullptr, a->peak_cap, a->frame_count, a->B, a->edges, n_nodes, a->n_edges,
                        a->node_start, a->node_peaks, a->edge_off, a->match_off, stream);
@@ -37,6 +315,10 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
                       stream);
 }
 
-// Number of kernel launches snb_bottomup_postproc enqueues per call (detect, finalize, prepare,
-// score, match, assemble); the frame_count memset is a memset node, not a kernel.
-extern "C" int snb_bottomup_launches_per_call(void) { return 6; }
+// Kernel launches per call: detect + fused tail (2), or detect + 5 stand-alone kernels (6).
+extern "C" int snb_bottomup_launches_per_call(const snb_bottomup_args* a) {
+  if (!a) return 2;
+  const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
+                                                      a->n_points);
+  return (!(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024) ? 2 : 6;
+}

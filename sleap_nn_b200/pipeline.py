@@ -35,9 +35,16 @@ class BottomUpResult:
     peak_vals: torch.Tensor       # (B, peak_cap)
     peak_channels: torch.Tensor   # (B, peak_cap) i32
     status: torch.Tensor          # (1,) i32, SNB_STATUS_* bits
+    done: Optional[torch.cuda.Event] = None  # set in two-stream mode: the tail ran on another stream
+
+    def wait(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Make `stream` (default: current) wait for this batch's tail kernel."""
+        if self.done is not None:
+            (stream or torch.cuda.current_stream(self.status.device)).wait_event(self.done)
 
     def to_lists(self):
         """One host sync: per-sample CPU tensors shaped like `PAFScorer.predict`'s first three outputs."""
+        self.wait()
         n = self.n_instances.cpu().tolist()
         status = int(self.status.item())
         if status:
@@ -65,6 +72,12 @@ class BottomUpPostproc:
             as `PAFScorer`.
         peak_cap, cand_cap, match_cap, inst_cap: per-frame table capacities; overflow sets a status
             bit (reported by `BottomUpResult.to_lists`), it never corrupts memory.
+        tail_stream: optional second (high-priority) CUDA stream: the streaming detect kernel runs on
+            the caller's current stream and the per-frame tail on `tail_stream`, so the tail of one
+            batch overlaps the detect pass of the next.
+        fused_tail: run everything after the detect kernel as one CTA per frame with shared-memory
+            tables (default; falls back automatically when the capacities do not fit).
+        keep_tables: also write the intermediate tables (candidates, matches) to global memory.
     """
 
     def __init__(self, n_nodes: int, edge_inds: Sequence[Tuple[int, int]], batch: int, cms_hw: Tuple[int, int],
@@ -73,7 +86,8 @@ class BottomUpPostproc:
                  max_edge_length_ratio: float = 0.25, dist_penalty_weight: float = 1.0, n_points: int = 10,
                  min_instance_peaks: Union[int, float] = 0, min_line_scores: float = 0.25, peak_cap: int = 256,
                  cand_cap: int = 4096, match_cap: int = 512, inst_cap: int = 64, lsap_max_dim: int = 32,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, tail_stream: Optional[torch.cuda.Stream] = None,
+                 fused_tail: bool = True, keep_tables: bool = True):
         self.device = torch.device(device) if device is not None else N.compute_device()
         self.n_nodes, self.batch = int(n_nodes), int(batch)
         self.edge_inds = [(int(a), int(b)) for a, b in edge_inds]
@@ -127,6 +141,23 @@ class BottomUpPostproc:
         if lsap_max_dim <= 32:
             a.lsap_ws = None
         a.ev_detect_begin = a.ev_detect_end = None
+        a.flags = 0 if fused_tail else N.FLAG_UNFUSED_TAIL
+        self.fused = int(N.lib.snb_bottomup_launches_per_call(C.byref(a))) == 2
+        if self.fused and not keep_tables:  # optional outputs of the fused tail
+            for k in ("node_start", "node_peaks", "edge_off", "match_off", "cand_edge", "cand_epi", "cand_score",
+                      "m_edge", "m_src", "m_dst", "m_score", "m_count"):
+                setattr(a, k, None)
+        self.tail_stream = tail_stream
+        self._ev_handoff = self._ev_done = None
+        a.tail_stream = a.ev_handoff = a.ev_tail_done = None
+        if tail_stream is not None:
+            with torch.cuda.device(dev):
+                self._ev_handoff, self._ev_done = torch.cuda.Event(), torch.cuda.Event()
+                for e in (self._ev_handoff, self._ev_done):  # torch creates the cudaEvent lazily on first record
+                    e.record(torch.cuda.current_stream(dev))
+                torch.cuda.synchronize(dev)
+            a.tail_stream = tail_stream.cuda_stream
+            a.ev_handoff, a.ev_tail_done = self._ev_handoff.cuda_event, self._ev_done.cuda_event
 
     # ------------------------------------------------------------------ device-resident path
     def __call__(self, cms: torch.Tensor, pafs: torch.Tensor, detect_events=None) -> BottomUpResult:
@@ -161,11 +192,11 @@ class BottomUpPostproc:
         N.check(N.lib.snb_bottomup_postproc(C.byref(a), N.stream_ptr(self.device)), "snb_bottomup_postproc")
         b = self.buf
         return BottomUpResult(b["n_inst"], b["inst_xy"], b["inst_val"], b["inst_score"], b["frame_count"],
-                              b["peak_xy"], b["peak_val"], b["peak_chan"], b["status"])
+                              b["peak_xy"], b["peak_val"], b["peak_chan"], b["status"], self._ev_done)
 
     @property
     def launches_per_call(self) -> int:
-        return int(N.lib.snb_bottomup_launches_per_call())
+        return int(N.lib.snb_bottomup_launches_per_call(C.byref(self._args)))
 
     # ------------------------------------------------------------------ host-buffer path
     def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor):

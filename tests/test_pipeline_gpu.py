@@ -19,20 +19,44 @@ def test_fused_pipeline_matches_reference_golden(name):
     B, Nn, H, W = cms.shape
     mip = float(d["min_instance_peaks"])
     mip = int(mip) if mip == int(mip) else mip
-    pipe = BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), cms_stride=int(d["stride"]), pafs_stride=int(d["stride"]),
-                            min_instance_peaks=mip)
-    assert list(pipe.sorted_edge_inds) == d["sorted_edge_inds"].tolist()
-    for layout in ("nchw", "view"):
+    kw = dict(cms_stride=int(d["stride"]), pafs_stride=int(d["stride"]), min_instance_peaks=mip)
+    side = torch.cuda.Stream(priority=-1)
+    variants = {
+        "fused": BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), **kw),
+        "fused-lean-2streams": BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), keep_tables=False,
+                                                tail_stream=side, **kw),
+        "unfused": BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), fused_tail=False, **kw),
+    }
+    assert variants["fused"].fused and not variants["unfused"].fused
+    assert variants["fused"].launches_per_call == 2 and variants["unfused"].launches_per_call == 6
+    for name_, pipe in variants.items():
+      assert list(pipe.sorted_edge_inds) == d["sorted_edge_inds"].tolist()
+      for layout in ("nchw", "view"):
         res = pipe(cms, pafs if layout == "nchw" else pafs.permute(0, 2, 3, 1))
         inst, pv, sc = res.to_lists()
         eq(npy(res.n_peaks), np.bincount(d["pk_s"], minlength=B).astype(np.int32))
         want_inst, want_pv, want_sc = ragged(d, "inst"), ragged(d, "inst_pv"), ragged(d, "inst_sc")
         for b in range(B):
-            assert inst[b].shape == want_inst[b].shape
+            assert inst[b].shape == want_inst[b].shape, name_
             eq(np.isnan(npy(inst[b])), np.isnan(npy(want_inst[b])))
             close(npy(inst[b]), npy(want_inst[b]), atol=1e-4)
             eq(npy(pv[b]), npy(want_pv[b]))
             close(npy(sc[b]), npy(want_sc[b]), rtol=1e-5, atol=1e-5)
+    # fused and unfused tails must agree bit for bit on every table they both write
+    a, u = variants["fused"], variants["unfused"]
+    a(cms, pafs); u(cms, pafs)
+    torch.cuda.synchronize()
+    for k in ("frame_count", "peak_xy", "peak_val", "peak_chan", "n_inst", "m_count"):
+        if k.startswith("peak"):
+            n = npy(a.buf["frame_count"])
+            for b in range(B):
+                eq(npy(a.buf[k][b, : n[b]]), npy(u.buf[k][b, : n[b]]))
+        else:
+            eq(npy(a.buf[k]), npy(u.buf[k]))
+    ni = npy(a.buf["n_inst"])
+    for b in range(B):
+        eq(npy(a.buf["inst_xy"][b, : ni[b]]), npy(u.buf["inst_xy"][b, : ni[b]]))
+        eq(npy(a.buf["inst_score"][b, : ni[b]]), npy(u.buf["inst_score"][b, : ni[b]]))
 
 
 def test_fused_pipeline_full_size_vs_oracle():
