@@ -44,6 +44,12 @@ extern "C" {
 
 int snb_abi_version(void);
 
+/* Device-visible alias of a PINNED host buffer (cudaHostGetDevicePointer).  Lets the bottom-up chain
+ * sample the PAF tensor in place over PCIe when the maps arrive in host memory: only the sampled
+ * sectors cross the link instead of the whole tensor.  SNB_ERR_UNSUPPORTED if the buffer is not
+ * pinned / mapped. */
+int snb_host_device_pointer(void* host_ptr, void** device_ptr);
+
 /* ---------------------------------------------------------------- peaks (inference/ops/peaks.py)
  *
  * snb_local_peaks: fused 3x3 NMS + threshold + ordered peak emission + integral refinement.
@@ -305,6 +311,19 @@ int snb_bottomup_postproc(const snb_bottomup_args* args, void* stream);
 long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
                                        int n_sorted, int n_points);
 int snb_bottomup_launches_per_call(const snb_bottomup_args* args);
+
+/* snb_pack_instances: append one batch's padded instance tables (the outputs of snb_bottomup_postproc /
+ * snb_assemble) to a packed per-rank result table at a DEVICE-side running offset, so a rank can run its
+ * whole frame shard with no host synchronisation and gather once at the end (the
+ * reference concatenates per-sample python lists, inference/streaming.py:187-255).
+ *   cursor: 24 bytes {u64 rows packed, u64 frames packed, u32 ticket}, zeroed before the first call.
+ *   o_xy (out_cap,N,2), o_val (out_cap,N), o_score (out_cap), o_frame (out_cap) = frame_base + b,
+ *   o_count[frames packed + b] = instances of that frame (may be NULL).  Overflow of out_cap sets
+ *   SNB_STATUS_INSTANCE_OVERFLOW and drops the frame's rows (the cursor still advances). */
+int snb_pack_instances(const int* n_inst, int B, int inst_cap, int n_nodes, const float* inst_xy,
+                       const float* inst_val, const float* inst_score, int frame_base, void* cursor,
+                       long long out_cap, float* o_xy, float* o_val, float* o_score, int* o_frame, int* o_count,
+                       int* status, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,7 @@ _ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
 # name -> argtypes; every function returns int.  Keep in the order of include/sleapnn_b200.h.
 SIGNATURES = {
     "snb_abi_version": [],
+    "snb_host_device_pointer": [_p, C.POINTER(_p)],
     "snb_local_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_local_peaks_detect": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
     "snb_local_peaks_finalize": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
@@ -61,6 +62,7 @@ SIGNATURES = {
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
+    "snb_pack_instances": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p],
 }
 RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
 FLAG_UNFUSED_TAIL = 1

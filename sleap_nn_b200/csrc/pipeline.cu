@@ -237,6 +237,67 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   }
 }
 
+// Padded per-frame instance tables -> packed rows appended at a DEVICE-side running offset, so that a
+// rank can accumulate the results of many batches with no host synchronisation and gather them once
+// at the end of its frame shard (sleap_nn_b200/sharding.py).  One CTA per frame; the frame's offset
+// is cursor[0] (rows already packed by earlier calls) + the prefix of the earlier frames of this call.
+// The LAST CTA to finish advances cursor[0] by the call's total and cursor[1] by B (frames packed).
+__global__ void __launch_bounds__(128)
+pack_instances_kernel(const int* __restrict__ n_inst, int B, int inst_cap, int n_nodes, const float* __restrict__ xy,
+                      const float* __restrict__ val, const float* __restrict__ score, int frame_base,
+                      unsigned long long* __restrict__ cursor, unsigned* __restrict__ ticket, long long out_cap,
+                      float* __restrict__ o_xy, float* __restrict__ o_val, float* __restrict__ o_score,
+                      int* __restrict__ o_frame, int* __restrict__ o_count, int* __restrict__ status) {
+  const int b = blockIdx.x;
+  __shared__ long long s_off;
+  __shared__ int s_total;
+  if (threadIdx.x < 32) {
+    int before = 0, total = 0;
+    for (int i = threadIdx.x; i < B; i += 32) {
+      const int c = min(n_inst[i], inst_cap);
+      total += c;
+      if (i < b) before += c;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      before += __shfl_xor_sync(FULL, before, d);
+      total += __shfl_xor_sync(FULL, total, d);
+    }
+    if (threadIdx.x == 0) {
+      s_off = (long long)cursor[0] + before;
+      s_total = total;
+    }
+  }
+  __syncthreads();
+  const int n = min(n_inst[b], inst_cap);
+  const long long off = s_off;
+  if (threadIdx.x == 0 && o_count) o_count[(long long)cursor[1] + b] = n;
+  if (off + n > out_cap) {
+    if (threadIdx.x == 0) atomicOr(status, SNB_STATUS_INSTANCE_OVERFLOW);
+  } else {
+    const long long src = (long long)b * inst_cap;
+    for (int i = threadIdx.x; i < n * n_nodes; i += blockDim.x) {
+      o_xy[2 * (off * n_nodes + i)] = xy[2 * (src * n_nodes + i)];
+      o_xy[2 * (off * n_nodes + i) + 1] = xy[2 * (src * n_nodes + i) + 1];
+      o_val[off * n_nodes + i] = val[src * n_nodes + i];
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      o_score[off + i] = score[src + i];
+      o_frame[off + i] = frame_base + b;
+    }
+  }
+  // every CTA has read cursor[] before the last one updates it
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == (unsigned)(B - 1)) {
+      *ticket = 0;
+      cursor[0] += (unsigned long long)s_total;
+      cursor[1] += (unsigned long long)B;
+      __threadfence();
+    }
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -321,4 +382,20 @@ extern "C" int snb_bottomup_launches_per_call(const snb_bottomup_args* a) {
   const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
                                                       a->n_points);
   return (!(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024) ? 2 : 6;
+}
+
+// Append one batch's instances to a packed per-rank result table (see pack_instances_kernel).
+// cursor: 2 x u64 {rows packed, frames packed} + ticket u32, zeroed by the caller before the first call.
+extern "C" int snb_pack_instances(const int* n_inst, int B, int inst_cap, int n_nodes, const float* inst_xy,
+                                  const float* inst_val, const float* inst_score, int frame_base, void* cursor,
+                                  long long out_cap, float* o_xy, float* o_val, float* o_score, int* o_frame,
+                                  int* o_count, int* status, void* stream) {
+  if (B < 0 || inst_cap <= 0 || n_nodes <= 0 || !cursor) return SNB_ERR_BAD_ARG;
+  if (B == 0) return SNB_OK;
+  unsigned long long* cur = (unsigned long long*)cursor;
+  pack_instances_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(n_inst, B, inst_cap, n_nodes, inst_xy, inst_val, inst_score,
+                                                             frame_base, cur, (unsigned*)(cur + 2), out_cap, o_xy, o_val,
+                                                             o_score, o_frame, o_count, status);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
 }

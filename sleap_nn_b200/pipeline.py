@@ -177,14 +177,18 @@ class BottomUpPostproc:
             pafs = pafs.permute(0, 2, 3, 1)  # channels-first tensor -> the channels-last VIEW (no copy)
         elif pafs.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
+        return self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events)
+
+    def _launch(self, cms_ptr: int, cms_strides, pafs_ptr: int, pafs_shape, pafs_strides, detect_events=None) -> BottomUpResult:
+        """Fill the argument block from raw device-visible pointers and enqueue the chain."""
         a = self._args
-        a.cms = N.ptr(cms)
-        a.cms_sb, a.cms_sc, a.cms_sh, a.cms_sw = cms.stride()
-        a.pafs = N.ptr(pafs)
-        a.paf_H, a.paf_W = int(pafs.shape[1]), int(pafs.shape[2])
-        a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc = pafs.stride()
+        a.cms = cms_ptr
+        a.cms_sb, a.cms_sc, a.cms_sh, a.cms_sw = cms_strides
+        a.pafs = pafs_ptr
+        a.paf_H, a.paf_W = int(pafs_shape[1]), int(pafs_shape[2])
+        a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc = pafs_strides
         # max(H, W, 2E) really includes the channel dim (paf.py:457-461)
-        a.max_edge_length = self.max_edge_length_ratio * max(pafs.shape[-1], pafs.shape[-2], pafs.shape[-3]) * self.pafs_stride
+        a.max_edge_length = self.max_edge_length_ratio * max(pafs_shape[-1], pafs_shape[-2], pafs_shape[-3]) * self.pafs_stride
         if detect_events is not None:
             a.ev_detect_begin, a.ev_detect_end = detect_events[0].cuda_event, detect_events[1].cuda_event
         else:
@@ -199,15 +203,41 @@ class BottomUpPostproc:
         return int(N.lib.snb_bottomup_launches_per_call(C.byref(self._args)))
 
     # ------------------------------------------------------------------ host-buffer path
-    def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor):
-        """Host (ideally pinned) buffers in, per-sample CPU tensors out: H2D + chain + D2H.
+    def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor, zero_copy_pafs: bool = True):
+        """Host buffers in, per-sample CPU tensors out: H2D + chain + D2H.
 
+        The confidence maps are copied to the device (every element has to be looked at).  The PAF
+        tensor is only SAMPLED (n_points x 2 taps per candidate), so when `pafs_host` is pinned it is
+        read in place over PCIe through its device alias (`snb_host_device_pointer`) and only the
+        sampled sectors cross the link; an unpinned buffer is staged like the confidence maps.
+        `self.last_h2d_bytes` holds the bytes this call moved host -> device (copy + sampled sectors).
         Returns (instances, peak_scores, instance_scores) lists like `PAFScorer.predict`.
         """
+        if cms_host.dtype != torch.float32 or pafs_host.dtype != torch.float32:
+            raise TypeError("run_host expects fp32 host tensors")
+        if pafs_host.dim() != 4 or pafs_host.shape[0] != self.batch:
+            raise ValueError("pafs must be (B, 2E, H, W) or its (B, H, W, 2E) view")
+        if pafs_host.shape[1] == 2 * self.n_edges and pafs_host.shape[-1] != 2 * self.n_edges:
+            pafs_host = pafs_host.permute(0, 2, 3, 1)
+        elif pafs_host.shape[-1] != 2 * self.n_edges:
+            raise ValueError("pafs channel count must be 2 * n_edges")
         with torch.cuda.device(self.device):
             if not hasattr(self, "_stage_cms") or self._stage_cms.shape != cms_host.shape:
                 self._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
-                self._stage_pafs = torch.empty(pafs_host.shape, dtype=torch.float32, device=self.device)
             self._stage_cms.copy_(cms_host, non_blocking=True)
-            self._stage_pafs.copy_(pafs_host, non_blocking=True)
-            return self(self._stage_cms, self._stage_pafs).to_lists()
+            paf_alias = C.c_void_p()
+            zero_copy = bool(zero_copy_pafs and pafs_host.is_pinned() and N.lib.snb_host_device_pointer(
+                pafs_host.data_ptr(), C.byref(paf_alias)) == N.OK and paf_alias.value)
+            if zero_copy:
+                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), paf_alias.value,
+                                   tuple(pafs_host.shape), pafs_host.stride())
+            else:
+                if not hasattr(self, "_stage_pafs") or self._stage_pafs.shape != pafs_host.shape:
+                    self._stage_pafs = torch.empty(pafs_host.shape, dtype=torch.float32, device=self.device)
+                self._stage_pafs.copy_(pafs_host, non_blocking=True)
+                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), N.ptr(self._stage_pafs),
+                                   tuple(pafs_host.shape), self._stage_pafs.stride())
+            out = res.to_lists()
+            self.last_h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
+            self.last_zero_copy = zero_copy
+            return out

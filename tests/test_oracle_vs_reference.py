@@ -1,0 +1,123 @@
+"""Pin oracle/ against the LIVE reference (unmodified files loaded in place from /root/reference).
+
+Runs only where the reference tree is mounted (the build container); skipped elsewhere - there the
+committed golden vectors (tests/test_oracle_golden.py) carry the pin.  Fresh random inputs here, so this
+is independent evidence from the goldens: the oracle restates the reference, it does not memorise it.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import paf as opaf
+from oracle import peaks as opeaks
+from oracle import ref_loader, synth
+from oracle import targets as otgt
+from tests.helpers import FLT_MIN, candidate_table, close, eq, npy
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def R():
+    return ref_loader.ref()
+
+
+@pytest.mark.parametrize("seed,shape,thr", [(0, (2, 3, 40, 36), 0.2), (1, (1, 5, 33, 65), 0.6), (2, (3, 2, 16, 16), 0.95)])
+def test_local_and_global_peaks(R, seed, shape, thr):
+    g = torch.Generator().manual_seed(seed)
+    cms = torch.rand(shape, generator=g)
+    for a, b in zip(opeaks.local_peaks_rough(cms, thr), R.peaks.find_local_peaks_rough(cms, threshold=thr)):
+        eq(npy(a), npy(b))
+    for size in (3, 5, 6):
+        a = opeaks.local_peaks(cms, thr, "integral", size)
+        b = R.peaks.find_local_peaks(cms, threshold=thr, refinement="integral", integral_patch_size=size)
+        close(npy(a[0]), npy(b[0]), atol=1e-6)
+        for x, y in zip(a[1:], b[1:]):
+            eq(npy(x), npy(y))
+    for a, b in zip(opeaks.global_peaks_rough(cms, 0.1), R.peaks.find_global_peaks_rough(cms, threshold=0.1)):
+        eq(npy(a), npy(b))
+    a = opeaks.global_peaks(cms, thr, "integral", 5)
+    b = R.peaks.find_global_peaks(cms, threshold=thr, refinement="integral", integral_patch_size=5)
+    close(npy(a[0]), npy(b[0]), atol=1e-6)
+    eq(npy(a[1]), npy(b[1]))
+
+
+def test_loop_restatement_is_the_reference(R):
+    """The 4-nested-loop statement of the algorithm (what the CUDA kernel implements) == the reference."""
+    g = torch.Generator().manual_seed(5)
+    cms = torch.rand((2, 3, 12, 14), generator=g)
+    cms[0, 1, 4, 4] = float("nan")
+    for a, b in zip(opeaks.local_peaks_rough_loops(cms, 0.3), R.peaks.find_local_peaks_rough(cms, threshold=0.3)):
+        eq(npy(a), npy(b))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_bottomup_chain_on_synthetic_frames(R, seed):
+    n_nodes, n_inst, hw, stride = 4, 2, (160, 192), 2
+    edges = synth.chain_edges(n_nodes)
+    poses = synth.make_poses(seed, 2, n_inst, n_nodes, hw, edges=edges, margin=40.0, step=20.0)
+    cms, pafs = synth.render(poses, hw, stride, edges, seed=seed)
+    pts, vals, si, ci = R.peaks.find_local_peaks(cms, threshold=0.2, refinement="integral")
+    o = opeaks.local_peaks(cms, 0.2, "integral")
+    close(npy(o[0]), npy(pts), atol=1e-6)
+    eq(npy(o[3]), npy(ci))
+    B = cms.shape[0]
+    peaks, pvs, pcs = (synth.split_by_sample(x, si, B) for x in (pts * stride, vals, ci))
+    pafs_v = pafs.permute(0, 2, 3, 1)
+    scorer = R.paf.PAFScorer(part_names=[str(i) for i in range(n_nodes)], edges=[(str(a), str(b)) for a, b in edges],
+                             pafs_stride=stride)
+    want = scorer.predict(pafs_v, peaks, pvs, pcs)
+    got = opaf.predict(pafs_v, peaks, pvs, pcs, edges, n_nodes, stride)
+    for b in range(B):
+        assert got[0][b].shape == want[0][b].shape
+        close(npy(got[0][b]), npy(want[0][b]), atol=1e-6)
+        eq(npy(got[1][b]), npy(want[1][b]))
+        close(npy(got[2][b]), npy(want[2][b]), rtol=1e-6, atol=1e-6)
+    # the PAF graph, keyed by (edge, src, dst): candidate order inside an edge is implementation-defined
+    ei, epi, sc = scorer.score_paf_lines(pafs_v, peaks, pcs)
+    oi, oepi, osc = opaf.score_lines_batch(pafs_v, peaks, pcs, edges, 10, stride, 0.25, 1.0, n_nodes)
+    for b in range(B):
+        w, g_ = candidate_table(ei[b], epi[b], sc[b]), candidate_table(oi[b], oepi[b], osc[b])
+        assert w.keys() == g_.keys()
+        for k in w:
+            assert abs(w[k] - g_[k]) <= 1e-6 + 1e-6 * abs(w[k]) or (np.isnan(w[k]) and np.isnan(g_[k]))
+
+
+def test_targets(R):
+    g = torch.Generator().manual_seed(3)
+    pts = torch.rand((1, 3, 4, 2), generator=g) * torch.tensor([90.0, 60.0])
+    pts[0, 1, 2] = float("nan")
+    xv, yv = R.data_utils.make_grid_vectors(60, 90, 2)
+    oxv, oyv = otgt.grid_vectors(60, 90, 2)
+    eq(npy(xv), npy(oxv)); eq(npy(yv), npy(oyv))
+    close(npy(otgt.multi_confmaps(pts, xv, yv, 3.0)), npy(R.confidence_maps.make_multi_confmaps(pts, xv, yv, 3.0)),
+          rtol=1e-6, atol=FLT_MIN)
+    close(npy(otgt.confmaps(pts[0], xv, yv, 2.0)), npy(R.confidence_maps.make_confmaps(pts[0], xv, yv, 2.0)),
+          rtol=1e-6, atol=FLT_MIN)
+    e = torch.tensor([[0, 1], [1, 2], [2, 3]])
+    srcs, dsts = pts[0][:, e[:, 0]], pts[0][:, e[:, 1]]
+    close(npy(otgt.multi_pafs(xv, yv, srcs, dsts, 2.5)), npy(R.edge_maps.make_multi_pafs(xv, yv, srcs, dsts, 2.5)),
+          rtol=1e-6, atol=1e-7)
+    close(npy(otgt.pafs(xv, yv, srcs[0], dsts[0], 1.5)), npy(R.edge_maps.make_pafs(xv, yv, srcs[0], dsts[0], 1.5)),
+          rtol=1e-6, atol=1e-7)
+    close(npy(otgt.generate_pafs(pts, (60, 90), 1.5, 2, e, True)),
+          npy(R.edge_maps.generate_pafs(pts, (60, 90), sigma=1.5, output_stride=2, edge_inds=e, flatten_channels=True)),
+          rtol=1e-6, atol=1e-7)
+
+
+def test_lsap_and_toposort_against_the_third_party_libraries(R):
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        nr, nc = rng.integers(1, 9, 2)
+        cost = rng.standard_normal((nr, nc))
+        if rng.random() < 0.3:
+            cost = np.round(cost, 1)  # ties
+        r, c = opaf.lsap_jv(cost)
+        wr, wc = linear_sum_assignment(cost)
+        eq(r, wr); eq(c, wc)
+    for edges in ([(0, 1), (1, 2), (1, 3)], [(2, 0), (0, 1), (0, 3), (3, 4)], [(0, 1), (2, 3)], [(0, 1), (0, 2), (1, 2)]):
+        types = [R.paf.EdgeType(a, b) for a, b in edges]
+        assert tuple(R.paf.toposort_edges(types)) == tuple(opaf.toposort_edge_order(edges))

@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""Per-kernel roofline lines for the rows of SURVEY.md section 8(d) that bench.py's headline does not cover.
+
+    python tools/bench_kernels.py [--iters 200] [--only k1_cfg4,k2_cfg2,k7_cfg4,k8_cfg4,chain_cfg4]
+
+One JSON line per kernel: algorithmic bytes per launch, average launch time over `iters`
+launches (CUDA events on the launching stream, after warm-up, inputs/outputs rotating over buffers whose
+total exceeds the 126 MB L2), achieved GB/s and its fraction of MEASURED_PEAKS.json's hbm_gbs.
+Not part of the product; results are copied into profiles/ by hand.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from sleap_nn_b200 import _native as N  # noqa: E402
+from sleap_nn_b200 import synthetic  # noqa: E402
+from sleap_nn_b200.data.utils import make_grid_vectors  # noqa: E402
+
+
+def peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def timed(fn, iters, warm=10):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        fn(i)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters  # ms per launch
+
+
+def line(name, kernel, algo_bytes, ms, units, unit_name, extra=None):
+    peak, src = peak_gbs()
+    ach = algo_bytes / (ms / 1e3) / 1e9
+    d = {"bench": name, "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ms,
+         "achieved_GBps": ach, "peak_GBps": peak, "peak_source": src, "frac": ach / peak,
+         f"{unit_name}_per_s": units / (ms / 1e3)}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d), flush=True)
+
+
+def k2_cfg2(dev, iters):
+    """cfg2: find_global_peaks + integral refine on (256,13,80,80) crops."""
+    B, Cn, H, W = 256, 13, 80, 80
+    g = torch.Generator(device=dev).manual_seed(0)
+    bufs = []
+    for _ in range(4):  # 4 x 85 MB > L2
+        pts = torch.rand((B, 1, Cn, 2), generator=g, device=dev) * 60 + 10
+        xv, yv = make_grid_vectors(H, W, 1)
+        from sleap_nn_b200.data.confidence_maps import _confmaps
+        cms = _confmaps(pts, xv, yv, 3.0, torch.float32, dev)
+        cms += torch.rand(cms.shape, generator=g, device=dev) * 1e-3
+        bufs.append(cms)
+    rpc, nch, nbytes = C.c_int(), C.c_int(), C.c_longlong()
+    N.check(N.lib.snb_global_peaks_workspace(B, Cn, H, W, C.byref(rpc), C.byref(nch), C.byref(nbytes)), "ws")
+    ws = torch.zeros(((nbytes.value + 3) // 4,), dtype=torch.int32, device=dev)
+    pts_o = torch.empty((B, Cn, 2), device=dev)
+    val_o = torch.empty((B, Cn), device=dev)
+    st = N.stream_ptr(dev)
+
+    def fn(i):
+        x = bufs[i % len(bufs)]
+        N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), st), "k2")
+
+    ms = timed(fn, iters)
+    line("k2_cfg2", "global_peaks_kernel", 4 * B * Cn * H * W, ms, B, "crops",
+         {"shape": [B, Cn, H, W], "valid_peaks": int((val_o > 0).sum())})
+
+
+def _flies_poses(n_frames, seed=0):
+    edges = synthetic.chain_edges(32)
+    return edges, synthetic.random_poses(seed, n_frames, 8, 32, (1024, 1024), edges, margin=200.0, step=24.0,
+                                         min_limb=8.0, min_sep=10.0)
+
+
+def k7_cfg4(dev, iters, bf16=False):
+    """cfg4 targets: make_multi_confmaps, 32 nodes, 8 instances, sigma 2.5 x stride 2, out 512x512."""
+    G = 8
+    edges, poses = _flies_poses(G)
+    xv, yv = make_grid_vectors(1024, 1024, 2)
+    xd, yd, pts = xv.to(dev), yv.to(dev), poses.to(dev).contiguous()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    outs = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(3)]
+    st = N.stream_ptr(dev)
+    den = float(2 * (2.5 * 2) ** 2)
+
+    def fn(i):
+        N.check(N.lib.snb_confmaps(N.ptr(pts), G, 8, 32, N.ptr(xd), N.ptr(yd), 512, 512, den, int(bf16),
+                                   N.ptr(outs[i % 3]), st), "k7")
+
+    ms = timed(fn, iters)
+    esz = 2 if bf16 else 4
+    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
+         {"frames_per_launch": G, "out_dtype": str(dt)})
+
+
+def k8_cfg4(dev, iters, bf16=False):
+    """cfg4 targets: make_multi_pafs, 31 edges, 8 instances, sigma 2.5, out (31,2,512,512) per frame."""
+    edges, poses = _flies_poses(4)
+    e = torch.tensor(edges, dtype=torch.int64)
+    xv, yv = make_grid_vectors(1024, 1024, 2)
+    xd, yd = xv.to(dev), yv.to(dev)
+    pd = poses.to(dev)
+    srcs = [pd[f][:, e[:, 0]].contiguous() for f in range(4)]
+    dsts = [pd[f][:, e[:, 1]].contiguous() for f in range(4)]
+    dt = torch.bfloat16 if bf16 else torch.float32
+    outs = [torch.empty((31, 2, 512, 512), dtype=dt, device=dev) for _ in range(4)]
+    st = N.stream_ptr(dev)
+    den = float(2 * 2.5 ** 2)
+
+    def fn(i):
+        k = i % 4
+        N.check(N.lib.snb_pafs(N.ptr(srcs[k]), N.ptr(dsts[k]), 8, 31, N.ptr(xd), N.ptr(yd), 512, 512, den, 1,
+                               int(bf16), N.ptr(outs[k]), st), "k8")
+
+    ms = timed(fn, iters)
+    esz = 2 if bf16 else 4
+    line("k8_cfg4" + ("_bf16" if bf16 else ""), "pafs_kernel", esz * 31 * 2 * 512 * 512, ms, 1, "frames",
+         {"frames_per_launch": 1, "out_dtype": str(dt)})
+
+
+def chain_cfg4(dev, iters):
+    """cfg4 inference: 32 nodes / 31 edges / 8 instances per frame, full chain on a batch of 8 frames."""
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+    Bn = 8
+    inputs = []
+    for s in range(2):  # 2 x (268 + 520 MB)
+        edges, poses = _flies_poses(Bn, seed=s)
+        inputs.append(synthetic.render_batch(poses, (1024, 1024), 2, edges, dev, seed=s))
+    pipe = BottomUpPostproc(32, edges, Bn, (512, 512), cms_stride=2, pafs_stride=2, device=dev, peak_cap=512,
+                            cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False)
+    res = pipe(*inputs[0])
+    inst, _, _ = res.to_lists()
+    n_inst = sum(len(x) for x in inst)
+    n_peaks = int(res.n_peaks.sum())
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    main = torch.cuda.current_stream(dev)
+    for a, b in evs:
+        a.record(main); b.record(main)
+    torch.cuda.synchronize()
+    ms = timed(lambda i: pipe(*inputs[i % 2], detect_events=evs[i % iters]), iters)
+    torch.cuda.synchronize()
+    det = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+    algo = 4 * Bn * 32 * 512 * 512
+    line("chain_cfg4", "detect+tail (whole chain, one stream)", algo, ms, Bn, "frames",
+         {"frames_per_launch": Bn, "instances_found": n_inst, "instances_planted": Bn * 8, "peaks": n_peaks,
+          "launches_per_call": pipe.launches_per_call, "fused_tail": pipe.fused})
+    line("k1_cfg4", "local_peaks_detect_vec4 (in situ)", algo, det, Bn, "frames", {"frames_per_launch": Bn})
+
+
+ALL = {"k2_cfg2": k2_cfg2, "k7_cfg4": k7_cfg4, "k7_cfg4_bf16": lambda d, i: k7_cfg4(d, i, True),
+       "k8_cfg4": k8_cfg4, "k8_cfg4_bf16": lambda d, i: k8_cfg4(d, i, True), "chain_cfg4": chain_cfg4}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--only", default=",".join(ALL))
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    for name in args.only.split(","):
+        try:
+            ALL[name](dev, args.iters)
+        except Exception as e:  # keep going: one failing config must not hide the others
+            print(json.dumps({"bench": name, "error": f"{type(e).__name__}: {e}"}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
