@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 1
+#define SNB_ABI_VERSION 2
 
 #define SNB_OK 0
 #define SNB_ERR_BAD_ARG (-1)
@@ -298,6 +298,19 @@ typedef struct snb_bottomup_args {
   void* ev_handoff;
   void* ev_tail_done;
   int flags; /* SNB_FLAG_* */
+  /* ---- ABI v2: the BottomUpLayer / group_scored_batch epilogue (layers/bottomup.py:95-236,
+   * inference/streaming.py:147-255), all optional.
+   * max_peaks_per_node > 0 with skip_flag != NULL: the batch-wide guard of layers/bottomup.py:128-148 - if any
+   *   node of any frame has more peaks than the limit, *skip_flag is set and the epilogue emits all-NaN outputs.
+   * out_kpts != NULL: snb_bottomup_outputs is enqueued after the tail with the five fields below. */
+  int max_peaks_per_node;
+  int* skip_flag;       /* 1 int, zeroed by snb_bottomup_postproc at the start of every call */
+  int max_instances;    /* rows per frame of the out_* tensors (>= 1) */
+  float input_scale;    /* PreprocInfo.input_scale */
+  const float* eff_scale; /* (B,) PreprocInfo.eff_scale or NULL */
+  float* out_kpts;      /* (B, max_instances, C, 2) */
+  float* out_vals;      /* (B, max_instances, C) */
+  float* out_scores;    /* (B, max_instances) */
 } snb_bottomup_args;
 
 #define SNB_FLAG_UNFUSED_TAIL 1 /* chain the stand-alone kernels instead of the fused per-frame tail */
@@ -311,6 +324,19 @@ int snb_bottomup_postproc(const snb_bottomup_args* args, void* stream);
 long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
                                        int n_sorted, int n_points);
 int snb_bottomup_launches_per_call(const snb_bottomup_args* args);
+
+/* snb_bottomup_outputs: the tail of group_scored_batch (inference/streaming.py:196-243) on device.
+ *   Per frame: when n_inst > max_instances keep the top max_instances by instance score, in the order of
+ *   np.argsort(scores)[::-1] (descending; NaN first; equal scores: higher index first), otherwise keep
+ *   assembly order; coordinates are divided by fl32(input_scale) and then by eff_scale[b] (two separately
+ *   rounded fp32 divisions, as `p / info.input_scale` and `p / eff[i]` are; dividing by exactly 1.0f is the
+ *   identity, so the reference's `!= 1.0` short-circuits need no branch); rows >= n_inst are NaN.
+ *   skip_flag (may be NULL): non-zero -> every output is NaN (the skip_paf short-circuit, :296-318).
+ *   out_kpts (B, max_instances, N, 2), out_vals (B, max_instances, N), out_scores (B, max_instances). */
+int snb_bottomup_outputs(const int* n_inst, const float* inst_xy, const float* inst_val, const float* inst_score,
+                         int B, int inst_cap, int n_nodes, int max_instances, float input_scale,
+                         const float* eff_scale, const int* skip_flag, float* out_kpts, float* out_vals,
+                         float* out_scores, void* stream);
 
 /* snb_pack_instances: append one batch's padded instance tables (the outputs of snb_bottomup_postproc /
  * snb_assemble) to a packed per-rank result table at a DEVICE-side running offset, so a rank can run its

@@ -62,6 +62,7 @@ SIGNATURES = {
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
+    "snb_bottomup_outputs": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "snb_pack_instances": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p],
 }
 RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
@@ -89,6 +90,8 @@ class BottomUpArgs(C.Structure):
         ("inst_xy", _p), ("inst_val", _p), ("inst_score", _p), ("n_inst", _p), ("status", _p),
         ("ev_detect_begin", _p), ("ev_detect_end", _p),
         ("tail_stream", _p), ("ev_handoff", _p), ("ev_tail_done", _p), ("flags", _i),
+        ("max_peaks_per_node", _i), ("skip_flag", _p), ("max_instances", _i), ("input_scale", _f),
+        ("eff_scale", _p), ("out_kpts", _p), ("out_vals", _p), ("out_scores", _p),
     ]
 
 

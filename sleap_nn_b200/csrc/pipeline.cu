@@ -144,6 +144,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     if (lane == 0) edge_offsets(s_edges, n_nodes, E, s_ns, s_eo, s_mo);
   }
   __syncthreads();
+  if (a.max_peaks_per_node > 0 && a.skip_flag) {  // layers/bottomup.py:128-148: batch-wide guard
+    bool over = false;
+    for (int k = tid; k < n_nodes; k += TAIL_THREADS) over = over || (s_ns[k + 1] - s_ns[k] > a.max_peaks_per_node);
+    if (over) atomicOr(a.skip_flag, 1);
+  }
   const int M = s_eo[E];
   const bool cand_ok = M <= a.cand_cap;
   if (!cand_ok && tid == 0) atomicOr(a.status, SNB_STATUS_CAND_OVERFLOW);
@@ -298,6 +303,69 @@ pack_instances_kernel(const int* __restrict__ n_inst, int B, int inst_cap, int n
   }
 }
 
+// Batch-wide max_peaks_per_node guard for the unfused chain (the fused tail checks it in place).
+__global__ void node_guard_kernel(const int* __restrict__ node_start, int B, int n_nodes, int limit, int* skip_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_nodes) return;
+  const int b = i / n_nodes, k = i % n_nodes;
+  const int* ns = node_start + (long long)b * (n_nodes + 1);
+  if (ns[k + 1] - ns[k] > limit) atomicOr(skip_flag, 1);
+}
+
+// group_scored_batch's epilogue (inference/streaming.py:196-243): top-N by score when truncating,
+// undo input / effective scale, NaN-pad to (B, max_instances, N, ...).  One CTA per frame.
+__global__ void __launch_bounds__(128)
+bottomup_outputs_kernel(const int* __restrict__ n_inst, const float* __restrict__ inst_xy,
+                        const float* __restrict__ inst_val, const float* __restrict__ inst_score, int inst_cap,
+                        int n_nodes, int max_instances, float input_scale, const float* __restrict__ eff_scale,
+                        const int* __restrict__ skip_flag, float* __restrict__ out_kpts, float* __restrict__ out_vals,
+                        float* __restrict__ out_scores) {
+  extern __shared__ int s_src[];  // s_src[r] = source row of output row r
+  const int b = blockIdx.x;
+  const bool skip = skip_flag && *skip_flag;
+  const int n = skip ? 0 : min(n_inst[b], inst_cap);
+  const int keep = min(n, max_instances);
+  const float* sc = inst_score + (long long)b * inst_cap;
+  if (n > max_instances) {
+    // position of row i in np.argsort(scores)[::-1]: NaN first, then descending; equal -> higher index first
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float si = sc[i];
+      const bool ni = isnan(si);
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const float sj = sc[j];
+        const bool nj = isnan(sj);
+        bool before;  // does j come before i?
+        if (ni || nj) before = (nj && !ni) || (nj && ni && j > i);
+        else before = (sj > si) || (sj == si && j > i);
+        rank += before ? 1 : 0;
+      }
+      if (rank < max_instances) s_src[rank] = i;
+    }
+  } else {
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) s_src[i] = i;
+  }
+  __syncthreads();
+  const float eff = eff_scale ? eff_scale[b] : 1.0f;
+  const long long ob = (long long)b * max_instances;
+  for (int t = threadIdx.x; t < max_instances * n_nodes; t += blockDim.x) {
+    const int r = t / n_nodes, k = t - r * n_nodes;
+    float x = NAN, y = NAN, v = NAN;
+    if (r < keep) {
+      const long long s = ((long long)b * inst_cap + s_src[r]) * n_nodes + k;
+      x = __fdiv_rn(__fdiv_rn(inst_xy[2 * s], input_scale), eff);
+      y = __fdiv_rn(__fdiv_rn(inst_xy[2 * s + 1], input_scale), eff);
+      v = inst_val[s];
+    }
+    out_kpts[2 * (ob * n_nodes + t)] = x;
+    out_kpts[2 * (ob * n_nodes + t) + 1] = y;
+    out_vals[ob * n_nodes + t] = v;
+  }
+  for (int r = threadIdx.x; r < max_instances; r += blockDim.x)
+    out_scores[ob + r] = (r < keep) ? sc[s_src[r]] : NAN;
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -321,6 +389,7 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
   cudaStream_t tail_st = a->tail_stream ? (cudaStream_t)a->tail_stream : st;
   // buffers of this pipeline instance may still be read by its previous tail
   if (a->tail_stream && a->ev_tail_done) cudaStreamWaitEvent(st, (cudaEvent_t)a->ev_tail_done, 0);
+  if (a->skip_flag && cudaMemsetAsync(a->skip_flag, 0, sizeof(int), st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
   int rc = snb_local_peaks_detect(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
                                   a->peak_threshold, a->peak_cap, a->frame_count, a->keys, a->ev_detect_begin,
                                   a->ev_detect_end, stream);
@@ -342,7 +411,28 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
     rc = unfused_tail(a, (void*)tail_st);
     if (rc != SNB_OK) return rc;
   }
+  if (a->out_kpts) {
+    rc = snb_bottomup_outputs(a->n_inst, a->inst_xy, a->inst_val, a->inst_score, a->B, a->inst_cap, a->C,
+                              a->max_instances, a->input_scale, a->eff_scale, a->skip_flag, a->out_kpts, a->out_vals,
+                              a->out_scores, (void*)tail_st);
+    if (rc != SNB_OK) return rc;
+  }
   if (a->tail_stream && a->ev_tail_done) cudaEventRecord((cudaEvent_t)a->ev_tail_done, tail_st);
+  return SNB_OK;
+}
+
+extern "C" int snb_bottomup_outputs(const int* n_inst, const float* inst_xy, const float* inst_val,
+                                    const float* inst_score, int B, int inst_cap, int n_nodes, int max_instances,
+                                    float input_scale, const float* eff_scale, const int* skip_flag, float* out_kpts,
+                                    float* out_vals, float* out_scores, void* stream) {
+  if (B < 0 || inst_cap <= 0 || n_nodes <= 0 || max_instances <= 0) return SNB_ERR_BAD_ARG;
+  if (B == 0) return SNB_OK;
+  const size_t smem = sizeof(int) * (size_t)max_instances;
+  if (smem > 48 * 1024) return SNB_ERR_UNSUPPORTED;
+  bottomup_outputs_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(n_inst, inst_xy, inst_val, inst_score, inst_cap, n_nodes,
+                                                                 max_instances, input_scale, eff_scale, skip_flag,
+                                                                 out_kpts, out_vals, out_scores);
+  SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
 
@@ -360,6 +450,12 @@ static int unfused_tail(const snb_bottomup_args* a, void* stream) {
   rc = snb_paf_prepare(a->peak_chan, nullptr, a->peak_cap, a->frame_count, a->B, a->edges, n_nodes, a->n_edges,
                        a->node_start, a->node_peaks, a->edge_off, a->match_off, stream);
   if (rc != SNB_OK) return rc;
+  if (a->max_peaks_per_node > 0 && a->skip_flag) {
+    const int n = a->B * n_nodes;
+    node_guard_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a->node_start, a->B, n_nodes,
+                                                                       a->max_peaks_per_node, a->skip_flag);
+    SNB_LAUNCH_CHECK();
+  }
   rc = snb_paf_score(a->pafs, a->paf_sb, a->paf_sy, a->paf_sx, a->paf_sc, a->paf_H, a->paf_W, a->t_table, a->n_points,
                      a->pafs_stride, a->max_edge_length, a->dist_penalty_weight, a->peak_xy, nullptr, a->peak_cap,
                      a->B, a->edges, n_nodes, a->n_edges, a->node_start, a->node_peaks, a->edge_off, nullptr,
@@ -381,7 +477,8 @@ extern "C" int snb_bottomup_launches_per_call(const snb_bottomup_args* a) {
   if (!a) return 2;
   const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
                                                       a->n_points);
-  return (!(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024) ? 2 : 6;
+  const bool fused = !(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024;
+  return (fused ? 2 : 6 + ((a->max_peaks_per_node > 0 && a->skip_flag) ? 1 : 0)) + (a->out_kpts ? 1 : 0);
 }
 
 // Append one batch's instances to a packed per-rank result table (see pack_instances_kernel).

@@ -36,11 +36,47 @@ class BottomUpResult:
     peak_channels: torch.Tensor   # (B, peak_cap) i32
     status: torch.Tensor          # (1,) i32, SNB_STATUS_* bits
     done: Optional[torch.cuda.Event] = None  # set in two-stream mode: the tail ran on another stream
+    # group_scored_batch-shaped outputs (inference/streaming.py:196-243); filled in the same call when the
+    # pipeline was built with max_instances, else by .outputs()
+    pred_keypoints: Optional[torch.Tensor] = None        # (B, I, N, 2) NaN-padded, scale-undone
+    pred_peak_values: Optional[torch.Tensor] = None      # (B, I, N)
+    pred_instance_scores: Optional[torch.Tensor] = None  # (B, I)
+    skip_flag: Optional[torch.Tensor] = None             # (1,) i32: the max_peaks_per_node guard tripped
+    _pipe: Optional["BottomUpPostproc"] = None
+    _scales: Tuple[float, Optional[torch.Tensor]] = (1.0, None)
 
     def wait(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Make `stream` (default: current) wait for this batch's tail kernel."""
         if self.done is not None:
             (stream or torch.cuda.current_stream(self.status.device)).wait_event(self.done)
+
+    def outputs(self, max_instances: Optional[int] = None):
+        """(pred_keypoints (B,I,N,2), pred_peak_values (B,I,N), instance_scores (B,I)) device tensors with the
+        semantics of `group_scored_batch` (inference/streaming.py:147-255): NaN padding, top-N by score when
+        truncating, input / effective scale undone, all-NaN when the max_peaks_per_node guard tripped.
+
+        With a fixed `max_instances` (given here or at construction) nothing synchronises with the host; with
+        None the per-batch maximum instance count is read back first (the reference's `_infer_max_instances`).
+        """
+        if max_instances is None and self.pred_keypoints is not None:
+            return self.pred_keypoints, self.pred_peak_values, self.pred_instance_scores
+        self.wait()
+        pipe, dev = self._pipe, self.status.device
+        B, cap, Nn = self.instances.shape[0], self.instances.shape[1], self.instances.shape[2]
+        if max_instances is None:
+            skipped = self.skip_flag is not None and bool(self.skip_flag.item())
+            max_instances = 0 if skipped else int(self.n_instances.clamp(max=cap).max().item()) if B else 0
+        I = max(int(max_instances), 1)
+        with torch.cuda.device(dev):
+            k = torch.empty((B, I, Nn, 2), dtype=torch.float32, device=dev)
+            v = torch.empty((B, I, Nn), dtype=torch.float32, device=dev)
+            s = torch.empty((B, I), dtype=torch.float32, device=dev)
+            scale, eff = self._scales
+            N.check(N.lib.snb_bottomup_outputs(N.ptr(self.n_instances), N.ptr(self.instances), N.ptr(self.peak_scores),
+                                               N.ptr(self.instance_scores), B, cap, Nn, I, float(scale), N.ptr(eff),
+                                               N.ptr(self.skip_flag), N.ptr(k), N.ptr(v), N.ptr(s), N.stream_ptr(dev)),
+                    "snb_bottomup_outputs")
+        return k, v, s
 
     def to_lists(self):
         """One host sync: per-sample CPU tensors shaped like `PAFScorer.predict`'s first three outputs."""
@@ -75,6 +111,10 @@ class BottomUpPostproc:
         tail_stream: optional second (high-priority) CUDA stream: the streaming detect kernel runs on
             the caller's current stream and the per-frame tail on `tail_stream`, so the tail of one
             batch overlaps the detect pass of the next.
+        max_instances: when given, every call also fills `(B, max_instances, N, ...)` NaN-padded outputs with
+            `group_scored_batch` semantics (top-N by score, scales undone) in the same launch chain.
+        max_peaks_per_node: the batch-wide guard of `BottomUpLayer` (layers/bottomup.py:128-148): if any node of
+            any frame has more peaks, the outputs are all-NaN.
         fused_tail: run everything after the detect kernel as one CTA per frame with shared-memory
             tables (default; falls back automatically when the capacities do not fit).
         keep_tables: also write the intermediate tables (candidates, matches) to global memory.
@@ -87,7 +127,8 @@ class BottomUpPostproc:
                  min_instance_peaks: Union[int, float] = 0, min_line_scores: float = 0.25, peak_cap: int = 256,
                  cand_cap: int = 4096, match_cap: int = 512, inst_cap: int = 64, lsap_max_dim: int = 32,
                  device: Optional[torch.device] = None, tail_stream: Optional[torch.cuda.Stream] = None,
-                 fused_tail: bool = True, keep_tables: bool = True):
+                 fused_tail: bool = True, keep_tables: bool = True, max_instances: Optional[int] = None,
+                 max_peaks_per_node: Optional[int] = None):
         self.device = torch.device(device) if device is not None else N.compute_device()
         self.n_nodes, self.batch = int(n_nodes), int(batch)
         self.edge_inds = [(int(a), int(b)) for a, b in edge_inds]
@@ -147,6 +188,23 @@ class BottomUpPostproc:
             for k in ("node_start", "node_peaks", "edge_off", "match_off", "cand_edge", "cand_epi", "cand_score",
                       "m_edge", "m_src", "m_dst", "m_score", "m_count"):
                 setattr(a, k, None)
+        self.max_instances = None if max_instances is None else max(int(max_instances), 1)
+        self.max_peaks_per_node = max_peaks_per_node
+        a.max_peaks_per_node, a.skip_flag = 0, None
+        a.max_instances, a.input_scale, a.eff_scale = 1, 1.0, None
+        a.out_kpts = a.out_vals = a.out_scores = None
+        self._out = None
+        with torch.cuda.device(dev):
+            if max_peaks_per_node is not None:
+                self._skip_flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+                a.max_peaks_per_node, a.skip_flag = int(max_peaks_per_node), N.ptr(self._skip_flag)
+            else:
+                self._skip_flag = None
+            if self.max_instances is not None:
+                I = self.max_instances
+                self._out = (f32(B, I, Nn, 2), f32(B, I, Nn), f32(B, I))
+                a.max_instances = I
+                a.out_kpts, a.out_vals, a.out_scores = (N.ptr(t) for t in self._out)
         self.tail_stream = tail_stream
         self._ev_handoff = self._ev_done = None
         a.tail_stream = a.ev_handoff = a.ev_tail_done = None
@@ -160,12 +218,14 @@ class BottomUpPostproc:
             a.ev_handoff, a.ev_tail_done = self._ev_handoff.cuda_event, self._ev_done.cuda_event
 
     # ------------------------------------------------------------------ device-resident path
-    def __call__(self, cms: torch.Tensor, pafs: torch.Tensor, detect_events=None) -> BottomUpResult:
+    def __call__(self, cms: torch.Tensor, pafs: torch.Tensor, detect_events=None, input_scale: float = 1.0,
+                 eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
         """Enqueue the chain on the current stream of `self.device`; returns padded device tensors.
 
         cms (B, N, H, W) fp32 CUDA; pafs (B, 2E, Hp, Wp) or (B, Hp, Wp, 2E) fp32 CUDA, any strides.
         `detect_events` = (torch.cuda.Event, torch.cuda.Event) recorded around the streaming
-        detect kernel (for the benchmark's roofline figure).
+        detect kernel (for the benchmark's roofline figure).  `input_scale` / `eff_scale` (B,) are
+        `PreprocInfo`'s scale factors, undone in the `.outputs()` tensors (streaming.py:190-196).
         """
         if not (cms.is_cuda and pafs.is_cuda) or cms.dtype != torch.float32 or pafs.dtype != torch.float32:
             raise TypeError("BottomUpPostproc expects fp32 CUDA tensors; use .run_host() for host buffers")
@@ -177,11 +237,20 @@ class BottomUpPostproc:
             pafs = pafs.permute(0, 2, 3, 1)  # channels-first tensor -> the channels-last VIEW (no copy)
         elif pafs.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
-        return self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events)
+        return self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events,
+                            input_scale, eff_scale)
 
-    def _launch(self, cms_ptr: int, cms_strides, pafs_ptr: int, pafs_shape, pafs_strides, detect_events=None) -> BottomUpResult:
+    def _launch(self, cms_ptr: int, cms_strides, pafs_ptr: int, pafs_shape, pafs_strides, detect_events=None,
+                input_scale: float = 1.0, eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
         """Fill the argument block from raw device-visible pointers and enqueue the chain."""
         a = self._args
+        if eff_scale is not None:
+            eff_scale = eff_scale.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+            if eff_scale.numel() == 1 and self.batch != 1:
+                eff_scale = eff_scale.expand(self.batch).contiguous()
+            if eff_scale.numel() != self.batch:
+                raise ValueError("eff_scale must hold one factor per sample")
+        a.input_scale, a.eff_scale = float(input_scale), N.ptr(eff_scale)
         a.cms = cms_ptr
         a.cms_sb, a.cms_sc, a.cms_sh, a.cms_sw = cms_strides
         a.pafs = pafs_ptr
@@ -195,8 +264,10 @@ class BottomUpPostproc:
             a.ev_detect_begin = a.ev_detect_end = None
         N.check(N.lib.snb_bottomup_postproc(C.byref(a), N.stream_ptr(self.device)), "snb_bottomup_postproc")
         b = self.buf
+        k, v, sc = self._out if self._out is not None else (None, None, None)
         return BottomUpResult(b["n_inst"], b["inst_xy"], b["inst_val"], b["inst_score"], b["frame_count"],
-                              b["peak_xy"], b["peak_val"], b["peak_chan"], b["status"], self._ev_done)
+                              b["peak_xy"], b["peak_val"], b["peak_chan"], b["status"], self._ev_done,
+                              k, v, sc, self._skip_flag, self, (float(input_scale), eff_scale))
 
     @property
     def launches_per_call(self) -> int:
