@@ -215,10 +215,11 @@ int snb_confmaps(const float* points, int G, int I, int N, const float* xv, cons
                  int out_bf16, void* out, void* stream);
 
 /* snb_pafs: make_pafs (edge_maps.py:120-164; accumulate = 0, I = 1, NaNs kept) and make_multi_pafs
- *   (:167-220; accumulate = 1: per-instance NaN -> 0, summed in instance order).
- *   srcs/dsts (I,E,2); out (E,2,h,w) fp32 or bf16.  The weight is exp(-(d2*d2)/den) on the SQUARED
+ *   (:167-220; accumulate = 1: per-instance NaN -> 0, summed in instance order), for G frames in one launch
+ *   (the reference API is per frame: G = 1).
+ *   srcs/dsts (G,I,E,2); out (G,E,2,h,w) fp32 or bf16.  The weight is exp(-(d2*d2)/den) on the SQUARED
  *   point-segment distance d2, exactly as distance_to_edge + gaussian_pdf compose in the reference. */
-int snb_pafs(const float* srcs, const float* dsts, int I, int E, const float* xv, const float* yv, int h, int w,
+int snb_pafs(const float* srcs, const float* dsts, int G, int I, int E, const float* xv, const float* yv, int h, int w,
              float den, int accumulate, int out_bf16, void* out, void* stream);
 
 /* distance_to_edge (edge_maps.py:15-78; apply_pdf = 0) and make_edge_maps (:81-117; apply_pdf = 1).
@@ -321,6 +322,7 @@ typedef struct snb_bottomup_args {
  * Otherwise, or with SNB_FLAG_UNFUSED_TAIL, the stand-alone kernels are chained and those tables
  * are required. */
 int snb_bottomup_postproc(const snb_bottomup_args* args, void* stream);
+int snb_bottomup_args_size(void); /* sizeof(snb_bottomup_args): lets a binding check its mirror of the layout */
 long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
                                        int n_sorted, int n_points);
 int snb_bottomup_launches_per_call(const snb_bottomup_args* args);

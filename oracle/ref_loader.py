@@ -6,7 +6,7 @@ golden vectors and by `tests/test_oracle_vs_reference.py` (skipped when the
 reference tree is absent) to pin `oracle/` against the reference itself.
 
 `import sleap_nn` fails here (sleap_io / omegaconf / lightning are absent), so the
-eight hot-path files are exec'd individually under empty namespace packages and
+hot-path files (and the five caller-side files of the section-8f rows) are exec'd individually under empty namespace packages and
 stub modules for the names they import but never touch on this path
 (SURVEY.md section 8c).  No reference source is copied: files are read where they
 lie.
@@ -31,6 +31,12 @@ _HOT_FILES = [
     ("sleap_nn.inference.ops.crops", "sleap_nn/inference/ops/crops.py"),
     ("sleap_nn.inference.ops.peaks", "sleap_nn/inference/ops/peaks.py"),
     ("sleap_nn.inference.ops.paf", "sleap_nn/inference/ops/paf.py"),
+    # the callers either side of the path (SURVEY.md section 8f "next" rows): pure attrs / torch / numpy / scipy
+    ("sleap_nn.inference.preprocess_info", "sleap_nn/inference/preprocess_info.py"),
+    ("sleap_nn.inference.outputs", "sleap_nn/inference/outputs.py"),
+    ("sleap_nn.inference.streaming", "sleap_nn/inference/streaming.py"),
+    ("sleap_nn.inference.ops.coord", "sleap_nn/inference/ops/coord.py"),
+    ("sleap_nn.inference.ops.identity", "sleap_nn/inference/ops/identity.py"),
 ]
 
 _NAMESPACE_PKGS = [
@@ -132,6 +138,34 @@ def load(prefix: str = "_sleapnn_ref") -> dict:
         sys.modules.update(saved)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def reference_imports(prefix: str = "_sleapnn_ref"):
+    """Temporarily register the loaded reference modules under their real `sleap_nn.*` names.
+
+    A few reference functions import lazily at CALL time (`group_scored_batch` does
+    `from sleap_nn.inference.ops.paf import PAFScorer`, streaming.py:163); wrap such calls in this.
+    """
+    ref()
+    saved = {k: v for k, v in sys.modules.items() if k == "sleap_nn" or k.startswith("sleap_nn.")}
+    for k in saved:
+        del sys.modules[k]
+    added = []
+    try:
+        for k, m in list(sys.modules.items()):
+            if k.startswith(prefix + "."):
+                real = k[len(prefix) + 1:]
+                sys.modules[real] = m
+                added.append(real)
+        yield
+    finally:
+        for k in added:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
 _CACHE = None
 
 
@@ -152,5 +186,10 @@ def ref() -> types.SimpleNamespace:
             edge_maps=mods["edge_maps"],
             data_utils=full["sleap_nn.data.utils"],
             instance_cropping=mods["instance_cropping"],
+            preprocess_info=mods["preprocess_info"],
+            outputs=mods["outputs"],
+            streaming=mods["streaming"],
+            coord=mods["coord"],
+            identity=mods["identity"],
         )
     return _CACHE

@@ -57,11 +57,12 @@ SIGNATURES = {
     "snb_scatter_instances": [_p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     "snb_interp1d": [_p, _i, _p, _i, _p, _i, _i, _i, _ll, _p, _p],
     "snb_confmaps": [_p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _p, _p],
-    "snb_pafs": [_p, _p, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
+    "snb_pafs": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
+    "snb_bottomup_args_size": [],
     "snb_bottomup_outputs": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "snb_pack_instances": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p],
 }
@@ -122,6 +123,9 @@ def _load() -> C.CDLL:
 
 lib = _load()
 ABI_VERSION = lib.snb_abi_version()
+if lib.snb_bottomup_args_size() != C.sizeof(BottomUpArgs):
+    raise NativeLibraryError(
+        f"snb_bottomup_args layout mismatch: library {lib.snb_bottomup_args_size()} bytes, binding {C.sizeof(BottomUpArgs)}")
 
 
 def check(rc: int, what: str) -> None:

@@ -14,3 +14,6 @@ extern "C" int snb_host_device_pointer(void* host_ptr, void** device_ptr) {
   *device_ptr = d;
   return SNB_OK;
 }
+
+// sizeof(snb_bottomup_args), so a binding can verify its mirror of the struct layout.
+extern "C" int snb_bottomup_args_size(void) { return (int)sizeof(snb_bottomup_args); }

@@ -353,6 +353,59 @@ __device__ __forceinline__ Best best_warp(Best a) {
   return a;
 }
 
+// Shared epilogue: thread 0 holds the CTA's Best `r`; publish it, let the plane's last CTA combine the
+// chunk partials, then warp 0 of that CTA applies the threshold and the integral refinement.
+__device__ __forceinline__ void global_peaks_finish(Best r, const float* __restrict__ plane, int plane_id, int chunk,
+                                                    int n_chunks, int H, int W, long long sh, long long sw, float thr,
+                                                    int refine_size, float* __restrict__ part_v,
+                                                    int* __restrict__ part_xy, unsigned* __restrict__ tickets,
+                                                    float* __restrict__ out_xy, float* __restrict__ out_val,
+                                                    Best* s_best, bool* s_last) {
+  if (threadIdx.x == 0) {
+    if (n_chunks > 1) {
+      const long long slot = (long long)plane_id * n_chunks + chunk;
+      part_v[slot] = r.v;
+      part_xy[2 * slot] = r.x;
+      part_xy[2 * slot + 1] = r.y;
+      __threadfence();
+      const unsigned t = atomicAdd(tickets + plane_id, 1u);
+      *s_last = (t == (unsigned)(n_chunks - 1));
+      if (*s_last) {
+        __threadfence();
+        tickets[plane_id] = 0;  // self-reset so the workspace can be reused without a memset
+        r = Best{__ldcg(part_v + (long long)plane_id * n_chunks), __ldcg(part_xy + 2LL * plane_id * n_chunks),
+                 __ldcg(part_xy + 2LL * plane_id * n_chunks + 1)};
+        for (int k = 1; k < n_chunks; ++k) {
+          const long long s2 = (long long)plane_id * n_chunks + k;
+          r = best_merge(r, Best{__ldcg(part_v + s2), __ldcg(part_xy + 2 * s2), __ldcg(part_xy + 2 * s2 + 1)});
+        }
+      }
+    } else {
+      *s_last = true;
+    }
+    if (*s_last) s_best[0] = r;
+  }
+  __syncthreads();
+  if (*s_last && threadIdx.x < 32) {  // warp 0 of the plane's last CTA: threshold + refinement
+    const Best b = s_best[0];
+    // An empty plane (H*W == 0) cannot occur: the host rejects it.
+    const bool low = b.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
+    float fx = low ? NAN : (float)b.x, fy = low ? NAN : (float)b.y;
+    if (!low && refine_size > 0) {
+      float ox, oy;
+      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, threadIdx.x, &ox, &oy);
+      fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
+      fy = __fadd_rn(fy, oy);
+    }
+    if (threadIdx.x == 0) {
+      out_xy[2 * plane_id] = fx;
+      out_xy[2 * plane_id + 1] = fy;
+      out_val[plane_id] = low ? 0.f : b.v;
+    }
+  }
+}
+
+// Generic variant: any strides, any chunk size; one associative (v, x, y) merge per element.
 __global__ void __launch_bounds__(256)
 global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                     long long sw, int vec_ok, int rows_per_chunk, int n_chunks, float thr, int refine_size,
@@ -395,50 +448,120 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
   acc = best_warp(acc);
   if (lane_id() == 0) s_best[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    Best r = s_best[0];
+  Best r = s_best[0];
+  if (threadIdx.x == 0)
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = best_merge(r, s_best[w]);
-    if (n_chunks > 1) {
-      const long long slot = (long long)plane_id * n_chunks + chunk;
-      part_v[slot] = r.v;
-      part_xy[2 * slot] = r.x;
-      part_xy[2 * slot + 1] = r.y;
-      __threadfence();
-      const unsigned t = atomicAdd(tickets + plane_id, 1u);
-      s_last = (t == (unsigned)(n_chunks - 1));
-      if (s_last) {
-        __threadfence();
-        tickets[plane_id] = 0;  // self-reset so the workspace can be reused without a memset
-        r = Best{__ldcg(part_v + (long long)plane_id * n_chunks), __ldcg(part_xy + 2LL * plane_id * n_chunks),
-                 __ldcg(part_xy + 2LL * plane_id * n_chunks + 1)};
-        for (int k = 1; k < n_chunks; ++k) {
-          const long long s2 = (long long)plane_id * n_chunks + k;
-          r = best_merge(r, Best{__ldcg(part_v + s2), __ldcg(part_xy + 2 * s2), __ldcg(part_xy + 2 * s2 + 1)});
+  global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, sw, thr, refine_size, part_v, part_xy, tickets,
+                      out_xy, out_val, s_best, &s_last);
+}
+
+// Register-resident variant (the product path for vectorisable planes whose chunk is <= V*1024 elements).
+// The first version above spent ~40 issue slots per 16-byte load on the (v, x, y) merge and ran at 32 % of the
+// HBM roofline.  Here a thread issues ALL of its 128-bit loads up front and keeps the values in registers:
+// pass 1 is one FMNMX per element (+ NaN detection), the CTA agrees on the maximum m, pass 2 looks for
+// elements equal to m (a rare branch) and reduces min(x), min(y) - the reference's two independent arg-maxes
+// (ops/peaks.py:103-111).  A chunk that contains a NaN takes the exact generic merge over the same registers.
+template <int V>
+__global__ void __launch_bounds__(256)
+global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+                         int rows_per_chunk, int n_chunks, float thr, int refine_size, float* __restrict__ part_v,
+                         int* __restrict__ part_xy, unsigned* __restrict__ tickets, float* __restrict__ out_xy,
+                         float* __restrict__ out_val) {
+  const int plane_id = blockIdx.x / n_chunks;
+  const int chunk = blockIdx.x % n_chunks;
+  const int b = plane_id / C, c = plane_id % C;
+  const float* plane = cms + (long long)b * sb + (long long)c * sc;
+  const int y0 = chunk * rows_per_chunk;
+  const int y1 = min(H, y0 + rows_per_chunk);
+  const int W4 = W >> 2;
+  const int n4 = (y1 - y0) * W4;
+  const bool contig = (sh == W);
+  const float* base = plane + (long long)y0 * sh;
+  float4 v[V];
+#pragma unroll
+  for (int u = 0; u < V; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < n4) {
+      const float* p = contig ? base + 4LL * i : base + (long long)(i / W4) * sh + 4 * (i % W4);
+      v[u] = ldg_stream4(p);
+    } else {
+      v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // loses to (or ties harmlessly with) real data
+    }
+  }
+  float m = -INFINITY;
+  bool has_nan = false;
+#pragma unroll
+  for (int u = 0; u < V; ++u) {
+    m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
+    has_nan = has_nan || (v[u].x != v[u].x) || (v[u].y != v[u].y) || (v[u].z != v[u].z) || (v[u].w != v[u].w);
+  }
+  __shared__ float s_m[8];
+  __shared__ int s_x[8], s_y[8];
+  __shared__ Best s_best[8];
+  __shared__ bool s_last;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, d));
+  if (lane == 0) s_m[warp] = m;
+  const int any_nan = __syncthreads_or(has_nan ? 1 : 0);
+  Best r;
+  if (any_nan) {
+    // exact generic merge over the registers (NaN ranks above everything; min x / min y among the NaNs)
+    Best acc{-INFINITY, 0x7fffffff, 0x7fffffff};
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < n4) {
+        const int y = y0 + i / W4, x = 4 * (i % W4);
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const Best o{e[k], x + k, y};
+          acc = any ? best_merge(acc, o) : o;
+          any = true;
         }
       }
-    } else {
-      s_last = true;
     }
-    if (s_last) s_best[0] = r;
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x < 32) {  // warp 0 of the plane's last CTA: threshold + refinement
-    const Best r = s_best[0];
-    // An empty plane (H*W == 0) cannot occur: the host rejects it.
-    const bool low = r.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
-    float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
-    if (!low && refine_size > 0) {
-      float ox, oy;
-      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, threadIdx.x, &ox, &oy);
-      fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
-      fy = __fadd_rn(fy, oy);
+    acc = best_warp(acc);
+    if (lane == 0) s_best[warp] = acc;
+    __syncthreads();
+    r = s_best[0];
+    if (threadIdx.x == 0)
+      for (int w = 1; w < 8; ++w) r = best_merge(r, s_best[w]);
+    __syncthreads();  // s_best[0] is rewritten by the epilogue
+  } else {
+    m = s_m[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+    int bx = 0x7fffffff, by = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      if (v[u].x == m || v[u].y == m || v[u].z == m || v[u].w == m) {  // rare
+        const int i = threadIdx.x + u * 256;
+        if (i < n4) {
+          const int y = y0 + i / W4, x = 4 * (i % W4);
+          const int k = (v[u].x == m) ? 0 : ((v[u].y == m) ? 1 : ((v[u].z == m) ? 2 : 3));  // first match = min x
+          bx = min(bx, x + k);
+          by = min(by, y);
+        }
+      }
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      bx = min(bx, __shfl_xor_sync(FULL, bx, d));
+      by = min(by, __shfl_xor_sync(FULL, by, d));
+    }
+    if (lane == 0) { s_x[warp] = bx; s_y[warp] = by; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      out_xy[2 * plane_id] = fx;
-      out_xy[2 * plane_id + 1] = fy;
-      out_val[plane_id] = low ? 0.f : r.v;
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { bx = min(bx, s_x[w]); by = min(by, s_y[w]); }
     }
+    r = Best{m, bx, by};
   }
+  global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, 1, thr, refine_size, part_v, part_xy, tickets,
+                      out_xy, out_val, s_best, &s_last);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -713,8 +836,21 @@ extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, lo
   int* part_xy = (int*)(part_v + planes * nc);
   const int vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
                   (((uintptr_t)cms) % 16 == 0);
-  global_peaks_kernel<<<(unsigned)(planes * nc), 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold,
-                                                               refine_size, part_v, part_xy, tickets, out_xy, out_val);
+  static const bool force_generic = getenv("SNB_GLOBAL_GENERIC") != nullptr;  // A/B: the first, merge-per-element kernel
+  const long long chunk4 = ((long long)rpc * W) >> 2;  // 128-bit loads per chunk
+  const unsigned grid = (unsigned)(planes * nc);
+  if (vec && !force_generic && chunk4 <= 8 * 256) {
+#define SNB_GP(V)                                                                                                   \
+  global_peaks_regs_kernel<V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \
+                                                    part_xy, tickets, out_xy, out_val)
+    if (chunk4 <= 2 * 256) SNB_GP(2);
+    else if (chunk4 <= 4 * 256) SNB_GP(4);
+    else SNB_GP(8);
+#undef SNB_GP
+  } else {
+    global_peaks_kernel<<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold, refine_size,
+                                              part_v, part_xy, tickets, out_xy, out_val);
+  }
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

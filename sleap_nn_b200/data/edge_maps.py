@@ -47,20 +47,33 @@ def make_edge_maps(xv: torch.Tensor, yv: torch.Tensor, edge_source: torch.Tensor
     return out.to(edge_source.device)
 
 
-def _pafs(xv, yv, srcs, dsts, sigma, accumulate: bool, out_dtype, dev) -> torch.Tensor:
+def _pafs(xv, yv, srcs, dsts, sigma, accumulate: bool, out_dtype, dev, batched: bool = False) -> torch.Tensor:
+    """srcs/dsts (I, E, 2) -> (E, 2, h, w); with `batched` (G, I, E, 2) -> (G, E, 2, h, w) in one launch."""
     xd, yd, s, d = _f32(xv, dev), _f32(yv, dev), _f32(srcs, dev), _f32(dsts, dev)
-    I, E = int(s.shape[0]), int(s.shape[1])
+    G = int(s.shape[0]) if batched else 1
+    I, E = int(s.shape[-3]), int(s.shape[-2])
     h, w = int(yd.shape[0]), int(xd.shape[0])
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("part affinity fields are produced in float32 or bfloat16")
-    out = torch.empty((E, 2, h, w), dtype=out_dtype, device=dev)
+    out = torch.empty((G, E, 2, h, w) if batched else (E, 2, h, w), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
         N.check(
-            N.lib.snb_pafs(N.ptr(s), N.ptr(d), I, E, N.ptr(xd), N.ptr(yd), h, w, float(2 * sigma**2), int(accumulate),
+            N.lib.snb_pafs(N.ptr(s), N.ptr(d), G, I, E, N.ptr(xd), N.ptr(yd), h, w, float(2 * sigma**2), int(accumulate),
                            int(out_dtype == torch.bfloat16), N.ptr(out), N.stream_ptr(dev)),
             "snb_pafs",
         )
     return out
+
+
+def make_multi_pafs_batch(xv: torch.Tensor, yv: torch.Tensor, edge_sources: torch.Tensor, edge_destinations: torch.Tensor,
+                          sigma: float, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """`make_multi_pafs` for G frames in one launch (an extension; the reference API is per frame).
+
+    edge_sources / edge_destinations (G, n_instances, n_edges, 2) -> (G, n_edges, 2, grid_h, grid_w).
+    """
+    dev = N.compute_device(edge_sources)
+    out = _pafs(xv, yv, edge_sources, edge_destinations, sigma, True, out_dtype, dev, batched=True)
+    return out.to(edge_sources.device)
 
 
 def make_pafs(xv: torch.Tensor, yv: torch.Tensor, edge_source: torch.Tensor, edge_destination: torch.Tensor,

@@ -288,10 +288,10 @@ class BottomUpPostproc:
             raise TypeError("run_host expects fp32 host tensors")
         if pafs_host.dim() != 4 or pafs_host.shape[0] != self.batch:
             raise ValueError("pafs must be (B, 2E, H, W) or its (B, H, W, 2E) view")
-        if pafs_host.shape[1] == 2 * self.n_edges and pafs_host.shape[-1] != 2 * self.n_edges:
-            pafs_host = pafs_host.permute(0, 2, 3, 1)
-        elif pafs_host.shape[-1] != 2 * self.n_edges:
+        channels_first = pafs_host.shape[1] == 2 * self.n_edges and pafs_host.shape[-1] != 2 * self.n_edges
+        if not channels_first and pafs_host.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
+        view = (lambda t: t.permute(0, 2, 3, 1)) if channels_first else (lambda t: t)
         with torch.cuda.device(self.device):
             if not hasattr(self, "_stage_cms") or self._stage_cms.shape != cms_host.shape:
                 self._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
@@ -300,14 +300,16 @@ class BottomUpPostproc:
             zero_copy = bool(zero_copy_pafs and pafs_host.is_pinned() and N.lib.snb_host_device_pointer(
                 pafs_host.data_ptr(), C.byref(paf_alias)) == N.OK and paf_alias.value)
             if zero_copy:
+                pv = view(pafs_host)
                 res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), paf_alias.value,
-                                   tuple(pafs_host.shape), pafs_host.stride())
-            else:
+                                   tuple(pv.shape), pv.stride())
+            else:  # stage in the host tensor's own memory order (a dense copy), then take the channels-last view
                 if not hasattr(self, "_stage_pafs") or self._stage_pafs.shape != pafs_host.shape:
-                    self._stage_pafs = torch.empty(pafs_host.shape, dtype=torch.float32, device=self.device)
+                    self._stage_pafs = torch.empty_strided(tuple(pafs_host.shape), pafs_host.stride(), dtype=torch.float32,
+                                                           device=self.device)
                 self._stage_pafs.copy_(pafs_host, non_blocking=True)
-                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), N.ptr(self._stage_pafs),
-                                   tuple(pafs_host.shape), self._stage_pafs.stride())
+                pv = view(self._stage_pafs)
+                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), N.ptr(pv), tuple(pv.shape), pv.stride())
             out = res.to_lists()
             self.last_h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
             self.last_zero_copy = zero_copy

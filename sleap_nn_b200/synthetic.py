@@ -67,10 +67,10 @@ def render_batch(poses: torch.Tensor, img_hw: Tuple[int, int], stride: int, edge
             cms += torch.rand(cms.shape, generator=g, device=device) * noise
         e = torch.tensor(list(edges), dtype=torch.int64).reshape(-1, 2)
         E = int(e.shape[0])
-        pafs = torch.empty((B, 2 * E, h, w), dtype=torch.float32, device=device)
-        pd = poses.to(device)
-        for b in range(B):
-            if E:
-                pafs[b] = _pafs(xv, yv, pd[b][:, e[:, 0]], pd[b][:, e[:, 1]], sigma_paf, True, torch.float32,
-                                device).reshape(2 * E, h, w)
+        if E:
+            pd = poses.to(device)
+            pafs = _pafs(xv, yv, pd[:, :, e[:, 0]], pd[:, :, e[:, 1]], sigma_paf, True, torch.float32, device,
+                         batched=True).reshape(B, 2 * E, h, w)
+        else:
+            pafs = torch.empty((B, 0, h, w), dtype=torch.float32, device=device)
     return cms, pafs

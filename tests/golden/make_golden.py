@@ -268,6 +268,48 @@ def targets(R):
     save("ref_targets.npz", **out)
 
 
+def f1_outputs(R):
+    """group_scored_batch (inference/streaming.py:147-255) on the frames of ref_pipeline_tree.npz: NaN padding,
+    top-N by score, input / effective scale undo, the skip_paf short-circuit."""
+    d = np.load(os.path.join(HERE, "ref_pipeline_tree.npz"))
+    cms, pafs = torch.from_numpy(d["cms"]), torch.from_numpy(d["pafs"])
+    edges, n_nodes, stride = d["edges"].tolist(), int(d["n_nodes"]), int(d["stride"])
+    B = cms.shape[0]
+    pts, vals, si, ci = R.peaks.find_local_peaks(cms, threshold=0.2, refinement="integral")
+    pts = pts * stride
+    peaks, pvals, pch = (synth.split_by_sample(x, si, B) for x in (pts, vals, ci))
+    names = [str(i) for i in range(n_nodes)]
+    kwargs = dict(part_names=names, edges=[(str(a), str(b)) for a, b in edges], pafs_stride=stride,
+                  max_edge_length_ratio=0.25, dist_penalty_weight=1.0, n_points=10,
+                  min_instance_peaks=int(d["min_instance_peaks"]), min_line_scores=0.25)  # int = a count (float = fraction)
+    scorer = R.paf.PAFScorer(**kwargs)
+    ei, epi, ls = scorer.score_paf_lines(pafs.permute(0, 2, 3, 1), peaks, pch)
+    out = {}
+    cases = [
+        ("dyn", None, 1.0, [1.0, 1.0, 1.0], False),
+        ("top2", 2, 0.5, [1.0, 0.75, 1.25], False),
+        ("pad6", 6, 1.0, [0.5, 0.5, 0.5], False),
+        ("one", 1, 2.0, [1.0, 1.0, 1.0], False),
+        ("skip3", 3, 1.0, [1.0, 1.0, 1.0], True),
+        ("skipdyn", None, 1.0, [1.0, 1.0, 1.0], True),
+    ]
+    for tag, max_inst, scale, eff, skip in cases:
+        info = R.preprocess_info.PreprocInfo(eff_scale=torch.tensor(eff), input_scale=scale)
+        sb = R.streaming.ScoredBatch(cms_peaks=peaks, cms_peak_vals=pvals, cms_peak_channel_inds=pch,
+                                     edge_inds=[] if skip else ei, edge_peak_inds=[] if skip else epi,
+                                     line_scores=[] if skip else ls, info=info, n_samples=B, n_nodes=n_nodes,
+                                     skip_paf=skip)
+        with ref_loader.reference_imports():  # group_scored_batch imports PAFScorer lazily by its real module name
+            res = R.streaming.group_scored_batch(sb, R.streaming.GroupingParams(paf_scorer_kwargs=kwargs, max_instances=max_inst))
+        out.update({f"{tag}_kpts": res.pred_keypoints, f"{tag}_vals": res.pred_peak_values, f"{tag}_scores": res.instance_scores,
+                    f"{tag}_max_instances": np.int64(-1 if max_inst is None else max_inst), f"{tag}_input_scale": np.float64(scale),
+                    f"{tag}_eff": np.asarray(eff, np.float32), f"{tag}_skip": np.bool_(skip)})
+    out["cases"] = np.asarray([c[0] for c in cases])
+    # the smallest per-node peak count that trips / does not trip the max_peaks_per_node guard on these frames
+    out["max_node_peaks"] = np.int64(max(int((c == k).sum()) for c in pch for k in range(n_nodes)))
+    save("ref_f1_outputs.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -280,6 +322,7 @@ def main():
                  edges=synth.star_chain_edges(8, fan=2), step=26.0, min_instance_peaks=2)
     assembly_cases(R)
     targets(R)
+    f1_outputs(R)
 
 
 if __name__ == "__main__":

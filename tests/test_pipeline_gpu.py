@@ -110,3 +110,61 @@ def test_capacity_overflow_is_reported_not_silent():
     assert int(res.n_peaks.max()) > 16
     with pytest.raises(RuntimeError, match="overflowed"):
         res.to_lists()
+
+
+# ----------------------------------------------------------------- group_scored_batch epilogue
+def _f1_pipe(d, **kw):
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    cms = T(d["cms"]).cuda()
+    B, Nn, H, W = cms.shape
+    mip = float(d["min_instance_peaks"])
+    return BottomUpPostproc(Nn, d["edges"].tolist(), B, (H, W), cms_stride=int(d["stride"]), pafs_stride=int(d["stride"]),
+                            min_instance_peaks=int(mip) if mip == int(mip) else mip, **kw)
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_outputs_epilogue_matches_reference_group_scored_batch(fixed):
+    """NaN padding, top-N by score, scale undo and the skip short-circuit vs the reference's own
+    group_scored_batch (inference/streaming.py:147-255) run on the same frames (ref_f1_outputs.npz)."""
+    d, f1 = golden("ref_pipeline_tree.npz"), golden("ref_f1_outputs.npz")
+    cms, pafs = T(d["cms"]).cuda(), T(d["pafs"]).cuda()
+    for tag in f1["cases"].tolist():
+        mi = int(f1[f"{tag}_max_instances"])
+        mi = None if mi < 0 else mi
+        skip = bool(f1[f"{tag}_skip"])
+        if fixed and mi is None:
+            continue
+        kw = dict(max_peaks_per_node=(int(f1["max_node_peaks"]) - 1 if skip else int(f1["max_node_peaks"])))
+        pipe = _f1_pipe(d, max_instances=mi if fixed else None, **kw)
+        res = pipe(cms, pafs, input_scale=float(f1[f"{tag}_input_scale"]), eff_scale=T(f1[f"{tag}_eff"]))
+        k, v, s = res.outputs() if fixed else res.outputs(mi)
+        assert bool(res.skip_flag.item()) == skip
+        want_k, want_v, want_s = f1[f"{tag}_kpts"], f1[f"{tag}_vals"], f1[f"{tag}_scores"]
+        assert tuple(k.shape) == want_k.shape, (tag, tuple(k.shape), want_k.shape)
+        eq(np.isnan(npy(k)), np.isnan(want_k))
+        close(npy(k), want_k, atol=1e-4)
+        eq(npy(v), want_v)
+        close(npy(s), want_s, rtol=1e-5, atol=1e-5)
+        if fixed:
+            assert pipe.launches_per_call == 3 and res.pred_keypoints is k
+
+
+def test_outputs_topn_order_with_ties_and_nan():
+    """np.argsort(scores)[::-1][:n]: NaN first, then descending, equal scores -> higher index first."""
+    from sleap_nn_b200 import _native as N
+
+    dev = torch.device("cuda", 0)
+    scores = torch.tensor([[0.5, float("nan"), 0.9, 0.5, 0.1, 0.9]], device=dev)
+    n = torch.tensor([6], dtype=torch.int32, device=dev)
+    xy = torch.arange(6 * 2 * 2, dtype=torch.float32, device=dev).reshape(1, 6, 2, 2)
+    val = torch.arange(6 * 2, dtype=torch.float32, device=dev).reshape(1, 6, 2)
+    I = 4
+    k = torch.empty((1, I, 2, 2), device=dev); v = torch.empty((1, I, 2), device=dev); s = torch.empty((1, I), device=dev)
+    N.check(N.lib.snb_bottomup_outputs(N.ptr(n), N.ptr(xy), N.ptr(val), N.ptr(scores), 1, 6, 2, I, 1.0, None, None,
+                                       N.ptr(k), N.ptr(v), N.ptr(s), N.stream_ptr(dev)), "outputs")
+    order = np.argsort(scores[0].cpu().numpy(), kind="stable")[::-1][:I]
+    assert order.tolist() == [1, 5, 2, 3]
+    eq(npy(s[0]), npy(scores[0].cpu())[order])
+    eq(npy(k[0]), npy(xy[0].cpu())[order])
+    eq(npy(v[0]), npy(val[0].cpu())[order])

@@ -81,7 +81,7 @@ def k2_cfg2(dev, iters):
         N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), st), "k2")
 
     ms = timed(fn, iters)
-    line("k2_cfg2", "global_peaks_kernel", 4 * B * Cn * H * W, ms, B, "crops",
+    line("k2_cfg2", "global_peaks_regs_kernel", 4 * B * Cn * H * W, ms, B, "crops",
          {"shape": [B, Cn, H, W], "valid_peaks": int((val_o > 0).sum())})
 
 
@@ -108,33 +108,41 @@ def k7_cfg4(dev, iters, bf16=False):
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
-    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
+    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_rows_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
          {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
-def k8_cfg4(dev, iters, bf16=False):
-    """cfg4 targets: make_multi_pafs, 31 edges, 8 instances, sigma 2.5, out (31,2,512,512) per frame."""
-    edges, poses = _flies_poses(4)
+def k8_cfg4(dev, iters, bf16=False, G=1):
+    """cfg4 targets: make_multi_pafs, 31 edges, 8 instances, sigma 2.5, out (G,31,2,512,512) per launch."""
+    n_sets = max(2, 4 // G)
+    edges, poses = _flies_poses(G * n_sets)
     e = torch.tensor(edges, dtype=torch.int64)
     xv, yv = make_grid_vectors(1024, 1024, 2)
     xd, yd = xv.to(dev), yv.to(dev)
-    pd = poses.to(dev)
-    srcs = [pd[f][:, e[:, 0]].contiguous() for f in range(4)]
-    dsts = [pd[f][:, e[:, 1]].contiguous() for f in range(4)]
+    pd = poses.to(dev).reshape(n_sets, G, 8, 32, 2)
+    srcs = [pd[f][:, :, e[:, 0]].contiguous() for f in range(n_sets)]
+    dsts = [pd[f][:, :, e[:, 1]].contiguous() for f in range(n_sets)]
     dt = torch.bfloat16 if bf16 else torch.float32
-    outs = [torch.empty((31, 2, 512, 512), dtype=dt, device=dev) for _ in range(4)]
+    outs = [torch.empty((G, 31, 2, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
     st = N.stream_ptr(dev)
     den = float(2 * 2.5 ** 2)
 
     def fn(i):
-        k = i % 4
-        N.check(N.lib.snb_pafs(N.ptr(srcs[k]), N.ptr(dsts[k]), 8, 31, N.ptr(xd), N.ptr(yd), 512, 512, den, 1,
+        k = i % n_sets
+        N.check(N.lib.snb_pafs(N.ptr(srcs[k]), N.ptr(dsts[k]), G, 8, 31, N.ptr(xd), N.ptr(yd), 512, 512, den, 1,
                                int(bf16), N.ptr(outs[k]), st), "k8")
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
-    line("k8_cfg4" + ("_bf16" if bf16 else ""), "pafs_kernel", esz * 31 * 2 * 512 * 512, ms, 1, "frames",
-         {"frames_per_launch": 1, "out_dtype": str(dt)})
+    line(f"k8_cfg4_g{G}" + ("_bf16" if bf16 else ""), "pafs_rows_kernel", esz * G * 31 * 2 * 512 * 512, ms, G, "frames",
+         {"frames_per_launch": G, "out_dtype": str(dt)})
+
+
+def memset_ref(dev, iters):
+    """Reference point for the store-bound kernels: cudaMemsetAsync (torch zero_) of 268 MB, rotating buffers."""
+    bufs = [torch.empty((268435456 // 4,), dtype=torch.float32, device=dev) for _ in range(3)]
+    ms = timed(lambda i: bufs[i % 3].zero_(), iters)
+    line("memset_268MB", "cudaMemsetAsync (reference, not ours)", 268435456, ms, 1, "launches")
 
 
 def chain_cfg4(dev, iters):
@@ -167,7 +175,9 @@ def chain_cfg4(dev, iters):
 
 
 ALL = {"k2_cfg2": k2_cfg2, "k7_cfg4": k7_cfg4, "k7_cfg4_bf16": lambda d, i: k7_cfg4(d, i, True),
-       "k8_cfg4": k8_cfg4, "k8_cfg4_bf16": lambda d, i: k8_cfg4(d, i, True), "chain_cfg4": chain_cfg4}
+       "k8_cfg4": k8_cfg4, "k8_cfg4_g8": lambda d, i: k8_cfg4(d, i, False, 8),
+       "k8_cfg4_bf16": lambda d, i: k8_cfg4(d, i, True), "k8_cfg4_g8_bf16": lambda d, i: k8_cfg4(d, i, True, 8),
+       "memset_ref": memset_ref, "chain_cfg4": chain_cfg4}
 
 
 def main():
