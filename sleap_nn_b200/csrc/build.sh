@@ -10,5 +10,6 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
        -ftz=false -prec-div=true -prec-sqrt=true -fmad=true
        -Xcompiler -fPIC -Xcompiler -fvisibility=default ${SNB_NVCC_EXTRA:-})
 SRCS=("${HERE}"/*.cu)
-"${NVCC}" "${FLAGS[@]}" -shared -o "${OUT}/libsleapnn_b200.so" "${SRCS[@]}" -lcudart
-echo "built ${OUT}/libsleapnn_b200.so"
+LIBNAME="${SNB_LIB_NAME:-libsleapnn_b200.so}"  # SNB_LIB_NAME / SNB_NVCC_EXTRA: profiling variants (tools/)
+"${NVCC}" "${FLAGS[@]}" -shared -o "${OUT}/${LIBNAME}" "${SRCS[@]}" -lcudart
+echo "built ${OUT}/${LIBNAME}"

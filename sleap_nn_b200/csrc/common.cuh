@@ -38,6 +38,7 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t smem_u32_early(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ int div_up(int a, int b) { return (a + b - 1) / b; }
 
@@ -81,6 +82,7 @@ __device__ __forceinline__ void integral_refine(const float* __restrict__ plane,
 // Warp-cooperative variant: the size x size taps are spread over the 32 lanes (one DRAM/L2 round
 // trip instead of size^2 serial ones); fp64 partial sums are combined by shuffles.  All lanes
 // return the same offsets.
+template <bool GLOBAL_MEM = true>  // false: `plane` points into shared memory (plain loads, not ld.global.nc)
 __device__ __forceinline__ void integral_refine_warp(const float* __restrict__ plane, int H, int W, long long sh,
                                                      long long sw, float px, float py, int size, int lane, float* ox,
                                                      float* oy) {
@@ -96,7 +98,10 @@ __device__ __forceinline__ void integral_refine_warp(const float* __restrict__ p
     const int j = t / size, i = t - j * size;
     const int yy = y0 + j, xx = x0 + i;
     float p = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) p = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      const float* q = plane + (long long)yy * sh + (long long)xx * sw;
+      p = GLOBAL_MEM ? __ldg(q) : *q;
+    }
     z += (double)p;
     sx += (double)__fmul_rn(g0 + (float)i, p);
     sy += (double)__fmul_rn(g0 + (float)j, p);
@@ -111,6 +116,63 @@ __device__ __forceinline__ void integral_refine_warp(const float* __restrict__ p
   *ox = __fdiv_rn((float)sx, zf);
   *oy = __fdiv_rn((float)sy, zf);
 }
+
+// Q peaks at once: the Q x size^2 taps are all in flight before anything is reduced, so a warp that owns many
+// peaks (busy frames: hundreds of peaks per frame) pays one memory round trip per Q peaks instead of one per peak.
+// Same arithmetic as integral_refine_warp.  plane[q] == nullptr marks an unused slot (offsets returned as 0).
+template <int Q>
+__device__ __forceinline__ void integral_refine_warp_multi(const float* const (&plane)[Q], int H, int W, long long sh,
+                                                           long long sw, const float (&px)[Q], const float (&py)[Q],
+                                                           int size, int lane, float (&ox)[Q], float (&oy)[Q]) {
+  const float half_f = 0.5f * (float)size;
+  const int half_i = size / 2;
+  const float g0 = -0.5f * (float)(size - 1);
+  int x0[Q], y0[Q];
+  double z[Q], sx[Q], sy[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    x0[q] = (int)truncf(__fadd_rn(__fadd_rn(__fsub_rn(px[q], half_f), 0.5f), (float)half_i)) - half_i;
+    y0[q] = (int)truncf(__fadd_rn(__fadd_rn(__fsub_rn(py[q], half_f), 0.5f), (float)half_i)) - half_i;
+    z[q] = sx[q] = sy[q] = 0.0;
+  }
+  for (int t = lane; t < size * size; t += 32) {
+    const int j = t / size, i = t - j * size;
+    float p[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int yy = y0[q] + j, xx = x0[q] + i;
+      p[q] = 0.f;
+      if (plane[q] && yy >= 0 && yy < H && xx >= 0 && xx < W) p[q] = __ldg(plane[q] + (long long)yy * sh + (long long)xx * sw);
+    }
+    const float gx = g0 + (float)i, gy = g0 + (float)j;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      z[q] += (double)p[q];
+      sx[q] += (double)__fmul_rn(gx, p[q]);
+      sy[q] += (double)__fmul_rn(gy, p[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      z[q] += __shfl_xor_sync(FULL, z[q], d);
+      sx[q] += __shfl_xor_sync(FULL, sx[q], d);
+      sy[q] += __shfl_xor_sync(FULL, sy[q], d);
+    }
+    const float zf = (float)z[q];
+    ox[q] = __fdiv_rn((float)sx[q], zf);
+    oy[q] = __fdiv_rn((float)sy[q], zf);
+  }
+}
+
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that tie up no registers ----------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_early(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- mbarrier + bulk async copy (cp.async.bulk, the 1-D TMA path; SASS: UBLKCP) -------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -254,6 +254,8 @@ struct AsmFrame {
   const int* ns; const int* np_; int n_nodes;
   const int* edges; const int* sorted; int n_sorted;
   const int* m_edge; const int* m_src; const int* m_dst; const float* m_score; int K;
+  const int* mo = nullptr;  // optional (n_edges+1) per-edge offsets into the match list (matches grouped by edge):
+                            // visits [mo[e], min(mo[e+1], K)) instead of scanning all K matches for every edge
   int min_instance_peaks; float min_line_scores;
   int* owner; int* order; int* id_count; int* id_rank; unsigned char* fa; unsigned char* fb;
   int inst_cap; float* oxy; float* oval; float* osc; int* n_inst_out; int* status;
@@ -267,7 +269,8 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   for (int se = 0; se < f.n_sorted; ++se) {
     const int e = f.sorted[se];
     const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
-    for (int m = 0; m < K; ++m) {
+    const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+    for (int m = m_lo; m < m_hi; ++m) {
       if (f.m_edge[m] != e) continue;
       if (!(f.m_score[m] >= f.min_line_scores)) continue;  // paf.py:993
       const int sp = f.m_src[m], dp = f.m_dst[m];
@@ -345,7 +348,8 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       const int e = f.sorted[se];
       const int sn = f.edges[2 * e];
       if (sn < 0 || sn >= f.n_nodes) continue;
-      for (int m = 0; m < K; ++m) {
+      const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+      for (int m = m_lo; m < m_hi; ++m) {
         if (f.m_edge[m] != e || !(f.m_score[m] >= f.min_line_scores)) continue;
         const int sp = f.m_src[m];
         if (sp < 0 || sp >= f.ns[sn + 1] - f.ns[sn]) continue;

@@ -564,6 +564,121 @@ global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, lon
                       out_xy, out_val, s_best, &s_last);
 }
 
+// Persistent ring variant (the product path for planes that fit one shared-memory stage, e.g. cfg2's 80x80
+// crops).  With one CTA per small plane the loads are in flight for only about a third of a CTA's life (the
+// rest is reductions + the refinement's dependent taps), which capped K2 at ~54 % of the HBM roofline.  Here a
+// persistent CTA walks planes p, p + grid, ... through a 3-stage shared-memory ring filled by cp.async
+// (LDGSTS, no registers tied up): the loads of the next two planes are always in flight while the current one
+// is reduced out of shared memory, and the refinement reads its 5x5 taps from the same stage.
+constexpr int GP_STAGES = 3;
+
+__global__ void __launch_bounds__(256)
+global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int H, int W, long long sb, long long sc,
+                         long long sh, float thr, int refine_size, float* __restrict__ out_xy,
+                         float* __restrict__ out_val) {
+  extern __shared__ __align__(16) float gp_ring[];
+  __shared__ float s_m[8];
+  __shared__ int s_x[8], s_y[8];
+  __shared__ Best s_best[8];
+  const int plane_elems = H * W, n4 = plane_elems >> 2, W4 = W >> 2;
+  const bool contig = (sh == W);
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  auto issue = [&](int p, int stage) {
+    if (p < n_planes) {
+      const float* base = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
+      float* dst = gp_ring + (size_t)stage * plane_elems;
+      for (int i = tid; i < n4; i += 256) {
+        const float* src = contig ? base + 4LL * i : base + (long long)(i / W4) * sh + 4 * (i % W4);
+        cp_async16(dst + 4 * i, src);
+      }
+    }
+    cp_async_commit();  // always commit (possibly empty) so the group count is uniform
+  };
+  const int p0 = blockIdx.x, step = gridDim.x;
+  issue(p0, 0);
+  issue(p0 + step, 1);
+  int it = 0;
+  for (int p = p0; p < n_planes; p += step, ++it) {
+    issue(p + 2 * step, (it + 2) % GP_STAGES);  // refills the stage consumed in the previous iteration
+    cp_async_wait<2>();                          // everything but the two newest groups has landed: plane p is in
+    __syncthreads();
+    const float* st = gp_ring + (size_t)(it % GP_STAGES) * plane_elems;
+    const float4* st4 = reinterpret_cast<const float4*>(st);
+    float m = -INFINITY;
+    bool has_nan = false;
+    for (int i = tid; i < n4; i += 256) {
+      const float4 v = st4[i];
+      m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      has_nan = has_nan || (v.x != v.x) || (v.y != v.y) || (v.z != v.z) || (v.w != v.w);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, d));
+    if (lane == 0) s_m[warp] = m;
+    const int any_nan = __syncthreads_or(has_nan ? 1 : 0);
+    if (any_nan) {  // exact generic merge (NaN ranks above everything; min x / min y among the NaNs)
+      Best acc{-INFINITY, 0x7fffffff, 0x7fffffff};
+      bool any = false;
+      for (int i = tid; i < plane_elems; i += 256) {
+        const Best o{st[i], i % W, i / W};
+        acc = any ? best_merge(acc, o) : o;
+        any = true;
+      }
+      acc = best_warp(acc);
+      if (lane == 0) s_best[warp] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        Best r = s_best[0];
+        for (int w = 1; w < 8; ++w) r = best_merge(r, s_best[w]);
+        s_best[0] = r;
+      }
+    } else {
+      m = s_m[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, s_m[w]);
+      int bx = 0x7fffffff, by = 0x7fffffff;
+      for (int i = tid; i < n4; i += 256) {
+        const float4 v = st4[i];
+        if (v.x == m || v.y == m || v.z == m || v.w == m) {  // rare
+          const int k = (v.x == m) ? 0 : ((v.y == m) ? 1 : ((v.z == m) ? 2 : 3));  // first match = min x in the chunk
+          bx = min(bx, 4 * (i % W4) + k);
+          by = min(by, i / W4);
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        bx = min(bx, __shfl_xor_sync(FULL, bx, d));
+        by = min(by, __shfl_xor_sync(FULL, by, d));
+      }
+      if (lane == 0) { s_x[warp] = bx; s_y[warp] = by; }
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { bx = min(bx, s_x[w]); by = min(by, s_y[w]); }
+        s_best[0] = Best{m, bx, by};
+      }
+    }
+    __syncthreads();
+    if (tid < 32) {  // threshold (ops/peaks.py:121-129) + integral refinement out of the shared-memory stage
+      const Best b = s_best[0];
+      const bool low = b.v < thr;  // false for NaN, like torch
+      float fx = low ? NAN : (float)b.x, fy = low ? NAN : (float)b.y;
+      if (!low && refine_size > 0) {
+        float ox, oy;
+        integral_refine_warp<false>(st, H, W, W, 1, fx, fy, refine_size, lane, &ox, &oy);
+        fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
+        fy = __fadd_rn(fy, oy);
+      }
+      if (tid == 0) {
+        out_xy[2 * p] = fx;
+        out_xy[2 * p + 1] = fy;
+        out_val[p] = low ? 0.f : b.v;
+      }
+    }
+    __syncthreads();  // everyone is done with this stage (and s_best) before the next iteration refills it
+  }
+  cp_async_wait<0>();
+}
+
 // ----------------------------------------------------------------------------------------
 // K3: crop_bboxes.  One thread per output element; top-left = trunc(tl + size//2) - size//2
 // in fp32 exactly as ops/crops.py:85-90; taps outside the image are 0.
@@ -839,7 +954,23 @@ extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, lo
   static const bool force_generic = getenv("SNB_GLOBAL_GENERIC") != nullptr;  // A/B: the first, merge-per-element kernel
   const long long chunk4 = ((long long)rpc * W) >> 2;  // 128-bit loads per chunk
   const unsigned grid = (unsigned)(planes * nc);
-  if (vec && !force_generic && chunk4 <= 8 * 256) {
+  static const bool no_ring = getenv("SNB_GLOBAL_NO_RING") != nullptr;  // A/B: one CTA per plane, values in registers
+  const size_t ring_smem = (size_t)GP_STAGES * H * W * sizeof(float);
+  if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
+          cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      attr_set = true;
+    }
+    int per_sm = (int)((220 * 1024) / (ring_smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+    const long long want = (long long)sm_count() * per_sm;
+    const unsigned rgrid = (unsigned)(planes < want ? planes : want);
+    global_peaks_ring_kernel<<<rgrid, 256, ring_smem, st>>>(cms, (int)planes, C, H, W, sb, sc, sh, threshold, refine_size,
+                                                           out_xy, out_val);
+  } else if (vec && !force_generic && chunk4 <= 8 * 256) {
 #define SNB_GP(V)                                                                                                   \
   global_peaks_regs_kernel<V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \
                                                     part_xy, tickets, out_xy, out_val)

@@ -58,6 +58,17 @@ __host__ __device__ inline TailLayout tail_layout(int peak_cap, int n_nodes, int
 
 constexpr int TAIL_THREADS = 256;
 
+// Profiling build only (-DSNB_TAIL_TIMING, tools/tail_phases.py): thread 0 of every CTA stamps clock64() at
+// the phase boundaries into asm_ws (unused by the fused tail), 16 ints per frame.
+#ifdef SNB_TAIL_TIMING
+#define SNB_STAMP(k)                                                                       \
+  do {                                                                                     \
+    if (threadIdx.x == 0 && a.asm_ws) a.asm_ws[blockIdx.x * 16 + (k)] = (int)(clock64() - t_start); \
+  } while (0)
+#else
+#define SNB_STAMP(k) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomup_args a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n_warps = TAIL_THREADS / 32;
@@ -79,6 +90,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_nodes = a.C, E = a.n_edges;
+#ifdef SNB_TAIL_TIMING
+  const long long t_start = clock64();
+#endif
   // small read-only tables -> shared memory once (the sequential phases would otherwise pay an L2
   // round trip per dependent access)
   int* s_edges = (int*)(smem + L.edges);
@@ -110,34 +124,46 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     }
   }
 
+  SNB_STAMP(0);
   // ---- 2. value + integral refinement, one warp per peak (taps fetched in parallel)
   const float* frame = a.cms + (long long)b * a.cms_sb;
-  for (int i = warp; i < n; i += n_warps) {
-    const uint32_t key = s_keys[i];
-    const int c = (int)(key % (uint32_t)a.C);
-    const uint32_t yx = key / (uint32_t)a.C;
-    const int x = (int)(yx % (uint32_t)a.W), y = (int)(yx / (uint32_t)a.W);
-    const float* plane = frame + (long long)c * a.cms_sc;
-    float fx = (float)x, fy = (float)y;
-    if (a.refine_size > 0) {
-      float ox, oy;
-      integral_refine_warp(plane, a.H, a.W, a.cms_sh, a.cms_sw, fx, fy, a.refine_size, lane, &ox, &oy);
-      fx = __fadd_rn(fx, ox);
-      fy = __fadd_rn(fy, oy);
+  constexpr int RQ = 4;  // peaks refined together by one warp (their taps are all in flight at once)
+  for (int i0 = warp * RQ; i0 < n; i0 += n_warps * RQ) {
+    const float* plane[RQ];
+    float fx[RQ], fy[RQ], ox[RQ], oy[RQ];
+    int cc[RQ], xi[RQ], yi[RQ];
+#pragma unroll
+    for (int q = 0; q < RQ; ++q) {
+      const int i = i0 + q;
+      plane[q] = nullptr; fx[q] = fy[q] = 0.f; cc[q] = xi[q] = yi[q] = 0;
+      if (i < n) {
+        const uint32_t key = s_keys[i];
+        cc[q] = (int)(key % (uint32_t)a.C);
+        const uint32_t yx = key / (uint32_t)a.C;
+        xi[q] = (int)(yx % (uint32_t)a.W); yi[q] = (int)(yx / (uint32_t)a.W);
+        plane[q] = frame + (long long)cc[q] * a.cms_sc;
+        fx[q] = (float)xi[q]; fy[q] = (float)yi[q];
+      }
     }
-    if (a.cms_stride != 1.0f) {
-      fx = __fmul_rn(fx, a.cms_stride);
-      fy = __fmul_rn(fy, a.cms_stride);
-    }
-    if (lane == 0) {
-      const float v = __ldg(plane + (long long)y * a.cms_sh + (long long)x * a.cms_sw);
-      s_xy[2 * i] = fx; s_xy[2 * i + 1] = fy; s_val[i] = v; s_chan[i] = c;
-      const long long o = (long long)b * a.peak_cap + i;
-      a.peak_xy[2 * o] = fx; a.peak_xy[2 * o + 1] = fy; a.peak_val[o] = v; a.peak_chan[o] = c;
+    if (a.refine_size > 0) integral_refine_warp_multi<RQ>(plane, a.H, a.W, a.cms_sh, a.cms_sw, fx, fy, a.refine_size, lane, ox, oy);
+    if (lane < RQ) {  // lane q finishes peak i0 + q
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        if (lane != q || i0 + q >= n) continue;
+        float x = fx[q], y = fy[q];
+        if (a.refine_size > 0) { x = __fadd_rn(x, ox[q]); y = __fadd_rn(y, oy[q]); }
+        if (a.cms_stride != 1.0f) { x = __fmul_rn(x, a.cms_stride); y = __fmul_rn(y, a.cms_stride); }
+        const int i = i0 + q;
+        const float v = __ldg(plane[q] + (long long)yi[q] * a.cms_sh + (long long)xi[q] * a.cms_sw);
+        s_xy[2 * i] = x; s_xy[2 * i + 1] = y; s_val[i] = v; s_chan[i] = cc[q];
+        const long long o = (long long)b * a.peak_cap + i;
+        a.peak_xy[2 * o] = x; a.peak_xy[2 * o + 1] = y; a.peak_val[o] = v; a.peak_chan[o] = cc[q];
+      }
     }
   }
   __syncthreads();
 
+  SNB_STAMP(1);
   // ---- 3. group peaks by node, candidate / match offsets
   if (warp == 0) {
     group_by_node_warp(s_chan, n, n_nodes, s_ns, s_cursor, s_np, lane);
@@ -164,6 +190,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     }
   }
 
+  SNB_STAMP(2);
   // ---- 4. PAF line scores, one thread per candidate
   if (cand_ok) {
     ScoreArgs sa{a.pafs, a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc, a.paf_H, a.paf_W, s_t, a.n_points,
@@ -181,6 +208,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   }
   __syncthreads();
 
+  SNB_STAMP(3);
   // ---- 5. per-edge optimal assignment, one warp per edge (lane 0 runs scipy's algorithm)
   if (cand_ok && lane == 0) {
     for (int k = warp; k < E; k += n_warps) {
@@ -222,6 +250,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     if (tid == 0) a.m_count[b] = n_matches;
   }
 
+  SNB_STAMP(4);
   // ---- 6. greedy assembly by warp 0
   if (warp == 0) {
     AsmFrame f;
@@ -229,6 +258,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     f.ns = s_ns; f.np_ = s_np; f.n_nodes = n_nodes;
     f.edges = s_edges; f.sorted = s_sorted; f.n_sorted = a.n_sorted;
     f.m_edge = s_m_edge; f.m_src = s_m_src; f.m_dst = s_m_dst; f.m_score = s_m_score; f.K = n_matches;
+    f.mo = s_mo;  // the tail wrote edge k's matches at [s_mo[k], s_mo[k+1])
     f.min_instance_peaks = a.min_instance_peaks; f.min_line_scores = a.min_line_scores;
     f.owner = (int*)(smem + L.owner); f.order = (int*)(smem + L.order);
     f.id_count = (int*)(smem + L.idc); f.id_rank = (int*)(smem + L.idr);
@@ -240,6 +270,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     f.n_inst_out = a.n_inst + b; f.status = a.status;
     assemble_frame_warp(f, lane);
   }
+  SNB_STAMP(5);
 }
 
 // Padded per-frame instance tables -> packed rows appended at a DEVICE-side running offset, so that a
