@@ -93,6 +93,39 @@ int snb_global_peaks(const float* cms, int B, int C, int H, int W, long long sb,
                      long long sw, float threshold, int refine_size, void* workspace, float* out_xy, float* out_val,
                      void* stream);
 
+/* The coordinate ladder of the inference layers (inference/ops/coord.py:27-90), fusable into the peak kernels'
+ * epilogues.  Applied in this order, each step one separately rounded fp32 op like the tensor op it replaces:
+ *   xy * stride (undo_stride) -> / input_scale (undo_input_scale) -> / eff_scale[b] (undo_eff_scale)
+ *   -> + crop_offset[b] (add_crop_offset) -> / eff_scale2[b] (TopDownLayer, layers/topdown.py:268-272).
+ * NULL pointers skip a step; multiplying / dividing by exactly 1.0f is the identity.  scatter[b] (snb_global_peaks_ex
+ * only) redirects sample b's output row (TopDownLayer's valid_idx scatter, layers/topdown.py:281-289); < 0 drops it. */
+typedef struct snb_coord_ladder {
+  float stride;
+  float input_scale;
+  const float* eff_scale;   /* (B,) */
+  const float* crop_offset; /* (B, 2) x, y */
+  const float* eff_scale2;  /* (B,) */
+  const int* scatter;       /* (B,) */
+} snb_coord_ladder;
+
+/* snb_global_peaks + the ladder: CenteredInstanceLayer.postprocess (layers/centered_instance.py:199-230) and the
+ * un-crop step of TopDownLayer._run_stage_2 (layers/topdown.py:259-289) in the same launch.  out_xy / out_val are
+ * indexed by the scattered row; rows nobody writes keep whatever the caller put there (NaN-fill them first). */
+int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                        long long sw, float threshold, int refine_size, void* workspace,
+                        const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream);
+
+/* CentroidLayer.postprocess after find_local_peaks (layers/centroid.py:196-258) on the padded table written by
+ * snb_local_peaks (whose xy_scale already applied the stride): / input_scale, per-frame top max_instances by value
+ * when there are more (torch.topk order), NaN padding, / eff_scale[b].  out_xy (B,max_instances,2), out_val (B,max_instances). */
+int snb_peaks_topk(const int* frame_count, int B, int cap, const float* xy, const float* val, int max_instances,
+                   float input_scale, const float* eff_scale, float* out_xy, float* out_val, void* stream);
+
+/* undo_stride / undo_input_scale / undo_eff_scale / add_crop_offset (ops/coord.py:27-90) as one elementwise op on
+ * contiguous (n_samples, pairs_per_sample, 2) coordinates. */
+int snb_coord_ladder_apply(const float* xy, long long n_samples, long long pairs_per_sample,
+                           const snb_coord_ladder* ladder, float* out, void* stream);
+
 /* crop_bboxes (ops/crops.py:31-124).  images (S,C,H,W) of elem_size bytes (1,2,4,8), bboxes
  * (n,4,2) fp32, sample_inds int64; crop_h/crop_w are read from bbox 0 by the caller, as the
  * reference does (ops/crops.py:66-67).  out (n,C,crop_h,crop_w) contiguous. */

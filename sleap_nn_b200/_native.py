@@ -39,6 +39,9 @@ SIGNATURES = {
     "snb_pack_peaks": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_global_peaks_workspace": [_i, _i, _i, _i, _ip, _ip, _llp],
     "snb_global_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p],
+    "snb_global_peaks_ex": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
+    "snb_peaks_topk": [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p],
+    "snb_coord_ladder_apply": [_p, _ll, _ll, _p, _p, _p],
     "snb_crop_bboxes": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_centered_bboxes": [_p, _ll, _f, _f, _p, _p],
     "snb_integral_regression": [_p, _ll, _i, _i, _p, _p, _p, _p, _p],
@@ -94,6 +97,13 @@ class BottomUpArgs(C.Structure):
         ("max_peaks_per_node", _i), ("skip_flag", _p), ("max_instances", _i), ("input_scale", _f),
         ("eff_scale", _p), ("out_kpts", _p), ("out_vals", _p), ("out_scores", _p),
     ]
+
+
+class CoordLadder(C.Structure):
+    """Mirror of `snb_coord_ladder` (include/sleapnn_b200.h)."""
+
+    _fields_ = [("stride", _f), ("input_scale", _f), ("eff_scale", _p), ("crop_offset", _p), ("eff_scale2", _p),
+                ("scatter", _p)]
 
 
 class NativeLibraryError(RuntimeError):

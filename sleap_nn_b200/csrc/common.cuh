@@ -166,6 +166,26 @@ __device__ __forceinline__ void integral_refine_warp_multi(const float* const (&
   }
 }
 
+// ---- the coordinate ladder of the inference layers (inference/ops/coord.py:27-90), fused into the peak
+// kernels' epilogues.  Each step is one separately rounded fp32 op, exactly like the tensor op it replaces;
+// x * 1.0f and x / 1.0f are identities, so the reference's `== 1` short-circuits need no branch.
+struct Ladder {
+  float stride;          // undo_stride:      xy * stride
+  float input_scale;     // undo_input_scale: xy / input_scale
+  const float* eff;      // undo_eff_scale:   xy / eff[b]        (NULL = skip)
+  const float* off;      // add_crop_offset:  xy + off[b]        (NULL = skip)
+  const float* eff2;     // TopDownLayer:     xy / eff2[b] after the crop offset (NULL = skip)
+  const int* scatter;    // output row of sample b (NULL = b; negative = drop)
+};
+__device__ __forceinline__ Ladder ladder_identity() { return Ladder{1.f, 1.f, nullptr, nullptr, nullptr, nullptr}; }
+__device__ __forceinline__ void ladder_apply(const Ladder& L, int b, float& x, float& y) {
+  x = __fdiv_rn(__fmul_rn(x, L.stride), L.input_scale);
+  y = __fdiv_rn(__fmul_rn(y, L.stride), L.input_scale);
+  if (L.eff) { const float e = L.eff[b]; x = __fdiv_rn(x, e); y = __fdiv_rn(y, e); }
+  if (L.off) { x = __fadd_rn(x, L.off[2 * b]); y = __fadd_rn(y, L.off[2 * b + 1]); }
+  if (L.eff2) { const float e = L.eff2[b]; x = __fdiv_rn(x, e); y = __fdiv_rn(y, e); }
+}
+
 // ---- cp.async (LDGSTS): 16-byte global -> shared copies that tie up no registers ----------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_early(smem_dst)), "l"(gmem_src) : "memory");

@@ -177,28 +177,37 @@ match_structured_kernel(const float* __restrict__ cand_score, const int* __restr
     m_count[b] = cand_ok ? klimit : 0;
     if (K > klimit) atomicOr(status, SNB_STATUS_MATCH_OVERFLOW);
   }
-  if (lane != 0 || !cand_ok) return;
+  if (!cand_ok) return;
   const int s = edges[2 * k], d = edges[2 * k + 1];
   const int n_src = ns[s + 1] - ns[s], n_dst = ns[d + 1] - ns[d];
   const int n_match = min(n_src, n_dst);
   if (n_match == 0 || mo[k] + n_match > klimit) return;
   const int dim = max(n_src, n_dst);
-  void* ws;
-  if (dim <= LSAP_SMEM_DIM) ws = s_ws[warp];
-  else if (dim <= ws_max_dim && ws_global) ws = (unsigned char*)ws_global + (size_t)prob * lsap_ws_bytes(ws_max_dim);
-  else { atomicOr(status, SNB_STATUS_LSAP_TOO_LARGE); return; }
   const float* sc = cand_score + tbl_start(cand_start, cand_stride, b) + eo[k];
   auto cost = [&](int i, int j) -> double {
     const float x = sc[i * n_dst + j];
     return isnan(x) ? (double)INFINITY : -(double)x;
   };
   const long long o = tbl_start(match_start, match_stride, b) + mo[k];
-  if (!lsap_solve(n_src, n_dst, cost, ws, m_src + o, m_dst + o)) {
-    atomicOr(status, SNB_STATUS_LSAP_INFEASIBLE);
-    for (int r = 0; r < n_match; ++r) { m_edge[o + r] = k; m_src[o + r] = -1; m_dst[o + r] = -1; m_score[o + r] = NAN; }
+  bool ok = true;
+  if (dim <= LSAP_SMEM_DIM) {  // all 32 lanes: one free column per lane
+    ok = lsap_solve_warp(n_src, n_dst, cost, s_ws[warp], m_src + o, m_dst + o, lane);
+  } else if (dim <= ws_max_dim && ws_global) {
+    if (lane == 0)
+      ok = lsap_solve(n_src, n_dst, cost, (unsigned char*)ws_global + (size_t)prob * lsap_ws_bytes(ws_max_dim), m_src + o,
+                      m_dst + o);
+    ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+    __syncwarp();
+  } else {
+    if (lane == 0) atomicOr(status, SNB_STATUS_LSAP_TOO_LARGE);
     return;
   }
-  for (int r = 0; r < n_match; ++r) {
+  if (!ok) {
+    if (lane == 0) atomicOr(status, SNB_STATUS_LSAP_INFEASIBLE);
+    for (int r = lane; r < n_match; r += 32) { m_edge[o + r] = k; m_src[o + r] = -1; m_dst[o + r] = -1; m_score[o + r] = NAN; }
+    return;
+  }
+  for (int r = lane; r < n_match; r += 32) {
     m_edge[o + r] = k;
     m_score[o + r] = sc[m_src[o + r] * n_dst + m_dst[o + r]];  // -cost, paf.py:592-594
   }

@@ -163,6 +163,98 @@ __device__ bool lsap_solve(int n_rows, int n_cols, CostFn cost, void* ws, int* o
 
 
 
+// Warp-cooperative version for max(n_rows, n_cols) <= 32: bit-identical results (same fp64 expressions per
+// column, same tie rules), but the scan over the free columns - the inner loop of every Dijkstra step - runs one
+// column per lane.  Lane `it` holds free_[it]; scipy's scan order and tie rule (among equal reduced costs take
+// the LAST unassigned column met, else the FIRST minimum) become two ballots.  in_sr / in_sc are 32-bit masks.
+// Called by all 32 lanes convergently; `ws` as for lsap_solve (shared memory).  Frames with hundreds of
+// peaks spend most of the serial solver's time in shared-memory latency chains; this removes them.
+template <typename CostFn>
+__device__ bool lsap_solve_warp(int n_rows, int n_cols, CostFn cost, void* ws, int* out_row, int* out_col, int lane) {
+  const bool transposed = n_cols < n_rows;
+  const int nr = transposed ? n_cols : n_rows;
+  const int nc = transposed ? n_rows : n_cols;
+  if (nr == 0) return true;
+  double* u = (double*)ws;
+  double* v = u + nr;
+  double* spc = v + nc;
+  int* path = (int*)(spc + nc);
+  int* col4row = path + nc;
+  int* row4col = col4row + nr;
+  auto c_at = [&](int i, int j) -> double { return transposed ? cost(j, i) : cost(i, j); };
+  if (lane < nr) { u[lane] = 0.0; col4row[lane] = -1; }
+  if (lane < nc) { v[lane] = 0.0; row4col[lane] = -1; path[lane] = -1; }
+  __syncwarp();
+  for (int cur = 0; cur < nr; ++cur) {
+    if (lane < nc) spc[lane] = INFINITY;
+    int my_col = nc - 1 - lane;  // free_[it] = nc - 1 - it
+    unsigned in_sr = 0, in_sc = 0;
+    int n_free = nc, i = cur, sink = -1;
+    double min_val = 0.0;
+    __syncwarp();
+    while (sink == -1) {
+      in_sr |= 1u << i;
+      const double ui = u[i];
+      const bool active = lane < n_free;
+      double val = INFINITY;
+      bool unassigned = false;
+      if (active) {
+        const int j = my_col;
+        const double r = min_val + c_at(i, j) - ui - v[j];
+        if (r < spc[j]) { path[j] = i; spc[j] = r; }
+        val = spc[j];
+        unassigned = row4col[j] == -1;
+      }
+      double m = val;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) m = fmin(m, __shfl_xor_sync(FULL, m, d));
+      if (m == INFINITY) return false;  // infeasible (uniform)
+      const unsigned eq = __ballot_sync(FULL, active && val == m);
+      const unsigned eq_un = __ballot_sync(FULL, active && val == m && unassigned);
+      const int pick = eq_un ? (31 - __clz(eq_un)) : (__ffs(eq) - 1);
+      min_val = m;
+      const int j = __shfl_sync(FULL, my_col, pick);
+      const int rc = row4col[j];
+      if (rc == -1) sink = j; else i = rc;
+      in_sc |= 1u << j;
+      const int last_col = __shfl_sync(FULL, my_col, n_free - 1);
+      if (lane == pick) my_col = last_col;  // free_[pick] = free_[--n_free]
+      --n_free;
+      __syncwarp();
+    }
+    if (lane == 0) u[cur] += min_val;
+    if (lane < nr && lane != cur && ((in_sr >> lane) & 1u)) u[lane] += min_val - spc[col4row[lane]];
+    if (lane < nc && ((in_sc >> lane) & 1u)) v[lane] -= min_val - spc[lane];
+    __syncwarp();
+    if (lane == 0) {
+      int j = sink;
+      while (true) {
+        const int ii = path[j];
+        row4col[j] = ii;
+        const int prev = col4row[ii];
+        col4row[ii] = j;
+        j = prev;
+        if (ii == cur) break;
+      }
+    }
+    __syncwarp();
+  }
+  if (!transposed) {
+    if (lane < nr) { out_row[lane] = lane; out_col[lane] = col4row[lane]; }
+  } else {
+    // original rows = our columns: report ascending original row
+    const bool has = lane < nc && row4col[lane] >= 0;
+    const unsigned mk = __ballot_sync(FULL, has);
+    if (has) {
+      const int k = __popc(mk & ((1u << lane) - 1));
+      out_row[k] = lane;
+      out_col[k] = row4col[lane];
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-frame grouping of peaks by node (one warp).  ns[0..N] = exclusive prefix of peaks per node,
 // node_peaks = peak indices grouped by node, ascending inside a node (a STABLE grouping: the

@@ -353,6 +353,19 @@ __device__ __forceinline__ Best best_warp(Best a) {
   return a;
 }
 
+// Output of one (sample, channel): coordinate ladder, optional row scatter (TopDownLayer's valid_idx).
+__device__ __forceinline__ void write_global_peak(const Ladder& lad, int plane_id, int C, float fx, float fy, float v,
+                                                  float* __restrict__ out_xy, float* __restrict__ out_val) {
+  const int b = plane_id / C, c = plane_id - b * C;
+  ladder_apply(lad, b, fx, fy);  // NaN coordinates stay NaN
+  const int row = lad.scatter ? lad.scatter[b] : b;
+  if (row < 0) return;
+  const long long o = (long long)row * C + c;
+  out_xy[2 * o] = fx;
+  out_xy[2 * o + 1] = fy;
+  out_val[o] = v;
+}
+
 // Shared epilogue: thread 0 holds the CTA's Best `r`; publish it, let the plane's last CTA combine the
 // chunk partials, then warp 0 of that CTA applies the threshold and the integral refinement.
 __device__ __forceinline__ void global_peaks_finish(Best r, const float* __restrict__ plane, int plane_id, int chunk,
@@ -360,7 +373,7 @@ __device__ __forceinline__ void global_peaks_finish(Best r, const float* __restr
                                                     int refine_size, float* __restrict__ part_v,
                                                     int* __restrict__ part_xy, unsigned* __restrict__ tickets,
                                                     float* __restrict__ out_xy, float* __restrict__ out_val,
-                                                    Best* s_best, bool* s_last) {
+                                                    Best* s_best, bool* s_last, const Ladder& lad, int C) {
   if (threadIdx.x == 0) {
     if (n_chunks > 1) {
       const long long slot = (long long)plane_id * n_chunks + chunk;
@@ -397,11 +410,7 @@ __device__ __forceinline__ void global_peaks_finish(Best r, const float* __restr
       fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
       fy = __fadd_rn(fy, oy);
     }
-    if (threadIdx.x == 0) {
-      out_xy[2 * plane_id] = fx;
-      out_xy[2 * plane_id + 1] = fy;
-      out_val[plane_id] = low ? 0.f : b.v;
-    }
+    if (threadIdx.x == 0) write_global_peak(lad, plane_id, C, fx, fy, low ? 0.f : b.v, out_xy, out_val);
   }
 }
 
@@ -410,7 +419,7 @@ __global__ void __launch_bounds__(256)
 global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                     long long sw, int vec_ok, int rows_per_chunk, int n_chunks, float thr, int refine_size,
                     float* __restrict__ part_v, int* __restrict__ part_xy, unsigned* __restrict__ tickets,
-                    float* __restrict__ out_xy, float* __restrict__ out_val) {
+                    float* __restrict__ out_xy, float* __restrict__ out_val, Ladder lad) {
   const int plane_id = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x % n_chunks;
   const int b = plane_id / C, c = plane_id % C;
@@ -452,7 +461,7 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
   if (threadIdx.x == 0)
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = best_merge(r, s_best[w]);
   global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, sw, thr, refine_size, part_v, part_xy, tickets,
-                      out_xy, out_val, s_best, &s_last);
+                      out_xy, out_val, s_best, &s_last, lad, C);
 }
 
 // Register-resident variant (the product path for vectorisable planes whose chunk is <= V*1024 elements).
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(256)
 global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                          int rows_per_chunk, int n_chunks, float thr, int refine_size, float* __restrict__ part_v,
                          int* __restrict__ part_xy, unsigned* __restrict__ tickets, float* __restrict__ out_xy,
-                         float* __restrict__ out_val) {
+                         float* __restrict__ out_val, Ladder lad) {
   const int plane_id = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x % n_chunks;
   const int b = plane_id / C, c = plane_id % C;
@@ -561,7 +570,7 @@ global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, lon
     r = Best{m, bx, by};
   }
   global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, 1, thr, refine_size, part_v, part_xy, tickets,
-                      out_xy, out_val, s_best, &s_last);
+                      out_xy, out_val, s_best, &s_last, lad, C);
 }
 
 // Persistent ring variant (the product path for planes that fit one shared-memory stage, e.g. cfg2's 80x80
@@ -575,7 +584,7 @@ constexpr int GP_STAGES = 3;
 __global__ void __launch_bounds__(256)
 global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int H, int W, long long sb, long long sc,
                          long long sh, float thr, int refine_size, float* __restrict__ out_xy,
-                         float* __restrict__ out_val) {
+                         float* __restrict__ out_val, Ladder lad) {
   extern __shared__ __align__(16) float gp_ring[];
   __shared__ float s_m[8];
   __shared__ int s_x[8], s_y[8];
@@ -668,11 +677,7 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
         fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
         fy = __fadd_rn(fy, oy);
       }
-      if (tid == 0) {
-        out_xy[2 * p] = fx;
-        out_xy[2 * p + 1] = fy;
-        out_val[p] = low ? 0.f : b.v;
-      }
+      if (tid == 0) write_global_peak(lad, p, C, fx, fy, low ? 0.f : b.v, out_xy, out_val);
     }
     __syncthreads();  // everyone is done with this stage (and s_best) before the next iteration refills it
   }
@@ -779,6 +784,61 @@ __global__ void centered_bboxes_kernel(const float* __restrict__ c, long long n,
   o[2] = xr; o[3] = yt;
   o[4] = xr; o[5] = yb;
   o[6] = xl; o[7] = yb;
+}
+
+// CentroidLayer.postprocess after find_local_peaks (inference/layers/centroid.py:196-258): per frame, when
+// there are more peaks than max_instances keep the top max_instances by VALUE (torch.topk: descending; equal
+// values: lower index first), else keep (y, x, channel) order; coordinates / input_scale, NaN padding, then
+// / eff_scale[b].  The table's coordinates already carry the stride (snb_local_peaks' xy_scale).  One CTA / frame.
+__global__ void __launch_bounds__(128)
+peaks_topk_kernel(const int* __restrict__ frame_count, int cap, const float* __restrict__ xy,
+                  const float* __restrict__ val, int max_instances, float input_scale, const float* __restrict__ eff,
+                  float* __restrict__ o_xy, float* __restrict__ o_val) {
+  extern __shared__ int s_src[];
+  const int b = blockIdx.x;
+  const int n = min(frame_count[b], cap);
+  const int keep = min(n, max_instances);
+  const float* v = val + (long long)b * cap;
+  if (n > max_instances) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float vi = v[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float vj = v[j];
+        rank += (vj > vi || (vj == vi && j < i)) ? 1 : 0;
+      }
+      if (rank < max_instances) s_src[rank] = i;
+    }
+  } else {
+    for (int i = threadIdx.x; i < keep; i += blockDim.x) s_src[i] = i;
+  }
+  __syncthreads();
+  const float e = eff ? eff[b] : 1.0f;
+  for (int r = threadIdx.x; r < max_instances; r += blockDim.x) {
+    float x = NAN, y = NAN, pv = NAN;
+    if (r < keep) {
+      const long long s = (long long)b * cap + s_src[r];
+      x = __fdiv_rn(__fdiv_rn(xy[2 * s], input_scale), e);
+      y = __fdiv_rn(__fdiv_rn(xy[2 * s + 1], input_scale), e);
+      pv = val[s];
+    }
+    const long long o = (long long)b * max_instances + r;
+    o_xy[2 * o] = x;
+    o_xy[2 * o + 1] = y;
+    o_val[o] = pv;
+  }
+}
+
+// The coordinate ladder as a stand-alone elementwise op (inference/ops/coord.py:27-90): coords is
+// (n_samples, pairs_per_sample, 2) contiguous.
+__global__ void coord_ladder_kernel(const float* __restrict__ xy, long long n_pairs, long long pairs_per_sample,
+                                    Ladder lad, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  float x = xy[2 * i], y = xy[2 * i + 1];
+  ladder_apply(lad, (int)(i / pairs_per_sample), x, y);
+  out[2 * i] = x;
+  out[2 * i + 1] = y;
 }
 
 static inline int grid_for(long long work_items, int per_block, int max_blocks) {
@@ -937,7 +997,17 @@ extern "C" int snb_global_peaks_workspace(int B, int C, int H, int W, int* rows_
 extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
                                 long long sw, float threshold, int refine_size, void* workspace, float* out_xy,
                                 float* out_val, void* stream_) {
+  return snb_global_peaks_ex(cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, workspace, nullptr, out_xy, out_val,
+                             stream_);
+}
+
+extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                                   long long sw, float threshold, int refine_size, void* workspace,
+                                   const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  Ladder lad{1.f, 1.f, nullptr, nullptr, nullptr, nullptr};
+  if (ladder) lad = Ladder{ladder->stride, ladder->input_scale, ladder->eff_scale, ladder->crop_offset, ladder->eff_scale2,
+                           ladder->scatter};
   int rpc, nc;
   long long nbytes;
   const int rc = snb_global_peaks_workspace(B, C, H, W, &rpc, &nc, &nbytes);
@@ -969,18 +1039,18 @@ extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, lo
     const long long want = (long long)sm_count() * per_sm;
     const unsigned rgrid = (unsigned)(planes < want ? planes : want);
     global_peaks_ring_kernel<<<rgrid, 256, ring_smem, st>>>(cms, (int)planes, C, H, W, sb, sc, sh, threshold, refine_size,
-                                                           out_xy, out_val);
+                                                           out_xy, out_val, lad);
   } else if (vec && !force_generic && chunk4 <= 8 * 256) {
 #define SNB_GP(V)                                                                                                   \
   global_peaks_regs_kernel<V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \
-                                                    part_xy, tickets, out_xy, out_val)
+                                                    part_xy, tickets, out_xy, out_val, lad)
     if (chunk4 <= 2 * 256) SNB_GP(2);
     else if (chunk4 <= 4 * 256) SNB_GP(4);
     else SNB_GP(8);
 #undef SNB_GP
   } else {
     global_peaks_kernel<<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold, refine_size,
-                                              part_v, part_xy, tickets, out_xy, out_val);
+                                              part_v, part_xy, tickets, out_xy, out_val, lad);
   }
   SNB_LAUNCH_CHECK();
   return SNB_OK;
@@ -1033,6 +1103,31 @@ extern "C" int snb_centered_bboxes(const float* centers, long long n, float half
   if (n <= 0) return SNB_OK;
   centered_bboxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(centers, n, half_h, half_w,
                                                                                          out);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_peaks_topk(const int* frame_count, int B, int cap, const float* xy, const float* val,
+                              int max_instances, float input_scale, const float* eff_scale, float* out_xy,
+                              float* out_val, void* stream_) {
+  if (B < 0 || cap <= 0 || max_instances <= 0) return SNB_ERR_BAD_ARG;
+  if (B == 0) return SNB_OK;
+  const size_t smem = sizeof(int) * (size_t)max_instances;
+  if (smem > 48 * 1024) return SNB_ERR_UNSUPPORTED;
+  peaks_topk_kernel<<<B, 128, smem, (cudaStream_t)stream_>>>(frame_count, cap, xy, val, max_instances, input_scale,
+                                                            eff_scale, out_xy, out_val);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_coord_ladder_apply(const float* xy, long long n_samples, long long pairs_per_sample,
+                                      const snb_coord_ladder* ladder, float* out, void* stream_) {
+  if (!ladder || n_samples < 0 || pairs_per_sample < 0) return SNB_ERR_BAD_ARG;
+  const long long n = n_samples * pairs_per_sample;
+  if (n == 0) return SNB_OK;
+  const Ladder lad{ladder->stride, ladder->input_scale, ladder->eff_scale, ladder->crop_offset, ladder->eff_scale2,
+                   nullptr};
+  coord_ladder_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(xy, n, pairs_per_sample, lad, out);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   __syncthreads();
 
   SNB_STAMP(3);
-  // ---- 5. per-edge optimal assignment, one warp per edge (lane 0 runs scipy's algorithm)
-  if (cand_ok && lane == 0) {
+  // ---- 5. per-edge optimal assignment, one warp per edge (scipy's algorithm; the scan over free columns runs
+  //         one column per lane when the problem fits 32 x 32, else lane 0 solves it serially in global scratch)
+  if (cand_ok) {
     for (int k = warp; k < E; k += n_warps) {
       const int s = s_edges[2 * k], d = s_edges[2 * k + 1];
       if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) continue;
@@ -218,23 +219,31 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
       const int n_match = min(n_src, n_dst);
       if (n_match == 0 || s_mo[k] + n_match > klimit) continue;
       const int dim = max(n_src, n_dst);
-      void* ws;
-      if (dim <= 32) ws = smem + L.lsap + warp * (int)lsap_ws_bytes(32);
-      else if (dim <= a.lsap_max_dim && a.lsap_ws)
-        ws = (unsigned char*)a.lsap_ws + ((size_t)b * E + k) * lsap_ws_bytes(a.lsap_max_dim);
-      else { atomicOr(a.status, SNB_STATUS_LSAP_TOO_LARGE); continue; }
       const float* sc = s_score + s_eo[k];
       auto cost = [&](int i, int j) -> double {
         const float x = sc[i * n_dst + j];
         return isnan(x) ? (double)INFINITY : -(double)x;
       };
       const int o = s_mo[k];
-      if (!lsap_solve(n_src, n_dst, cost, ws, s_m_src + o, s_m_dst + o)) {
-        atomicOr(a.status, SNB_STATUS_LSAP_INFEASIBLE);
-        for (int r = 0; r < n_match; ++r) { s_m_edge[o + r] = k; s_m_src[o + r] = -1; s_m_dst[o + r] = -1; s_m_score[o + r] = NAN; }
+      bool ok = true;
+      if (dim <= 32) {
+        ok = lsap_solve_warp(n_src, n_dst, cost, smem + L.lsap + warp * (int)lsap_ws_bytes(32), s_m_src + o, s_m_dst + o, lane);
+      } else if (dim <= a.lsap_max_dim && a.lsap_ws) {
+        if (lane == 0)
+          ok = lsap_solve(n_src, n_dst, cost, (unsigned char*)a.lsap_ws + ((size_t)b * E + k) * lsap_ws_bytes(a.lsap_max_dim),
+                          s_m_src + o, s_m_dst + o);
+        ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+        __syncwarp();
+      } else {
+        if (lane == 0) atomicOr(a.status, SNB_STATUS_LSAP_TOO_LARGE);
         continue;
       }
-      for (int r = 0; r < n_match; ++r) {
+      if (!ok) {
+        if (lane == 0) atomicOr(a.status, SNB_STATUS_LSAP_INFEASIBLE);
+        for (int r = lane; r < n_match; r += 32) { s_m_edge[o + r] = k; s_m_src[o + r] = -1; s_m_dst[o + r] = -1; s_m_score[o + r] = NAN; }
+        continue;
+      }
+      for (int r = lane; r < n_match; r += 32) {
         s_m_edge[o + r] = k;
         s_m_score[o + r] = sc[s_m_src[o + r] * n_dst + s_m_dst[o + r]];
       }

@@ -1,0 +1,116 @@
+"""Device-resident `postprocess()` of the reference's inference layers.
+
+Each class replaces the post-model half of one reference layer with a short launch chain and no host
+synchronisation when the output shape is fixed:
+
+    CentroidPostproc          CentroidLayer.postprocess        (inference/layers/centroid.py:196-258)
+    CenteredInstancePostproc  CenteredInstanceLayer.postprocess (inference/layers/centered_instance.py:199-230)
+                              + TopDownLayer._run_stage_2's un-crop / scatter (inference/layers/topdown.py:259-289)
+    BottomUpPostproc          BottomUpLayer.postprocess         (sleap_nn_b200/pipeline.py)
+
+Knob names follow `PostprocessConfig` / `PreprocInfo`; returned tensors live on the device.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from sleap_nn_b200 import _native as N
+from sleap_nn_b200.inference.ops.coord import make_ladder
+from sleap_nn_b200.inference.ops.peaks import DEFAULT_PEAK_CAP, local_peaks_padded
+from sleap_nn_b200.pipeline import BottomUpPostproc  # noqa: F401  (re-export: the third layer)
+
+
+def _refine_size(refinement: Optional[str], integral_patch_size: int) -> int:
+    return int(integral_patch_size) if refinement == "integral" else 0
+
+
+class CentroidPostproc:
+    """confmaps (B, 1, H, W) -> pred_centroids (B, max_instances, 2), pred_centroid_values (B, max_instances).
+
+    find_local_peaks -> x stride -> / input_scale -> per-frame top-k by value when there are more peaks than
+    `max_instances` -> NaN padding -> / eff_scale.  Two launches (K1 + the top-k epilogue reuse the padded peak
+    table) plus the key sort; with `max_instances=None` the busiest frame's count is read back first
+    (`_infer_max_instances`, centroid.py:264-270), which is the only host sync.
+    """
+
+    def __init__(self, peak_threshold: float = 0.2, refinement: Optional[str] = "integral", integral_patch_size: int = 5,
+                 max_instances: Optional[int] = None, peak_cap: int = DEFAULT_PEAK_CAP):
+        self.peak_threshold, self.refine_size = float(peak_threshold), _refine_size(refinement, integral_patch_size)
+        self.max_instances, self.peak_cap = max_instances, int(peak_cap)
+
+    def __call__(self, confmaps: torch.Tensor, output_stride: int = 1, input_scale: float = 1.0,
+                 eff_scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if not confmaps.is_cuda or confmaps.dtype != torch.float32:
+            raise TypeError("CentroidPostproc expects an fp32 CUDA tensor")
+        dev, B = confmaps.device, int(confmaps.shape[0])
+        with torch.cuda.device(dev):
+            count, xy, val, _chan, status, cap = local_peaks_padded(confmaps.detach(), self.peak_threshold,
+                                                                    self.refine_size, float(output_stride), self.peak_cap)
+            max_inst = self.max_instances
+            if not max_inst:
+                max_inst = int(count.clamp(max=cap).max().item()) if B else 0
+            max_inst = max(int(max_inst), 1)  # always at least one slot (centroid.py:222-223)
+            o_xy = torch.empty((B, max_inst, 2), dtype=torch.float32, device=dev)
+            o_val = torch.empty((B, max_inst), dtype=torch.float32, device=dev)
+            eff = None if eff_scale is None else eff_scale.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+            if eff is not None and eff.numel() == 1 and B != 1:
+                eff = eff.expand(B).contiguous()
+            N.check(N.lib.snb_peaks_topk(N.ptr(count), B, cap, N.ptr(xy), N.ptr(val), max_inst, float(input_scale),
+                                         N.ptr(eff), N.ptr(o_xy), N.ptr(o_val), N.stream_ptr(dev)), "snb_peaks_topk")
+        self.last_status = status  # SNB_STATUS_PEAK_OVERFLOW if a frame had more than peak_cap peaks
+        return o_xy, o_val
+
+
+class CenteredInstancePostproc:
+    """confmaps (n, N, h, w) -> keypoints + values in ONE launch, ladder and un-crop scatter included.
+
+    Stand-alone (CenteredInstanceLayer): returns (n, 1, N, 2), (n, 1, N) with stride / input_scale / eff_scale
+    undone.  Inside a top-down pipeline pass `crop_topleft` (n, 2), `per_crop_eff_scale` (n,) and
+    `scatter_rows` (n,) = b * max_instances + i of each crop together with `out_shape=(B, max_instances)`:
+    the kernel adds the crop offset, divides by the per-crop scale and writes straight into the NaN-filled
+    (B, max_instances, N, 2) / (B, max_instances, N) tensors (topdown.py:259-289).
+    """
+
+    def __init__(self, peak_threshold: float = 0.2, refinement: Optional[str] = "integral", integral_patch_size: int = 5):
+        self.peak_threshold, self.refine_size = float(peak_threshold), _refine_size(refinement, integral_patch_size)
+        self._ws = None
+
+    def __call__(self, confmaps: torch.Tensor, output_stride: int = 1, input_scale: float = 1.0,
+                 eff_scale: Optional[torch.Tensor] = None, crop_topleft: Optional[torch.Tensor] = None,
+                 per_crop_eff_scale: Optional[torch.Tensor] = None, scatter_rows: Optional[torch.Tensor] = None,
+                 out_shape: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if not confmaps.is_cuda or confmaps.dtype != torch.float32:
+            raise TypeError("CenteredInstancePostproc expects an fp32 CUDA tensor")
+        dev = confmaps.device
+        n, Cn, H, W = (int(v) for v in confmaps.shape)
+        with torch.cuda.device(dev):
+            if scatter_rows is not None:
+                if out_shape is None:
+                    raise ValueError("scatter_rows needs out_shape=(B, max_instances)")
+                rows = int(out_shape[0]) * int(out_shape[1])
+                kpts = torch.full((rows, Cn, 2), float("nan"), dtype=torch.float32, device=dev)
+                vals = torch.full((rows, Cn), float("nan"), dtype=torch.float32, device=dev)
+            else:
+                kpts = torch.empty((n, Cn, 2), dtype=torch.float32, device=dev)
+                vals = torch.empty((n, Cn), dtype=torch.float32, device=dev)
+            if n * Cn:
+                rpc, nch, nbytes = C.c_int(), C.c_int(), C.c_longlong()
+                N.check(N.lib.snb_global_peaks_workspace(n, Cn, H, W, C.byref(rpc), C.byref(nch), C.byref(nbytes)), "workspace")
+                need = (nbytes.value + 3) // 4
+                if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+                    self._ws = torch.zeros((need,), dtype=torch.int32, device=dev)  # tickets self-reset after each use
+                lad, keep = make_ladder(dev, n, stride=float(output_stride), input_scale=float(input_scale),
+                                        eff_scale=eff_scale, crop_offset=crop_topleft, eff_scale2=per_crop_eff_scale,
+                                        scatter=scatter_rows)
+                x = confmaps.detach()
+                N.check(N.lib.snb_global_peaks_ex(N.ptr(x), n, Cn, H, W, *x.stride(), self.peak_threshold, self.refine_size,
+                                                  N.ptr(self._ws), C.byref(lad), N.ptr(kpts), N.ptr(vals), N.stream_ptr(dev)),
+                        "snb_global_peaks_ex")
+                del keep
+        if scatter_rows is not None:
+            return kpts.view(out_shape[0], out_shape[1], Cn, 2), vals.view(out_shape[0], out_shape[1], Cn)
+        return kpts.unsqueeze(1), vals.unsqueeze(1)

@@ -310,6 +310,75 @@ def f1_outputs(R):
     save("ref_f1_outputs.npz", **out)
 
 
+def f2_layers(R):
+    """CentroidLayer / CenteredInstanceLayer / TopDownLayer post-model arithmetic, composed from the reference's own
+    ops in the order the layers call them (layers/centroid.py:196-258, layers/centered_instance.py:199-230,
+    layers/topdown.py:259-289)."""
+    Cd = R.coord
+    out = {}
+    g = torch.Generator().manual_seed(321)
+    # ---- centroid: 3 frames with 5 / 2 / 0 blobs on a (64, 80) stride-2 map
+    hw, stride = (128, 160), 2
+    xv, yv = R.data_utils.make_grid_vectors(hw[0], hw[1], stride)
+    pts = torch.full((3, 5, 1, 2), float("nan"))
+    pts[0, :, 0] = torch.tensor([[20.0, 30.0], [60.5, 90.25], [120.0, 40.0], [140.0, 110.0], [75.0, 20.0]])
+    pts[1, :2, 0] = torch.tensor([[33.0, 64.0], [100.0, 100.0]])
+    amp = torch.tensor([0.9, 0.5, 0.7, 0.95, 0.6])
+    cms = torch.zeros((3, 1, len(yv), len(xv)))
+    for b in range(3):
+        for i in range(5):
+            cms[b] = torch.maximum(cms[b], amp[i] * R.confidence_maps.make_multi_confmaps(pts[b:b + 1, i:i + 1], xv, yv, 3.0)[0])
+    cms = cms + torch.rand(cms.shape, generator=g) * 1e-3
+    out["cen_cms"] = cms
+    eff = torch.tensor([1.0, 0.8, 1.25])
+    for tag, max_inst, scale in (("dyn", None, 1.0), ("top3", 3, 0.5), ("pad7", 7, 2.0)):
+        peaks, vals, si, _ = R.peaks.find_local_peaks(cms, threshold=0.2, refinement="integral", integral_patch_size=5)
+        peaks = Cd.undo_input_scale(Cd.undo_stride(peaks, stride), scale)
+        B = cms.shape[0]
+        mi = max_inst or int(torch.bincount(si.long(), minlength=B).max())
+        padded = torch.full((B, mi, 2), float("nan"))
+        pvals = torch.full((B, mi), float("nan"))
+        for b in range(B):
+            sp, sv = peaks[si == b], vals[si == b]
+            if sp.numel() == 0:
+                continue
+            if sp.shape[0] > mi:
+                sv, idx = torch.topk(sv, mi)
+                sp = sp[idx]
+            padded[b, : sp.shape[0]] = sp
+            pvals[b, : sp.shape[0]] = sv
+        padded = Cd.undo_eff_scale(padded, eff)
+        out.update({f"cen_{tag}_xy": padded, f"cen_{tag}_val": pvals, f"cen_{tag}_max": np.int64(-1 if max_inst is None else max_inst),
+                    f"cen_{tag}_scale": np.float64(scale)})
+    out["cen_eff"] = eff
+    out["cen_stride"] = np.int64(stride)
+    # ---- centered instance: 6 crops, 4 nodes, (40, 40) stride-2 maps; one node below threshold
+    xv2, yv2 = R.data_utils.make_grid_vectors(80, 80, 2)
+    cpts = torch.rand((6, 4, 2), generator=g) * 60 + 10
+    ccms = R.confidence_maps.make_confmaps(cpts, xv2, yv2, 3.0) + torch.rand((6, 4, 40, 40), generator=g) * 1e-3
+    ccms[2, 1] *= 0.1
+    out["ci_cms"] = ccms
+    pk, pv = R.peaks.find_global_peaks(ccms, threshold=0.2, refinement="integral", integral_patch_size=5)
+    eff6 = torch.tensor([1.0, 0.5, 1.0, 1.5, 0.75, 1.0])
+    lad = Cd.undo_eff_scale(Cd.undo_input_scale(Cd.undo_stride(pk, 2), 0.5), eff6)
+    out.update(ci_xy=lad.unsqueeze(1), ci_val=pv.unsqueeze(1), ci_eff=eff6, ci_scale=np.float64(0.5))
+    # ---- top-down un-crop: the 6 crops belong to (b, i) slots of a (B=3, max_inst=3) layout
+    valid_idx = torch.tensor([[0, 0], [0, 2], [1, 0], [1, 1], [2, 1], [2, 2]])
+    cents = torch.rand((6, 2), generator=g) * 300 + 50
+    bboxes = R.instance_cropping.make_centered_bboxes(cents, 80, 80)
+    eff3 = torch.tensor([1.0, 0.8, 1.25])
+    per_crop_eff = eff3[valid_idx[:, 0]]
+    k3 = Cd.undo_input_scale(Cd.undo_stride(pk, 2), 1.0)  # the inner layer's own ladder (eff_scale all ones there)
+    sized = Cd.add_crop_offset(k3, bboxes[:, 0, :])
+    img = sized / per_crop_eff.view(-1, 1, 1)
+    full = torch.full((3, 3, 4, 2), float("nan"))
+    fullv = torch.full((3, 3, 4), float("nan"))
+    full[valid_idx[:, 0], valid_idx[:, 1]] = img
+    fullv[valid_idx[:, 0], valid_idx[:, 1]] = pv
+    out.update(td_valid_idx=valid_idx, td_topleft=bboxes[:, 0, :], td_eff=eff3, td_xy=full, td_val=fullv)
+    save("ref_f2_layers.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -323,6 +392,7 @@ def main():
     assembly_cases(R)
     targets(R)
     f1_outputs(R)
+    f2_layers(R)
 
 
 if __name__ == "__main__":

@@ -329,3 +329,57 @@ def test_interp1d(pg):
     q = torch.tensor([-1.0, 0.5, 2.5, 3.0, 9.0])
     want = np.array([-1.0, 2.0, 0.0, 8 / 3, 8 + 5 * 16 / 3], np.float32)  # linear extrapolation at both ends
     close(npy(interp1d(xs, ys, q)), want, rtol=1e-6, atol=1e-6)  # eps in the slope denominator
+
+
+def test_warp_lsap_structured_matcher_matches_scipy(pg):
+    """The warp-cooperative solver (one free column per lane, dims <= 32) through snb_match_structured:
+    rectangular, heavily tied and partially infinite problems, 200 frames in one launch, vs scipy."""
+    from scipy.optimize import linear_sum_assignment
+
+    from sleap_nn_b200 import _native as N
+
+    dev = torch.device("cuda", 0)
+    g = np.random.default_rng(11)
+    B = 200
+    dims = [(int(g.integers(1, 33)), int(g.integers(1, 33))) for _ in range(B)]
+    dims[0], dims[1], dims[2] = (32, 32), (1, 32), (32, 1)
+    cand_stride, match_stride = 32 * 32, 32
+    score = np.zeros((B, cand_stride), np.float32)
+    node_start = np.zeros((B, 3), np.int32)
+    edge_off = np.zeros((B, 2), np.int32)
+    match_off = np.zeros((B, 2), np.int32)
+    want = []
+    for b, (ns, nd) in enumerate(dims):
+        s = g.normal(size=(ns, nd)).astype(np.float32)
+        if b % 3 == 0:
+            s = g.integers(0, 3, size=(ns, nd)).astype(np.float32)  # many ties
+        if b % 5 == 0 and ns * nd > 1:
+            s[g.integers(0, ns), g.integers(0, nd)] = np.nan  # NaN -> +inf cost (still feasible)
+        if b % 7 == 0:
+            s[:] = 1.0  # everything tied
+        score[b, : ns * nd] = s.reshape(-1)
+        node_start[b] = [0, ns, ns + nd]
+        edge_off[b] = [0, ns * nd]
+        match_off[b] = [0, min(ns, nd)]
+        cost = -s.astype(np.float64)
+        cost[np.isnan(cost)] = np.inf
+        want.append(linear_sum_assignment(cost) + (s,))
+    t = lambda a: torch.from_numpy(a).to(dev)
+    edges = torch.tensor([[0, 1]], dtype=torch.int32, device=dev)
+    m_edge = torch.full((B, match_stride), -7, dtype=torch.int32, device=dev)
+    m_src, m_dst = torch.full_like(m_edge, -7), torch.full_like(m_edge, -7)
+    m_score = torch.zeros((B, match_stride), dtype=torch.float32, device=dev)
+    m_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    d_score, d_ns, d_eo, d_mo = t(score), t(node_start), t(edge_off), t(match_off)
+    N.check(N.lib.snb_match_structured(N.ptr(d_score), None, cand_stride, N.ptr(edges), 2, 1, N.ptr(d_ns), N.ptr(d_eo),
+                                       N.ptr(d_mo), None, match_stride, None, 32, B, N.ptr(m_edge), N.ptr(m_src),
+                                       N.ptr(m_dst), N.ptr(m_score), N.ptr(m_count), N.ptr(status), N.stream_ptr(dev)),
+            "snb_match_structured")
+    assert int(status.item()) == 0
+    ms, md, msc, mc = npy(m_src), npy(m_dst), npy(m_score), npy(m_count)
+    for b, (r, c, s) in enumerate(want):
+        k = len(r)
+        assert mc[b] == k
+        eq(ms[b, :k], r.astype(np.int32)); eq(md[b, :k], c.astype(np.int32))
+        eq(msc[b, :k], s[r, c])
