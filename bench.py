@@ -48,6 +48,7 @@ WORKLOAD = dict(
 B, N_NODES, N_INST, IMG_HW, STRIDE = 64, 5, 2, (1024, 1024), 2
 ALGO_BYTES_PER_FRAME = 4 * N_NODES * 512 * 512  # K1 reads every confidence-map element once
 METRIC, UNIT = "bottom-up post-proc frames/s", "frames/s"
+emit = lambda obj: print(json.dumps(obj), flush=True)  # replaced in main() by a writer on the saved stdout descriptor
 
 
 def measured_peaks():
@@ -161,7 +162,7 @@ def run_reference(args, rank: int):
     dt = time.perf_counter() - t0
     fps = frames_per_step * args.steps / dt
     sample = f"{frames_per_step} frames/step of the cfg3 batch, {args.steps} steps, torch CPU ops, {torch.get_num_threads()} threads"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, frames_per_step=frames_per_step),
@@ -170,7 +171,7 @@ def run_reference(args, rank: int):
         "gpu_launches": 0,
         "note": "reference is pure Python/ATen with no native path and cannot be installed offline (needs sleap-io, "
                 "lightning, omegaconf): this arm times oracle/, the CPU port of its op chain, on the host cores",
-    }), flush=True)
+    }))
 
 
 # --------------------------------------------------------------------------- our arm
@@ -340,7 +341,7 @@ def run_ours(args, rank: int, world: int):
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{args.cpu_calls} x 16 frames of the same cfg3 batch ({per_call:.2f} s/call), "
                                               "oracle/ torch-CPU port of the reference chain"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -364,6 +365,13 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 (e.g. NCCL's version banner) goes to
+    # stderr instead, and the line itself is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+    emit = lambda obj: os.write(json_fd, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -373,7 +381,7 @@ def main():
         # convenience: `python bench.py --gpus N` re-launches itself under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=json_fd))
     run_ours(args, rank, world)
 
 

@@ -684,6 +684,116 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
   cp_async_wait<0>();
 }
 
+// Warp-per-plane variant (the product path for small vectorisable planes, e.g. cfg2's 80x80 crops).  The ring
+// kernel above still spends five CTA-wide barriers and a serial warp-0 refinement per plane, during which the
+// other seven warps of the CTA idle: it measured 2.6 TB/s (40 % of the HBM roofline).  Here ONE WARP owns a
+// plane end to end and never meets a barrier: a rolling window of U 128-bit streaming loads per lane stays in
+// flight (U*512 B per warp) and the loop is branch-free (~12 issue slots per load: a first attempt that computed
+// positions on a "new maximum" branch took that branch in almost every warp-step and spent 68).  The reference's
+// two independent arg-maxes (ops/peaks.py:103-111) are min(x), min(y) over the elements equal to the maximum; a
+// tie inside one lane's sequence or a NaN (max.NaN poisons the running maximum) sends the warp to the exact
+// generic merge.  One 32-thread CTA per plane, so
+// the hardware scheduler spreads the planes evenly over the 148 SMs (cfg2: 22.5 planes per SM, all resident).
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+template <int U, bool CONTIG>
+__global__ void __launch_bounds__(32)
+global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+                         float thr, int refine_size, float* __restrict__ out_xy, float* __restrict__ out_val,
+                         Ladder lad) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const float* plane = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
+  const int W4 = W >> 2, n4 = H * W4;
+  // Load cursor of this lane: 128-bit load number `li` = lane + 32 * (loads issued so far); for strided planes the
+  // (row, column) pair is advanced incrementally (no integer division in the loop).
+  int li = lane, ly = lane / W4, lx4 = lane - ly * W4;
+  const int dy32 = 32 / W4, dx32 = 32 - dy32 * W4;
+  auto load_next = [&]() -> float4 {
+    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (li < n4) v = ldg_stream4(CONTIG ? plane + 4LL * li : plane + (long long)ly * sh + 4 * lx4);
+    li += 32;
+    if (!CONTIG) {
+      ly += dy32;
+      lx4 += dx32;
+      if (lx4 >= W4) { lx4 -= W4; ++ly; }
+    }
+    return v;
+  };
+  float4 buf[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) buf[u] = load_next();
+  // Per lane, branch-free: running maximum m (max.NaN: a NaN sticks), the number kbest of the FIRST load that
+  // reached it, and whether a later load tied with it.
+  float m = -INFINITY;
+  int kbest = 0, k = 0;
+  bool tie = false;
+  for (int base = 0; base < n4; base += 32 * U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u, ++k) {
+      const float4 v = buf[u];
+      buf[u] = load_next();
+      const float mx = fmax_nan(fmax_nan(v.x, v.y), fmax_nan(v.z, v.w));
+      const bool up = mx > m;
+      tie = up ? false : (tie || mx == m);
+      kbest = up ? k : kbest;
+      m = fmax_nan(m, mx);
+    }
+  }
+  // Warp: the plane maximum and the lanes that hold it.  Exactly one un-tied holder is the common case; several
+  // holders still give min(x), min(y) exactly; a tie INSIDE a holder's own sequence (plateaus, saturated maps) or a
+  // NaN sends the warp to the exact generic merge below.
+  float gm = m;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) gm = fmax_nan(gm, __shfl_xor_sync(FULL, gm, d));
+  Best r{gm, 0x7fffffff, 0x7fffffff};
+  const bool low_all = gm < thr;  // below threshold the position is never reported (ops/peaks.py:121-129)
+  if (!low_all) {
+    const bool holder = (m == gm);
+    const bool exact = (gm != gm) || __any_sync(FULL, holder && tie);
+    if (exact) {
+      Best acc{-INFINITY, 0x7fffffff, 0x7fffffff};
+      bool any = false;
+      for (int i = lane; i < H * W; i += 32) {
+        const int y = i / W, x = i - y * W;
+        const Best o{__ldg(plane + (long long)y * sh + x), x, y};
+        acc = any ? best_merge(acc, o) : o;
+        any = true;
+      }
+      r = best_warp(acc);
+    } else {
+      int bx = 0x7fffffff, by = 0x7fffffff;
+      if (holder) {  // re-read the one 16-byte word that held the maximum (an L2 hit) to find the element
+        const int i = lane + 32 * kbest;
+        const int y = i / W4, x4 = i - y * W4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(plane + (long long)y * sh + 4 * x4));
+        const int e = (v.x == gm) ? 0 : ((v.y == gm) ? 1 : ((v.z == gm) ? 2 : 3));  // first match = min x of the word
+        bx = 4 * x4 + e;
+        by = y;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        bx = min(bx, __shfl_xor_sync(FULL, bx, d));
+        by = min(by, __shfl_xor_sync(FULL, by, d));
+      }
+      r.x = bx;
+      r.y = by;
+    }
+  }
+  const bool low = r.v < thr;  // false for NaN, like torch (ops/peaks.py:121)
+  float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
+  if (!low && refine_size > 0) {
+    float ox, oy;
+    integral_refine_warp(plane, H, W, sh, 1, fx, fy, refine_size, lane, &ox, &oy);
+    fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
+    fy = __fadd_rn(fy, oy);
+  }
+  if (lane == 0) write_global_peak(lad, p, C, fx, fy, low ? 0.f : r.v, out_xy, out_val);
+}
+
 // ----------------------------------------------------------------------------------------
 // K3: crop_bboxes.  One thread per output element; top-left = trunc(tl + size//2) - size//2
 // in fp32 exactly as ops/crops.py:85-90; taps outside the image are 0.
@@ -1025,8 +1135,16 @@ extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W,
   const long long chunk4 = ((long long)rpc * W) >> 2;  // 128-bit loads per chunk
   const unsigned grid = (unsigned)(planes * nc);
   static const bool no_ring = getenv("SNB_GLOBAL_NO_RING") != nullptr;  // A/B: one CTA per plane, values in registers
+  static const bool use_ring = getenv("SNB_GLOBAL_RING") != nullptr;    // A/B: the persistent cp.async ring kernel
   const size_t ring_smem = (size_t)GP_STAGES * H * W * sizeof(float);
-  if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
+  if (vec && !force_generic && !use_ring && !no_ring && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
+    if (sh == W)
+      global_peaks_warp_kernel<8, true><<<(unsigned)planes, 32, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold, refine_size,
+                                                                        out_xy, out_val, lad);
+    else
+      global_peaks_warp_kernel<8, false><<<(unsigned)planes, 32, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold,
+                                                                         refine_size, out_xy, out_val, lad);
+  } else if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
     static bool attr_set = false;
     if (!attr_set) {
       if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=

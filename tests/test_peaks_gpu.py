@@ -167,6 +167,39 @@ def test_global_peaks_vs_oracle(pf, opeaks, shape):
     assert npy(got[0])[0, 1].tolist() == [7.0, 2.0]
 
 
+def test_global_peaks_small_plane_edge_cases(pf, opeaks):
+    """The warp-per-plane kernel (planes <= 16K elements): ties inside one lane's load sequence, across lanes and
+    inside one 16-byte word, plateaus, NaN, -inf, a ragged tail (H*W/4 not a multiple of 32) and strided views."""
+    g = torch.Generator().manual_seed(7)
+    cms = torch.rand((3, 6, 44, 36), generator=g)
+    cms[0, 0, 30, 5] = cms[0, 0, 2, 33] = 3.0            # tie in different lanes
+    cms[0, 1, 3, 4] = cms[0, 1, 35, 0] = 3.0             # word 31 and word 319 = 31 + 32*9: the same lane
+    cms[0, 2, 9, 17] = cms[0, 2, 9, 18] = 3.0            # tie inside one 16-byte word
+    cms[0, 3] = 0.7                                      # plateau above the threshold -> (0, 0)
+    cms[0, 4, 20, 20] = float("nan")                     # NaN is the greatest value
+    cms[0, 5, 10, 3] = float("nan"); cms[0, 5, 4, 30] = float("nan")
+    cms[1, 0] = float("-inf")
+    cms[1, 1] = 0.05                                     # plateau below the threshold -> NaN, 0
+    cms[1, 2, 43, 35] = 9.0                              # last element of the ragged tail
+    cms[1, 3, 0, 0] = 9.0
+    cms[1, 4, 17, 8] = float("inf")
+    for thr in (0.2, float("-inf")):
+        want = opeaks.global_peaks_rough(cms, thr)
+        got = pf.find_global_peaks_rough(cms.cuda(), thr)
+        eq(npy(got[0]), npy(want[0])); eq(npy(got[1]), npy(want[1]))
+    want = opeaks.global_peaks(cms, 0.2, "integral")
+    got = pf.find_global_peaks(cms.cuda(), 0.2, "integral")
+    close(npy(got[0]), npy(want[0]), atol=REFINE_ATOL); eq(npy(got[1]), npy(want[1]))
+    # strided views: a row-cropped window (row stride != W) and a channel slice of a wider tensor
+    big = torch.rand((2, 8, 50, 48), generator=g)
+    big[0, 2, 11, 12] = big[0, 2, 40, 9] = 5.0
+    view = big[:, 1:7, 3:47, 8:44]
+    assert not view.is_contiguous()
+    want = opeaks.global_peaks(view.contiguous(), 0.2, "integral")
+    got = pf.find_global_peaks(big.cuda()[:, 1:7, 3:47, 8:44], 0.2, "integral")
+    close(npy(got[0]), npy(want[0]), atol=REFINE_ATOL); eq(npy(got[1]), npy(want[1]))
+
+
 def test_full_size_properties(pf):
     """BASELINE cfg3 map size (5 x 512 x 512 per frame): size-independent properties.
 

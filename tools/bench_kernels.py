@@ -81,7 +81,7 @@ def k2_cfg2(dev, iters):
         N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), st), "k2")
 
     ms = timed(fn, iters)
-    line("k2_cfg2", "global_peaks_ring_kernel", 4 * B * Cn * H * W, ms, B, "crops",
+    line("k2_cfg2", "global_peaks_warp_kernel", 4 * B * Cn * H * W, ms, B, "crops",
          {"shape": [B, Cn, H, W], "valid_peaks": int((val_o > 0).sum())})
 
 
