@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 2
+#define SNB_ABI_VERSION 3
 
 #define SNB_OK 0
 #define SNB_ERR_BAD_ARG (-1)
@@ -41,6 +41,7 @@ extern "C" {
 #define SNB_STATUS_INSTANCE_OVERFLOW 16 /* a frame produced more instances than `inst_cap`       */
 #define SNB_STATUS_BAD_INDEX 32         /* an index argument pointed outside its table           */
 #define SNB_STATUS_MATCH_OVERFLOW 64    /* a frame had more matches than `match_cap`             */
+#define SNB_STATUS_LSAP_INVALID 128     /* scipy would raise "matrix contains invalid numeric entries" (NaN / -inf cost) */
 
 int snb_abi_version(void);
 
@@ -262,6 +263,48 @@ int snb_edge_distance(const float* points, const float* xv, const float* yv, int
 
 /* gaussian_pdf (data/utils.py:114-125): out = exp(-(x*x)/den). */
 int snb_gaussian_pdf(const float* x, long long n, float den, float* out, void* stream);
+
+/* ------------------------------------ multi-class identity (inference/ops/identity.py, data/identity.py)
+ *
+ * snb_classify_peaks: group_class_peaks (ops/identity.py:13-71) and, with class_maps != NULL, the whole of
+ *   classify_peaks_from_maps (:74-149) in one launch; one warp per (sample, channel) group.
+ *   class_maps (n_samples, K, H, W) fp32 with element strides (ms, mk, mh, mw), or NULL when `probs` is given.
+ *   Peaks are the concatenated lists find_local_peaks returns: peak_xy (P,2) in class-map pixels, peak_val (P),
+ *   sample_inds / channel_inds (P) int32, in any order.
+ *   probs (P, K): OUTPUT when class_maps != NULL (class_maps[sample, :, round(y), round(x)], half-to-even,
+ *     clamped), INPUT otherwise.
+ *   Per group the peaks (ascending index) are assigned to classes by scipy.optimize.linear_sum_assignment
+ *   semantics on cost = -(double)prob; a match is kept only when prob == max over the peak's classes.
+ *   g_peak / g_class (n_samples*n_channels, K) int64 + g_count (n_samples*n_channels): optional per-group kept
+ *     matches in row order (feed snb_pack_class_matches).
+ *   o_xy (n_samples, K, n_channels, 2), o_val, o_prob (n_samples, K, n_channels): optional fixed-size outputs,
+ *     NaN-filled here.
+ *   status bits: LSAP_INVALID (NaN or +inf probability: scipy raises ValueError), LSAP_INFEASIBLE,
+ *     LSAP_TOO_LARGE (a group or K exceeds 128). */
+int snb_classify_peaks(const float* class_maps, int n_samples, int K, int H, int W, long long ms, long long mk,
+                       long long mh, long long mw, const float* peak_xy, const float* peak_val, const int* sample_inds,
+                       const int* channel_inds, long long P, int n_channels, float* probs, long long* g_peak,
+                       long long* g_class, int* g_count, float* o_xy, float* o_val, float* o_prob, int* status,
+                       void* stream);
+/* Per-group matches -> the concatenated (peak_inds, class_inds) of group_class_peaks in (sample, channel) order;
+ * o_peak / o_class hold at most min(P, n_groups*K) entries, total[0] = how many were written. */
+int snb_pack_class_matches(const long long* g_peak, const long long* g_class, const int* g_count, int n_groups, int K,
+                           long long* o_peak, long long* o_class, int* total, void* stream);
+
+/* get_class_inds_from_vectors (ops/identity.py:152-173): ONE assignment over probs (n, K); rows without a class
+ * get -1 / NaN.  workspace: snb_class_inds_workspace_bytes(n, K) bytes. */
+long long snb_class_inds_workspace_bytes(int n, int K);
+int snb_class_inds_from_vectors(const float* probs, int n, int K, void* workspace, long long* o_inds, float* o_probs,
+                                int* status, void* stream);
+
+/* make_class_vectors (data/identity.py:10-32): class_inds (n) fp32 (is_float) or int32 -> out (n, K) int32 one-hot,
+ * index < 0 -> zero row; index >= K sets SNB_STATUS_BAD_INDEX (F.one_hot raises). */
+int snb_class_vectors(const void* class_inds, int is_float, int n, int K, int* out, int* status, void* stream);
+
+/* make_class_maps (data/identity.py:35-82): confmaps (I, h, w) contiguous fp32, onehot = snb_class_vectors output
+ * (I, K) read as (K, I) like the reference's reshape; threshold already fp32; out (K, h, w). */
+int snb_class_maps(const float* confmaps, const int* onehot, int I, int K, int h, int w, float threshold, float* out,
+                   void* stream);
 
 /* ------------------------------------------------------------ fused bottom-up post-processing
  *

@@ -37,6 +37,7 @@ _HOT_FILES = [
     ("sleap_nn.inference.streaming", "sleap_nn/inference/streaming.py"),
     ("sleap_nn.inference.ops.coord", "sleap_nn/inference/ops/coord.py"),
     ("sleap_nn.inference.ops.identity", "sleap_nn/inference/ops/identity.py"),
+    ("sleap_nn.data.identity", "sleap_nn/data/identity.py"),
 ]
 
 _NAMESPACE_PKGS = [
@@ -190,6 +191,7 @@ def ref() -> types.SimpleNamespace:
             outputs=mods["outputs"],
             streaming=mods["streaming"],
             coord=mods["coord"],
-            identity=mods["identity"],
+            identity=full["sleap_nn.inference.ops.identity"],
+            data_identity=full["sleap_nn.data.identity"],
         )
     return _CACHE

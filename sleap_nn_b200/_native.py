@@ -25,6 +25,7 @@ STATUS_LSAP_TOO_LARGE = 8
 STATUS_INSTANCE_OVERFLOW = 16
 STATUS_BAD_INDEX = 32
 STATUS_MATCH_OVERFLOW = 64
+STATUS_LSAP_INVALID = 128
 
 _i, _ll, _f, _p = C.c_int, C.c_longlong, C.c_float, C.c_void_p
 _ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
@@ -63,13 +64,19 @@ SIGNATURES = {
     "snb_pafs": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
+    "snb_classify_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p,
+                           _p, _p],
+    "snb_pack_class_matches": [_p, _p, _p, _i, _i, _p, _p, _p, _p],
+    "snb_class_inds_from_vectors": [_p, _i, _i, _p, _p, _p, _p, _p],
+    "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
+    "snb_class_maps": [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
     "snb_bottomup_args_size": [],
     "snb_bottomup_outputs": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "snb_pack_instances": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p],
 }
-RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
+RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_class_inds_workspace_bytes": [_i, _i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
 FLAG_UNFUSED_TAIL = 1
 
 

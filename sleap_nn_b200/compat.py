@@ -29,6 +29,8 @@ ALIASES = {
     "sleap_nn.inference.ops.paf": "sleap_nn_b200.inference.ops.paf",
     "sleap_nn.data.confidence_maps": "sleap_nn_b200.data.confidence_maps",
     "sleap_nn.data.edge_maps": "sleap_nn_b200.data.edge_maps",
+    "sleap_nn.inference.ops.identity": "sleap_nn_b200.inference.ops.identity",
+    "sleap_nn.data.identity": "sleap_nn_b200.data.identity",
 }
 
 _saved: Optional[Dict[str, Optional[types.ModuleType]]] = None

@@ -379,6 +379,63 @@ def f2_layers(R):
     save("ref_f2_layers.npz", **out)
 
 
+def f3_identity(R):
+    """Multi-class identity grouping (inference/ops/identity.py) and class-map targets (data/identity.py)."""
+    I, D = R.identity, R.data_identity
+    g = torch.Generator().manual_seed(303)
+    out = {}
+    # --- classify_peaks_from_maps: S=3 samples, K=3 classes, C=4 channels, 40x48 maps
+    S, K, Cn, H, W = 3, 3, 4, 40, 48
+    class_maps = torch.softmax(torch.randn((S, K, H, W), generator=g) * 2.0, dim=1)
+    pts, vals, si, ci = [], [], [], []
+    for s in range(S):
+        for c in range(Cn):
+            n = [2, 3, 5, 1, 0, 4, 3, 2, 3, 1, 2, 6][s * Cn + c]  # fewer, equal and more peaks than classes
+            for _ in range(n):
+                pts.append([float(torch.rand((), generator=g)) * (W + 6) - 3, float(torch.rand((), generator=g)) * (H + 6) - 3])
+                vals.append(float(torch.rand((), generator=g)))
+                si.append(s); ci.append(c)
+    pts = torch.tensor(pts, dtype=torch.float32)
+    pts[0] = torch.tensor([10.5, 7.5]); pts[1] = torch.tensor([11.5, 8.5])  # round-half-even: 10, 8 / 12, 8
+    pts[2] = torch.tensor([-0.5, 39.5]); pts[3] = torch.tensor([47.5, 0.5])
+    vals = torch.tensor(vals, dtype=torch.float32)
+    si = torch.tensor(si, dtype=torch.int32); ci = torch.tensor(ci, dtype=torch.int32)
+    p, v, cp = I.classify_peaks_from_maps(class_maps, pts, vals, si, ci, Cn)
+    out.update(cl_maps=class_maps, cl_pts=pts, cl_vals=vals, cl_si=si, cl_ci=ci, cl_out_pts=p, cl_out_vals=v, cl_out_probs=cp)
+    # --- group_class_peaks on explicit probabilities, peaks NOT sorted by sample, int64 index tensors
+    P = 23
+    probs = torch.rand((P, 4), generator=g)
+    probs[5] = probs[6]  # identical rows: the assignment decides
+    si2 = torch.randint(0, 3, (P,), generator=g); ci2 = torch.randint(0, 2, (P,), generator=g)
+    pi, cl = I.group_class_peaks(probs, si2, ci2, 3, 2)
+    out.update(gr_probs=probs, gr_si=si2, gr_ci=ci2, gr_peak_inds=pi, gr_class_inds=cl)
+    # --- get_class_inds_from_vectors: tall, wide, square
+    for tag, shape in (("tall", (6, 3)), ("wide", (3, 5)), ("square", (4, 4)), ("big", (40, 7))):
+        m = torch.softmax(torch.randn(shape, generator=g) * 1.5, dim=1)
+        inds, pr = I.get_class_inds_from_vectors(m)
+        out.update({f"vec_{tag}_probs": m, f"vec_{tag}_inds": inds, f"vec_{tag}_vals": pr})
+    # --- class vectors / class maps (the reference's own known answers, tests/data/test_identity.py:13-33)
+    out["cv_float"] = D.make_class_vectors(torch.Tensor([0, 2, 1, -1]), 3)
+    out["cv_int"] = D.make_class_vectors(torch.tensor([3, -1, 0, 0, 1], dtype=torch.int32), 5)
+    xv, yv = R.data_utils.make_grid_vectors(32, 32, output_stride=1)
+    cms = R.confidence_maps.make_confmaps(torch.Tensor([[[4, 6], [18, 24]]]).to(torch.float32), xv, yv, sigma=2)
+    out.update(cm_small_cms=cms, cm_small=D.make_class_maps(cms, class_inds=torch.Tensor([1, 0]), n_classes=2, threshold=0.2))
+    # overlapping blobs, 3 instances / 4 classes with one unlabeled instance (the reshape quirk shows when I != K)
+    xv, yv = R.data_utils.make_grid_vectors(64, 80, output_stride=2)
+    ptsm = torch.tensor([[[20.0, 20.0], [30.0, 26.0], [60.0, 50.0]]])
+    cms3 = R.confidence_maps.make_confmaps(ptsm, xv, yv, sigma=6.0)
+    out.update(cm_multi_cms=cms3,
+               cm_multi=D.make_class_maps(cms3, class_inds=torch.tensor([2, -1, 0], dtype=torch.int32), n_classes=4, threshold=0.1))
+    inst = torch.rand((1, 4, 5, 2), generator=g) * torch.tensor([96.0, 64.0])
+    inst[0, 1, 2] = float("nan")
+    inst[0, 3] = float("nan")  # a padded (missing) instance
+    out.update(gen_inst=inst,
+               gen_nodes=D.generate_class_maps(inst, (64, 96), 3, torch.tensor([1, 0, 2], dtype=torch.int32), 3, output_stride=2),
+               gen_centroids=D.generate_class_maps(inst[:, :, 0, :], (64, 96), 3, torch.tensor([1, 0, 2], dtype=torch.int32), 3,
+                                                   class_map_threshold=0.3, sigma=2.0, output_stride=4, is_centroids=True))
+    save("ref_f3_identity.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -393,6 +450,7 @@ def main():
     targets(R)
     f1_outputs(R)
     f2_layers(R)
+    f3_identity(R)
 
 
 if __name__ == "__main__":

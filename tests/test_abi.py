@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     assert set(table) == set(decl), set(table) ^ set(decl)
     for name, argtypes in table.items():
         assert len(argtypes) == decl[name], f"{name}: ctypes arity {len(argtypes)} != header {decl[name]}"
-    assert N.ABI_VERSION == 2
+    assert N.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -111,6 +111,18 @@ REFERENCE_SIGNATURES = {
         "gaussian_pdf": ["x", "sigma"],
     },
     "sleap_nn_b200.inference.utils": {"interp1d": ["x", "y", "xnew"]},
+    "sleap_nn_b200.inference.ops.identity": {
+        "group_class_peaks": ["peak_class_probs", "peak_sample_inds", "peak_channel_inds", "n_samples", "n_channels"],
+        "classify_peaks_from_maps": ["class_maps", "peak_points", "peak_vals", "peak_sample_inds", "peak_channel_inds",
+                                     "n_channels"],
+        "get_class_inds_from_vectors": ["peak_class_probs"],
+    },
+    "sleap_nn_b200.data.identity": {
+        "make_class_vectors": ["class_inds", "n_classes"],
+        "make_class_maps": ["confmaps", "class_inds", "n_classes", "threshold"],
+        "generate_class_maps": ["instances", "img_hw", "num_instances", "class_inds", "num_tracks", "class_map_threshold",
+                                "sigma", "output_stride", "is_centroids"],
+    },
     "sleap_nn_b200.data.instance_cropping": {"make_centered_bboxes": ["centroids", "box_height", "box_width"]},
 }
 
@@ -148,6 +160,8 @@ def test_reference_signatures_table_matches_the_reference_when_present():
         "sleap_nn_b200.data.edge_maps": [R.edge_maps],
         "sleap_nn_b200.data.utils": [R.data_utils],
         "sleap_nn_b200.inference.utils": [R.interp],
+        "sleap_nn_b200.inference.ops.identity": [R.identity],
+        "sleap_nn_b200.data.identity": [R.data_identity],
         "sleap_nn_b200.data.instance_cropping": [R.instance_cropping],
     }
     for modname, fns in REFERENCE_SIGNATURES.items():
