@@ -256,6 +256,24 @@ int snb_confmaps(const float* points, int G, int I, int N, const float* xv, cons
 int snb_pafs(const float* srcs, const float* dsts, int G, int I, int E, const float* xv, const float* yv, int h, int w,
              float den, int accumulate, int out_bf16, void* out, void* stream);
 
+/* snb_confmaps with a strided point source, for batched dataset-side target generation (the call sites of
+ *   generate_confmaps / generate_multiconfmaps / generate_class_maps in data/custom_datasets.py:1305-1327, 1489,
+ *   1788, 2835, 2986): frame g / instance i / channel n reads its (x, y) pair at points + g*sg + i*si + n*sn
+ *   (element strides), so (G,I,N,2), centroids (G,I,2) and the instance<->channel swapped view of
+ *   generate_class_maps (data/identity.py:122-129) need no transposed copy.
+ *   n_valid (G) or NULL: instances i >= n_valid[g] are missing (`instances[:, :num_instances]`,
+ *   confidence_maps.py:79-84).  oob_w / oob_h > 0: filter_oob_points (data/providers.py:38-69) applied on the fly. */
+int snb_confmaps_ex(const float* points, int G, int I, int N, long long sg, long long si, long long sn,
+                    const int* n_valid, float oob_w, float oob_h, const float* xv, const float* yv, int h, int w,
+                    float den, int out_bf16, void* out, void* stream);
+
+/* generate_pafs (edge_maps.py:250-323) for G frames in one launch: get_edge_points (:223-247) gathers the edge
+ *   endpoints from instances (G, I, N, 2) through edges (E, 2) int32 inside the kernel; in_xmax / in_ymax > 0 apply the
+ *   in-image instance filter (:293-297; pass xv[-1], yv[-1]); then make_multi_pafs.  out (G, E, 2, h, w). */
+int snb_pafs_from_instances(const float* instances, int G, int I, int N, const int* edges, int E, float in_xmax,
+                            float in_ymax, const float* xv, const float* yv, int h, int w, float den, int out_bf16,
+                            void* out, void* stream);
+
 /* distance_to_edge (edge_maps.py:15-78; apply_pdf = 0) and make_edge_maps (:81-117; apply_pdf = 1).
  *   points (n_pts,2) or NULL for the (yv, xv) meshgrid with n_pts = h*w; out (n_pts,E). */
 int snb_edge_distance(const float* points, const float* xv, const float* yv, int w, long long n_pts,
@@ -301,10 +319,12 @@ int snb_class_inds_from_vectors(const float* probs, int n, int K, void* workspac
  * index < 0 -> zero row; index >= K sets SNB_STATUS_BAD_INDEX (F.one_hot raises). */
 int snb_class_vectors(const void* class_inds, int is_float, int n, int K, int* out, int* status, void* stream);
 
-/* make_class_maps (data/identity.py:35-82): confmaps (I, h, w) contiguous fp32, onehot = snb_class_vectors output
- * (I, K) read as (K, I) like the reference's reshape; threshold already fp32; out (K, h, w). */
-int snb_class_maps(const float* confmaps, const int* onehot, int I, int K, int h, int w, float threshold, float* out,
-                   void* stream);
+/* make_class_maps (data/identity.py:35-82) for G frames in one launch (the reference API is per frame: G = 1).
+ *   confmaps (G, I, h, w) contiguous fp32 per-instance maps, class_inds (G, I) int32 (-1 = no class), n_valid (G) or
+ *   NULL = per-frame instance count (the datasets' num_instances slice); threshold already fp32; out (G, K, h, w).
+ *   The reference reshapes (not transposes) the (I, K) one-hot matrix to (K, I); that indexing is reproduced. */
+int snb_class_maps(const float* confmaps, const int* class_inds, const int* n_valid, int G, int I, int K, int h, int w,
+                   float threshold, float* out, void* stream);
 
 /* ------------------------------------------------------------ fused bottom-up post-processing
  *

@@ -23,6 +23,7 @@ REF_ROOT = os.environ.get("SLEAPNN_REFERENCE_ROOT", "/root/reference")
 
 # (module name, path relative to REF_ROOT) in dependency order.
 _HOT_FILES = [
+    ("sleap_nn.data.providers", "sleap_nn/data/providers.py"),  # only filter_oob_points is used (sleap_io stays a stub)
     ("sleap_nn.data.instance_cropping", "sleap_nn/data/instance_cropping.py"),
     ("sleap_nn.data.utils", "sleap_nn/data/utils.py"),
     ("sleap_nn.data.confidence_maps", "sleap_nn/data/confidence_maps.py"),
@@ -106,7 +107,6 @@ def load(prefix: str = "_sleapnn_ref") -> dict:
             ("sleap_io.io.skeleton", dict(SkeletonYAMLDecoder=_Anything)),
             ("sleap_nn.data.skia_augmentation", {}),
             ("sleap_nn.config.utils", {}),
-            ("sleap_nn.data.providers", {}),
         ]:
             if name not in sys.modules:
                 sys.modules[name] = _stub(name, **attrs)
@@ -193,5 +193,6 @@ def ref() -> types.SimpleNamespace:
             coord=mods["coord"],
             identity=full["sleap_nn.inference.ops.identity"],
             data_identity=full["sleap_nn.data.identity"],
+            providers=full["sleap_nn.data.providers"],
         )
     return _CACHE

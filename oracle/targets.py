@@ -127,3 +127,41 @@ def generate_pafs(instances, img_hw, sigma=1.5, output_stride=2, edge_inds=None,
     if flatten_channels:
         out = out.reshape(-1, yv.shape[0], xv.shape[0])
     return out
+
+
+def filter_oob_points(points: torch.Tensor, img_height: int, img_width: int) -> torch.Tensor:
+    """Keypoints with a negative coordinate, x >= width or y >= height become NaN (both coordinates).
+    sleap_nn/data/providers.py:38-69."""
+    out = points.clone()
+    flat = out.reshape(-1, 2)
+    for k in range(flat.shape[0]):
+        x, y = float(flat[k, 0]), float(flat[k, 1])
+        if x < 0 or x >= img_width or y < 0 or y >= img_height:
+            flat[k, 0] = float("nan")
+            flat[k, 1] = float("nan")
+    return flat.reshape(points.shape)
+
+
+def batched_dataset_targets(instances, num_instances, edges, img_hw, tracks=None):
+    """The per-frame target calls of the datasets' __getitem__ (data/custom_datasets.py:1305-1327, 1489-1511, 1788,
+    2835, 2986) over a collated batch, stacked the way the default collate stacks samples.  Knobs are the ones
+    tests/golden/make_golden.py:f4_batched_targets uses."""
+    from oracle import identity as oid
+
+    H, W = img_hw
+    out = {k: [] for k in ("confidence_maps", "part_affinity_fields", "centroid_maps", "single_maps", "class_maps",
+                           "class_maps_centroids")}
+    for b in range(instances.shape[0]):
+        n = int(num_instances[b])
+        fr = instances[b]
+        out["confidence_maps"].append(generate_multiconfmaps(fr, (H, W), n, sigma=1.5, output_stride=2))
+        out["part_affinity_fields"].append(generate_pafs(fr, (H, W), sigma=4.0, output_stride=4,
+                                                         edge_inds=torch.as_tensor(edges), flatten_channels=True))
+        out["centroid_maps"].append(generate_multiconfmaps(fr[:, :, 0, :], (H, W), n, sigma=2.0, output_stride=2,
+                                                           is_centroids=True))
+        out["single_maps"].append(generate_confmaps(filter_oob_points(fr[:, 0], H, W), (H, W), sigma=1.5, output_stride=2))
+        if tracks is not None and n > 0:
+            out["class_maps"].append(oid.generate_class_maps(fr, (H, W), n, tracks[b, :n], 4, 0.2, 3.0, 2))
+            out["class_maps_centroids"].append(oid.generate_class_maps(fr[:, :, 0, :], (H, W), n, tracks[b, :n], 4, 0.1,
+                                                                       3.0, 4, is_centroids=True))
+    return {k: torch.stack(v) for k, v in out.items() if v}

@@ -62,6 +62,8 @@ SIGNATURES = {
     "snb_interp1d": [_p, _i, _p, _i, _p, _i, _i, _i, _ll, _p, _p],
     "snb_confmaps": [_p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _p, _p],
     "snb_pafs": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
+    "snb_confmaps_ex": [_p, _i, _i, _i, _ll, _ll, _ll, _p, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
+    "snb_pafs_from_instances": [_p, _i, _i, _i, _p, _i, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_classify_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p,
@@ -69,7 +71,7 @@ SIGNATURES = {
     "snb_pack_class_matches": [_p, _p, _p, _i, _i, _p, _p, _p, _p],
     "snb_class_inds_from_vectors": [_p, _i, _i, _p, _p, _p, _p, _p],
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
-    "snb_class_maps": [_p, _p, _i, _i, _i, _i, _f, _p, _p],
+    "snb_class_maps": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
     "snb_bottomup_args_size": [],

@@ -242,28 +242,44 @@ __global__ void class_vectors_kernel(const void* __restrict__ class_inds, int is
   out[t] = (valid && idx == k) ? 1 : 0;
 }
 
-// make_class_maps (data/identity.py:35-82).  confmaps (I, h, w) contiguous, weights = the (I, K) one-hot matrix
-// REINTERPRETED as (K, I) exactly like the reference's reshape (class c, instance i reads flat[c*I + i]).
+// make_class_maps (data/identity.py:35-82) for G frames.  cms (G, I, h, w) contiguous per-instance confidence maps,
+// class_inds (G, I) int32 (-1 = no class), n_valid (G) or NULL = the datasets' per-frame num_instances (instances
+// beyond it do not exist for that frame: the reference slices them away before building the maps).
 //   total = sum_i cm_i (in instance order) ; share_i = cm_i > thr ? cm_i / total : 0 ;
-//   out[c] = max_i (share_i * w[c][i]) with torch.max's NaN propagation.
-// One thread per pixel; the I shares of a pixel are staged in shared memory (s_share[i][tid]).
+//   out[c] = max_i (share_i * w[c][i]) with torch.max's NaN propagation,
+// where w is the (Ig, K) one-hot matrix REINTERPRETED as (K, Ig) exactly like the reference's reshape: class c /
+// instance i reads flat element f = c*Ig + i, i.e. row f / K, column f % K of the one-hot matrix.
+// One thread per pixel, grid = (pixel blocks, G); the Ig shares of a pixel are staged in shared memory.
 __global__ void __launch_bounds__(128)
-class_maps_kernel(const float* __restrict__ cms, const int* __restrict__ onehot, int I, int K, long long hw, float thr,
-                  float* __restrict__ out) {
-  extern __shared__ float s_share[];  // I x 128
-  const int tid = threadIdx.x;
+class_maps_kernel(const float* __restrict__ cms, const int* __restrict__ class_inds, const int* __restrict__ n_valid,
+                  int I, int K, long long hw, float thr, float* __restrict__ out) {
+  extern __shared__ float s_dyn[];
+  float* s_share = s_dyn;            // I x 128
+  float* s_w = s_dyn + (size_t)I * 128;  // K x Ig
+  const int tid = threadIdx.x, g = blockIdx.y;
+  const int Ig = n_valid ? min(max(n_valid[g], 0), I) : I;
+  const float* fcms = cms + (long long)g * I * hw;
+  float* fout = out + (long long)g * K * hw;
+  for (int f = tid; f < K * Ig; f += blockDim.x) {
+    const int r = f / K, k = f - r * K;
+    s_w[f] = (class_inds[(long long)g * I + r] == k) ? 1.f : 0.f;
+  }
+  __syncthreads();
   for (long long px = (long long)blockIdx.x * blockDim.x + tid; px < hw; px += (long long)gridDim.x * blockDim.x) {
-    float total = __ldg(cms + px);
-    for (int i = 1; i < I; ++i) total = __fadd_rn(total, __ldg(cms + (long long)i * hw + px));
-    for (int i = 0; i < I; ++i) {
-      const float v = __ldg(cms + (long long)i * hw + px);
+    if (Ig == 0) {  // torch.max over an empty instance axis raises in the reference; emit zeros
+      for (int c = 0; c < K; ++c) fout[(long long)c * hw + px] = 0.f;
+      continue;
+    }
+    float total = __ldg(fcms + px);
+    for (int i = 1; i < Ig; ++i) total = __fadd_rn(total, __ldg(fcms + (long long)i * hw + px));
+    for (int i = 0; i < Ig; ++i) {
+      const float v = __ldg(fcms + (long long)i * hw + px);
       s_share[i * 128 + tid] = (v > thr) ? __fdiv_rn(v, total) : 0.f;
     }
     for (int c = 0; c < K; ++c) {
-      float acc = __fmul_rn(s_share[tid], (float)__ldg(onehot + (long long)c * I));
-      for (int i = 1; i < I; ++i)
-        acc = max_nan_propagating(acc, __fmul_rn(s_share[i * 128 + tid], (float)__ldg(onehot + (long long)c * I + i)));
-      out[(long long)c * hw + px] = acc;
+      float acc = __fmul_rn(s_share[tid], s_w[c * Ig]);
+      for (int i = 1; i < Ig; ++i) acc = max_nan_propagating(acc, __fmul_rn(s_share[i * 128 + tid], s_w[c * Ig + i]));
+      fout[(long long)c * hw + px] = acc;
     }
   }
 }
@@ -331,19 +347,22 @@ extern "C" int snb_class_vectors(const void* class_inds, int is_float, int n, in
   return SNB_OK;
 }
 
-extern "C" int snb_class_maps(const float* confmaps, const int* onehot, int I, int K, int h, int w, float threshold,
-                              float* out, void* stream) {
-  if (I <= 0 || K < 0 || h < 0 || w < 0) return SNB_ERR_BAD_ARG;
+extern "C" int snb_class_maps(const float* confmaps, const int* class_inds, const int* n_valid, int G, int I, int K,
+                              int h, int w, float threshold, float* out, void* stream) {
+  if (G < 0 || I <= 0 || K < 0 || h < 0 || w < 0) return SNB_ERR_BAD_ARG;
   const long long hw = (long long)h * w;
-  if (hw == 0 || K == 0) return SNB_OK;
-  const size_t smem = (size_t)I * 128 * sizeof(float);
+  if (hw == 0 || K == 0 || G == 0) return SNB_OK;
+  if (G > 65535) return SNB_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)I * 128 + (size_t)K * I) * sizeof(float);
   if (smem > 200 * 1024) return SNB_ERR_UNSUPPORTED;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(class_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return SNB_ERR_CUDA_LAUNCH;
   long long blocks = (hw + 127) / 128;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  class_maps_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(confmaps, onehot, I, K, hw, threshold, out);
+  const long long cap = (148LL * 16 + G - 1) / G;
+  if (blocks > cap) blocks = cap < 1 ? 1 : cap;
+  class_maps_kernel<<<dim3((unsigned)blocks, G), 128, smem, (cudaStream_t)stream>>>(confmaps, class_inds, n_valid, I, K,
+                                                                                   hw, threshold, out);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

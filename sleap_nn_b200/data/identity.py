@@ -25,6 +25,15 @@ def _class_vectors_dev(class_inds: torch.Tensor, n_classes: int, dev: torch.devi
     return out
 
 
+def _class_inds_i32(class_inds: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """Class indices as int32 on `dev`; float indices truncate toward zero like the reference's `.long()`, and every
+    negative value means "no class" (data/identity.py:24-31)."""
+    ci = class_inds.detach().to(dev)
+    if ci.dtype.is_floating_point:
+        ci = torch.where(ci >= 0, ci, torch.full_like(ci, -1.0))
+    return ci.to(torch.int32).contiguous()
+
+
 def make_class_vectors(class_inds: torch.Tensor, n_classes: int) -> torch.Tensor:
     """One-hot int32 rows `(n_instances, n_classes)`; an index of -1 gives an all-zero row (data/identity.py:10-32)."""
     dev = N.compute_device(class_inds)
@@ -44,13 +53,16 @@ def make_class_maps(confmaps: torch.Tensor, class_inds: torch.Tensor, n_classes:
     cms = confmaps.detach().to(device=dev, dtype=torch.float32).reshape(-1, h, w).contiguous()
     if cms.shape[0] != n_inst:
         raise ValueError("make_class_maps expects confmaps of shape (1, n_instances, height, width)")
-    onehot = _class_vectors_dev(class_inds, n_classes, dev)
-    if onehot.numel() != int(n_classes) * n_inst:  # the reference's reshape to [n_classes, n_instances, 1, 1] fails too
-        raise RuntimeError(f"shape '[{n_classes}, {n_inst}, 1, 1]' is invalid for input of size {onehot.numel()}")
+    if int(class_inds.shape[0]) != n_inst:  # the reference's reshape to [n_classes, n_instances, 1, 1] fails too
+        raise RuntimeError(f"shape '[{n_classes}, {n_inst}, 1, 1]' is invalid for input of size "
+                           f"{int(class_inds.shape[0]) * int(n_classes)}")
+    ci = _class_inds_i32(class_inds, dev).reshape(1, n_inst)
+    if n_inst and int(ci.max()) >= int(n_classes):
+        raise RuntimeError("Class values must be smaller than num_classes.")  # F.one_hot's error
     out = torch.empty((1, int(n_classes), h, w), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib.snb_class_maps(N.ptr(cms), N.ptr(onehot), n_inst, int(n_classes), h, w, float(threshold), N.ptr(out),
-                                     N.stream_ptr(dev)), "snb_class_maps")
+        N.check(N.lib.snb_class_maps(N.ptr(cms), N.ptr(ci), None, 1, n_inst, int(n_classes), h, w, float(threshold),
+                                     N.ptr(out), N.stream_ptr(dev)), "snb_class_maps")
     return out.to(confmaps.device)
 
 

@@ -436,6 +436,42 @@ def f3_identity(R):
     save("ref_f3_identity.npz", **out)
 
 
+def f4_batched_targets(R):
+    """Dataset call sites (data/custom_datasets.py:1305-1327, 1489-1511, 1788, 2835, 2986): the reference's
+    per-frame generate_* calls on a collated batch of frames, stacked like the default collate does."""
+    g = torch.Generator().manual_seed(404)
+    B, I, Nn, H, W = 4, 4, 5, 64, 96
+    edges = [[0, 1], [1, 2], [1, 3], [3, 4]]
+    inst = torch.rand((B, 1, I, Nn, 2), generator=g) * torch.tensor([W + 10.0, H + 10.0]) - 5.0  # some nodes off-frame
+    num = torch.tensor([4, 2, 3, 0])
+    inst[1, 0, 2:] = float("nan")          # padded slots of frame 1
+    inst[2, 0, 3] = float("nan")
+    inst[2, 0, 0, 2] = float("nan")        # a missing node
+    inst[0, 0, 3] = inst[0, 0, 3] * 0 + torch.tensor([-3.0, 200.0])  # an instance entirely outside the frame
+    inst[3, 0] = float("nan")              # an empty frame
+    tracks = torch.tensor([[0, 2, 1, 3], [1, 0, -1, -1], [2, -1, 0, -1], [-1, -1, -1, -1]], dtype=torch.int32)
+    out = dict(instances=inst, num_instances=num, edges=torch.tensor(edges), tracks=tracks)
+    CM, EM, ID = R.confidence_maps, R.edge_maps, R.data_identity
+    cms, pafs, cen, single, cls, cls_cen = [], [], [], [], [], []
+    for b in range(B):
+        n = int(num[b])
+        cms.append(CM.generate_multiconfmaps(inst[b], img_hw=(H, W), num_instances=n, sigma=1.5, output_stride=2))
+        pafs.append(EM.generate_pafs(inst[b], img_hw=(H, W), sigma=4.0, output_stride=4, edge_inds=torch.Tensor(edges),
+                                     flatten_channels=True))
+        cen.append(CM.generate_multiconfmaps(inst[b][:, :, 0, :], img_hw=(H, W), num_instances=n, sigma=2.0, output_stride=2,
+                                             is_centroids=True))
+        one = R.providers.filter_oob_points(inst[b][:, 0], H, W)  # (1, N, 2): the first instance as a "crop" sample
+        single.append(CM.generate_confmaps(one, img_hw=(H, W), sigma=1.5, output_stride=2))
+        if n > 0:
+            cls.append(ID.generate_class_maps(inst[b], (H, W), n, tracks[b, :n], 4, class_map_threshold=0.2, sigma=3.0,
+                                              output_stride=2))
+            cls_cen.append(ID.generate_class_maps(inst[b][:, :, 0, :], (H, W), n, tracks[b, :n], 4, class_map_threshold=0.1,
+                                                  sigma=3.0, output_stride=4, is_centroids=True))
+    out.update(confidence_maps=torch.stack(cms), part_affinity_fields=torch.stack(pafs), centroid_maps=torch.stack(cen),
+               single_maps=torch.stack(single), class_maps=torch.stack(cls), class_maps_centroids=torch.stack(cls_cen))
+    save("ref_f4_batched_targets.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -451,6 +487,7 @@ def main():
     f1_outputs(R)
     f2_layers(R)
     f3_identity(R)
+    f4_batched_targets(R)
 
 
 if __name__ == "__main__":
