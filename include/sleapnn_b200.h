@@ -326,6 +326,32 @@ int snb_class_vectors(const void* class_inds, int is_float, int n, int K, int* o
 int snb_class_maps(const float* confmaps, const int* class_inds, const int* n_valid, int G, int I, int K, int h, int w,
                    float threshold, float* out, void* stream);
 
+/* ------------------------------------------------------ post-inference filters (inference/filters.py)
+ *
+ * snb_filter_instances: FilterPipeline.apply (inference/filters.py:100-163) on the padded outputs, one warp per
+ *   frame, in the reference's fixed order: min_peak_value (:165-176) -> node count (:178-197) -> score filters
+ *   (:199-243) -> greedy overlap NMS by bbox IoU or OKS (:245-344) -> centroid-distance NMS (:375-412); a dropped
+ *   instance slot is NaN-filled in every field present (_nan_out_where, :346-373).  Thresholds that the reference
+ *   compares against fp32 tensors are passed as fp32; the ones it compares as python floats (`.item()`) as double.
+ *   A value <= 0 (overlapping == 0) disables its stage.  overlapping: 1 = "iou", 2 = "oks" (the caller applies the
+ *   single-node OKS -> IoU fallback of :134-147).  oks_kappa_sq = fl32(0.1**2).
+ *   kpts (B,I,N,2), vals (B,I,N), scores (B,I), centroids (B,I,2), centroid_vals (B,I): any may be NULL (the matching
+ *   Outputs field is None), each o_* must be NULL exactly when its input is.  Inputs are not modified. */
+typedef struct snb_filter_config {
+  float min_peak_value;
+  float min_visible_node_fraction;
+  float min_instance_score;
+  float min_mean_node_score;
+  float oks_kappa_sq;
+  int min_visible_nodes;
+  int overlapping;
+  double overlapping_threshold;
+  double min_centroid_distance_sq;
+} snb_filter_config;
+int snb_filter_instances(const snb_filter_config* cfg, int B, int I, int N, const float* kpts, const float* vals,
+                         const float* scores, const float* centroids, const float* centroid_vals, float* o_kpts,
+                         float* o_vals, float* o_scores, float* o_centroids, float* o_centroid_vals, void* stream);
+
 /* ------------------------------------------------------------ fused bottom-up post-processing
  *
  * snb_bottomup_postproc enqueues K1 -> K4 -> K5 -> K6 on `stream` with padded tables: no host

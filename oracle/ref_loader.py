@@ -39,6 +39,7 @@ _HOT_FILES = [
     ("sleap_nn.inference.ops.coord", "sleap_nn/inference/ops/coord.py"),
     ("sleap_nn.inference.ops.identity", "sleap_nn/inference/ops/identity.py"),
     ("sleap_nn.data.identity", "sleap_nn/data/identity.py"),
+    ("sleap_nn.inference.filters", "sleap_nn/inference/filters.py"),
 ]
 
 _NAMESPACE_PKGS = [
@@ -194,5 +195,6 @@ def ref() -> types.SimpleNamespace:
             identity=full["sleap_nn.inference.ops.identity"],
             data_identity=full["sleap_nn.data.identity"],
             providers=full["sleap_nn.data.providers"],
+            filters=full["sleap_nn.inference.filters"],
         )
     return _CACHE

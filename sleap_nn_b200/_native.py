@@ -72,6 +72,7 @@ SIGNATURES = {
     "snb_class_inds_from_vectors": [_p, _i, _i, _p, _p, _p, _p, _p],
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
     "snb_class_maps": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
+    "snb_filter_instances": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
     "snb_bottomup_args_size": [],
@@ -113,6 +114,14 @@ class CoordLadder(C.Structure):
 
     _fields_ = [("stride", _f), ("input_scale", _f), ("eff_scale", _p), ("crop_offset", _p), ("eff_scale2", _p),
                 ("scatter", _p)]
+
+
+class FilterConfigStruct(C.Structure):
+    """Mirror of `snb_filter_config` (include/sleapnn_b200.h)."""
+
+    _fields_ = [("min_peak_value", _f), ("min_visible_node_fraction", _f), ("min_instance_score", _f),
+                ("min_mean_node_score", _f), ("oks_kappa_sq", _f), ("min_visible_nodes", _i), ("overlapping", _i),
+                ("overlapping_threshold", C.c_double), ("min_centroid_distance_sq", C.c_double)]
 
 
 class NativeLibraryError(RuntimeError):

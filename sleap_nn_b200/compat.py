@@ -31,7 +31,10 @@ ALIASES = {
     "sleap_nn.data.edge_maps": "sleap_nn_b200.data.edge_maps",
     "sleap_nn.inference.ops.identity": "sleap_nn_b200.inference.ops.identity",
     "sleap_nn.data.identity": "sleap_nn_b200.data.identity",
+    "sleap_nn.inference.ops.coord": "sleap_nn_b200.inference.ops.coord",
 }
+# sleap_nn.inference.filters is NOT aliased wholesale: the reference module also re-exports `Outputs`; a maintainer
+# swaps `FilterPipeline` / `FilterConfig` for sleap_nn_b200.inference.filters' (see INTEGRATION.md).
 
 _saved: Optional[Dict[str, Optional[types.ModuleType]]] = None
 

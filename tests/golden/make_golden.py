@@ -472,6 +472,86 @@ def f4_batched_targets(R):
     save("ref_f4_batched_targets.npz", **out)
 
 
+FILTER_CASES = {
+    "peak": dict(min_peak_value=0.3),
+    "nodes": dict(min_visible_nodes=3, min_visible_node_fraction=0.5),
+    "scores": dict(min_instance_score=0.4, min_mean_node_score=0.45),
+    "iou": dict(overlapping=True, overlapping_threshold=0.5, overlapping_method="iou"),
+    "oks": dict(overlapping=True, overlapping_threshold=0.3, overlapping_method="oks"),
+    "all": dict(min_peak_value=0.25, min_visible_nodes=2, min_visible_node_fraction=0.3, min_instance_score=0.2,
+                min_mean_node_score=0.3, overlapping=True, overlapping_threshold=0.4, overlapping_method="oks"),
+}
+
+
+def filter_inputs(seed: int):
+    """(B, I, N) = (6, 8, 6) poses with near-duplicates, missing nodes, empty slots and a score spread."""
+    g = torch.Generator().manual_seed(seed)
+    B, I, Nn = 6, 8, 6
+    kpts = torch.full((B, I, Nn, 2), float("nan"))
+    for b in range(B):
+        base = torch.rand((3, 1, 2), generator=g) * 300 + 50 + torch.cumsum(torch.rand((3, Nn, 2), generator=g) * 30 - 10, dim=1)
+        for i in range(I - 1):  # slot I-1 stays empty
+            jitter = [0.0, 0.0, 0.0, 1.5, 6.0, 14.0, 40.0][i]
+            kpts[b, i] = base[i % 3] + (torch.rand((Nn, 2), generator=g) - 0.5) * 2 * jitter
+    drop = torch.rand((B, I, Nn), generator=g) < 0.2
+    kpts[drop] = float("nan")
+    kpts[0, 1, :, 0] = float("nan")  # x missing everywhere, y present: "any coordinate" vs "both coordinates"
+    vals = torch.rand((B, I, Nn), generator=g)
+    vals[torch.isnan(kpts).any(-1)] = float("nan")
+    scores = torch.rand((B, I), generator=g)
+    scores[:, I - 1] = float("nan")
+    scores[2, 3] = float("nan")  # a NaN score on a live instance sorts first
+    return kpts, vals, scores
+
+
+def f4_filters(R):
+    """FilterPipeline (inference/filters.py) on synthetic Outputs; every decision is certified to have a margin."""
+    from oracle import filters as ofil
+
+    FP, FC, Out = R.filters.FilterPipeline, R.filters.FilterConfig, R.outputs.Outputs
+    seed = 500
+    while True:  # re-draw until no similarity / score sits within 1e-4 of a threshold it is compared with
+        kpts, vals, scores = filter_inputs(seed)
+        k = kpts.numpy()
+        ok = True
+        for b in range(k.shape[0]):
+            for i in range(k.shape[1]):
+                for j in range(k.shape[1]):
+                    if i != j:
+                        ok &= all(abs(ofil.bbox_iou(k[b, i], k[b, j]) - t) > 1e-4 for t in (0.5,))
+                        ok &= all(abs(ofil.oks(k[b, i], k[b, j]) - t) > 1e-4 for t in (0.3, 0.4))
+        ok &= bool((torch.nan_to_num(scores - 0.4, nan=1.0).abs() > 1e-4).all() and (torch.nan_to_num(scores - 0.2, nan=1.0).abs() > 1e-4).all())
+        ok &= bool((torch.nan_to_num(vals - 0.3, nan=1.0).abs() > 1e-5).all() and (torch.nan_to_num(vals - 0.25, nan=1.0).abs() > 1e-5).all())
+        m = torch.nan_to_num(torch.nanmean(vals, dim=-1), nan=0.0)
+        ok &= bool(((m - 0.45).abs() > 1e-4).all() and ((m - 0.3).abs() > 1e-4).all())
+        if ok:
+            break
+        seed += 1
+    out = dict(kpts=kpts, vals=vals, scores=scores, seed=np.int64(seed))
+    for tag, kw in FILTER_CASES.items():
+        r = FP.run(Out(pred_keypoints=kpts, pred_peak_values=vals, instance_scores=scores), FC(**kw))
+        out.update({f"{tag}_kpts": r.pred_keypoints, f"{tag}_vals": r.pred_peak_values, f"{tag}_scores": r.instance_scores})
+    # no instance scores: the overlap NMS visits the slots in index order
+    r = FP.run(Out(pred_keypoints=kpts, pred_peak_values=vals), FC(overlapping=True, overlapping_threshold=0.5))
+    out.update(noscore_kpts=r.pred_keypoints, noscore_vals=r.pred_peak_values)
+    # centroid-only outputs: score gate + distance NMS
+    g = torch.Generator().manual_seed(77)
+    cen = torch.rand((5, 9, 2), generator=g) * 200
+    cen[:, 4] = cen[:, 1] + torch.tensor([3.0, -4.0])      # 5 px from slot 1
+    cen[:, 6] = cen[:, 2] + torch.tensor([9.0, 12.0])      # 15 px from slot 2
+    cen[1, 3] = float("nan"); cen[3, 0, 1] = float("nan")
+    cenv = torch.rand((5, 9), generator=g)
+    cenv[1, 3] = float("nan"); cenv[4, 7] = float("nan")
+    out.update(cen=cen, cenv=cenv)
+    r = FP.run(Out(pred_centroids=cen, pred_centroid_values=cenv), FC(min_instance_score=0.3, min_centroid_distance=12.0))
+    out.update(cen_a=r.pred_centroids, cenv_a=r.pred_centroid_values)
+    r = FP.run(Out(pred_centroids=cen, pred_centroid_values=cenv, instance_scores=1 - cenv), FC(min_centroid_distance=20.0))
+    out.update(cen_b=r.pred_centroids, cenv_b=r.pred_centroid_values, cens_b=r.instance_scores)
+    r = FP.run(Out(pred_centroids=cen, instance_scores=cenv), FC(min_instance_score=0.5, min_centroid_distance=6.0))
+    out.update(cen_c=r.pred_centroids, cens_c=r.instance_scores)
+    save("ref_f4_filters.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -488,6 +568,7 @@ def main():
     f2_layers(R)
     f3_identity(R)
     f4_batched_targets(R)
+    f4_filters(R)
 
 
 if __name__ == "__main__":

@@ -146,6 +146,23 @@ def test_api_mirrors_reference_signatures():
         assert callable(getattr(pg.PAFScorer, m))
 
 
+def test_filter_config_mirrors_the_reference_when_present():
+    import attrs
+
+    from oracle import ref_loader
+    from sleap_nn_b200.inference import filters as ours
+
+    assert [a.name for a in attrs.fields(ours.FilterConfig)] == [
+        "min_peak_value", "min_instance_score", "min_mean_node_score", "min_visible_nodes", "min_visible_node_fraction",
+        "overlapping", "overlapping_threshold", "overlapping_method", "min_centroid_distance"]
+    if not ref_loader.available():
+        pytest.skip("reference tree not present on this box")
+    theirs = ref_loader.ref().filters.FilterConfig
+    assert [(a.name, a.default) for a in attrs.fields(ours.FilterConfig)] == [(a.name, a.default) for a in attrs.fields(theirs)]
+    for m in ("apply", "run", "__call__"):
+        assert callable(getattr(ours.FilterPipeline, m))
+
+
 def test_reference_signatures_table_matches_the_reference_when_present():
     """In the build container, check REFERENCE_SIGNATURES against the real reference modules."""
     from oracle import ref_loader

@@ -1,0 +1,122 @@
+"""GPU parity of the post-inference filter pipeline: sleap_nn_b200.inference.filters against golden
+vectors produced by the unmodified reference FilterPipeline and against the CPU oracle on random batches.  Which
+slots survive is an integer decision: bit-exact (inputs certified to keep every similarity / score away from its
+threshold); surviving values are copies of the inputs: bit-exact too."""
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import T, eq, golden, npy
+from tests.test_oracle_golden import FILTER_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fl():
+    from sleap_nn_b200.inference import filters
+
+    return filters
+
+
+def test_filter_pipeline_golden(fl):
+    d = golden("ref_f4_filters.npz")
+    for dev in ("cuda", "cpu"):
+        kpts, vals, scores = (T(d[k]).to(dev) for k in ("kpts", "vals", "scores"))
+        for tag, kw in FILTER_CASES.items():
+            out = fl.FilterPipeline.run(fl.FilterableOutputs(kpts, vals, scores), fl.FilterConfig(**kw))
+            assert out.pred_keypoints.device.type == dev
+            eq(npy(out.pred_keypoints), d[f"{tag}_kpts"]); eq(npy(out.pred_peak_values), d[f"{tag}_vals"])
+            eq(npy(out.instance_scores), d[f"{tag}_scores"])
+        eq(npy(kpts), d["kpts"])  # inputs are never modified
+    out = fl.FilterPipeline(fl.FilterConfig(overlapping=True, overlapping_threshold=0.5))(
+        fl.FilterableOutputs(T(d["kpts"]).cuda(), T(d["vals"]).cuda()))
+    eq(npy(out.pred_keypoints), d["noscore_kpts"]); eq(npy(out.pred_peak_values), d["noscore_vals"])
+    assert out.instance_scores is None
+    cen, cenv = T(d["cen"]).cuda(), T(d["cenv"]).cuda()
+    o = fl.FilterPipeline.run(fl.FilterableOutputs(pred_centroids=cen, pred_centroid_values=cenv),
+                              fl.FilterConfig(min_instance_score=0.3, min_centroid_distance=12.0))
+    eq(npy(o.pred_centroids), d["cen_a"]); eq(npy(o.pred_centroid_values), d["cenv_a"])
+    o = fl.FilterPipeline.run(fl.FilterableOutputs(pred_centroids=cen, pred_centroid_values=cenv, instance_scores=1 - cenv),
+                              fl.FilterConfig(min_centroid_distance=20.0))
+    eq(npy(o.pred_centroids), d["cen_b"]); eq(npy(o.pred_centroid_values), d["cenv_b"]); eq(npy(o.instance_scores), d["cens_b"])
+    o = fl.FilterPipeline.run(fl.FilterableOutputs(pred_centroids=cen, instance_scores=cenv),
+                              fl.FilterConfig(min_instance_score=0.5, min_centroid_distance=6.0))
+    eq(npy(o.pred_centroids), d["cen_c"]); eq(npy(o.instance_scores), d["cens_c"])
+    # defaults are the identity and return the very same object; centroid-only overlap NMS warns and is skipped
+    same = fl.FilterableOutputs(T(d["kpts"]).cuda())
+    assert fl.FilterPipeline.run(same, fl.FilterConfig()) is same
+    with pytest.warns(UserWarning):
+        o = fl.FilterPipeline.run(fl.FilterableOutputs(pred_centroids=cen), fl.FilterConfig(overlapping=True))
+    eq(npy(o.pred_centroids), d["cen"])
+
+
+def _certified(kpts, thr_iou, thr_oks):
+    from oracle import filters as ofil
+
+    k = kpts.numpy()
+    for b in range(k.shape[0]):
+        for i in range(k.shape[1]):
+            for j in range(k.shape[1]):
+                if i != j and (abs(ofil.bbox_iou(k[b, i], k[b, j]) - thr_iou) < 1e-4 or abs(ofil.oks(k[b, i], k[b, j]) - thr_oks) < 1e-4):
+                    return False
+    return True
+
+
+@pytest.mark.parametrize("B,I,Nn", [(3, 5, 1), (4, 40, 13), (2, 70, 4)])
+def test_filter_pipeline_vs_oracle_random(fl, B, I, Nn):
+    """More instance slots than lanes (I > 32), single-node skeletons (OKS falls back to IoU), heavy duplication."""
+    from oracle import filters as ofil
+
+    seed = 10 * I + Nn
+    while True:
+        g = torch.Generator().manual_seed(seed)
+        base = torch.rand((B, 6, 1, 2), generator=g) * 400 + torch.cumsum(torch.rand((B, 6, Nn, 2), generator=g) * 40 - 15, dim=2)
+        kpts = base[:, torch.randint(0, 6, (I,), generator=g)] + (torch.rand((B, I, Nn, 2), generator=g) - 0.5) * \
+            torch.tensor([0.0, 2.0, 8.0, 30.0])[torch.randint(0, 4, (B, I, 1, 1), generator=g)]
+        kpts[torch.rand((B, I, Nn), generator=g) < 0.25] = float("nan")
+        kpts[torch.rand((B, I), generator=g) < 0.15] = float("nan")
+        if _certified(kpts, 0.45, 0.35):
+            break
+        seed += 1000
+    vals = torch.rand((B, I, Nn), generator=g)
+    scores = torch.rand((B, I), generator=g)
+    scores[torch.rand((B, I), generator=g) < 0.1] = float("nan")
+    cfgs = [dict(overlapping=True, overlapping_threshold=0.45, overlapping_method="iou"),
+            dict(overlapping=True, overlapping_threshold=0.35, overlapping_method="oks"),
+            dict(min_peak_value=0.2, min_visible_nodes=1, min_visible_node_fraction=0.4, min_instance_score=0.15,
+                 min_mean_node_score=0.35, overlapping=True, overlapping_threshold=0.35, overlapping_method="oks")]
+    import warnings
+
+    for cfg in cfgs:
+        want = ofil.apply(cfg, kpts.numpy(), vals.numpy(), scores.numpy())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = fl.FilterPipeline.run(fl.FilterableOutputs(kpts.cuda(), vals.cuda(), scores.cuda()), fl.FilterConfig(**cfg))
+        eq(npy(got.pred_keypoints), want[0]); eq(npy(got.pred_peak_values), want[1]); eq(npy(got.instance_scores), want[2])
+    cen = torch.rand((B, I, 2), generator=g) * 120
+    cen[torch.rand((B, I), generator=g) < 0.1] = float("nan")
+    cfg = dict(min_instance_score=0.2, min_centroid_distance=9.0)
+    want = ofil.apply(cfg, scores=None, cen=cen.numpy(), cenv=scores.numpy())
+    got = fl.FilterPipeline.run(fl.FilterableOutputs(pred_centroids=cen.cuda(), pred_centroid_values=scores.cuda()), fl.FilterConfig(**cfg))
+    eq(npy(got.pred_centroids), want[3]); eq(npy(got.pred_centroid_values), want[4])
+
+
+def test_filters_on_the_bottomup_outputs(fl):
+    """End of the device chain: grouping outputs (B, I, N, 2) stay in HBM and are filtered there."""
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    dev = torch.device("cuda", 0)
+    edges = synthetic.chain_edges(5)
+    poses = synthetic.random_poses(5, 4, 3, 5, (256, 256), edges, margin=60.0, step=24.0)
+    cms, pafs = synthetic.render_batch(poses, (256, 256), 2, edges, dev)
+    pipe = BottomUpPostproc(5, edges, 4, tuple(cms.shape[-2:]), cms_stride=2, pafs_stride=2, device=dev)
+    k, v, s = pipe(cms, pafs).outputs(max_instances=6)
+    out = fl.FilterPipeline.run(fl.FilterableOutputs(k, v, s), fl.FilterConfig(min_visible_nodes=5, overlapping=True,
+                                                                                overlapping_threshold=0.8))
+    assert out.pred_keypoints.is_cuda and tuple(out.pred_keypoints.shape) == tuple(k.shape)
+    n_in = int((~torch.isnan(k).all(-1).all(-1)).sum())
+    n_out = int((~torch.isnan(out.pred_keypoints).all(-1).all(-1)).sum())
+    assert n_in == 12 and n_out == 12  # three well-separated full skeletons per frame survive
