@@ -314,3 +314,110 @@ class BottomUpPostproc:
             self.last_h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
             self.last_zero_copy = zero_copy
             return out
+
+
+class BottomUpHostStream:
+    """Software pipeline for batches that ARRIVE IN HOST MEMORY (a frame grabber, a decoder, another process).
+
+    `BottomUpPostproc.run_host` is synchronous: copy, compute, read back, and only then the next batch's copy
+    starts, so the PCIe link idles while the host unpacks results.  Here `depth` slots, each with its own CUDA
+    stream, staging buffer, table set and pinned result buffers, keep the link busy: while slot k's results are
+    read back and unpacked, slot k+1's confidence maps are already crossing PCIe.  The per-step work is unchanged
+    (every step copies its inputs host -> device and its results device -> host); only the idle gaps go.
+
+        stream = BottomUpHostStream(lambda: BottomUpPostproc(...), depth=2)
+        for cms_host, pafs_host in batches:            # pinned fp32 tensors
+            done = stream.submit(cms_host, pafs_host)  # results of the batch submitted `depth` calls ago, or None
+        rest = stream.drain()                          # the remaining results, in submission order
+
+    Results are `(instances, peak_scores, instance_scores)` per-sample lists like `PAFScorer.predict`.
+    """
+
+    def __init__(self, make_pipe, depth: int = 2, zero_copy_pafs: bool = True):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.pipes = [make_pipe() for _ in range(depth)]
+        self.device = self.pipes[0].device
+        self.zero_copy_pafs = zero_copy_pafs
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+            self.done = [torch.cuda.Event() for _ in range(depth)]
+        self._host = [None] * depth   # pinned result buffers per slot
+        self._busy = [False] * depth
+        self._next = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _result_buffers(self, k: int):
+        if self._host[k] is None:
+            b = self.pipes[k].buf
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._host[k] = dict(n_inst=pin(b["n_inst"]), status=pin(b["status"]), inst_xy=pin(b["inst_xy"]),
+                                 inst_val=pin(b["inst_val"]), inst_score=pin(b["inst_score"]))
+        return self._host[k]
+
+    def _collect(self, k: int):
+        self.done[k].synchronize()
+        self._busy[k] = False
+        h = self._host[k]
+        status = int(h["status"][0])
+        if status & N.STATUS_LSAP_INFEASIBLE:
+            raise ValueError("cost matrix is infeasible")
+        if status:
+            raise RuntimeError(f"bottom-up post-processing overflowed a fixed-capacity table (status 0x{status:x}); "
+                               "raise peak_cap / cand_cap / match_cap / inst_cap")
+        n = h["n_inst"].tolist()
+        xy, pv, sc = h["inst_xy"], h["inst_val"], h["inst_score"]
+        B = len(n)
+        # clone: the pinned buffers are reused by the slot's next batch
+        return ([xy[b, : n[b]].clone() for b in range(B)], [pv[b, : n[b]].clone() for b in range(B)],
+                [sc[b, : n[b]].clone() for b in range(B)])
+
+    def submit(self, cms_host: torch.Tensor, pafs_host: torch.Tensor):
+        """Enqueue one batch; returns the results of the batch that previously occupied the slot (or None)."""
+        k = self._next
+        self._next = (k + 1) % len(self.pipes)
+        out = self._collect(k) if self._busy[k] else None
+        pipe, st = self.pipes[k], self.streams[k]
+        if cms_host.dtype != torch.float32 or pafs_host.dtype != torch.float32:
+            raise TypeError("BottomUpHostStream expects fp32 host tensors")
+        channels_first = pafs_host.shape[1] == 2 * pipe.n_edges and pafs_host.shape[-1] != 2 * pipe.n_edges
+        view = (lambda t: t.permute(0, 2, 3, 1)) if channels_first else (lambda t: t)
+        h = self._result_buffers(k)
+        with torch.cuda.device(self.device), torch.cuda.stream(st):
+            if not hasattr(pipe, "_stage_cms") or pipe._stage_cms.shape != cms_host.shape:
+                pipe._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
+            pipe._stage_cms.copy_(cms_host, non_blocking=True)
+            alias = C.c_void_p()
+            zero_copy = bool(self.zero_copy_pafs and pafs_host.is_pinned() and N.lib.snb_host_device_pointer(
+                pafs_host.data_ptr(), C.byref(alias)) == N.OK and alias.value)
+            if zero_copy:
+                pv = view(pafs_host)
+                res = pipe._launch(N.ptr(pipe._stage_cms), pipe._stage_cms.stride(), alias.value, tuple(pv.shape), pv.stride())
+            else:
+                if not hasattr(pipe, "_stage_pafs") or pipe._stage_pafs.shape != pafs_host.shape:
+                    pipe._stage_pafs = torch.empty_strided(tuple(pafs_host.shape), pafs_host.stride(), dtype=torch.float32,
+                                                           device=self.device)
+                pipe._stage_pafs.copy_(pafs_host, non_blocking=True)
+                pv = view(pipe._stage_pafs)
+                res = pipe._launch(N.ptr(pipe._stage_cms), pipe._stage_cms.stride(), N.ptr(pv), tuple(pv.shape), pv.stride())
+            res.wait(st)
+            b = pipe.buf
+            for name in ("n_inst", "status", "inst_xy", "inst_val", "inst_score"):
+                h[name].copy_(b[name], non_blocking=True)
+            b["status"].zero_()  # sticky bits are reported once (after the copy above, in stream order)
+            self.done[k].record(st)
+        self._busy[k] = True
+        self.h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in h.values())
+        self.last_zero_copy = zero_copy
+        return out
+
+    def drain(self):
+        """Results of every batch still in flight, in submission order."""
+        outs = []
+        for i in range(len(self.pipes)):
+            k = (self._next + i) % len(self.pipes)
+            if self._busy[k]:
+                outs.append(self._collect(k))
+        return outs

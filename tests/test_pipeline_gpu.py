@@ -168,3 +168,34 @@ def test_outputs_topn_order_with_ties_and_nan():
     eq(npy(s[0]), npy(scores[0].cpu())[order])
     eq(npy(k[0]), npy(xy[0].cpu())[order])
     eq(npy(v[0]), npy(val[0].cpu())[order])
+
+
+def test_host_stream_pipelines_batches_and_matches_run_host():
+    """BottomUpHostStream (depth-2 H2D / compute / D2H pipeline) returns, in order, what run_host returns."""
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpHostStream, BottomUpPostproc
+
+    dev = torch.device("cuda", 0)
+    edges = synthetic.chain_edges(5)
+    make = lambda: BottomUpPostproc(5, edges, 3, (128, 128), cms_stride=2, pafs_stride=2, device=dev)
+    batches = []
+    for s in range(5):
+        poses = synthetic.random_poses(40 + s, 3, 2, 5, (256, 256), edges, margin=60.0, step=24.0)
+        cms, pafs = synthetic.render_batch(poses, (256, 256), 2, edges, dev, seed=s)
+        batches.append((cms.cpu().pin_memory(), pafs.cpu().pin_memory() if s % 2 == 0 else pafs.cpu()))  # pinned -> zero-copy
+    ref = make()
+    want = [ref.run_host(c, p) for c, p in batches]
+    hs = BottomUpHostStream(make, depth=2)
+    got = []
+    for c, p in batches:
+        r = hs.submit(c, p)
+        if r is not None:
+            got.append(r)
+    got += hs.drain()
+    assert len(got) == len(want) and hs.drain() == []
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert len(a) == len(b) == 3
+            for x, y in zip(a, b):
+                assert torch.equal(torch.nan_to_num(x, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
+    assert sum(len(x) for x in got[0][0]) == 6
