@@ -217,34 +217,56 @@ def run_ours(args, rank: int, world: int):
     inst, _, _ = res.to_lists()
     assert sum(len(x) for x in inst) == B * N_INST, "pipeline did not recover the planted instances"
 
-    # ---- device-resident timed region (value)
+    # ---- device-resident timed region (value).  Default: the eager multi-stream loop (one ctypes call per step).
+    # --graph: rotations of the pipeline are captured in a CUDA graph and replayed (one host launch per replay).
+    # Exactly --steps steps either way (the remainder of a partial replay runs eagerly).
     run_steps(max(args.warmup, 3))
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a_, b_ in ev:  # torch creates the cudaEvent lazily on first record; the C side re-records them in situ
-        a_.record(main)
-        b_.record(main)
-    torch.cuda.synchronize(dev)
+    graph, per_replay = None, 1
+    if args.graph and tail_stream is None:
+        from sleap_nn_b200.pipeline import capture_rotation
+
+        graph, per_replay = capture_rotation(pipes, inputs, streams, repeats=args.graph_repeats)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize(dev)
+    n_replays, n_rest = (args.steps // per_replay, args.steps % per_replay) if graph is not None else (0, args.steps)
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    all_streams = list({id(s): s for s in streams + ([tail_stream] if tail_stream is not None else [])}.values())
+
+    def timed_steps():
+        for _ in range(n_replays):
+            graph.replay()
+        if n_rest:
+            for s in all_streams:
+                s.wait_stream(main)
+            run_steps(n_rest)
+            for s in all_streams:
+                main.wait_stream(s)
+
     with ClockSampler(local) as clocks:
         barrier()
         t_begin.record(main)
-        all_streams = list({id(s): s for s in streams + ([tail_stream] if tail_stream is not None else [])}.values())
-        for s in all_streams:
-            s.wait_event(t_begin)
-        run_steps(args.steps, ev)
-        for s in all_streams:
-            done = torch.cuda.Event()
-            done.record(s)
-            main.wait_event(done)
+        timed_steps()
         t_end.record(main)
         barrier()
         # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
         if t_begin.elapsed_time(t_end) < 600 and rank == 0:
             t_fill = time.perf_counter()
             while time.perf_counter() - t_fill < 0.8:
-                run_steps(n_streams * 8)
+                timed_steps() if graph is not None else run_steps(n_streams * 8)
                 torch.cuda.synchronize(dev)
+    # in-situ timing of the detect kernel (events recorded by the C ABI around it) needs the eager loop: a separate,
+    # untimed pass of up to 200 steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 200))]
+    for a_, b_ in ev:  # torch creates the cudaEvent lazily on first record; the C side re-records them in situ
+        a_.record(main)
+        b_.record(main)
+    torch.cuda.synchronize(dev)
+    for s in all_streams:
+        s.wait_stream(main)
+    run_steps(len(ev), ev)
+    torch.cuda.synchronize(dev)
     ms_total = t_begin.elapsed_time(t_end)
     detect_ms = [a.elapsed_time(b) for a, b in ev]
     if world > 1:
@@ -328,7 +350,8 @@ def run_ours(args, rank: int, world: int):
             "config": dict(WORKLOAD, parallelism=f"frame-sharded x{world}, no collective", streams=n_streams,
                            input_batches=n_bufs, l2="inputs larger than L2: each batch is 872 MB and batches rotate",
                            tail="fused per-frame tail kernel" + (" on a high-priority second stream" if tail_stream is not None else ""),
-                           intermediate_tables_written=not args.lean),
+                           intermediate_tables_written=not args.lean,
+                           launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "in_flight": args.e2e_depth,
                     "pafs": ("sampled in place from pinned host memory (zero-copy): "
@@ -369,6 +392,10 @@ def main():
     ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the host-buffer pipeline (BottomUpHostStream)")
     ap.add_argument("--cpu-calls", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph-repeats", type=int, default=20, help="rotations of the pipeline captured per CUDA graph")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay CUDA graphs of --graph-repeats pipeline rotations instead of the eager launch loop (one host "
+                         "launch per replay; measured slower at N=1: the graph's three chains run in lockstep, see DESIGN.md)")
     ap.add_argument("--tail-stream", dest="tail_stream", action="store_true",
                     help="one detect stream + one high-priority tail stream instead of one stream per pipeline instance")
     ap.add_argument("--copy-pafs", action="store_true", help="e2e: stage the PAF tensor in HBM instead of sampling it in place")

@@ -199,3 +199,41 @@ def test_host_stream_pipelines_batches_and_matches_run_host():
             for x, y in zip(a, b):
                 assert torch.equal(torch.nan_to_num(x, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
     assert sum(len(x) for x in got[0][0]) == 6
+
+
+def test_cuda_graph_rotation_replays_the_chain():
+    """capture_rotation: a graph replay leaves in every pipe's tables exactly what the eager calls leave."""
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc, capture_rotation
+
+    dev = torch.device("cuda", 0)
+    edges = synthetic.chain_edges(5)
+    inputs = []
+    for s in range(3):
+        poses = synthetic.random_poses(70 + s, 4, 2, 5, (256, 256), edges, margin=60.0, step=24.0)
+        inputs.append(synthetic.render_batch(poses, (256, 256), 2, edges, dev, seed=s))
+    pipes = [BottomUpPostproc(5, edges, 4, (128, 128), cms_stride=2, pafs_stride=2, device=dev, max_instances=4) for _ in range(2)]
+    graph, n = capture_rotation(pipes, inputs)
+    assert n == 6
+    # the last step that touches pipe k in a rotation of 6 over 2 pipes / 3 inputs: step 4 -> pipe 0 / input 1, step 5 -> pipe 1 / input 2
+    want = []
+    for k, inp in ((0, 1), (1, 2)):
+        r = pipes[k](*inputs[inp])
+        want.append([t.clone() for t in (r.n_instances, r.instances, r.peak_scores, r.instance_scores, r.pred_keypoints)])
+    for p in pipes:
+        for name in ("n_inst", "inst_xy", "inst_val", "inst_score"):
+            p.buf[name].zero_()
+        p._out[0].zero_()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    for k in range(2):
+        b = pipes[k].buf
+        got = [b["n_inst"], b["inst_xy"], b["inst_val"], b["inst_score"], pipes[k]._out[0]]
+        assert int(got[0].sum()) == 8
+        n_i = got[0].tolist()
+        for g, w in zip(got[1:4], want[k][1:4]):
+            for f in range(4):  # rows beyond the count are scratch
+                assert torch.equal(torch.nan_to_num(g[f, : n_i[f]], nan=-1.0), torch.nan_to_num(w[f, : n_i[f]], nan=-1.0))
+        assert torch.equal(got[0], want[k][0])
+        assert torch.equal(torch.nan_to_num(got[4], nan=-1.0), torch.nan_to_num(want[k][4], nan=-1.0))
