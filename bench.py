@@ -247,7 +247,9 @@ def run_ours(args, rank: int, world: int):
     with ClockSampler(local) as clocks:
         barrier()
         t_begin.record(main)
+        h0 = time.perf_counter()
         timed_steps()
+        host_issue_us = (time.perf_counter() - h0) * 1e6 / max(args.steps, 1)  # host time to ISSUE one step (no sync)
         t_end.record(main)
         barrier()
         # keep the GPU busy a little longer if the region was too short for nvidia-smi to sample it
@@ -357,7 +359,7 @@ def run_ours(args, rank: int, world: int):
                     "pafs": ("sampled in place from pinned host memory (zero-copy): "
                              f"{paf_sector_bytes} B of 32-byte sectors per step instead of {host[0][1].numel() * 4} B"
                              if hs.last_zero_copy else "copied to the device every step")},
-            "gpu_launches": pipes[0].launches_per_call * args.steps,
+            "gpu_launches": pipes[0].launches_per_call * args.steps, "host_issue_us_per_step": host_issue_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": 335590000, "kernel": "local_peaks_detect_vec4<4,1,6>", "peak_source": which,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "avg_launch_ms": avg_detect_ms,

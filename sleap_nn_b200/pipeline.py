@@ -205,6 +205,7 @@ class BottomUpPostproc:
                 self._out = (f32(B, I, Nn, 2), f32(B, I, Nn), f32(B, I))
                 a.max_instances = I
                 a.out_kpts, a.out_vals, a.out_scores = (N.ptr(t) for t in self._out)
+        self._fast = {}
         self.tail_stream = tail_stream
         self._ev_handoff = self._ev_done = None
         a.tail_stream = a.ev_handoff = a.ev_tail_done = None
@@ -227,6 +228,16 @@ class BottomUpPostproc:
         detect kernel (for the benchmark's roofline figure).  `input_scale` / `eff_scale` (B,) are
         `PreprocInfo`'s scale factors, undone in the `.outputs()` tensors (streaming.py:190-196).
         """
+        # fast path: tensors this pipeline has already been launched on (a loop fed from a few fixed buffers, the
+        # steady state of a streaming pipeline) - a filled copy of the argument block is kept per input, so only the
+        # launch itself is left (~5 us of host time instead of ~25 us)
+        # (the block is a pure function of the key - pointers, strides, shapes, scale - so nothing is kept alive)
+        key = (cms.data_ptr(), pafs.data_ptr(), cms.stride(), pafs.stride(), tuple(cms.shape), tuple(pafs.shape),
+               cms.dtype, pafs.dtype, input_scale)
+        hit = self._fast.get(key) if (detect_events is None and eff_scale is None) else None
+        if hit is not None:
+            N.check(N.lib.snb_bottomup_postproc(C.byref(hit[0]), N.stream_ptr(self.device)), "snb_bottomup_postproc")
+            return hit[1]
         if not (cms.is_cuda and pafs.is_cuda) or cms.dtype != torch.float32 or pafs.dtype != torch.float32:
             raise TypeError("BottomUpPostproc expects fp32 CUDA tensors; use .run_host() for host buffers")
         if tuple(cms.shape) != (self.batch, self.n_nodes) + self.cms_hw:
@@ -237,8 +248,15 @@ class BottomUpPostproc:
             pafs = pafs.permute(0, 2, 3, 1)  # channels-first tensor -> the channels-last VIEW (no copy)
         elif pafs.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
-        return self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events,
-                            input_scale, eff_scale)
+        res = self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events,
+                           input_scale, eff_scale)
+        if detect_events is None and eff_scale is None:
+            if len(self._fast) >= 16:
+                self._fast.clear()
+            block = N.BottomUpArgs()
+            C.memmove(C.byref(block), C.byref(self._args), C.sizeof(N.BottomUpArgs))
+            self._fast[key] = (block, res)
+        return res
 
     def _launch(self, cms_ptr: int, cms_strides, pafs_ptr: int, pafs_shape, pafs_strides, detect_events=None,
                 input_scale: float = 1.0, eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
