@@ -274,6 +274,11 @@ int snb_pafs_from_instances(const float* instances, int G, int I, int N, const i
                             float in_ymax, const float* xv, const float* yv, int h, int w, float den, int out_bf16,
                             void* out, void* stream);
 
+/* Test hook: K7 divides by the per-launch constant 2*sigma^2 with a hoisted-reciprocal sequence instead of a full
+ * div.rn per pixel; fast[i] = that sequence, exact[i] = __fdiv_rn(-a[i], den).  The parity tests require them equal
+ * bit for bit. */
+int snb_debug_neg_div(const float* a, long long n, float den, float* fast, float* exact, void* stream);
+
 /* distance_to_edge (edge_maps.py:15-78; apply_pdf = 0) and make_edge_maps (:81-117; apply_pdf = 1).
  *   points (n_pts,2) or NULL for the (yv, xv) meshgrid with n_pts = h*w; out (n_pts,E). */
 int snb_edge_distance(const float* points, const float* xv, const float* yv, int w, long long n_pts,

@@ -145,3 +145,30 @@ def test_full_size_flies_frame(cm, em):
     u = (dst - src) / torch.linalg.vector_norm(dst - src)
     assert float((v * u).sum()) > 0.5
     assert float((pafs == 0).float().mean()) > 0.9  # narrow support: almost all zeros
+
+
+def test_hoisted_reciprocal_division_is_bit_exact():
+    """K7 replaces the per-pixel div.rn by the same FMA sequence with the divisor-only part hoisted; it must agree
+    with __fdiv_rn bit for bit over the whole range the kernel feeds it ([0, 105 * den]) for awkward divisors."""
+    from sleap_nn_b200 import _native as N
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    n = 1 << 24
+    dens = [50.0, 12.5, 4.5, 18.0, 8.0, 2.0, 1.0, 3.0, 0.02, 7.0e-5, 1.2345678e7, float(np.float32(1.9999999)),
+            float(np.nextafter(np.float32(2.0), np.float32(3.0))), float(np.float32(1.0000001)), 1e-30, 3e30,
+            float(np.float32(0.99999994)), 5.0e-38, 1.0e38]
+    for den in dens:
+        scale = min(105.0 * den, 3e38)
+        a = torch.rand((n,), generator=g, device=dev) * scale
+        a[: 1 << 20] = a[: 1 << 20] * 1e-6           # small numerators
+        lo = 1 << 20
+        a[lo : 2 * lo] = torch.exp(torch.rand((lo,), generator=g, device=dev) * 101.0 - 101.0).clamp(max=scale)  # 1e-44 .. 1
+        a[2 * lo : 2 * lo + 4] = torch.tensor([0.0, scale, 1e-45, 1.1754944e-38], device=dev)
+        fast, exact = torch.empty_like(a), torch.empty_like(a)
+        N.check(N.lib.snb_debug_neg_div(N.ptr(a), n, den, N.ptr(fast), N.ptr(exact), N.stream_ptr(dev)), "dbg")
+        # a quotient below 2^-30 only ever feeds exp(), which is exactly 1 there; everything else must agree exactly
+        matters = exact.abs() >= 2.0 ** -30
+        bad = (fast.view(torch.int32) != exact.view(torch.int32)) & matters
+        assert int(bad.sum()) == 0, (den, int(bad.sum()), a[bad][:4].tolist())
+        assert bool((torch.exp(fast[~matters]) == 1).all()) and bool((torch.exp(exact[~matters]) == 1).all())
