@@ -60,42 +60,79 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clocks / throttle reasons of the job's GPUs sampled every 100 ms while the timed region runs.
+
+    In-process NVML (nvidia-ml-py) when available - a query costs microseconds and takes no driver-wide lock;
+    falls back to spawning `nvidia-smi` (the recipe's clocks line).  Only rank 0 samples, for all GPUs of the job:
+    eight ranks each forking nvidia-smi five times a second measurably slowed the other ranks' kernel launches.
+    """
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+    def __init__(self, indices, enabled: bool = True):
+        self.indices, self.enabled = list(indices), enabled
+        self.sm, self.sm_max, self.reasons, self.n = [], None, set(), 0
+        self._stop, self._t, self._nvml = threading.Event(), None, None
+        if enabled:
+            try:
+                import pynvml
+
+                pynvml.nvmlInit()
+                self._nvml = pynvml
+                self._handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            except Exception:
+                self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        for h in self._handles:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.reasons |= {name for bit, name in bits.items() if mask & bit}
+        self.n += 1
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                              ",".join(str(i) for i in self.indices)], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if r and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+                self.sm_max = float(r[1])
+                self.reasons |= {n for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")}
+        self.n += 1
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self._nvml is not None else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml is not None else 0.3)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        if self.enabled:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": self.n, "gpus": self.indices, "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------- CPU port (oracle)
@@ -244,7 +281,7 @@ def run_ours(args, rank: int, world: int):
             for s in all_streams:
                 main.wait_stream(s)
 
-    with ClockSampler(local) as clocks:
+    with ClockSampler(range(world) if world > 1 else [local], enabled=(rank == 0)) as clocks:
         barrier()
         t_begin.record(main)
         h0 = time.perf_counter()
