@@ -309,6 +309,20 @@ int snb_classify_peaks(const float* class_maps, int n_samples, int K, int H, int
                        const int* channel_inds, long long P, int n_channels, float* probs, long long* g_peak,
                        long long* g_class, int* g_count, float* o_xy, float* o_val, float* o_prob, int* status,
                        void* stream);
+/* snb_classify_peaks on the PADDED peak table K1 writes (frame b owns slots [b*cap, b*cap + min(count, cap))), so
+ * the chain find_local_peaks -> classify stays on the device without a pack step.  xy_div: the peaks are divided by
+ * it before the class-map lookup and in o_xy (`peaks / class_maps_output_stride`, layers/bottomup_multiclass.py:86-87);
+ * probs is a scratch of n_samples*cap*K floats. */
+int snb_classify_peaks_padded(const float* class_maps, int n_samples, int K, int H, int W, long long ms, long long mk,
+                              long long mh, long long mw, const int* frame_count, int cap, const float* peak_xy,
+                              const float* peak_val, const int* peak_chan, float xy_div, int n_channels, float* probs,
+                              float* o_xy, float* o_val, float* o_prob, int* status, void* stream);
+/* BottomUpMultiClassLayer.postprocess after the classification (layers/bottomup_multiclass.py:99-146): xy (B,K,N,2) *
+ * class_stride / input_scale / eff_scale[b]; o_scores = nanmean of val over nodes; o_tracking = nanmean of prob;
+ * max_instances >= 0 applies _cap_instances_by_score (:148-190; np.argsort(scores)[::-1] order, NaN first). */
+int snb_multiclass_outputs(const float* xy, const float* val, const float* prob, int B, int K, int N, float class_stride,
+                           float input_scale, const float* eff_scale, int max_instances, float* o_kpts, float* o_vals,
+                           float* o_scores, float* o_tracking, void* stream);
 /* Per-group matches -> the concatenated (peak_inds, class_inds) of group_class_peaks in (sample, channel) order;
  * o_peak / o_class hold at most min(P, n_groups*K) entries, total[0] = how many were written. */
 int snb_pack_class_matches(const long long* g_peak, const long long* g_class, const int* g_count, int n_groups, int K,

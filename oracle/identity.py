@@ -150,3 +150,54 @@ def generate_class_maps(instances, img_hw, num_instances, class_inds, num_tracks
         points = instances[:, :num_instances, :, :].permute(0, 2, 1, 3)
     cms = multi_confmaps(points, xv, yv, sigma * output_stride)
     return class_maps(cms, class_inds, num_tracks, class_map_threshold)
+
+
+# ------------------------------------------------------------------ layer glue (layers/bottomup_multiclass.py)
+def cap_instances_by_score(instances, peak_scores, instance_scores, tracking_scores, max_instances: int):
+    """NaN-out all but the first `max_instances` entries of np.argsort(scores)[::-1] in frames with more present
+    classes than that.  layers/bottomup_multiclass.py:148-190 (NaN scores sort FIRST in that order)."""
+    inst, pv, sc, tr = (t.clone() for t in (instances, peak_scores, instance_scores, tracking_scores))
+    for b in range(sc.shape[0]):
+        row = sc[b].numpy()
+        present = int((~np.isnan(row)).sum())
+        if present <= max_instances:
+            continue
+        # ascending with NaN last and equal keys in index order, then reversed
+        asc = sorted(range(len(row)), key=lambda i: (1 if np.isnan(row[i]) else 0, row[i] if not np.isnan(row[i]) else 0.0, i))
+        keep = set(asc[::-1][:max_instances])
+        for k in range(len(row)):
+            if k not in keep:
+                inst[b, k] = float("nan"); pv[b, k] = float("nan"); sc[b, k] = float("nan"); tr[b, k] = float("nan")
+    return inst, pv, sc, tr
+
+
+def bottomup_multiclass_postprocess(cms, class_maps_t, cms_stride, class_stride, input_scale, eff_scale, max_instances=None,
+                                    threshold=0.2, refinement="integral", patch=5):
+    """BottomUpMultiClassLayer.postprocess, layers/bottomup_multiclass.py:75-146."""
+    from oracle import peaks as opeaks
+
+    pts, vals, si, ci = opeaks.local_peaks(cms, threshold, refinement, patch)
+    pts = pts * torch.tensor(float(cms_stride))
+    for_map = pts / torch.tensor(float(class_stride))
+    inst, pv, cp = classify_peaks_from_maps(class_maps_t, for_map, vals, si, ci, cms.shape[1])
+    inst = inst * torch.tensor(float(class_stride))
+    if input_scale != 1.0:
+        inst = inst / torch.tensor(float(input_scale), dtype=torch.float32)
+    if not bool((eff_scale == 1.0).all()):
+        inst = inst / eff_scale.view(-1, 1, 1, 1)
+
+    def nanmean_rows(t):
+        out = torch.empty(t.shape[:-1])
+        for idx in np.ndindex(*t.shape[:-1]):
+            row = t[idx]
+            keep = row[~torch.isnan(row)]
+            acc = torch.tensor(0.0)
+            for v in keep:
+                acc = acc + v
+            out[idx] = acc / len(keep) if len(keep) else float("nan")
+        return out
+
+    sc, tr = nanmean_rows(pv), nanmean_rows(cp)
+    if max_instances is not None:
+        inst, pv, sc, tr = cap_instances_by_score(inst, pv, sc, tr, max_instances)
+    return inst, pv, sc, tr

@@ -40,6 +40,9 @@ _HOT_FILES = [
     ("sleap_nn.inference.ops.identity", "sleap_nn/inference/ops/identity.py"),
     ("sleap_nn.data.identity", "sleap_nn/data/identity.py"),
     ("sleap_nn.inference.filters", "sleap_nn/inference/filters.py"),
+    # layer glue of the f3 row: only BottomUpMultiClassLayer.postprocess / _cap_instances_by_score are called, with a
+    # stand-in `self` (the base classes resolve to stubs)
+    ("sleap_nn.inference.layers.bottomup_multiclass", "sleap_nn/inference/layers/bottomup_multiclass.py"),
 ]
 
 _NAMESPACE_PKGS = [
@@ -48,6 +51,7 @@ _NAMESPACE_PKGS = [
     "sleap_nn.inference.ops",
     "sleap_nn.data",
     "sleap_nn.config",
+    "sleap_nn.inference.layers",
 ]
 
 
@@ -196,5 +200,6 @@ def ref() -> types.SimpleNamespace:
             data_identity=full["sleap_nn.data.identity"],
             providers=full["sleap_nn.data.providers"],
             filters=full["sleap_nn.inference.filters"],
+            bottomup_multiclass=full["sleap_nn.inference.layers.bottomup_multiclass"],
         )
     return _CACHE

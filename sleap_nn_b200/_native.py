@@ -69,6 +69,8 @@ SIGNATURES = {
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
     "snb_classify_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p,
                            _p, _p],
+    "snb_classify_peaks_padded": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _i, _p, _p, _p, _f, _i, _p, _p, _p, _p, _p, _p],
+    "snb_multiclass_outputs": [_p, _p, _p, _i, _i, _i, _f, _f, _p, _i, _p, _p, _p, _p, _p],
     "snb_pack_class_matches": [_p, _p, _p, _i, _i, _p, _p, _p, _p],
     "snb_class_inds_from_vectors": [_p, _i, _i, _p, _p, _p, _p, _p],
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(32)
 classify_peaks_kernel(const float* __restrict__ class_maps, int K, int H, int W, long long ms, long long mk,
                       long long mh, long long mw, const float* __restrict__ peak_xy,
                       const float* __restrict__ peak_val, const int* __restrict__ sample, const int* __restrict__ chan,
-                      long long P, int n_channels, float* __restrict__ probs, long long* __restrict__ g_peak,
+                      long long P, const int* __restrict__ frame_count, int cap, float xy_div, int n_channels,
+                      float* __restrict__ probs, long long* __restrict__ g_peak,
                       long long* __restrict__ g_class, int* __restrict__ g_count, float* __restrict__ o_xy,
                       float* __restrict__ o_val, float* __restrict__ o_prob, int* __restrict__ status) {
   __shared__ int members[ID_MAX_DIM];
@@ -58,12 +59,16 @@ classify_peaks_kernel(const float* __restrict__ class_maps, int K, int H, int W,
     }
   }
   if (g_count && lane == 0) g_count[blockIdx.x] = 0;
-  // members of the group in ascending peak index (torch.nonzero(mask) order, ops/identity.py:42-46)
+  // members of the group in ascending peak index (torch.nonzero(mask) order, ops/identity.py:42-46).  Padded
+  // tables (frame_count != NULL: frame s owns slots [s*cap, s*cap + min(count, cap)), the layout K1 writes) only
+  // scan their own frame.
   int n = 0;
   bool too_many = false;
-  for (long long base = 0; base < P; base += 32) {
+  const long long scan_lo = frame_count ? (long long)s * cap : 0;
+  const long long scan_hi = frame_count ? scan_lo + min(frame_count[s], cap) : P;
+  for (long long base = scan_lo; base < scan_hi; base += 32) {
     const long long i = base + lane;
-    const bool hit = i < P && sample[i] == s && chan[i] == c;
+    const bool hit = i < scan_hi && (frame_count ? true : sample[i] == s) && chan[i] == c;
     const unsigned m = __ballot_sync(FULL, hit);
     if (hit) {
       const int slot = n + __popc(m & ((1u << lane) - 1));
@@ -82,7 +87,9 @@ classify_peaks_kernel(const float* __restrict__ class_maps, int K, int H, int W,
     for (int t = lane; t < n * K; t += 32) {
       const int r = t / K, k = t - r * K;
       const int p = members[r];
-      const int ry = class_map_sub(peak_xy[2 * p + 1], H - 1), rx = class_map_sub(peak_xy[2 * p], W - 1);
+      // xy_div: `peaks / class_maps_output_stride` of the multi-class layer (layers/bottomup_multiclass.py:86-87)
+      const int ry = class_map_sub(__fdiv_rn(peak_xy[2 * p + 1], xy_div), H - 1);
+      const int rx = class_map_sub(__fdiv_rn(peak_xy[2 * p], xy_div), W - 1);
       probs[(long long)p * K + k] = __ldg(class_maps + (long long)s * ms + (long long)k * mk + (long long)ry * mh + (long long)rx * mw);
     }
     __syncwarp();
@@ -137,8 +144,8 @@ classify_peaks_kernel(const float* __restrict__ class_maps, int K, int H, int W,
       }
       if (o_xy) {
         const long long o = ((long long)s * K + k) * n_channels + c;
-        o_xy[2 * o] = peak_xy[2 * p];
-        o_xy[2 * o + 1] = peak_xy[2 * p + 1];
+        o_xy[2 * o] = __fdiv_rn(peak_xy[2 * p], xy_div);
+        o_xy[2 * o + 1] = __fdiv_rn(peak_xy[2 * p + 1], xy_div);
         o_val[o] = peak_val[p];
         o_prob[o] = pr;
       }
@@ -284,6 +291,76 @@ class_maps_kernel(const float* __restrict__ cms, const int* __restrict__ class_i
   }
 }
 
+// BottomUpMultiClassLayer.postprocess after classify_peaks_from_maps (layers/bottomup_multiclass.py:99-146), one
+// warp per frame: instances * class_maps_output_stride, / input_scale, / eff_scale[b] (each a separately rounded fp32
+// op; multiplying / dividing by exactly 1 is the identity, so the reference's `!= 1.0` short-circuits need no
+// branch), instance score = nanmean of the peak values over nodes, tracking score = nanmean of the class
+// probabilities, then _cap_instances_by_score (:148-190): when more than max_instances classes are present, keep
+// the first max_instances of np.argsort(scores)[::-1] - NaN scores FIRST (absent classes do take slots; a quirk
+// kept from the reference), then descending, equal scores by descending index - and NaN-out the rest.
+__global__ void __launch_bounds__(32)
+multiclass_outputs_kernel(const float* __restrict__ xy, const float* __restrict__ val, const float* __restrict__ prob,
+                          int K, int N, float class_stride, float input_scale, const float* __restrict__ eff_scale,
+                          int max_instances, float* __restrict__ o_kpts, float* __restrict__ o_vals,
+                          float* __restrict__ o_scores, float* __restrict__ o_tracking) {
+  extern __shared__ float s_score[];                               // K
+  unsigned char* s_drop = reinterpret_cast<unsigned char*>(s_score + K);  // K
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const float eff = eff_scale ? eff_scale[b] : 1.f;
+  for (int k = lane; k < K; k += 32) {
+    const long long base = ((long long)b * K + k) * N;
+    float sv = 0.f, sp = 0.f;
+    int nv = 0, np_ = 0;
+    for (int n = 0; n < N; ++n) {
+      const float v = val[base + n], p = prob[base + n];
+      if (v == v) { sv = __fadd_rn(sv, v); ++nv; }
+      if (p == p) { sp = __fadd_rn(sp, p); ++np_; }
+    }
+    s_score[k] = __fdiv_rn(sv, (float)nv);  // 0/0 = NaN for a class without peaks, like torch.nanmean
+    o_tracking[(long long)b * K + k] = __fdiv_rn(sp, (float)np_);
+    s_drop[k] = 0;
+  }
+  __syncwarp();
+  if (max_instances >= 0) {
+    int present = 0;
+    for (int k = lane; k < K; k += 32) present += (s_score[k] == s_score[k]) ? 1 : 0;
+    for (int d = 16; d > 0; d >>= 1) present += __shfl_xor_sync(FULL, present, d);
+    if (present > max_instances) {
+      for (int k = lane; k < K; k += 32) {  // rank of class k in np.argsort(scores)[::-1]
+        const float sk = s_score[k];
+        const bool kn = sk != sk;
+        int rank = 0;
+        for (int j = 0; j < K; ++j) {
+          if (j == k) continue;
+          const float sj = s_score[j];
+          const bool jn = sj != sj;
+          bool before;
+          if (kn || jn) before = (kn && jn) ? (j > k) : jn;
+          else before = (sj > sk) || (sj == sk && j > k);
+          rank += before ? 1 : 0;
+        }
+        s_drop[k] = rank >= max_instances ? 1 : 0;
+      }
+    }
+    __syncwarp();
+  }
+  for (int t = lane; t < K * N; t += 32) {
+    const int k = t / N;
+    const long long src = (long long)b * K * N + t;
+    const bool drop = s_drop[k] != 0;
+    float x = __fdiv_rn(__fdiv_rn(__fmul_rn(xy[2 * src], class_stride), input_scale), eff);
+    float y = __fdiv_rn(__fdiv_rn(__fmul_rn(xy[2 * src + 1], class_stride), input_scale), eff);
+    o_kpts[2 * src] = drop ? NAN : x;
+    o_kpts[2 * src + 1] = drop ? NAN : y;
+    o_vals[src] = drop ? NAN : val[src];
+  }
+  for (int k = lane; k < K; k += 32) {
+    const long long o = (long long)b * K + k;
+    o_scores[o] = s_drop[k] ? NAN : s_score[k];
+    if (s_drop[k]) o_tracking[o] = NAN;
+  }
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -302,8 +379,41 @@ extern "C" int snb_classify_peaks(const float* class_maps, int n_samples, int K,
   if (groups == 0) return SNB_OK;
   if (groups > 0x7fffffffLL) return SNB_ERR_UNSUPPORTED;
   classify_peaks_kernel<<<(unsigned)groups, 32, 0, (cudaStream_t)stream>>>(
-      class_maps, K, H, W, ms, mk, mh, mw, peak_xy, peak_val, sample_inds, channel_inds, P, n_channels, probs, g_peak,
-      g_class, g_count, o_xy, o_val, o_prob, status);
+      class_maps, K, H, W, ms, mk, mh, mw, peak_xy, peak_val, sample_inds, channel_inds, P, nullptr, 0, 1.0f, n_channels,
+      probs, g_peak, g_class, g_count, o_xy, o_val, o_prob, status);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_classify_peaks_padded(const float* class_maps, int n_samples, int K, int H, int W, long long ms,
+                                         long long mk, long long mh, long long mw, const int* frame_count, int cap,
+                                         const float* peak_xy, const float* peak_val, const int* peak_chan,
+                                         float xy_div, int n_channels, float* probs, float* o_xy, float* o_val,
+                                         float* o_prob, int* status, void* stream) {
+  if (n_samples < 0 || n_channels < 0 || K < 0 || cap <= 0 || !status || !class_maps || !frame_count || !peak_xy ||
+      !peak_val || !peak_chan || !probs || !o_xy || !o_val || !o_prob)
+    return SNB_ERR_BAD_ARG;
+  const long long groups = (long long)n_samples * n_channels;
+  if (groups == 0) return SNB_OK;
+  if (groups > 0x7fffffffLL) return SNB_ERR_UNSUPPORTED;
+  classify_peaks_kernel<<<(unsigned)groups, 32, 0, (cudaStream_t)stream>>>(
+      class_maps, K, H, W, ms, mk, mh, mw, peak_xy, peak_val, nullptr, peak_chan, (long long)n_samples * cap, frame_count,
+      cap, xy_div, n_channels, probs, nullptr, nullptr, nullptr, o_xy, o_val, o_prob, status);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_multiclass_outputs(const float* xy, const float* val, const float* prob, int B, int K, int N,
+                                      float class_stride, float input_scale, const float* eff_scale, int max_instances,
+                                      float* o_kpts, float* o_vals, float* o_scores, float* o_tracking, void* stream) {
+  if (B < 0 || K < 0 || N < 0 || !xy || !val || !prob || !o_kpts || !o_vals || !o_scores || !o_tracking)
+    return SNB_ERR_BAD_ARG;
+  if (B == 0 || K == 0) return SNB_OK;
+  const size_t smem = (size_t)K * (sizeof(float) + 1);
+  if (smem > 48 * 1024) return SNB_ERR_UNSUPPORTED;
+  multiclass_outputs_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(xy, val, prob, K, N, class_stride, input_scale,
+                                                                  eff_scale, max_instances, o_kpts, o_vals, o_scores,
+                                                                  o_tracking);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

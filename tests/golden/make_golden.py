@@ -552,6 +552,42 @@ def f4_filters(R):
     save("ref_f4_filters.npz", **out)
 
 
+def f3_multiclass_layer(R):
+    """BottomUpMultiClassLayer.postprocess (inference/layers/bottomup_multiclass.py:75-190) called on the unmodified
+    reference class with a stand-in `self`."""
+    import types
+
+    L = R.bottomup_multiclass.BottomUpMultiClassLayer
+    g = torch.Generator().manual_seed(606)
+    B, Nn, K, H, W = 3, 4, 4, 96, 128
+    edges = synth.chain_edges(Nn)
+    poses = synth.make_poses(61, B, 3, Nn, (H, W), edges=edges, margin=24.0, step=14.0)
+    xv, yv = R.data_utils.make_grid_vectors(H, W, 2)
+    cms = torch.stack([R.confidence_maps.make_multi_confmaps(poses[b : b + 1], xv, yv, 3.0)[0] for b in range(B)])
+    cms = cms + torch.rand(cms.shape, generator=g) * 1e-3
+    # class maps at stride 4: each animal's neighbourhood votes for "its" class, plus noise; frame 2 has an animal no
+    # class claims strongly
+    logits = torch.randn((B, K, H // 4, W // 4), generator=g) * 0.3
+    yy, xx = torch.meshgrid(torch.arange(H // 4) * 4.0, torch.arange(W // 4) * 4.0, indexing="ij")
+    for b in range(B):
+        for i in range(3):
+            c = poses[b, i].mean(0)
+            logits[b, (i + b) % K] += 4.0 * torch.exp(-((xx - c[0]) ** 2 + (yy - c[1]) ** 2) / (2 * 18.0**2))
+    class_maps = torch.softmax(logits, dim=1)
+    out = dict(cms=cms, class_maps=class_maps)
+    for tag, scale, eff, cap in (("plain", 1.0, [1.0, 1.0, 1.0], None), ("scaled", 0.5, [1.0, 0.8, 1.25], None),
+                                 ("cap2", 1.0, [1.0, 1.0, 1.0], 2), ("cap1", 0.5, [2.0, 1.0, 1.0], 1)):
+        cfg = types.SimpleNamespace(peak_threshold=0.2, effective_refinement="integral", integral_patch_size=5,
+                                    max_instances=None, return_confmaps=False, return_class_maps=False)
+        me = types.SimpleNamespace(postprocess_config=cfg, cms_output_stride=2, class_maps_output_stride=4, max_instances=cap,
+                                   _cap_instances_by_score=L._cap_instances_by_score)
+        info = R.preprocess_info.PreprocInfo(eff_scale=torch.tensor(eff), input_scale=scale)
+        o = L.postprocess(me, {"MultiInstanceConfmapsHead": cms, "ClassMapsHead": class_maps}, info)
+        out.update({f"{tag}_kpts": o.pred_keypoints, f"{tag}_vals": o.pred_peak_values, f"{tag}_scores": o.instance_scores,
+                    f"{tag}_tracking": o.instance_tracking_scores})
+    save("ref_f3_multiclass_layer.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -567,6 +603,7 @@ def main():
     f1_outputs(R)
     f2_layers(R)
     f3_identity(R)
+    f3_multiclass_layer(R)
     f4_batched_targets(R)
     f4_filters(R)
 

@@ -128,3 +128,30 @@ def test_class_maps_vs_oracle_random(dident):
         got = dident.make_class_maps(cms.cuda(), ci.cuda(), K, 0.2)
         assert tuple(got.shape) == (1, K, h, w)
         close(npy(got), npy(want), rtol=1e-6)
+
+
+def test_bottomup_multiclass_layer_golden():
+    """BottomUpMultiClassPostproc == the reference layer's postprocess (peaks -> class assignment -> scale ladder ->
+    nanmean scores -> cap), slot k == class k; which slots survive is bit-exact, coordinates within 1e-4 px."""
+    from sleap_nn_b200.inference.layers import BottomUpMultiClassPostproc
+
+    d = golden("ref_f3_multiclass_layer.npz")
+    cms, cmaps = T(d["cms"]).cuda(), T(d["class_maps"]).cuda()
+    for tag, scale, eff, cap in (("plain", 1.0, [1.0, 1.0, 1.0], None), ("scaled", 0.5, [1.0, 0.8, 1.25], None),
+                                 ("cap2", 1.0, [1.0, 1.0, 1.0], 2), ("cap1", 0.5, [2.0, 1.0, 1.0], 1)):
+        post = BottomUpMultiClassPostproc(0.2, "integral", 5, cms_output_stride=2, class_maps_output_stride=4, max_instances=cap)
+        k, v, s, t = post(cms, cmaps, input_scale=scale, eff_scale=torch.tensor(eff))
+        post.check()
+        assert k.is_cuda and tuple(k.shape) == d[f"{tag}_kpts"].shape
+        eq(np.isnan(npy(k)), np.isnan(d[f"{tag}_kpts"]))
+        close(npy(k), d[f"{tag}_kpts"], atol=1e-4); eq(npy(v), d[f"{tag}_vals"])
+        close(npy(s), d[f"{tag}_scores"], rtol=1e-6); close(npy(t), d[f"{tag}_tracking"], rtol=1e-6)
+    # a permuted class-map view is read in place; a NaN probability is reported like scipy's ValueError
+    post = BottomUpMultiClassPostproc(0.2, "integral", 5, 2, 4)
+    view = cmaps.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    k2, *_ = post(cms, view)
+    close(npy(k2), d["plain_kpts"], atol=1e-4)
+    bad = cmaps.clone(); bad[:, 1] = float("nan")
+    post(cms, bad)
+    with pytest.raises(ValueError):
+        post.check()
