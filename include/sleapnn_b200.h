@@ -371,6 +371,20 @@ int snb_filter_instances(const snb_filter_config* cfg, int B, int I, int N, cons
                          const float* scores, const float* centroids, const float* centroid_vals, float* o_kpts,
                          float* o_vals, float* o_scores, float* o_centroids, float* o_centroid_vals, void* stream);
 
+/* The numeric cores of the Labels-level filters (inference/ops/filters.py), float64 like the numpy arrays they read,
+ * for all frames of a Labels object in one launch.
+ * snb_nms_greedy_f64: _nms_greedy_iou (:330-366) / _nms_greedy_oks (:369-404) with _compute_iou_one_to_many (:407-436),
+ *   _instance_bbox (:300-316) and _compute_oks (:439-495).  pts (total, N, 2), scores (total); frame f owns instances
+ *   [frame_start[f], frame_start[f+1]) (max_per_frame = the largest frame, sizes shared memory); method 0 = iou, 1 = oks.
+ *   keep[frame_start[f] + k], k < keep_count[f]: kept LOCAL indices in keep order (np.argsort(scores)[::-1] visiting
+ *   order); remaining slots -1.
+ * snb_instance_stats_f64: _count_visible_nodes (:178-190) and _mean_node_score (:193-226; point_scores / mean_score
+ *   may be NULL). */
+int snb_nms_greedy_f64(const double* pts, const double* scores, const int* frame_start, int n_frames, int max_per_frame,
+                       int N, int method, double threshold, double kappa, int* keep, int* keep_count, void* stream);
+int snb_instance_stats_f64(const double* pts, const double* point_scores, long long total, int N, int* n_visible,
+                           double* mean_score, void* stream);
+
 /* ------------------------------------------------------------ fused bottom-up post-processing
  *
  * snb_bottomup_postproc enqueues K1 -> K4 -> K5 -> K6 on `stream` with padded tables: no host

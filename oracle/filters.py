@@ -170,3 +170,78 @@ def apply(cfg: Dict, kpts: Optional[np.ndarray] = None, vals: Optional[np.ndarra
         for b, i in drops:
             nan_out(b, i)
     return tuple(f.values())
+
+
+# --------------------------------------------------------------------------------------------------------------
+# The float64 numpy cores of the Labels-level filters, sleap_nn/inference/ops/filters.py (`ops/filters.py:NN`).
+# --------------------------------------------------------------------------------------------------------------
+def instance_bbox64(pts: np.ndarray) -> np.ndarray:
+    """ops/filters.py:300-316: [xmin, ymin, xmax, ymax] of the rows without NaN, zeros when there is none."""
+    rows = pts[_rows_present(pts)]
+    if rows.shape[0] == 0:
+        return np.zeros(4)
+    return np.array([rows[:, 0].min(), rows[:, 1].min(), rows[:, 0].max(), rows[:, 1].max()])
+
+
+def iou64(a: np.ndarray, b: np.ndarray) -> float:
+    """ops/filters.py:407-436 for one pair of boxes."""
+    iw = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
+    ih = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+    inter = iw * ih
+    union = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+    return inter / union if union > 0 else 0.0
+
+
+def oks64(a: np.ndarray, b: np.ndarray, kappa: float = 0.1) -> float:
+    """ops/filters.py:439-495: a's own bbox area is the scale; mean over the keypoints present in both."""
+    va, vb = _rows_present(a), _rows_present(b)
+    both = va & vb
+    if not both.any() or va.sum() < 2:
+        return 0.0
+    own = a[va]
+    scale_sq = (own[:, 0].max() - own[:, 0].min()) * (own[:, 1].max() - own[:, 1].min())
+    if scale_sq <= 0:
+        return 0.0
+    total, cnt = 0.0, 0
+    for n in np.flatnonzero(both):
+        d2 = (a[n, 0] - b[n, 0]) ** 2 + (a[n, 1] - b[n, 1]) ** 2
+        total += float(np.exp(-d2 / (2 * scale_sq * kappa**2)))
+        cnt += 1
+    return total / cnt
+
+
+def nms_greedy64(points_list, scores, threshold: float, method: str):
+    """ops/filters.py:330-404: visit in np.argsort(scores)[::-1] order (NaN first, ties by descending index), keep an
+    instance unless an already kept one is more similar than `threshold` (similarity(kept, candidate))."""
+    n = len(points_list)
+    asc = sorted(range(n), key=lambda i: (1 if np.isnan(scores[i]) else 0, scores[i] if not np.isnan(scores[i]) else 0.0, i))
+    boxes = [instance_bbox64(np.asarray(p, float)) for p in points_list]
+    kept = []
+    for idx in asc[::-1]:
+        if method == "iou":
+            hit = any(iou64(boxes[k], boxes[idx]) > threshold for k in kept)
+        else:
+            hit = any(oks64(np.asarray(points_list[k], float), np.asarray(points_list[idx], float)) > threshold for k in kept)
+        if not hit:
+            kept.append(idx)
+    return kept
+
+
+def count_visible64(pts: np.ndarray) -> int:
+    """ops/filters.py:178-190."""
+    return int(_rows_present(np.asarray(pts, float)).sum())
+
+
+def mean_node_score64(pts: np.ndarray, point_scores) -> Optional[float]:
+    """ops/filters.py:193-226: mean of the finite scores of the visible nodes; 0.0 when there is none."""
+    if point_scores is None or len(point_scores) == 0:
+        return None
+    vis = _rows_present(np.asarray(pts, float))
+    sc = np.asarray(point_scores, float)[vis]
+    sc = sc[~np.isnan(sc)]
+    if len(sc) == 0:
+        return 0.0
+    total = 0.0
+    for v in sc:
+        total += float(v)
+    return total / len(sc)

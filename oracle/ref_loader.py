@@ -40,6 +40,7 @@ _HOT_FILES = [
     ("sleap_nn.inference.ops.identity", "sleap_nn/inference/ops/identity.py"),
     ("sleap_nn.data.identity", "sleap_nn/data/identity.py"),
     ("sleap_nn.inference.filters", "sleap_nn/inference/filters.py"),
+    ("sleap_nn.inference.ops.filters", "sleap_nn/inference/ops/filters.py"),  # numpy cores + Labels-level wrappers (sio stubbed)
     # layer glue of the f3 row: only BottomUpMultiClassLayer.postprocess / _cap_instances_by_score are called, with a
     # stand-in `self` (the base classes resolve to stubs)
     ("sleap_nn.inference.layers.bottomup_multiclass", "sleap_nn/inference/layers/bottomup_multiclass.py"),
@@ -200,6 +201,7 @@ def ref() -> types.SimpleNamespace:
             data_identity=full["sleap_nn.data.identity"],
             providers=full["sleap_nn.data.providers"],
             filters=full["sleap_nn.inference.filters"],
+            ops_filters=full["sleap_nn.inference.ops.filters"],
             bottomup_multiclass=full["sleap_nn.inference.layers.bottomup_multiclass"],
         )
     return _CACHE

@@ -76,6 +76,8 @@ SIGNATURES = {
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
     "snb_class_maps": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
     "snb_filter_instances": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_nms_greedy_f64": [_p, _p, _p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _p, _p],
+    "snb_instance_stats_f64": [_p, _p, _ll, _i, _p, _p, _p],
     "snb_bottomup_postproc": [_p, _p],
     "snb_bottomup_launches_per_call": [_p],
     "snb_bottomup_args_size": [],

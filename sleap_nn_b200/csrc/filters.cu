@@ -290,6 +290,125 @@ filter_instances_kernel(FilterCfg cfg, int I, int N, const float* __restrict__ i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// The Labels-level filters of sleap_nn/inference/ops/filters.py (cited ops/filters.py:NN) work on float64 numpy
+// arrays taken from `instance.numpy()`; these are their numeric cores, for all frames of a Labels object in one
+// launch (CSR over frames).  Arithmetic is float64 throughout, like numpy's.
+// ------------------------------------------------------------------------------------------------------------------
+struct BoxD {
+  double x1, y1, x2, y2;
+  int rows;
+};
+
+// _compute_iou_one_to_many (ops/filters.py:407-436) on _instance_bbox boxes (:300-316; no valid point -> [0,0,0,0])
+__device__ __forceinline__ double iou_f64(const BoxD& a, const BoxD& b) {
+  const double iw = fmax(0.0, fmin(a.x2, b.x2) - fmax(a.x1, b.x1));
+  const double ih = fmax(0.0, fmin(a.y2, b.y2) - fmax(a.y1, b.y1));
+  const double inter = iw * ih;
+  const double uni = (a.x2 - a.x1) * (a.y2 - a.y1) + (b.x2 - b.x1) * (b.y2 - b.y1) - inter;
+  return uni > 0.0 ? inter / uni : 0.0;
+}
+
+// _compute_oks(points_a, points_b) (ops/filters.py:439-495): a is the instance that was just KEPT, scale = its bbox area
+__device__ __forceinline__ double oks_f64(const double* __restrict__ a, const BoxD& abox, const double* __restrict__ b,
+                                          int N, double kappa) {
+  double sum = 0.0;
+  int cnt = 0;
+  if (abox.rows < 2) return 0.0;
+  const double scale_sq = (abox.x2 - abox.x1) * (abox.y2 - abox.y1);
+  if (scale_sq <= 0.0) return 0.0;
+  const double den = 2.0 * scale_sq * (kappa * kappa);
+  for (int n = 0; n < N; ++n) {
+    const double ax = a[2 * n], ay = a[2 * n + 1], bx = b[2 * n], by = b[2 * n + 1];
+    if (ax != ax || ay != ay || bx != bx || by != by) continue;
+    const double dx = ax - bx, dy = ay - by;
+    sum += exp(-(dx * dx + dy * dy) / den);
+    ++cnt;
+  }
+  return cnt ? sum / (double)cnt : 0.0;
+}
+
+// np.argsort(scores)[::-1] (ops/filters.py:349, :387): ascending with NaN last and equal keys in index order,
+// reversed -> NaN first, then descending, equal keys by DESCENDING index.
+__device__ __forceinline__ bool argsort_reversed_before(double a, int ia, double b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an || bn) return (an && bn) ? (ia > ib) : an;
+  if (a != b) return a > b;
+  return ia > ib;
+}
+
+// One warp per frame: _nms_greedy_iou / _nms_greedy_oks (ops/filters.py:330-404).  keep[start .. start+count) = the kept
+// LOCAL indices in keep order (decreasing score), the rest of the frame's slots -1.
+__global__ void __launch_bounds__(32)
+nms_greedy_f64_kernel(const double* __restrict__ pts, const double* __restrict__ scores, const int* __restrict__ frame_start,
+                      int N, int method, double threshold, double kappa, int* __restrict__ keep,
+                      int* __restrict__ keep_count) {
+  extern __shared__ __align__(8) unsigned char s_raw[];
+  const int f = blockIdx.x, lane = threadIdx.x;
+  const int s0 = frame_start[f], n = frame_start[f + 1] - s0;
+  BoxD* box = reinterpret_cast<BoxD*>(s_raw);  // n
+  int* order = reinterpret_cast<int*>(box + n);
+  int* kept = order + n;
+  for (int i = lane; i < n; i += 32) {
+    BoxD bx{0.0, 0.0, 0.0, 0.0, 0};
+    const double* p = pts + (long long)(s0 + i) * N * 2;
+    for (int k = 0; k < N; ++k) {
+      const double x = p[2 * k], y = p[2 * k + 1];
+      if (x == x && y == y) {
+        if (bx.rows == 0) { bx.x1 = bx.x2 = x; bx.y1 = bx.y2 = y; }
+        else { bx.x1 = fmin(bx.x1, x); bx.x2 = fmax(bx.x2, x); bx.y1 = fmin(bx.y1, y); bx.y2 = fmax(bx.y2, y); }
+        ++bx.rows;
+      }
+    }
+    box[i] = bx;
+    keep[s0 + i] = -1;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (j != i && argsort_reversed_before(scores[s0 + j], j, scores[s0 + i], i)) ? 1 : 0;
+    order[rank] = i;
+  }
+  __syncwarp();
+  int nk = 0;
+  for (int r = 0; r < n; ++r) {
+    const int idx = order[r];
+    bool hit = false;
+    for (int k = lane; k < nk && !hit; k += 32) {
+      const int a = kept[k];
+      const double sim = method == 1 ? oks_f64(pts + (long long)(s0 + a) * N * 2, box[a], pts + (long long)(s0 + idx) * N * 2, N, kappa)
+                                     : iou_f64(box[a], box[idx]);
+      hit = sim > threshold;  // survivors are the ones with similarity <= threshold
+    }
+    if (!__any_sync(FULL, hit)) {
+      if (lane == 0) { kept[nk] = idx; keep[s0 + nk] = idx; }
+      ++nk;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) keep_count[f] = nk;
+}
+
+// _count_visible_nodes (ops/filters.py:178-190) and _mean_node_score (:193-226) for every instance: one thread each.
+__global__ void instance_stats_f64_kernel(const double* __restrict__ pts, const double* __restrict__ point_scores,
+                                          long long total, int N, int* __restrict__ n_visible,
+                                          double* __restrict__ mean_score) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int nv = 0, ns = 0;
+  double sum = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double x = pts[(i * N + k) * 2], y = pts[(i * N + k) * 2 + 1];
+    if (x == x && y == y) {
+      ++nv;
+      if (point_scores) {
+        const double v = point_scores[i * N + k];
+        if (v == v) { sum += v; ++ns; }
+      }
+    }
+  }
+  n_visible[i] = nv;
+  if (mean_score) mean_score[i] = ns ? sum / (double)ns : 0.0;  // no visible node / no finite score -> 0.0
+}
+
 }  // namespace snb
 
 using namespace snb;
@@ -314,6 +433,34 @@ extern "C" int snb_filter_instances(const snb_filter_config* cfg, int B, int I, 
                     cfg->min_centroid_distance_sq};
   filter_instances_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(c, I, N, kpts, vals, scores, centroids, centroid_vals,
                                                                o_kpts, o_vals, o_scores, o_centroids, o_centroid_vals);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_nms_greedy_f64(const double* pts, const double* scores, const int* frame_start, int n_frames,
+                                  int max_per_frame, int N, int method, double threshold, double kappa, int* keep,
+                                  int* keep_count, void* stream) {
+  if (n_frames < 0 || N < 0 || max_per_frame < 0 || (method != 0 && method != 1)) return SNB_ERR_BAD_ARG;
+  if (n_frames == 0) return SNB_OK;
+  if (!pts || !scores || !frame_start || !keep || !keep_count) return SNB_ERR_BAD_ARG;
+  const size_t smem = (size_t)max_per_frame * (sizeof(BoxD) + 2 * sizeof(int)) + 16;
+  if (smem > 200 * 1024) return SNB_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(nms_greedy_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return SNB_ERR_CUDA_LAUNCH;
+  nms_greedy_f64_kernel<<<n_frames, 32, smem, (cudaStream_t)stream>>>(pts, scores, frame_start, N, method, threshold, kappa,
+                                                                     keep, keep_count);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" int snb_instance_stats_f64(const double* pts, const double* point_scores, long long total, int N,
+                                      int* n_visible, double* mean_score, void* stream) {
+  if (total < 0 || N < 0) return SNB_ERR_BAD_ARG;
+  if (total == 0) return SNB_OK;
+  if (!pts || !n_visible) return SNB_ERR_BAD_ARG;
+  instance_stats_f64_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(pts, point_scores, total, N,
+                                                                                             n_visible, mean_score);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

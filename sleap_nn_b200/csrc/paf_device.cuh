@@ -373,6 +373,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       }
       const int pa = f.np_[f.ns[sn] + sp], pb = f.np_[f.ns[dn] + dp];
       const int ia = f.owner[pa], ib = f.owner[pb];
+      __syncwarp();  // every lane has read owner[] before lane 0 rewrites it below (WAR hazard found by racecheck)
       if (ia < 0 && ib < 0) {
         int mx = -1;
         for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);

@@ -588,6 +588,80 @@ def f3_multiclass_layer(R):
     save("ref_f3_multiclass_layer.npz", **out)
 
 
+def labels_fixture(seed: int):
+    """Plain-array description of a small Labels object: per frame a list of (kind, points (N,2) f64, score,
+    point_scores (N,) or None); kind 1 = predicted, 0 = user instance."""
+    g = np.random.default_rng(seed)
+    frames = []
+    for f in range(6):
+        n_pred = [0, 1, 3, 5, 7, 4][f]
+        base = g.uniform(40, 300, (3, 1, 2)) + np.cumsum(g.uniform(-12, 25, (3, 6, 2)), axis=1)
+        insts = []
+        for i in range(n_pred):
+            jitter = [0.0, 1.0, 5.0, 12.0, 30.0, 2.5, 60.0][i]
+            pts = base[i % 3] + g.uniform(-1, 1, (6, 2)) * jitter
+            pts[g.uniform(size=6) < 0.2] = np.nan
+            ps = g.uniform(0.05, 1.0, 6)
+            ps[np.isnan(pts).any(1)] = np.nan
+            insts.append((1, pts, float(g.uniform(0.05, 1.0)), ps if i % 4 != 3 else None))
+        if f in (2, 4):
+            insts.insert(1, (0, base[0] + 3.0, 1.0, None))  # a user instance between the predictions
+        frames.append(insts)
+    frames[3][1][1][:] = np.nan  # a prediction without any visible node
+    return frames
+
+
+def f4_labels_filters(R):
+    """The Labels-level filters of inference/ops/filters.py on fake Labels (sleap_io is a stub in this image: the fake
+    prediction class derives from the stub's PredictedInstance so the reference's isinstance checks pass)."""
+    import types
+
+    OF = R.ops_filters
+    Pred = type("PredictedInstance", (OF.sio.PredictedInstance,), {})
+
+    def build(frames):
+        lfs = []
+        for insts in frames:
+            objs = []
+            for uid, (kind, pts, score, ps) in enumerate(insts):
+                cls = Pred if kind else types.SimpleNamespace
+                o = cls()
+                o.uid, o._pts, o.score = uid, pts, score
+                o.numpy = (lambda p: (lambda: p))(pts)
+                o.skeleton = types.SimpleNamespace(nodes=list(range(pts.shape[0])))
+                o.points = {"score": ps} if ps is not None else {}
+                objs.append(o)
+            lfs.append(types.SimpleNamespace(instances=objs))
+        return types.SimpleNamespace(labeled_frames=lfs)
+
+    frames = labels_fixture(808)
+    out = {}
+    ragged("lab_n", [np.int64(len(f)) for f in frames], out)
+    flat = [x for f in frames for x in f]
+    out["lab_kind"] = np.array([x[0] for x in flat])
+    out["lab_pts"] = np.stack([x[1] for x in flat])
+    out["lab_score"] = np.array([x[2] for x in flat])
+    out["lab_ps"] = np.stack([x[3] if x[3] is not None else np.full(6, -1.0) for x in flat])
+    out["lab_has_ps"] = np.array([x[3] is not None for x in flat])
+    cases = {
+        "count": lambda L: OF.filter_by_node_count(L, min_visible_nodes=4, min_visible_node_fraction=0.6),
+        "conf": lambda L: OF.filter_by_node_confidence(L, min_mean_node_score=0.5, min_instance_score=0.3),
+        "iou": lambda L: OF.filter_overlapping_instances(L, threshold=0.45, method="iou"),
+        "oks": lambda L: OF.filter_overlapping_instances(L, threshold=0.3, method="oks"),
+    }
+    for tag, fn in cases.items():
+        L = fn(build(frames))
+        ragged(f"lab_{tag}", [np.array([o.uid for o in lf.instances], dtype=np.int64) for lf in L.labeled_frames], out)
+    # the numeric cores directly
+    pts = [x[1] for x in frames[4] if x[0]]
+    sc = np.array([x[2] for x in frames[4] if x[0]])
+    out["core_iou_keep"] = np.array(OF._nms_greedy_iou(np.array([OF._instance_bbox(types.SimpleNamespace(numpy=(lambda p: (lambda: p))(p)))
+                                                                 for p in pts]), sc, 0.45))
+    out["core_oks_keep"] = np.array(OF._nms_greedy_oks(pts, sc, 0.3))
+    out["core_oks_matrix"] = np.array([[OF._compute_oks(a, b) for b in pts] for a in pts])
+    save("ref_f4_labels_filters.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
@@ -606,6 +680,7 @@ def main():
     f3_multiclass_layer(R)
     f4_batched_targets(R)
     f4_filters(R)
+    f4_labels_filters(R)
 
 
 if __name__ == "__main__":

@@ -48,3 +48,26 @@ def candidate_table(edge_inds, edge_peak_inds, scores):
         out[(int(e[i]), int(p[i, 0]), int(p[i, 1]))] = float(s[i])
     assert len(out) == len(e), "duplicate candidates"
     return out
+
+
+def fake_labels(d):
+    """Rebuild the fake Labels object of tests/golden/make_golden.py:f4_labels_filters from ref_f4_labels_filters.npz.
+    Predictions are instances of a class NAMED PredictedInstance (what the duck-typed filters look for)."""
+    import types
+
+    Pred = type("PredictedInstance", (), {})
+    sizes = [int(d[f"lab_n_{i}"]) for i in range(int(d["lab_n_n"]))]
+    lfs, k = [], 0
+    for n in sizes:
+        objs = []
+        for uid in range(n):
+            o = Pred() if int(d["lab_kind"][k]) else types.SimpleNamespace()
+            pts = np.array(d["lab_pts"][k])
+            o.uid, o.score = uid, float(d["lab_score"][k])
+            o.numpy = (lambda p: (lambda: p))(pts)
+            o.skeleton = types.SimpleNamespace(nodes=list(range(pts.shape[0])))
+            o.points = {"score": np.array(d["lab_ps"][k])} if bool(d["lab_has_ps"][k]) else {}
+            objs.append(o)
+            k += 1
+        lfs.append(types.SimpleNamespace(instances=objs))
+    return types.SimpleNamespace(labeled_frames=lfs)

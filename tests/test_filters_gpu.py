@@ -120,3 +120,35 @@ def test_filters_on_the_bottomup_outputs(fl):
     n_in = int((~torch.isnan(k).all(-1).all(-1)).sum())
     n_out = int((~torch.isnan(out.pred_keypoints).all(-1).all(-1)).sum())
     assert n_in == 12 and n_out == 12  # three well-separated full skeletons per frame survive
+
+
+def test_labels_level_filters_golden():
+    """sleap_nn_b200.inference.ops.filters on fake Labels == the reference's ops/filters.py (kept instances per frame,
+    in order), and the numeric cores on plain arrays."""
+    from sleap_nn_b200.inference.ops import filters as opf
+    from tests.helpers import fake_labels
+
+    d = golden("ref_f4_labels_filters.npz")
+    cases = {
+        "count": lambda L: opf.filter_by_node_count(L, min_visible_nodes=4, min_visible_node_fraction=0.6),
+        "conf": lambda L: opf.filter_by_node_confidence(L, min_mean_node_score=0.5, min_instance_score=0.3),
+        "iou": lambda L: opf.filter_overlapping_instances(L, threshold=0.45, method="iou"),
+        "oks": lambda L: opf.filter_overlapping_instances(L, threshold=0.3, method="oks"),
+    }
+    for tag, fn in cases.items():
+        L = fake_labels(d)
+        assert fn(L) is L
+        for f, lf in enumerate(L.labeled_frames):
+            assert [o.uid for o in lf.instances] == d[f"lab_{tag}_{f}"].tolist(), (tag, f)
+    L = fake_labels(d)
+    assert opf.filter_by_node_count(L) is L and opf.filter_by_node_confidence(L) is L  # defaults: no-ops
+    with pytest.raises(ValueError):
+        opf.filter_overlapping_instances(L, method="giou")
+    pred = [o for o in fake_labels(d).labeled_frames[4].instances if type(o).__name__ == "PredictedInstance"]
+    pts, sc = [o.numpy() for o in pred], np.array([o.score for o in pred])
+    assert opf._nms_greedy_oks(pts, sc, 0.3) == d["core_oks_keep"].tolist()
+    from oracle import filters as ofil
+
+    boxes = np.array([ofil.instance_bbox64(p) for p in pts])
+    assert opf._nms_greedy_iou(boxes, sc, 0.45) == d["core_iou_keep"].tolist()
+    assert opf._nms_greedy_iou(np.zeros((0, 4)), np.zeros(0), 0.5) == [] and opf._nms_greedy_oks([], np.zeros(0), 0.5) == []
