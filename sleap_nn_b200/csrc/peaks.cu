@@ -97,7 +97,12 @@ local_peaks_detect_vec4(const float* __restrict__ cms, int n_rows, int C, int H,
           const float* plane = cms + (long long)b * sb + (long long)c * sc;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (e[k] > thr) {
+            // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same
+            // 128-bit word are already in registers, and a strict maximum must beat them too (same `v > nb`
+            // predicate, so NaN neighbours reject as in the reference).  On a blob's row only the ridge pixel
+            // (and at most the word-boundary pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads
+            // on busy maps (cfg4: 256 blobs per frame).
+            if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == 3 || e[k] > e[k + 1])) {
               const int x = 4 * xx4 + k;
               if (is_strict_max(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
             }

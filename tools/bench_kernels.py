@@ -145,17 +145,22 @@ def memset_ref(dev, iters):
     line("memset_268MB", "cudaMemsetAsync (reference, not ours)", 268435456, ms, 1, "launches")
 
 
-def chain_cfg4(dev, iters):
-    """cfg4 inference: 32 nodes / 31 edges / 8 instances per frame, full chain on a batch of 8 frames."""
+def chain_cfg4(dev, iters, Bn=64):
+    """cfg4 inference: 32 nodes / 31 edges / 8 instances per frame (256 peaks, ~2 k candidates per frame), full chain.
+
+    Batch 64 on two streams: the per-frame tail (one CTA per frame, ~230 us for such busy frames) needs at least as
+    many frames in flight as it takes to hide it under the next batch's detect pass (2.1 GB of maps, ~340 us); at
+    batch 8 the tail would run on 8 of the 148 SMs and dominate.
+    """
     from sleap_nn_b200.pipeline import BottomUpPostproc
-    Bn = 8
     inputs = []
-    for s in range(2):  # 2 x (268 + 520 MB)
+    for s in range(2):  # 2 x 64 x (33.5 + 65.0 MB) = 12.6 GB
         edges, poses = _flies_poses(Bn, seed=s)
         inputs.append(synthetic.render_batch(poses, (1024, 1024), 2, edges, dev, seed=s))
-    pipe = BottomUpPostproc(32, edges, Bn, (512, 512), cms_stride=2, pafs_stride=2, device=dev, peak_cap=512,
-                            cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False)
-    res = pipe(*inputs[0])
+    pipes = [BottomUpPostproc(32, edges, Bn, (512, 512), cms_stride=2, pafs_stride=2, device=dev, peak_cap=512,
+                              cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    res = pipes[0](*inputs[0])
     inst, _, _ = res.to_lists()
     n_inst = sum(len(x) for x in inst)
     n_peaks = int(res.n_peaks.sum())
@@ -164,13 +169,32 @@ def chain_cfg4(dev, iters):
     for a, b in evs:
         a.record(main); b.record(main)
     torch.cuda.synchronize()
-    ms = timed(lambda i: pipe(*inputs[i % 2], detect_events=evs[i % iters]), iters)
+
+    def step(i):
+        with torch.cuda.stream(streams[i % 2]):
+            pipes[i % 2](*inputs[i % 2], detect_events=evs[i % iters])
+
+    for s_ in streams:
+        s_.wait_stream(main)
+    for i in range(6):
+        step(i)
     torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(main)
+    for s_ in streams:
+        s_.wait_stream(main)
+    for i in range(iters):
+        step(i)
+    for s_ in streams:
+        main.wait_stream(s_)
+    t1.record(main)
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / iters
     det = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
     algo = 4 * Bn * 32 * 512 * 512
-    line("chain_cfg4", "detect+tail (whole chain, one stream)", algo, ms, Bn, "frames",
+    line("chain_cfg4", "detect+tail (whole chain, batch %d, two streams)" % Bn, algo, ms, Bn, "frames",
          {"frames_per_launch": Bn, "instances_found": n_inst, "instances_planted": Bn * 8, "peaks": n_peaks,
-          "launches_per_call": pipe.launches_per_call, "fused_tail": pipe.fused})
+          "launches_per_call": pipes[0].launches_per_call, "fused_tail": pipes[0].fused})
     line("k1_cfg4", "local_peaks_detect_vec4 (in situ)", algo, det, Bn, "frames", {"frames_per_launch": Bn})
 
 
