@@ -126,7 +126,15 @@ class FilterPipeline:
                         "snb_filter_instances")
         changes = {}
         for name in _FIELDS:
-            if outs[name] is not None:
-                src = getattr(outputs, name)
-                changes[name] = outs[name].to(device=out_dev, dtype=src.dtype if src.dtype.is_floating_point else torch.float32)
+            if outs[name] is None:
+                continue
+            src = getattr(outputs, name)
+            if src.dtype == torch.float32:
+                changes[name] = outs[name].to(out_dev)
+            else:
+                # the kernel decides in fp32 (the dtype every inference layer emits); values of another dtype are
+                # never rounded through it: the NaN pattern is applied to a copy of the original tensor
+                kept = src.detach().clone().to(torch.float64 if not src.dtype.is_floating_point else src.dtype)
+                kept[torch.isnan(outs[name]).to(out_dev)] = float("nan")
+                changes[name] = kept
         return _evolve(outputs, **changes)

@@ -152,3 +152,58 @@ def test_labels_level_filters_golden():
     boxes = np.array([ofil.instance_bbox64(p) for p in pts])
     assert opf._nms_greedy_iou(boxes, sc, 0.45) == d["core_iou_keep"].tolist()
     assert opf._nms_greedy_iou(np.zeros((0, 4)), np.zeros(0), 0.5) == [] and opf._nms_greedy_oks([], np.zeros(0), 0.5) == []
+
+
+def _ref_outputs(fl):
+    """`_make_outputs` of the reference's tests/inference/test_filters.py:30-57."""
+    kpts = torch.tensor([[[[1.0, 1.0], [2.0, 2.0], [3.0, 3.0], [4.0, 4.0]],
+                          [[10.0, 10.0], [11.0, 11.0], [12.0, 12.0], [13.0, 13.0]],
+                          [[20.0, 20.0], [21.0, 21.0], [22.0, 22.0], [23.0, 23.0]]]])
+    vals = torch.tensor([[[0.9, 0.8, 0.7, 0.6], [0.4, 0.3, 0.2, 0.1], [0.95, 0.05, 0.95, 0.05]]])
+    return fl.FilterableOutputs(kpts, vals, torch.tensor([[0.85, 0.30, 0.55]]))
+
+
+def test_reference_known_answers_replayed(fl):
+    """The known-answer tests of the reference's tests/inference/test_filters.py, through the CUDA pipeline."""
+    import pickle
+
+    FP, FC = fl.FilterPipeline, fl.FilterConfig
+    nan_all = lambda t: bool(torch.isnan(t).all())
+    nan_any = lambda t: bool(torch.isnan(t).any())
+    o = _ref_outputs(fl)
+    out = FP(FC())(o)                                                           # :65-70
+    assert torch.equal(out.pred_keypoints, o.pred_keypoints) and torch.equal(out.pred_peak_values, o.pred_peak_values)
+    out = FP(FC(min_peak_value=0.5))(o)                                         # :78-85
+    assert nan_all(out.pred_keypoints[0, 1]) and nan_all(out.pred_keypoints[0, 2, 1]) and not nan_any(out.pred_keypoints[0, 2, 0])
+    k = o.pred_keypoints.clone(); k[0, 2, 2:] = float("nan")                    # :93-108
+    out = FP(FC(min_visible_nodes=3))(fl.FilterableOutputs(k, o.pred_peak_values, o.instance_scores))
+    assert not nan_any(out.pred_keypoints[0, 0]) and not nan_any(out.pred_keypoints[0, 1]) and nan_all(out.pred_keypoints[0, 2])
+    k = o.pred_keypoints.clone(); k[0, 0, 2:] = float("nan"); k[0, 1, 1:] = float("nan")   # :116-129
+    out = FP(FC(min_visible_node_fraction=0.4))(fl.FilterableOutputs(k, o.pred_peak_values, o.instance_scores))
+    assert not nan_all(out.pred_keypoints[0, 0]) and nan_all(out.pred_keypoints[0, 1])
+    out = FP(FC(min_instance_score=0.5))(o)                                     # :137-143
+    assert not nan_any(out.pred_keypoints[0, 0]) and nan_all(out.pred_keypoints[0, 1]) and not nan_any(out.pred_keypoints[0, 2])
+    out = FP(FC(min_mean_node_score=0.5))(o)                                    # :151-157 (instance 2: mean exactly 0.5 is kept)
+    assert not nan_any(out.pred_keypoints[0, 0]) and nan_all(out.pred_keypoints[0, 1]) and not nan_any(out.pred_keypoints[0, 2])
+    two = fl.FilterableOutputs(torch.tensor([[[[10.0, 10.0], [12.0, 12.0]], [[10.1, 10.1], [12.1, 12.1]]]]),
+                               torch.tensor([[[0.9, 0.9], [0.5, 0.5]]]), torch.tensor([[0.9, 0.5]]))
+    out = FP(FC(overlapping=True, overlapping_threshold=0.5, overlapping_method="iou"))(two)  # :165-184
+    assert not nan_any(out.pred_keypoints[0, 0]) and nan_all(out.pred_keypoints[0, 1])
+    one = fl.FilterableOutputs(torch.tensor([[[[1.0, 1.0]], [[1.05, 1.05]]]]), torch.tensor([[[1.0], [1.0]]]), torch.tensor([[0.9, 0.5]]))
+    with pytest.warns(UserWarning):                                             # :192-208 (+ the single-node fallback, #586)
+        out = FP(FC(overlapping=True, overlapping_threshold=0.5, overlapping_method="oks"))(one)
+    assert int((~torch.isnan(out.pred_keypoints).all(dim=-1).all(dim=-1)).sum()) >= 1
+    a = [(0.0, 0.0), (10.0, 0.0), (0.0, 10.0), (10.0, 10.0)]                    # :303-333, float64 Outputs
+    b = [(0.1, 0.1), (10.1, 0.0), (0.0, 10.1), (10.1, 10.1)]
+    o64 = fl.FilterableOutputs(torch.tensor([[a, b]], dtype=torch.float64), torch.ones(1, 2, 4, dtype=torch.float64),
+                               torch.tensor([[0.9, 0.5]], dtype=torch.float64))
+    out = FP(FC(overlapping=True, overlapping_threshold=0.5, overlapping_method="oks"))(o64)
+    assert out.pred_keypoints.dtype == torch.float64 and torch.equal(out.pred_keypoints[0, 0], o64.pred_keypoints[0, 0])
+    assert nan_all(out.pred_keypoints[0, 1])
+    out = FP(FC(min_peak_value=0.1, min_visible_nodes=1, min_instance_score=0.5))(o)   # :342-349
+    assert nan_all(out.pred_keypoints[0, 1])
+    cfg = FC(min_peak_value=0.2, min_instance_score=0.3, overlapping=True, overlapping_threshold=0.5, overlapping_method="oks")
+    back = pickle.loads(pickle.dumps(cfg))                                      # :357-368
+    assert back == cfg and back.overlapping_method == "oks"
+    via_run, via_inst = FP.run(o, FC(min_instance_score=0.5)), FP(FC(min_instance_score=0.5))(o)   # :376-383
+    assert torch.equal(torch.nan_to_num(via_run.pred_keypoints, nan=-1.0), torch.nan_to_num(via_inst.pred_keypoints, nan=-1.0))
