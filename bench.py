@@ -220,8 +220,13 @@ def run_ours(args, rank: int, world: int):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    host_cpus = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one rank per GPU: keep this rank's pinned staging buffers on the GPU's own NUMA node (e2e leg)
+        from sleap_nn_b200.sharding import bind_host_to_gpu
+
+        host_cpus = None if args.no_numa_bind else bind_host_to_gpu(local)
     n_bufs, n_streams = args.buffers, args.streams
     edges, inputs = make_inputs(dev, n_bufs, seed0=100 * (rank + 1))
     # `--streams` pipeline instances, each with its own tables: instance i's detect kernel runs on the
@@ -393,6 +398,7 @@ def run_ours(args, rank: int, world: int):
                            launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "in_flight": args.e2e_depth,
+                    "host_cpus_rank0": ("all" if host_cpus is None else f"{len(host_cpus)} CPUs local to the GPU"),
                     "pafs": ("sampled in place from pinned host memory (zero-copy): "
                              f"{paf_sector_bytes} B of 32-byte sectors per step instead of {host[0][1].numel() * 4} B"
                              if hs.last_zero_copy else "copied to the device every step")},
@@ -438,6 +444,7 @@ def main():
     ap.add_argument("--tail-stream", dest="tail_stream", action="store_true",
                     help="one detect stream + one high-priority tail stream instead of one stream per pipeline instance")
     ap.add_argument("--copy-pafs", action="store_true", help="e2e: stage the PAF tensor in HBM instead of sampling it in place")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--lean", action="store_true", help="do not write candidate / match tables to global memory")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

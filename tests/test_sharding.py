@@ -137,3 +137,18 @@ def test_shard_runner_matches_per_batch_pipeline():
             np.testing.assert_array_equal(got[1][s + b].numpy(), pv[b].numpy())
             np.testing.assert_array_equal(got[2][s + b].numpy(), sc[b].numpy())
     assert sum(len(x) for x in got[0]) == n_frames * n_inst
+
+
+def test_host_locality_helpers_are_safe_without_a_gpu():
+    """bind_host_to_gpu must never narrow the process to nothing: no sysfs entry / no GPU -> no change."""
+    import os
+
+    from sleap_nn_b200.sharding import _parse_cpulist, bind_host_to_gpu, gpu_local_cpus
+
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    assert _parse_cpulist("5") == [5]
+    before = os.sched_getaffinity(0)
+    assert gpu_local_cpus(0, sysfs_root="/nonexistent") == []
+    assert bind_host_to_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
