@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 3
+#define SNB_ABI_VERSION 4
 
 #define SNB_OK 0
 #define SNB_ERR_BAD_ARG (-1)
@@ -137,6 +137,28 @@ int snb_crop_bboxes(const void* images, int elem_size, int S, int C, int H, int 
 /* make_centered_bboxes (data/instance_cropping.py:129-171): centers (n,2) -> out (n,4,2),
  * half_h = box_height / 2, half_w = box_width / 2 (already fp32). */
 int snb_centered_bboxes(const float* centers, long long n, float half_h, float half_w, float* out, void* stream);
+
+/* TopDownLayer stage B + the bookkeeping of stage 2 (layers/topdown.py:98-120, 186-236, 415-466), one launch:
+ * valid = no NaN coordinate; optional greedy centroid NMS per frame (descending value, IoU of crop_h x crop_w boxes
+ * centred on the centroids > nms_threshold drops; frames with <= 1 valid centroid untouched); then the valid (b, i)
+ * pairs in torch.nonzero order as a crop list.  centroids (B, I, 2) are in IMAGE space; eff_scale (B) or NULL takes them
+ * to sized space (x eff) for the boxes.  Outputs: n_valid (1), frame_off (B+1), and with capacity B*I rows:
+ * sample_inds (int64), rows (= b*I + i), crop_bboxes (., 4, 2) = make_centered_bboxes in sized space, crop_topleft
+ * (., 2), crop_eff (.); per slot: row_to_crop (B*I) (-1 = none), valid_mask (B, I) bytes, centroids_img (B, I, 2) =
+ * (c x eff) / eff, full_bboxes (B, I, 4, 2) = box / eff or NaN.  Needs snb_topdown_select_smem_bytes(B, I) <= 200 KB. */
+long long snb_topdown_select_smem_bytes(int B, int I);
+int snb_topdown_select(const float* centroids, const float* centroid_vals, int B, int I, const float* eff_scale,
+                       int crop_h, int crop_w, int centroid_nms, float nms_threshold, int* n_valid, int* frame_off,
+                       long long* sample_inds, int* rows, int* row_to_crop, float* crop_bboxes, float* crop_topleft,
+                       float* crop_eff, unsigned char* valid_mask, float* centroids_img, float* full_bboxes,
+                       void* stream);
+
+/* The lift of stage 2 (layers/topdown.py:259-291): stage-2 keypoints kpts (n, n_nodes, 2) / vals (n, n_nodes) of the
+ * crop list -> full_kpts (n_slots, n_nodes, 2) = (kpts + crop_topleft) / crop_eff, full_crop_kpts (same shape, may be
+ * NULL) = kpts, full_vals (n_slots, n_nodes); slots without a crop get NaN.  n_slots = B * max_instances. */
+int snb_topdown_lift(const float* kpts, const float* vals, int n_nodes, long long n_slots, const int* row_to_crop,
+                     const float* crop_topleft, const float* crop_eff, float* full_kpts, float* full_crop_kpts,
+                     float* full_vals, void* stream);
 
 /* integral_regression (ops/peaks.py:66-86) on contiguous (n_planes,h,w) patches. */
 int snb_integral_regression(const float* patches, long long n_planes, int h, int w, const float* xv,
@@ -333,6 +355,16 @@ int snb_pack_class_matches(const long long* g_peak, const long long* g_class, co
 long long snb_class_inds_workspace_bytes(int n, int K);
 int snb_class_inds_from_vectors(const float* probs, int n, int K, void* workspace, long long* o_inds, float* o_probs,
                                 int* status, void* stream);
+
+/* The per-frame re-assignment of TopDownLayer._run_stage_2 (layers/topdown.py:343-371): probs (n, K) are the class
+ * vectors of the flattened crops, frame b owning crops [frame_off[b], frame_off[b+1]); rows_of_crop[r] = b*I + i.
+ * One get_class_inds_from_vectors per frame, scattered into full_class_inds (B, I, n_nodes) int64 (-1 fill, the class
+ * broadcast over the node axis), full_tracking (B, I) (NaN fill) and, when not NULL, full_vectors (B, I, K) (NaN fill).
+ * workspace: snb_class_inds_grouped_workspace_bytes(B, I, K) bytes. */
+long long snb_class_inds_grouped_workspace_bytes(int B, int I, int K);
+int snb_class_inds_grouped(const float* probs, int K, const int* frame_off, const int* rows_of_crop, int B, int I,
+                           int n_nodes, void* workspace, long long* full_class_inds, float* full_tracking,
+                           float* full_vectors, int* status, void* stream);
 
 /* make_class_vectors (data/identity.py:10-32): class_inds (n) fp32 (is_float) or int32 -> out (n, K) int32 one-hot,
  * index < 0 -> zero row; index >= K sets SNB_STATUS_BAD_INDEX (F.one_hot raises). */

@@ -44,6 +44,12 @@ _HOT_FILES = [
     # layer glue of the f3 row: only BottomUpMultiClassLayer.postprocess / _cap_instances_by_score are called, with a
     # stand-in `self` (the base classes resolve to stubs)
     ("sleap_nn.inference.layers.bottomup_multiclass", "sleap_nn/inference/layers/bottomup_multiclass.py"),
+    # layer glue of the f2 row: postprocess / _run_stage_2 / _centroid_nms_mask are called with stand-in `self` objects
+    ("sleap_nn.inference.layers.centered_instance", "sleap_nn/inference/layers/centered_instance.py"),
+    ("sleap_nn.inference.layers.single_instance", "sleap_nn/inference/layers/single_instance.py"),
+    ("sleap_nn.inference.layers.centroid", "sleap_nn/inference/layers/centroid.py"),
+    ("sleap_nn.inference.layers.topdown", "sleap_nn/inference/layers/topdown.py"),
+    ("sleap_nn.inference.layers.topdown_multiclass", "sleap_nn/inference/layers/topdown_multiclass.py"),
 ]
 
 _NAMESPACE_PKGS = [
@@ -203,5 +209,9 @@ def ref() -> types.SimpleNamespace:
             filters=full["sleap_nn.inference.filters"],
             ops_filters=full["sleap_nn.inference.ops.filters"],
             bottomup_multiclass=full["sleap_nn.inference.layers.bottomup_multiclass"],
+            centered_instance=full["sleap_nn.inference.layers.centered_instance"],
+            single_instance=full["sleap_nn.inference.layers.single_instance"],
+            topdown=full["sleap_nn.inference.layers.topdown"],
+            topdown_multiclass=full["sleap_nn.inference.layers.topdown_multiclass"],
         )
     return _CACHE

@@ -45,6 +45,8 @@ SIGNATURES = {
     "snb_coord_ladder_apply": [_p, _ll, _ll, _p, _p, _p],
     "snb_crop_bboxes": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_centered_bboxes": [_p, _ll, _f, _f, _p, _p],
+    "snb_topdown_select": [_p, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "snb_topdown_lift": [_p, _p, _i, _ll, _p, _p, _p, _p, _p, _p, _p],
     "snb_integral_regression": [_p, _ll, _i, _i, _p, _p, _p, _p, _p],
     "snb_dilate8": [_p, _ll, _i, _i, _p, _p],
     "snb_paf_prepare": [_p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p],
@@ -73,6 +75,7 @@ SIGNATURES = {
     "snb_multiclass_outputs": [_p, _p, _p, _i, _i, _i, _f, _f, _p, _i, _p, _p, _p, _p, _p],
     "snb_pack_class_matches": [_p, _p, _p, _i, _i, _p, _p, _p, _p],
     "snb_class_inds_from_vectors": [_p, _i, _i, _p, _p, _p, _p, _p],
+    "snb_class_inds_grouped": [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
     "snb_class_maps": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
     "snb_filter_instances": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -84,7 +87,8 @@ SIGNATURES = {
     "snb_bottomup_outputs": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "snb_pack_instances": [_p, _i, _i, _i, _p, _p, _p, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p],
 }
-RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_class_inds_workspace_bytes": [_i, _i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
+RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_class_inds_workspace_bytes": [_i, _i],
+                   "snb_class_inds_grouped_workspace_bytes": [_i, _i, _i], "snb_topdown_select_smem_bytes": [_i, _i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
 FLAG_UNFUSED_TAIL = 1
 
 

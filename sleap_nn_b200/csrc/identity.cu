@@ -179,17 +179,13 @@ __global__ void pack_class_matches_kernel(const long long* __restrict__ g_peak, 
   }
 }
 
-// get_class_inds_from_vectors (ops/identity.py:152-173): ONE assignment over (n, K); one warp.
-__global__ void __launch_bounds__(32)
-class_inds_from_vectors_kernel(const float* __restrict__ probs, int n, int K, void* __restrict__ ws, int* __restrict__ rows,
-                               int* __restrict__ cols, long long* __restrict__ o_inds, float* __restrict__ o_probs,
-                               int* __restrict__ status) {
-  const int lane = threadIdx.x;
-  for (int i = lane; i < n; i += 32) {
-    o_inds[i] = -1;
-    o_probs[i] = NAN;
-  }
-  if (n == 0 || K == 0) return;
+// get_class_inds_from_vectors (ops/identity.py:152-173) for ONE group of n rows x K classes, by one warp: the optimal
+// assignment on cost = -(double)prob; emit(row, class, prob) is called once per matched row.  Returns false (and
+// raises a status bit) on NaN / +inf probabilities or an infeasible matrix, like scipy.
+template <typename Emit>
+__device__ __forceinline__ bool class_inds_group(const float* __restrict__ probs, int n, int K, void* ws, int* rows,
+                                                 int* cols, int lane, int* __restrict__ status, Emit emit) {
+  if (n == 0 || K == 0) return true;
   bool bad = false;
   for (long long t = lane; t < (long long)n * K; t += 32) {
     const float v = probs[t];
@@ -197,7 +193,7 @@ class_inds_from_vectors_kernel(const float* __restrict__ probs, int n, int K, vo
   }
   if (__any_sync(FULL, bad)) {
     if (lane == 0) atomicOr(status, SNB_STATUS_LSAP_INVALID);
-    return;
+    return false;
   }
   __syncwarp();
   auto cost = [&](int i, int j) -> double { return -(double)probs[(long long)i * K + j]; };
@@ -215,14 +211,61 @@ class_inds_from_vectors_kernel(const float* __restrict__ probs, int n, int K, vo
   }
   if (!ok) {
     if (lane == 0) atomicOr(status, SNB_STATUS_LSAP_INFEASIBLE);
-    return;
+    return false;
   }
   const int n_match = min(n, K);
   for (int t = lane; t < n_match; t += 32) {
     const int r = rows[t], k = cols[t];
-    o_inds[r] = k;
-    o_probs[r] = probs[(long long)r * K + k];
+    emit(r, k, probs[(long long)r * K + k]);
   }
+  return true;
+}
+
+// ONE assignment over (n, K); one warp.
+__global__ void __launch_bounds__(32)
+class_inds_from_vectors_kernel(const float* __restrict__ probs, int n, int K, void* __restrict__ ws, int* __restrict__ rows,
+                               int* __restrict__ cols, long long* __restrict__ o_inds, float* __restrict__ o_probs,
+                               int* __restrict__ status) {
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n; i += 32) {
+    o_inds[i] = -1;
+    o_probs[i] = NAN;
+  }
+  __syncwarp();
+  class_inds_group(probs, n, K, ws, rows, cols, lane, status, [&](int r, int k, float p) {
+    o_inds[r] = k;
+    o_probs[r] = p;
+  });
+}
+
+// TopDownLayer._run_stage_2's per-frame re-assignment (layers/topdown.py:343-371): the crops of a batch arrive
+// flattened, but a class may be claimed once PER FRAME, so frame b's crops [frame_off[b], frame_off[b+1]) form one
+// group.  One warp per frame: NaN / -1 fill of the frame's (max_inst, ...) slots, the assignment, and the scatter of
+//   pred_class_inds[b, i, :] = class,  instance_tracking_scores[b, i] = prob,  pred_class_vectors[b, i, :] = vector
+// through rows[r] = b * max_inst + i.
+__global__ void __launch_bounds__(32)
+class_inds_grouped_kernel(const float* __restrict__ probs, int K, const int* __restrict__ frame_off,
+                          const int* __restrict__ rows_of_crop, int I, int n_nodes, unsigned char* __restrict__ ws_all,
+                          long long ws_stride, int max_dim, long long* __restrict__ full_class_inds,
+                          float* __restrict__ full_tracking, float* __restrict__ full_vectors, int* __restrict__ status) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  for (long long t = lane; t < (long long)I * n_nodes; t += 32) full_class_inds[(long long)b * I * n_nodes + t] = -1;
+  for (int t = lane; t < I; t += 32) full_tracking[(long long)b * I + t] = NAN;
+  if (full_vectors)
+    for (long long t = lane; t < (long long)I * K; t += 32) full_vectors[(long long)b * I * K + t] = NAN;
+  __syncwarp();
+  const int r0 = frame_off[b], n = frame_off[b + 1] - r0;
+  if (n <= 0) return;
+  if (full_vectors)
+    for (long long t = lane; t < (long long)n * K; t += 32)
+      full_vectors[(long long)rows_of_crop[r0 + t / K] * K + t % K] = probs[(long long)r0 * K + t];
+  unsigned char* ws = ws_all + (long long)b * ws_stride;
+  int* rows = reinterpret_cast<int*>(ws + lsap_ws_bytes(max_dim));
+  class_inds_group(probs + (long long)r0 * K, n, K, ws, rows, rows + max_dim, lane, status, [&](int r, int k, float p) {
+    const long long slot = rows_of_crop[r0 + r];
+    for (int c = 0; c < n_nodes; ++c) full_class_inds[slot * n_nodes + c] = k;
+    full_tracking[slot] = p;
+  });
 }
 
 // make_class_vectors (data/identity.py:10-32): one-hot int32 rows; index < 0 -> zeros.  Indices arrive as fp32 or
@@ -442,6 +485,27 @@ extern "C" int snb_class_inds_from_vectors(const float* probs, int n, int K, voi
   int* rows = (int*)((char*)workspace + lsap_ws_bytes(d));
   class_inds_from_vectors_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(probs, n, K, workspace, rows, rows + d, o_inds,
                                                                     o_probs, status);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
+extern "C" long long snb_class_inds_grouped_workspace_bytes(int B, int I, int K) {
+  const long long per = (snb_class_inds_workspace_bytes(I, K) + 15) & ~15LL;
+  return per * (B < 1 ? 1 : B);
+}
+
+extern "C" int snb_class_inds_grouped(const float* probs, int K, const int* frame_off, const int* rows_of_crop, int B,
+                                     int I, int n_nodes, void* workspace, long long* full_class_inds,
+                                     float* full_tracking, float* full_vectors, int* status, void* stream) {
+  if (B < 0 || I < 0 || K < 0 || n_nodes < 0 || !status) return SNB_ERR_BAD_ARG;
+  if (B == 0) return SNB_OK;
+  if (!workspace || !frame_off || !full_class_inds || !full_tracking) return SNB_ERR_BAD_ARG;
+  const int d = (I > K ? I : K) < 1 ? 1 : (I > K ? I : K);
+  class_inds_grouped_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(probs, K, frame_off, rows_of_crop, I, n_nodes,
+                                                               (unsigned char*)workspace,
+                                                               (snb_class_inds_workspace_bytes(I, K) + 15) & ~15LL, d,
+                                                               full_class_inds,
+                                                               full_tracking, full_vectors, status);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }

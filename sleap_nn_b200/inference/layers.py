@@ -187,3 +187,180 @@ class BottomUpMultiClassPostproc:
             raise ValueError("cost matrix is infeasible")
         if bits:
             raise RuntimeError(f"multi-class post-processing overflowed a fixed-capacity table (status 0x{bits:x})")
+
+
+class SingleInstancePostproc:
+    """confmaps (B, N, H, W) -> pred_keypoints (B, 1, N, 2), pred_peak_values (B, 1, N) in ONE launch.
+
+    `SingleInstanceLayer.postprocess` (inference/layers/single_instance.py:71-106): find_global_peaks -> undo_stride ->
+    undo_input_scale -> undo_eff_scale, the ladder running in the arg-max kernel's epilogue.
+    """
+
+    def __init__(self, peak_threshold: float = 0.2, refinement: Optional[str] = "integral", integral_patch_size: int = 5):
+        self._inner = CenteredInstancePostproc(peak_threshold, refinement, integral_patch_size)
+
+    def __call__(self, confmaps: torch.Tensor, output_stride: int = 1, input_scale: float = 1.0,
+                 eff_scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._inner(confmaps, output_stride=output_stride, input_scale=input_scale, eff_scale=eff_scale)
+
+
+def _aligned_ws(nbytes: int, dev: torch.device) -> Tuple[torch.Tensor, int]:
+    ws = torch.empty((int(nbytes) + 15,), dtype=torch.uint8, device=dev)
+    return ws, (ws.data_ptr() + 15) & ~15
+
+
+def _raise_for_class_status(status: torch.Tensor) -> None:
+    bits = int(status.item())
+    if bits & N.STATUS_LSAP_INVALID:
+        raise ValueError("matrix contains invalid numeric entries")
+    if bits & N.STATUS_LSAP_INFEASIBLE:
+        raise ValueError("cost matrix is infeasible")
+
+
+class CenteredInstanceMultiClassPostproc(CenteredInstancePostproc):
+    """Stand-alone `CenteredInstanceMultiClassLayer.postprocess` (inference/layers/topdown_multiclass.py:79-145).
+
+    confmaps (n, N, h, w) + class vectors (n, K) -> dict with `pred_keypoints` (n, 1, N, 2), `pred_peak_values`
+    (n, 1, N), `pred_class_inds` (n, 1, N) int64, `pred_class_probs` (n, 1, K) (the raw vectors) and
+    `instance_tracking_scores` (n, 1): ONE assignment over all crops, as the stand-alone layer does.  Inside a
+    top-down pipeline the assignment must run per frame: `TopDownPostproc` does that on the device.
+    """
+
+    def classify(self, confmaps: torch.Tensor, class_vectors: torch.Tensor, output_stride: int = 1,
+                 input_scale: float = 1.0, eff_scale: Optional[torch.Tensor] = None) -> dict:
+        kpts, vals = self(confmaps, output_stride=output_stride, input_scale=input_scale, eff_scale=eff_scale)
+        dev = confmaps.device
+        n, K = (int(v) for v in class_vectors.shape)
+        Nn = int(confmaps.shape[1])
+        probs = class_vectors.detach().to(device=dev, dtype=torch.float32).contiguous()
+        inds = torch.full((n,), -1, dtype=torch.int64, device=dev)
+        cp = torch.full((n,), float("nan"), dtype=torch.float32, device=dev)
+        if n:
+            with torch.cuda.device(dev):
+                ws, ws_ptr = _aligned_ws(N.lib.snb_class_inds_workspace_bytes(n, K), dev)
+                status = torch.zeros((1,), dtype=torch.int32, device=dev)
+                N.check(N.lib.snb_class_inds_from_vectors(N.ptr(probs), n, K, ws_ptr, N.ptr(inds), N.ptr(cp), N.ptr(status),
+                                                          N.stream_ptr(dev)), "snb_class_inds_from_vectors")
+                _raise_for_class_status(status)
+                del ws
+        return dict(pred_keypoints=kpts, pred_peak_values=vals,
+                    pred_class_inds=inds.view(n, 1, 1).expand(-1, -1, Nn), pred_class_probs=probs.unsqueeze(1),
+                    instance_tracking_scores=cp.unsqueeze(1))
+
+
+class TopDownPostproc:
+    """`TopDownLayer.predict` after the centroid stage (inference/layers/topdown.py:98-289), on the device.
+
+    `__call__(image, centroids, centroid_vals, model, ...)`:
+
+    1. `snb_topdown_select` - NaN-centroid mask, optional greedy centroid NMS (`_centroid_nms_mask`, topdown.py:415-446),
+       the valid (b, i) list in `nonzero` order, sized-space crop boxes, image-space centroids and boxes: one launch.
+    2. the number of crops is read back (the crop tensor's batch dimension; the reference's `nonzero` syncs too).
+    3. `snb_crop_bboxes` picks the crops out of the (uint8 or float) sized image.
+    4. `model(crops)` - the caller's centred-instance network (PyTorch / cuDNN) -> confmaps (n, N, h, w), or
+       `(confmaps, class_vectors (n, K))` for the multi-class variant.
+    5. `snb_global_peaks_ex` (arg-max + refinement + the stage-2 ladder) and `snb_topdown_lift` (crop offset, per-crop
+       eff_scale, scatter into the NaN-filled (B, max_inst, ...) outputs): two launches.
+    6. multi-class only: `snb_class_inds_grouped` - one assignment PER FRAME (topdown.py:343-371), scattered.
+
+    Returns a dict with the reference `Outputs` field names.
+    """
+
+    def __init__(self, crop_size: Tuple[int, int], peak_threshold: float = 0.2, refinement: Optional[str] = "integral",
+                 integral_patch_size: int = 5, centroid_nms: bool = False, centroid_nms_threshold: float = 0.5,
+                 return_crops: bool = False, return_class_vectors: bool = False, n_nodes: int = 1):
+        self.crop_size = (int(crop_size[0]), int(crop_size[1]))
+        self.stage2 = CenteredInstancePostproc(peak_threshold, refinement, integral_patch_size)
+        self.centroid_nms, self.centroid_nms_threshold = bool(centroid_nms), float(centroid_nms_threshold)
+        self.return_crops, self.return_class_vectors = bool(return_crops), bool(return_class_vectors)
+        self.n_nodes = int(n_nodes)  # only used for the shape of the all-NaN result when no centroid is valid
+
+    def select(self, centroids: torch.Tensor, centroid_vals: torch.Tensor, eff_scale: Optional[torch.Tensor] = None) -> dict:
+        """Stage B + crop list (step 1); every tensor stays on the device."""
+        if not centroids.is_cuda:
+            raise TypeError("TopDownPostproc expects CUDA tensors")
+        dev = centroids.device
+        B, I = int(centroids.shape[0]), int(centroids.shape[1])
+        cen = centroids.detach().to(torch.float32).contiguous()
+        val = centroid_vals.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eff = None if eff_scale is None else eff_scale.detach().to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if eff is not None and eff.numel() != B:
+            raise ValueError("eff_scale must hold one factor per frame")
+        cap = max(B * I, 1)
+        i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        out = dict(n_valid=i32(1), frame_off=i32(B + 1), sample_inds=torch.empty((cap,), dtype=torch.int64, device=dev),
+                   rows=i32(cap), row_to_crop=i32(cap), crop_bboxes=f32(cap, 4, 2), crop_topleft=f32(cap, 2),
+                   crop_eff=f32(cap), valid_mask=torch.empty((B, I), dtype=torch.uint8, device=dev),
+                   centroids_img=f32(B, I, 2), full_bboxes=f32(B, I, 4, 2), centroid_vals=val)
+        with torch.cuda.device(dev):
+            N.check(N.lib.snb_topdown_select(N.ptr(cen), N.ptr(val), B, I, N.ptr(eff), self.crop_size[0], self.crop_size[1],
+                                             int(self.centroid_nms), self.centroid_nms_threshold, N.ptr(out["n_valid"]),
+                                             N.ptr(out["frame_off"]), N.ptr(out["sample_inds"]), N.ptr(out["rows"]),
+                                             N.ptr(out["row_to_crop"]), N.ptr(out["crop_bboxes"]), N.ptr(out["crop_topleft"]),
+                                             N.ptr(out["crop_eff"]), N.ptr(out["valid_mask"]), N.ptr(out["centroids_img"]),
+                                             N.ptr(out["full_bboxes"]), N.stream_ptr(dev)), "snb_topdown_select")
+        return out
+
+    def __call__(self, image: torch.Tensor, centroids: torch.Tensor, centroid_vals: torch.Tensor, model,
+                 eff_scale: Optional[torch.Tensor] = None, output_stride: int = 1, input_scale: float = 1.0) -> dict:
+        if not image.is_cuda or image.dim() != 4:
+            raise TypeError("TopDownPostproc expects a (B, C, H, W) CUDA image (the sized image of the centroid stage)")
+        dev = image.device
+        B, I = int(centroids.shape[0]), int(centroids.shape[1])
+        sel = self.select(centroids, centroid_vals, eff_scale)
+        n = int(sel["n_valid"].item())  # the one host sync: the crop tensor's batch dimension
+        ch, cw = self.crop_size
+        st = lambda: N.stream_ptr(dev)
+        res = dict(pred_centroids=sel["centroids_img"], pred_centroid_values=sel["centroid_vals"],
+                   instance_scores=sel["centroid_vals"], valid_mask=sel["valid_mask"].bool())
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            kp = vals = class_vectors = None
+            Nn = self.n_nodes
+            if n:
+                S, Cn, H, W = (int(v) for v in image.shape)
+                crops = torch.empty((n, Cn, ch, cw), dtype=image.dtype, device=dev)
+                status = torch.zeros((1,), dtype=torch.int32, device=dev)
+                N.check(N.lib.snb_crop_bboxes(N.ptr(image), image.element_size(), S, Cn, H, W, *image.stride(),
+                                              N.ptr(sel["crop_bboxes"]), N.ptr(sel["sample_inds"]), n, ch, cw, N.ptr(crops),
+                                              N.ptr(status), st()), "snb_crop_bboxes")
+                raw = model(crops)
+                cms, class_vectors = raw if isinstance(raw, (tuple, list)) else (raw, None)
+                Nn = int(cms.shape[1])
+                k4, v3 = self.stage2(cms, output_stride=output_stride, input_scale=input_scale)
+                kp, vals = k4.squeeze(1).contiguous(), v3.squeeze(1).contiguous()
+                if self.return_crops:
+                    full = torch.zeros((B * I, Cn, ch, cw), dtype=crops.dtype, device=dev)
+                    full.index_copy_(0, sel["rows"][:n].long(), crops)  # topdown.py:293-303 (debug output)
+                    res["crops"] = full.view(B, I, Cn, ch, cw)
+            full_kpts, full_crop, full_vals = f32(B, I, Nn, 2), f32(B, I, Nn, 2), f32(B, I, Nn)
+            N.check(N.lib.snb_topdown_lift(N.ptr(kp), N.ptr(vals), Nn, B * I, N.ptr(sel["row_to_crop"]),
+                                           N.ptr(sel["crop_topleft"]), N.ptr(sel["crop_eff"]), N.ptr(full_kpts),
+                                           N.ptr(full_crop), N.ptr(full_vals), st()), "snb_topdown_lift")
+            res.update(pred_keypoints=full_kpts, pred_peak_values=full_vals)
+            if n:  # the reference's empty early return carries no crop keypoints / boxes (topdown.py:218-233)
+                res.update(pred_crop_keypoints=full_crop, instance_bboxes=sel["full_bboxes"])
+            if class_vectors is not None:
+                K = int(class_vectors.shape[1])
+                probs = class_vectors.detach().to(device=dev, dtype=torch.float32).contiguous()
+                ws, ws_ptr = _aligned_ws(N.lib.snb_class_inds_grouped_workspace_bytes(B, I, K), dev)
+                cls = torch.empty((B, I, Nn), dtype=torch.int64, device=dev)
+                trk = f32(B, I)
+                vec = f32(B, I, K) if self.return_class_vectors else None
+                status = torch.zeros((1,), dtype=torch.int32, device=dev)
+                N.check(N.lib.snb_class_inds_grouped(N.ptr(probs), K, N.ptr(sel["frame_off"]), N.ptr(sel["rows"]), B, I, Nn,
+                                                     ws_ptr, N.ptr(cls), N.ptr(trk), N.ptr(vec), N.ptr(status), st()),
+                        "snb_class_inds_grouped")
+                self.last_class_status = status  # LSAP_INVALID / INFEASIBLE bits; `check()` raises like scipy
+                res.update(pred_class_inds=cls, instance_tracking_scores=trk)
+                if vec is not None:
+                    res["pred_class_vectors"] = vec
+                del ws
+        return res
+
+    def check(self) -> None:
+        """Synchronise and raise (ValueError, like scipy) if the last class assignment met an invalid matrix."""
+        s = getattr(self, "last_class_status", None)
+        if s is not None:
+            _raise_for_class_status(s)

@@ -662,8 +662,112 @@ def f4_labels_filters(R):
     save("ref_f4_labels_filters.npz", **out)
 
 
+def topdown_model_tables(seed: int, n_nodes: int, n_classes: int, crop_hw):
+    """Fixed tables of the stand-in centred-instance "network": every op it applies is an exactly rounded elementwise
+    fp32 op (or a max), so the CPU reference run and the CUDA test see bit-identical confidence maps."""
+    g = torch.Generator().manual_seed(seed)
+    gain = torch.rand((n_nodes, *crop_hw), generator=g) * 0.5 + 0.5
+    pattern = torch.rand((n_nodes, *crop_hw), generator=g) * 1e-3
+    cgain = torch.rand((n_classes, *crop_hw), generator=g) * 0.5 + 0.5
+    return gain, pattern, cgain
+
+
+from tests.helpers import topdown_model  # noqa: E402  (shared with the tests)
+
+
+def f2_topdown(R):
+    """TopDownLayer._centroid_nms_mask / _run_stage_2 (layers/topdown.py:186-466), CenteredInstanceLayer.postprocess,
+    CenteredInstanceMultiClassLayer.postprocess (layers/topdown_multiclass.py:79-145) and SingleInstanceLayer.postprocess
+    (layers/single_instance.py:71-106) called on the unmodified reference classes with stand-in `self` objects; the
+    centred-instance "network" is `topdown_model`."""
+    import types
+
+    T, TM = R.topdown.TopDownLayer, R.topdown_multiclass.CenteredInstanceMultiClassLayer
+    CI, SI = R.centered_instance.CenteredInstanceLayer, R.single_instance.SingleInstanceLayer
+    P = R.preprocess_info.PreprocInfo
+    g = torch.Generator().manual_seed(909)
+    B, I, H, W, crop_hw, Nn, K = 4, 4, 96, 128, (24, 32), 3, 3
+    cen = torch.full((B, I, 2), float("nan"))
+    cen[0, :3] = torch.tensor([[30.2, 20.7], [90.5, 60.1], [60.0, 80.9]])
+    cen[1] = torch.tensor([[40.0, 40.0], [44.5, 42.25], [100.3, 30.6], [15.1, 70.4]])  # 0 and 1 overlap heavily
+    cen[2, 2] = torch.tensor([64.0, 48.0])
+    cen_val = torch.where(torch.isnan(cen[..., 0]), torch.tensor(float("nan")), torch.rand((B, I), generator=g) * 0.7 + 0.3)
+    cen_val[1, 0], cen_val[1, 1] = 0.61, 0.83  # the later slot wins the NMS
+    eff = torch.tensor([1.0, 0.8, 1.25, 1.0])
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    img = torch.rand((B, 1, H, W), generator=g) * 40.0
+    for b in range(B):
+        for i in range(I):
+            if torch.isnan(cen[b, i, 0]):
+                continue
+            for k in range(3):  # three blobs scattered around each (sized-space) centroid
+                c = cen[b, i] * eff[b] + (torch.rand(2, generator=g) - 0.5) * 16.0
+                img[b, 0] += 200.0 * torch.exp(-((xx - c[0]) ** 2 + (yy - c[1]) ** 2) / (2 * 2.5**2))
+    img_u8 = img.clamp(0, 255).to(torch.uint8)
+    gain, pattern, cgain = topdown_model_tables(910, Nn, K, crop_hw)
+    out = dict(image=img_u8, centroids=cen, centroid_vals=cen_val, eff=eff, gain=gain, pattern=pattern, cgain=cgain,
+               crop_hw=np.array(crop_hw))
+    cfg = types.SimpleNamespace(peak_threshold=0.2, effective_refinement="integral", integral_patch_size=5,
+                                return_confmaps=False, return_class_vectors=True)
+    extract = lambda raw: raw["CenteredInstanceConfmapsHead"]
+
+    def ci_predict(multiclass, stride, scale):
+        def predict(crops):
+            info = P(eff_scale=torch.ones(crops.shape[0]), input_scale=scale, output_stride=stride)
+            me2 = types.SimpleNamespace(postprocess_config=cfg, _extract_confmaps=extract)
+            if multiclass:
+                cms, vec = topdown_model(crops, gain, pattern, cgain)
+                return TM.postprocess(me2, {"CenteredInstanceConfmapsHead": cms, "ClassVectorsHead": vec}, info)
+            return CI.postprocess(me2, {"CenteredInstanceConfmapsHead": topdown_model(crops, gain, pattern)}, info)
+        return predict
+
+    cases = (("plain", False, False, 0.5, 1, 1.0), ("nms", True, False, 0.3, 2, 0.5), ("mc", False, True, 0.5, 1, 1.0),
+             ("mcnms", True, True, 0.3, 1, 1.0))
+    for tag, nms, multiclass, thr, stride, scale in cases:
+        inner = types.SimpleNamespace(predict=ci_predict(multiclass, stride, scale), postprocess_config=cfg)
+        me = types.SimpleNamespace(crop_size=crop_hw, centered_instance_layer=inner, return_crops=True, centroid_nms=nms,
+                                   centroid_nms_threshold=thr, _bbox_iou=T._bbox_iou, _infer_n_nodes=lambda: Nn)
+        with ref_loader.reference_imports():
+            valid = ~torch.isnan(cen).any(dim=-1)  # topdown.py:101
+            if nms:
+                valid = valid & T._centroid_nms_mask(me, cen, cen_val, valid)
+            o = T._run_stage_2(me, img_u8, cen * eff.view(-1, 1, 1), cen_val, valid, eff_scale=eff)  # topdown.py:147-150
+        out.update({f"{tag}_valid": valid, f"{tag}_kpts": o.pred_keypoints, f"{tag}_crop_kpts": o.pred_crop_keypoints,
+                    f"{tag}_vals": o.pred_peak_values, f"{tag}_centroids": o.pred_centroids,
+                    f"{tag}_scores": o.instance_scores, f"{tag}_bboxes": o.instance_bboxes, f"{tag}_crops": o.crops,
+                    f"{tag}_knobs": np.array([float(nms), float(multiclass), thr, float(stride), scale])})
+        if multiclass:
+            out.update({f"{tag}_class_inds": o.pred_class_inds, f"{tag}_tracking": o.instance_tracking_scores,
+                        f"{tag}_class_vectors": o.pred_class_vectors})
+    # no valid centroid at all: the early return (topdown.py:218-233)
+    me = types.SimpleNamespace(crop_size=crop_hw, centered_instance_layer=None, return_crops=False, _infer_n_nodes=lambda: Nn)
+    nan_cen = torch.full((2, 3, 2), float("nan"))
+    o = T._run_stage_2(me, img_u8[:2], nan_cen, torch.full((2, 3), float("nan")), torch.zeros((2, 3), dtype=torch.bool))
+    out.update(empty_kpts=o.pred_keypoints, empty_vals=o.pred_peak_values)
+    # stand-alone multi-class layer: ONE assignment over all crops; single-instance layer: the plain ladder
+    crops6 = img_u8[:1, :, :24, :32].repeat(6, 1, 1, 1).clone()
+    for r in range(6):
+        crops6[r] = img_u8[r % B, :, 8 * r : 8 * r + 24, 10 * r : 10 * r + 32]
+    cms6, vec6 = topdown_model(crops6, gain, pattern, cgain)
+    info6 = P(eff_scale=torch.tensor([1.0, 0.5, 1.0, 1.5, 0.75, 1.0]), input_scale=0.5, output_stride=2)
+    me2 = types.SimpleNamespace(postprocess_config=cfg, _extract_confmaps=extract)
+    with ref_loader.reference_imports():
+        o = TM.postprocess(me2, {"CenteredInstanceConfmapsHead": cms6, "ClassVectorsHead": vec6}, info6)
+    out.update(sa_crops=crops6, sa_eff=info6.eff_scale, sa_kpts=o.pred_keypoints, sa_vals=o.pred_peak_values,
+               sa_class_inds=o.pred_class_inds, sa_class_probs=o.pred_class_probs, sa_tracking=o.instance_tracking_scores)
+    me3 = types.SimpleNamespace(postprocess_config=cfg, _extract_confmaps=lambda raw: raw["SingleInstanceConfmapsHead"])
+    o = SI.postprocess(me3, {"SingleInstanceConfmapsHead": cms6}, info6)
+    out.update(si_kpts=o.pred_keypoints, si_vals=o.pred_peak_values)
+    save("ref_f2_topdown.npz", **out)
+
+
 def main():
     R = ref_loader.ref()
+    if len(sys.argv) > 1:  # regenerate only the named files' functions, e.g. `make_golden.py f2_topdown`
+        torch.set_num_threads(1)
+        for name in sys.argv[1:]:
+            globals()[name](R)
+        return
     torch.set_num_threads(1)  # reductions are then run-to-run reproducible
     peaks_minimal(R)
     peaks_random(R)
@@ -676,6 +780,7 @@ def main():
     targets(R)
     f1_outputs(R)
     f2_layers(R)
+    f2_topdown(R)
     f3_identity(R)
     f3_multiclass_layer(R)
     f4_batched_targets(R)

@@ -71,3 +71,14 @@ def fake_labels(d):
             k += 1
         lfs.append(types.SimpleNamespace(instances=objs))
     return types.SimpleNamespace(labeled_frames=lfs)
+
+
+def topdown_model(crops, gain, pattern, cgain=None):
+    """The stand-in centred-instance "network" of the top-down goldens (tests/golden/make_golden.py:f2_topdown):
+    crops (n, 1, h, w) uint8 / float -> confmaps (n, N, h, w) [, class vectors (n, K)].  Every op is an exactly
+    rounded elementwise fp32 op or a max, so CPU and CUDA runs see bit-identical maps."""
+    x = crops.to(torch.float32) * 0.00390625  # 1 / 256: exact
+    cms = x * gain.unsqueeze(0) + pattern.unsqueeze(0)
+    if cgain is None:
+        return cms
+    return cms, (x * cgain.unsqueeze(0)).amax(dim=(2, 3))

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     assert set(table) == set(decl), set(table) ^ set(decl)
     for name, argtypes in table.items():
         assert len(argtypes) == decl[name], f"{name}: ctypes arity {len(argtypes)} != header {decl[name]}"
-    assert N.ABI_VERSION == 3
+    assert N.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback_without_gpu():

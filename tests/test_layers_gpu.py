@@ -84,3 +84,120 @@ def test_peaks_topk_ties_and_overflow():
     N.check(N.lib.snb_peaks_topk(N.ptr(cnt), 1, 8, N.ptr(xy), N.ptr(val), 3, 1.0, None, N.ptr(o_xy), N.ptr(o_val),
                                  N.stream_ptr(dev)), "topk")
     assert o_val[0].tolist() == pytest.approx([0.9, 0.9, 0.5]) and o_xy[0, :, 0].tolist() == [2.0, 4.0, 8.0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Top-down composition (stage B + stage 2), multi-class per-frame assignment, single-instance layer
+# ---------------------------------------------------------------------------------------------------------------
+def _topdown_case(g, tag):
+    from tests.helpers import topdown_model
+
+    gain, pattern, cgain = (T(g[k]).cuda() for k in ("gain", "pattern", "cgain"))
+    nms, multiclass, thr, stride, scale = (float(v) for v in g[f"{tag}_knobs"])
+    model = (lambda c: topdown_model(c, gain, pattern, cgain)) if multiclass else (lambda c: topdown_model(c, gain, pattern))
+    return model, bool(nms), bool(multiclass), thr, int(stride), scale
+
+
+@pytest.mark.parametrize("tag", ["plain", "nms", "mc", "mcnms"])
+def test_topdown_postproc_golden(tag):
+    """TopDownPostproc vs TopDownLayer._centroid_nms_mask / _run_stage_2 run on the unmodified reference classes."""
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+
+    g = golden("ref_f2_topdown.npz")
+    model, nms, multiclass, thr, stride, scale = _topdown_case(g, tag)
+    post = TopDownPostproc(tuple(int(v) for v in g["crop_hw"]), peak_threshold=0.2, refinement="integral", centroid_nms=nms,
+                           centroid_nms_threshold=thr, return_crops=True, return_class_vectors=True)
+    o = post(T(g["image"]).cuda(), T(g["centroids"]).cuda(), T(g["centroid_vals"]).cuda(), model, eff_scale=T(g["eff"]).cuda(),
+             output_stride=stride, input_scale=scale)
+    post.check()
+    eq(npy(o["valid_mask"]), g[f"{tag}_valid"])
+    eq(npy(o["crops"]), g[f"{tag}_crops"])                      # integer crop pickup: bit-exact
+    eq(npy(o["pred_peak_values"]), g[f"{tag}_vals"])            # arg-max values: bit-exact
+    eq(np.isnan(npy(o["pred_keypoints"])), np.isnan(g[f"{tag}_kpts"]))
+    close(npy(o["pred_keypoints"]), g[f"{tag}_kpts"], atol=1e-4)      # refined coordinates: 1e-4 px
+    close(npy(o["pred_crop_keypoints"]), g[f"{tag}_crop_kpts"], atol=1e-4)
+    eq(npy(o["pred_centroids"]), g[f"{tag}_centroids"])         # (c * eff) / eff, separately rounded
+    eq(npy(o["instance_bboxes"]), g[f"{tag}_bboxes"])
+    eq(npy(o["instance_scores"]), g[f"{tag}_scores"])
+    if multiclass:
+        eq(npy(o["pred_class_inds"]), g[f"{tag}_class_inds"])   # per-frame optimal assignment: bit-exact
+        eq(npy(o["instance_tracking_scores"]), g[f"{tag}_tracking"])
+        eq(npy(o["pred_class_vectors"]), g[f"{tag}_class_vectors"])
+    else:
+        assert "pred_class_inds" not in o
+
+
+def test_topdown_postproc_no_valid_centroid():
+    """All-NaN centroids: no crop, no model call, all-NaN outputs of the right shape (topdown.py:218-233)."""
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+
+    g = golden("ref_f2_topdown.npz")
+    post = TopDownPostproc((24, 32), n_nodes=3)
+    cen = torch.full((2, 3, 2), float("nan"), device="cuda")
+
+    def model(_):
+        raise AssertionError("the network must not run when there is nothing to crop")
+
+    o = post(T(g["image"])[:2].cuda(), cen, torch.full((2, 3), float("nan"), device="cuda"), model)
+    eq(npy(o["pred_keypoints"]), g["empty_kpts"])
+    eq(npy(o["pred_peak_values"]), g["empty_vals"])
+    assert not npy(o["valid_mask"]).any() and "instance_bboxes" not in o
+
+
+def test_standalone_multiclass_and_single_instance_layers():
+    from sleap_nn_b200.inference.layers import CenteredInstanceMultiClassPostproc, SingleInstancePostproc
+    from tests.helpers import topdown_model
+
+    g = golden("ref_f2_topdown.npz")
+    gain, pattern, cgain = (T(g[k]).cuda() for k in ("gain", "pattern", "cgain"))
+    cms, vec = topdown_model(T(g["sa_crops"]).cuda(), gain, pattern, cgain)
+    o = CenteredInstanceMultiClassPostproc(0.2, "integral", 5).classify(cms, vec, output_stride=2, input_scale=0.5,
+                                                                         eff_scale=T(g["sa_eff"]))
+    close(npy(o["pred_keypoints"]), g["sa_kpts"], atol=1e-4)
+    eq(npy(o["pred_peak_values"]), g["sa_vals"])
+    eq(npy(o["pred_class_inds"]), g["sa_class_inds"])
+    eq(npy(o["pred_class_probs"]), g["sa_class_probs"])
+    eq(npy(o["instance_tracking_scores"]), g["sa_tracking"])
+    xy, val = SingleInstancePostproc(0.2, "integral", 5)(cms, output_stride=2, input_scale=0.5, eff_scale=T(g["sa_eff"]))
+    close(npy(xy), g["si_kpts"], atol=1e-4)
+    eq(npy(val), g["si_vals"])
+
+
+@pytest.mark.parametrize("seed,nms", [(0, False), (1, True), (2, True)])
+def test_topdown_postproc_random_vs_oracle(seed, nms):
+    """Seeded larger case (B=16, up to 12 centroids per frame, 5 classes) against the CPU oracle."""
+    from oracle import topdown as otd
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+    from tests.helpers import topdown_model
+
+    gen = torch.Generator().manual_seed(seed)
+    B, I, H, W, crop_hw, Nn, K = 16, 12, 160, 192, (32, 40), 4, 5
+    cen = torch.rand((B, I, 2), generator=gen) * torch.tensor([W - 1.0, H - 1.0])
+    cen[torch.rand((B, I), generator=gen) < 0.3] = float("nan")
+    cen[3] = float("nan")                      # a frame without any centroid
+    cen[5, 1:] = float("nan")                  # a frame with exactly one
+    val = torch.rand((B, I), generator=gen)
+    eff = torch.rand((B,), generator=gen) * 0.5 + 0.75
+    img = (torch.rand((B, 1, H, W), generator=gen) * 255).to(torch.uint8)
+    gain = torch.rand((Nn, *crop_hw), generator=gen) * 0.5 + 0.5
+    pattern = torch.rand((Nn, *crop_hw), generator=gen) * 1e-3
+    cgain = torch.rand((K, *crop_hw), generator=gen) * 0.5 + 0.5
+    want = otd.stage_2(img, cen, val, eff, crop_hw, lambda c: topdown_model(c, gain, pattern, cgain), nms=nms,
+                       nms_threshold=0.2, output_stride=2, input_scale=0.5)
+    post = TopDownPostproc(crop_hw, centroid_nms=nms, centroid_nms_threshold=0.2, return_crops=True, return_class_vectors=True)
+    gd, pd, cd = gain.cuda(), pattern.cuda(), cgain.cuda()
+    o = post(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd, cd), eff_scale=eff.cuda(), output_stride=2,
+             input_scale=0.5)
+    post.check()
+    eq(npy(o["valid_mask"]), want["valid"])
+    if nms:
+        assert want["valid"].sum() < (~np.isnan(npy(cen)).any(-1)).sum(), "the case must exercise the suppression"
+    eq(npy(o["crops"]), want["crops"])
+    eq(npy(o["pred_peak_values"]), want["vals"])
+    close(npy(o["pred_keypoints"]), want["kpts"], atol=1e-4)
+    close(npy(o["pred_crop_keypoints"]), want["crop_kpts"], atol=1e-4)
+    eq(npy(o["pred_centroids"]), want["centroids"])
+    eq(npy(o["instance_bboxes"]), want["bboxes"])
+    eq(npy(o["pred_class_inds"]), want["class_inds"])
+    eq(npy(o["instance_tracking_scores"]), want["tracking"])
+    eq(npy(o["pred_class_vectors"]), want["class_vectors"])
