@@ -127,6 +127,11 @@ int snb_peaks_topk(const int* frame_count, int B, int cap, const float* xy, cons
 int snb_coord_ladder_apply(const float* xy, long long n_samples, long long pairs_per_sample,
                            const snb_coord_ladder* ladder, float* out, void* stream);
 
+/* apply_input_scale (ops/coord.py:93-109): bilinear resize (align_corners=False, no antialias) of `planes` planes of
+ * H x W (element strides sp, sh, sw) to contiguous (planes, oh, ow).  dtype: 0 fp32, 1 fp16, 2 bf16. */
+int snb_bilinear_resize(const void* in, int dtype, long long planes, int H, int W, long long sp, long long sh,
+                        long long sw, int oh, int ow, void* out, void* stream);
+
 /* crop_bboxes (ops/crops.py:31-124).  images (S,C,H,W) of elem_size bytes (1,2,4,8), bboxes
  * (n,4,2) fp32, sample_inds int64; crop_h/crop_w are read from bbox 0 by the caller, as the
  * reference does (ops/crops.py:66-67).  out (n,C,crop_h,crop_w) contiguous. */
@@ -399,6 +404,9 @@ typedef struct snb_filter_config {
   double overlapping_threshold;
   double min_centroid_distance_sq;
 } snb_filter_config;
+/* FilterPipeline._bbox_iou / _oks (inference/filters.py:290-338) for one pair of keypoint sets a, b (N, 2), fp32
+ * (is_f64 = 0) or float64: out[0] = IoU of the two NaN-aware boxes, out[1] = OKS with the scale from a's box area. */
+int snb_pair_similarity(const void* a, const void* b, int N, int is_f64, double kappa, double* out, void* stream);
 int snb_filter_instances(const snb_filter_config* cfg, int B, int I, int N, const float* kpts, const float* vals,
                          const float* scores, const float* centroids, const float* centroid_vals, float* o_kpts,
                          float* o_vals, float* o_scores, float* o_centroids, float* o_centroid_vals, void* stream);

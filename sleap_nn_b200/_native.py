@@ -43,6 +43,7 @@ SIGNATURES = {
     "snb_global_peaks_ex": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
     "snb_peaks_topk": [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p],
     "snb_coord_ladder_apply": [_p, _ll, _ll, _p, _p, _p],
+    "snb_bilinear_resize": [_p, _i, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _p, _p],
     "snb_crop_bboxes": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p, _ll, _i, _i, _p, _p, _p],
     "snb_centered_bboxes": [_p, _ll, _f, _f, _p, _p],
     "snb_topdown_select": [_p, _p, _i, _i, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -78,6 +79,7 @@ SIGNATURES = {
     "snb_class_inds_grouped": [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "snb_class_vectors": [_p, _i, _i, _i, _p, _p, _p],
     "snb_class_maps": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
+    "snb_pair_similarity": [_p, _p, _i, _i, C.c_double, _p, _p],
     "snb_filter_instances": [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_nms_greedy_f64": [_p, _p, _p, _i, _i, _i, _i, C.c_double, C.c_double, _p, _p, _p],
     "snb_instance_stats_f64": [_p, _p, _ll, _i, _p, _p, _p],

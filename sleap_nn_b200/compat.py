@@ -33,10 +33,18 @@ ALIASES = {
     "sleap_nn.data.identity": "sleap_nn_b200.data.identity",
     "sleap_nn.inference.ops.coord": "sleap_nn_b200.inference.ops.coord",
 }
+# Reference modules that hold more than the hot path: when the real module is importable only these functions are
+# re-pointed on it; when it is not (a box with only this repo) the whole name resolves to this package's module.
+PATCHES = {
+    "sleap_nn.data.utils": ("sleap_nn_b200.data.utils", ("make_grid_vectors", "gaussian_pdf")),
+    "sleap_nn.data.instance_cropping": ("sleap_nn_b200.data.instance_cropping", ("make_centered_bboxes",)),
+    "sleap_nn.inference.utils": ("sleap_nn_b200.inference.utils", ("interp1d",)),
+}
 # sleap_nn.inference.filters is NOT aliased wholesale: the reference module also re-exports `Outputs`; a maintainer
 # swaps `FilterPipeline` / `FilterConfig` for sleap_nn_b200.inference.filters' (see INTEGRATION.md).
 
 _saved: Optional[Dict[str, Optional[types.ModuleType]]] = None
+_patched: Dict[str, Dict[str, object]] = {}
 
 
 def _ensure_parent(name: str) -> types.ModuleType:
@@ -69,6 +77,22 @@ def install() -> None:
         _saved[ref_name] = sys.modules.get(ref_name)
         sys.modules[ref_name] = ours
         setattr(parent, leaf, ours)
+    for ref_name, (our_name, names) in PATCHES.items():
+        ours = importlib.import_module(our_name)
+        parent_name, _, leaf = ref_name.rpartition(".")
+        parent = _ensure_parent(parent_name)
+        try:
+            real = sys.modules.get(ref_name) or importlib.import_module(ref_name)
+        except Exception:
+            real = None
+        if real is None or real is ours:
+            _saved[ref_name] = None
+            sys.modules[ref_name] = ours
+            setattr(parent, leaf, ours)
+        else:
+            _patched[ref_name] = {n: getattr(real, n, None) for n in names if hasattr(ours, n)}
+            for n in _patched[ref_name]:
+                setattr(real, n, getattr(ours, n))
 
 
 def uninstall() -> None:
@@ -88,6 +112,12 @@ def uninstall() -> None:
             parent = sys.modules.get(parent_name)
             if parent is not None:
                 setattr(parent, leaf, prev)
+    for ref_name, names in _patched.items():
+        real = sys.modules.get(ref_name)
+        for n, prev in names.items():
+            if real is not None:
+                setattr(real, n, prev) if prev is not None else delattr(real, n)
+    _patched.clear()
     for name in [n for n, m in sys.modules.items() if getattr(m, "__sleapnn_b200_stub__", False)]:
         sys.modules.pop(name, None)
     _saved = None

@@ -413,6 +413,59 @@ __global__ void instance_stats_f64_kernel(const double* __restrict__ pts, const 
 
 using namespace snb;
 
+// FilterPipeline._bbox_iou / _oks (filters.py:290-338) for ONE pair of keypoint sets, in the dtype the caller holds
+// (the reference computes in the tensors' dtype: fp32 inside the pipeline, float64 in its own unit tests).
+// out[0] = IoU, out[1] = OKS(a, b) with the scale taken from a.  A single thread: N is a handful of nodes.
+__global__ void pair_similarity_kernel(const void* __restrict__ a_, const void* __restrict__ b_, int N, int is_f64,
+                                       double kappa, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (is_f64) {
+    const double* a = (const double*)a_;
+    const double* b = (const double*)b_;
+    BoxD ba{INFINITY, INFINITY, -INFINITY, -INFINITY, 0}, bb = ba;
+    for (int n = 0; n < N; ++n) {
+      if (a[2 * n] == a[2 * n] && a[2 * n + 1] == a[2 * n + 1]) {
+        ba.x1 = fmin(ba.x1, a[2 * n]); ba.y1 = fmin(ba.y1, a[2 * n + 1]);
+        ba.x2 = fmax(ba.x2, a[2 * n]); ba.y2 = fmax(ba.y2, a[2 * n + 1]);
+        ++ba.rows;
+      }
+      if (b[2 * n] == b[2 * n] && b[2 * n + 1] == b[2 * n + 1]) {
+        bb.x1 = fmin(bb.x1, b[2 * n]); bb.y1 = fmin(bb.y1, b[2 * n + 1]);
+        bb.x2 = fmax(bb.x2, b[2 * n]); bb.y2 = fmax(bb.y2, b[2 * n + 1]);
+        ++bb.rows;
+      }
+    }
+    out[0] = (ba.rows == 0 || bb.rows == 0) ? 0.0 : iou_f64(ba, bb);
+    out[1] = oks_f64(a, ba, b, N, kappa);
+  } else {
+    const float* a = (const float*)a_;
+    const float* b = (const float*)b_;
+    InstBox ba{INFINITY, INFINITY, -INFINITY, -INFINITY, 0, 0}, bb = ba;
+    for (int n = 0; n < N; ++n) {
+      if (a[2 * n] == a[2 * n] && a[2 * n + 1] == a[2 * n + 1]) {
+        ba.x1 = fminf(ba.x1, a[2 * n]); ba.y1 = fminf(ba.y1, a[2 * n + 1]);
+        ba.x2 = fmaxf(ba.x2, a[2 * n]); ba.y2 = fmaxf(ba.y2, a[2 * n + 1]);
+        ++ba.rows;
+      }
+      if (b[2 * n] == b[2 * n] && b[2 * n + 1] == b[2 * n + 1]) {
+        bb.x1 = fminf(bb.x1, b[2 * n]); bb.y1 = fminf(bb.y1, b[2 * n + 1]);
+        bb.x2 = fmaxf(bb.x2, b[2 * n]); bb.y2 = fmaxf(bb.y2, b[2 * n + 1]);
+        ++bb.rows;
+      }
+    }
+    out[0] = bbox_iou(ba, bb);
+    out[1] = oks(a, ba, b, N, (float)(kappa * kappa));  // kappa**2 is a python float, cast once by the tensor op
+  }
+}
+
+extern "C" int snb_pair_similarity(const void* a, const void* b, int N, int is_f64, double kappa, double* out,
+                                   void* stream) {
+  if (N < 0 || !out) return SNB_ERR_BAD_ARG;
+  pair_similarity_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, b, N, is_f64, kappa, out);
+  SNB_LAUNCH_CHECK();
+  return SNB_OK;
+}
+
 extern "C" int snb_filter_instances(const snb_filter_config* cfg, int B, int I, int N, const float* kpts,
                                     const float* vals, const float* scores, const float* centroids,
                                     const float* centroid_vals, float* o_kpts, float* o_vals, float* o_scores,

@@ -75,6 +75,30 @@ class FilterPipeline:
     def run(cls, outputs, config: FilterConfig):
         return cls(config=config)(outputs)
 
+    @staticmethod
+    def _pair_similarity(a: torch.Tensor, b: torch.Tensor, kappa: float):
+        """(IoU, OKS) of two keypoint sets (N, 2), computed on the device in the tensors' dtype (fp32 or float64)."""
+        dev = N.compute_device(a, b)
+        f64 = a.dtype == torch.float64
+        dt = torch.float64 if f64 else torch.float32
+        a_d, b_d = (t.detach().to(device=dev, dtype=dt).reshape(-1, 2).contiguous() for t in (a, b))
+        out = torch.empty((2,), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            N.check(N.lib.snb_pair_similarity(N.ptr(a_d), N.ptr(b_d), int(a_d.shape[0]), int(f64), float(kappa), N.ptr(out),
+                                              N.stream_ptr(dev)), "snb_pair_similarity")
+        iou, oks = out.tolist()
+        return iou, oks
+
+    @staticmethod
+    def _bbox_iou(a: torch.Tensor, b: torch.Tensor) -> float:
+        """IoU of the boxes implied by two keypoint sets, NaN-aware (filters.py:290-307)."""
+        return FilterPipeline._pair_similarity(a, b, 0.1)[0]
+
+    @staticmethod
+    def _oks(a: torch.Tensor, b: torch.Tensor, kappa: float = 0.1) -> float:
+        """Object-keypoint similarity with the scale taken from a's own box area (filters.py:309-338)."""
+        return FilterPipeline._pair_similarity(a, b, kappa)[1]
+
     def apply(self, outputs):
         """Run all configured filters in the reference's cheap -> expensive order, in one kernel launch."""
         cfg = self.config

@@ -87,4 +87,33 @@ def add_crop_offset(peaks: torch.Tensor, crop_topleft: torch.Tensor) -> torch.Te
     return _apply(flat, crop_offset=crop_topleft.reshape(-1, 2)).reshape(shape)
 
 
-__all__: Tuple[str, ...] = ("undo_stride", "undo_input_scale", "undo_eff_scale", "add_crop_offset")
+_RESIZE_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def apply_input_scale(image: torch.Tensor, input_scale: float) -> torch.Tensor:
+    """Bilinear resize of an image batch by `input_scale` (ops/coord.py:93-109); 1.0 returns the input itself.
+
+    image (B, C, H, W) float -> (B, C, int(H * s), int(W * s)), same dtype and device: what
+    `F.interpolate(mode="bilinear", align_corners=False)` computes, in one kernel that reads the input through its
+    strides.
+    """
+    if input_scale == 1.0:
+        return image
+    if image.dim() != 4 or image.dtype not in _RESIZE_DTYPES:
+        raise TypeError("apply_input_scale expects a (B, C, H, W) float32 / float16 / bfloat16 tensor")
+    B, Cn, H, W = (int(v) for v in image.shape)
+    oh, ow = int(H * input_scale), int(W * input_scale)
+    if oh <= 0 or ow <= 0:
+        raise RuntimeError(f"Input and output sizes should be greater than 0, but got input (H: {H}, W: {W}) output (H: {oh}, W: {ow})")
+    dev = N.compute_device(image)
+    x = image.detach().to(dev)
+    if x.stride(0) != Cn * x.stride(1):  # (B, C) must collapse into one plane axis
+        x = x.contiguous()
+    out = torch.empty((B, Cn, oh, ow), dtype=x.dtype, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.snb_bilinear_resize(N.ptr(x), _RESIZE_DTYPES[x.dtype], B * Cn, H, W, x.stride(1), x.stride(2),
+                                          x.stride(3), oh, ow, N.ptr(out), N.stream_ptr(dev)), "snb_bilinear_resize")
+    return out.to(image.device)
+
+
+__all__: Tuple[str, ...] = ("undo_stride", "undo_input_scale", "undo_eff_scale", "add_crop_offset", "apply_input_scale")

@@ -201,3 +201,25 @@ def test_topdown_postproc_random_vs_oracle(seed, nms):
     eq(npy(o["pred_class_inds"]), want["class_inds"])
     eq(npy(o["instance_tracking_scores"]), want["tracking"])
     eq(npy(o["pred_class_vectors"]), want["class_vectors"])
+
+
+@pytest.mark.parametrize("shape,scale", [((2, 1, 8, 8), 0.5), ((1, 3, 37, 53), 0.75), ((2, 2, 20, 31), 2.0),
+                                         ((1, 1, 384, 384), 0.5), ((4, 1, 1024, 1024), 0.25), ((1, 1, 5, 7), 0.3)])
+def test_apply_input_scale_matches_oracle(shape, scale):
+    """apply_input_scale (ops/coord.py:93-109) vs the numpy restatement of F.interpolate's bilinear rule."""
+    from oracle.resize import apply_input_scale as want_fn
+    from sleap_nn_b200.inference.ops.coord import apply_input_scale
+
+    img = torch.rand(shape, generator=torch.Generator().manual_seed(7))
+    got = apply_input_scale(img.cuda(), scale)
+    want = want_fn(img.numpy(), scale)
+    assert got.is_cuda and tuple(got.shape) == want.shape
+    close(npy(got), want, rtol=1e-6, atol=1e-7)
+    # CPU tensors are accepted (staged to the device, result returned on the CPU); a strided view is read in place
+    close(npy(apply_input_scale(img, scale)), want, rtol=1e-6, atol=1e-7)
+    view = torch.rand((shape[0], shape[1], shape[2], shape[3] * 2), generator=torch.Generator().manual_seed(8)).cuda()[..., ::2]
+    close(npy(apply_input_scale(view, scale)), want_fn(npy(view), scale), rtol=1e-6, atol=1e-7)
+    assert apply_input_scale(img, 1.0) is img
+    half = apply_input_scale(img.cuda().half(), scale)
+    assert half.dtype == torch.float16
+    close(npy(half.float()), want_fn(img.half().float().numpy(), scale), rtol=2e-3, atol=1e-3)

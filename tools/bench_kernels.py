@@ -145,7 +145,7 @@ def memset_ref(dev, iters):
     line("memset_268MB", "cudaMemsetAsync (reference, not ours)", 268435456, ms, 1, "launches")
 
 
-def chain_cfg4(dev, iters, Bn=64):
+def chain_cfg4(dev, iters, Bn=64, n_streams=None):
     """cfg4 inference: 32 nodes / 31 edges / 8 instances per frame (256 peaks, ~2 k candidates per frame), full chain.
 
     Batch 64 on two streams: the per-frame tail (one CTA per frame, ~230 us for such busy frames) needs at least as
@@ -153,13 +153,15 @@ def chain_cfg4(dev, iters, Bn=64):
     batch 8 the tail would run on 8 of the 148 SMs and dominate.
     """
     from sleap_nn_b200.pipeline import BottomUpPostproc
+    n_streams = n_streams or int(os.environ.get("SNB_CHAIN_STREAMS", "4"))
+    Bn = int(os.environ.get("SNB_CHAIN_BATCH", Bn))
     inputs = []
     for s in range(2):  # 2 x 64 x (33.5 + 65.0 MB) = 12.6 GB
         edges, poses = _flies_poses(Bn, seed=s)
         inputs.append(synthetic.render_batch(poses, (1024, 1024), 2, edges, dev, seed=s))
     pipes = [BottomUpPostproc(32, edges, Bn, (512, 512), cms_stride=2, pafs_stride=2, device=dev, peak_cap=512,
-                              cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False) for _ in range(2)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+                              cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False) for _ in range(n_streams)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     res = pipes[0](*inputs[0])
     inst, _, _ = res.to_lists()
     n_inst = sum(len(x) for x in inst)
@@ -171,12 +173,12 @@ def chain_cfg4(dev, iters, Bn=64):
     torch.cuda.synchronize()
 
     def step(i):
-        with torch.cuda.stream(streams[i % 2]):
-            pipes[i % 2](*inputs[i % 2], detect_events=evs[i % iters])
+        with torch.cuda.stream(streams[i % n_streams]):
+            pipes[i % n_streams](*inputs[i % 2], detect_events=evs[i % iters])
 
     for s_ in streams:
         s_.wait_stream(main)
-    for i in range(6):
+    for i in range(3 * n_streams):
         step(i)
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -192,7 +194,7 @@ def chain_cfg4(dev, iters, Bn=64):
     ms = t0.elapsed_time(t1) / iters
     det = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
     algo = 4 * Bn * 32 * 512 * 512
-    line("chain_cfg4", "detect+tail (whole chain, batch %d, two streams)" % Bn, algo, ms, Bn, "frames",
+    line("chain_cfg4", "detect+tail (whole chain, batch %d, %d streams)" % (Bn, n_streams), algo, ms, Bn, "frames",
          {"frames_per_launch": Bn, "instances_found": n_inst, "instances_planted": Bn * 8, "peaks": n_peaks,
           "launches_per_call": pipes[0].launches_per_call, "fused_tail": pipes[0].fused})
     line("k1_cfg4", "local_peaks_detect_vec4 (in situ)", algo, det, Bn, "frames", {"frames_per_launch": Bn})
