@@ -40,6 +40,8 @@ PATCHES = {
     "sleap_nn.data.instance_cropping": ("sleap_nn_b200.data.instance_cropping", ("make_centered_bboxes",)),
     "sleap_nn.inference.utils": ("sleap_nn_b200.inference.utils", ("interp1d",)),
 }
+# sleap_nn.inference.streaming is likewise left alone (it also holds the spawn pool); `ScoredBatch`, `GroupingParams` and
+# `group_scored_batch` of sleap_nn_b200.inference.streaming are drop-ins for the three names of that seam.
 # sleap_nn.inference.filters is NOT aliased wholesale: the reference module also re-exports `Outputs`; a maintainer
 # swaps `FilterPipeline` / `FilterConfig` for sleap_nn_b200.inference.filters' (see INTEGRATION.md).
 

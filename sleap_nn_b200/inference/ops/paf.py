@@ -423,9 +423,10 @@ def toposort_edges(edge_types: List[EdgeType]) -> Tuple[int]:
     return tuple(order)
 
 
-def _assemble(peaks: _Frames, vals: _Frames, chans: _Frames, m_edge: _Frames, m_src: _Frames, m_dst: _Frames,
-              m_score: _Frames, n_nodes: int, sorted_edge_inds, edges_t: torch.Tensor, min_instance_peaks,
-              min_line_scores: float, dev):
+def _assemble_tables(peaks: _Frames, vals: _Frames, chans: _Frames, m_edge: _Frames, m_src: _Frames, m_dst: _Frames,
+                     m_score: _Frames, n_nodes: int, sorted_edge_inds, edges_t: torch.Tensor, min_instance_peaks,
+                     min_line_scores: float, dev):
+    """snb_assemble into padded device tables (B, inst_cap, ...) + per-frame counts; no host synchronisation."""
     B = len(chans.lens)
     if isinstance(min_instance_peaks, float):
         min_instance_peaks = int(min_instance_peaks * n_nodes) if min_instance_peaks > 0 else 0  # paf.py:791-802
@@ -449,6 +450,16 @@ def _assemble(peaks: _Frames, vals: _Frames, chans: _Frames, m_edge: _Frames, m_
                            N.stream_ptr(dev)),
         "snb_assemble",
     )
+    return inst_xy, inst_val, inst_score, n_inst, status
+
+
+def _assemble(peaks: _Frames, vals: _Frames, chans: _Frames, m_edge: _Frames, m_src: _Frames, m_dst: _Frames,
+              m_score: _Frames, n_nodes: int, sorted_edge_inds, edges_t: torch.Tensor, min_instance_peaks,
+              min_line_scores: float, dev):
+    B = len(chans.lens)
+    inst_xy, inst_val, inst_score, n_inst, status = _assemble_tables(peaks, vals, chans, m_edge, m_src, m_dst, m_score,
+                                                                     n_nodes, sorted_edge_inds, edges_t,
+                                                                     min_instance_peaks, min_line_scores, dev)
     n = n_inst.cpu().numpy()
     _status_check(status, "group_instances")
     xy, val, sc = inst_xy.cpu(), inst_val.cpu(), inst_score.cpu()
@@ -457,7 +468,8 @@ def _assemble(peaks: _Frames, vals: _Frames, chans: _Frames, m_edge: _Frames, m_
 
 
 def _group_frames(peaks, peak_vals, peak_channel_inds, match_edge_inds, match_src_peak_inds, match_dst_peak_inds,
-                  match_line_scores, n_nodes, sorted_edge_inds, edge_types, min_instance_peaks, min_line_scores):
+                  match_line_scores, n_nodes, sorted_edge_inds, edge_types, min_instance_peaks, min_line_scores,
+                  tables: bool = False):
     dev = N.compute_device(*[t for t in peaks if isinstance(t, torch.Tensor)])
     as_t = lambda seq: [torch.as_tensor(x) for x in seq]
     with torch.cuda.device(dev):
@@ -469,8 +481,9 @@ def _group_frames(peaks, peak_vals, peak_channel_inds, match_edge_inds, match_sr
         md = _Frames(as_t(match_dst_peak_inds), dev, torch.int32)
         msc = _Frames(as_t(match_line_scores), dev, torch.float32)
         edges_t = _edge_type_tensor(edge_types, dev)
-        return _assemble(pk, pv, pc, me, ms, md, msc, int(n_nodes), sorted_edge_inds, edges_t, min_instance_peaks,
-                         min_line_scores, dev)
+        fn = _assemble_tables if tables else _assemble
+        return fn(pk, pv, pc, me, ms, md, msc, int(n_nodes), sorted_edge_inds, edges_t, min_instance_peaks,
+                  min_line_scores, dev)
 
 
 def group_instances_sample(

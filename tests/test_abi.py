@@ -124,6 +124,14 @@ REFERENCE_SIGNATURES = {
                                 "sigma", "output_stride", "is_centroids"],
     },
     "sleap_nn_b200.data.instance_cropping": {"make_centered_bboxes": ["centroids", "box_height", "box_width"]},
+    "sleap_nn_b200.inference.ops.coord": {
+        "undo_stride": ["coords", "output_stride"],
+        "undo_input_scale": ["coords", "input_scale"],
+        "undo_eff_scale": ["coords", "eff_scale"],
+        "add_crop_offset": ["peaks", "crop_topleft"],
+        "apply_input_scale": ["image", "input_scale"],
+    },
+    "sleap_nn_b200.inference.streaming": {"group_scored_batch": ["scored", "params"]},
 }
 
 
@@ -180,8 +188,28 @@ def test_reference_signatures_table_matches_the_reference_when_present():
         "sleap_nn_b200.inference.ops.identity": [R.identity],
         "sleap_nn_b200.data.identity": [R.data_identity],
         "sleap_nn_b200.data.instance_cropping": [R.instance_cropping],
+        "sleap_nn_b200.inference.ops.coord": [R.coord],
+        "sleap_nn_b200.inference.streaming": [R.streaming],
     }
     for modname, fns in REFERENCE_SIGNATURES.items():
         for fn, params in fns.items():
             ref_fn = next(getattr(m, fn) for m in mods[modname] if hasattr(m, fn))
             assert list(inspect.signature(ref_fn).parameters) == params, fn
+
+
+def test_streaming_value_types_mirror_the_reference_when_present():
+    import attrs
+
+    from oracle import ref_loader
+    from sleap_nn_b200.inference import streaming as ours
+
+    assert [a.name for a in attrs.fields(ours.ScoredBatch)] == [
+        "cms_peaks", "cms_peak_vals", "cms_peak_channel_inds", "edge_inds", "edge_peak_inds", "line_scores", "info",
+        "n_samples", "n_nodes", "skip_paf", "cms", "pafs"]
+    assert [a.name for a in attrs.fields(ours.GroupingParams)] == [
+        "paf_scorer_kwargs", "max_instances", "return_confmaps", "return_pafs", "return_paf_graph"]
+    if not ref_loader.available():
+        pytest.skip("reference tree not present on this box")
+    theirs = ref_loader.ref().streaming
+    for name in ("ScoredBatch", "GroupingParams"):
+        assert [a.name for a in attrs.fields(getattr(ours, name))] == [a.name for a in attrs.fields(getattr(theirs, name))]

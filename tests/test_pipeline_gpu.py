@@ -237,3 +237,43 @@ def test_cuda_graph_rotation_replays_the_chain():
                 assert torch.equal(torch.nan_to_num(g[f, : n_i[f]], nan=-1.0), torch.nan_to_num(w[f, : n_i[f]], nan=-1.0))
         assert torch.equal(got[0], want[k][0])
         assert torch.equal(torch.nan_to_num(got[4], nan=-1.0), torch.nan_to_num(want[k][4], nan=-1.0))
+
+
+def test_group_scored_batch_seam_matches_reference():
+    """The ScoredBatch -> group_scored_batch seam (inference/streaming.py:42-255) as a drop-in: the scored batch comes
+    from this package's own peak / PAF-scoring kernels, the grouped outputs are the reference's (ref_f1_outputs.npz)."""
+    import types
+
+    from sleap_nn_b200.inference.paf_grouping import PAFScorer
+    from sleap_nn_b200.inference.peak_finding import find_local_peaks
+    from sleap_nn_b200.inference.streaming import GroupingParams, ScoredBatch, group_scored_batch
+
+    d, f1 = golden("ref_pipeline_tree.npz"), golden("ref_f1_outputs.npz")
+    cms, pafs = T(d["cms"]).cuda(), T(d["pafs"]).cuda()
+    edges, n_nodes, stride = d["edges"].tolist(), int(d["n_nodes"]), int(d["stride"])
+    B = cms.shape[0]
+    pts, vals, si, ci = find_local_peaks(cms, threshold=0.2, refinement="integral")
+    pts = pts * stride
+    split = lambda x: [x[si == b] for b in range(B)]
+    peaks, pvals, pch = split(pts), split(vals), split(ci)
+    kwargs = dict(part_names=[str(i) for i in range(n_nodes)], edges=[(str(a), str(b)) for a, b in edges], pafs_stride=stride,
+                  max_edge_length_ratio=0.25, dist_penalty_weight=1.0, n_points=10,
+                  min_instance_peaks=int(d["min_instance_peaks"]), min_line_scores=0.25)
+    ei, epi, ls = PAFScorer(**kwargs).score_paf_lines(pafs.permute(0, 2, 3, 1), peaks, pch)
+    for tag in f1["cases"].tolist():
+        mi = int(f1[f"{tag}_max_instances"])
+        skip = bool(f1[f"{tag}_skip"])
+        info = types.SimpleNamespace(eff_scale=T(f1[f"{tag}_eff"]), input_scale=float(f1[f"{tag}_input_scale"]))
+        sb = ScoredBatch(cms_peaks=peaks, cms_peak_vals=pvals, cms_peak_channel_inds=pch, edge_inds=[] if skip else ei,
+                         edge_peak_inds=[] if skip else epi, line_scores=[] if skip else ls, info=info, n_samples=B,
+                         n_nodes=n_nodes, skip_paf=skip, cms=cms)
+        res = group_scored_batch(sb.to_cpu(), GroupingParams(paf_scorer_kwargs=kwargs, max_instances=None if mi < 0 else mi,
+                                                             return_confmaps=True, return_paf_graph=True))
+        want_k, want_v, want_s = f1[f"{tag}_kpts"], f1[f"{tag}_vals"], f1[f"{tag}_scores"]
+        assert not res.pred_keypoints.is_cuda and tuple(res.pred_keypoints.shape) == want_k.shape, tag
+        eq(np.isnan(npy(res.pred_keypoints)), np.isnan(want_k))
+        close(npy(res.pred_keypoints), want_k, atol=1e-4)
+        eq(npy(res.pred_peak_values), want_v)
+        close(npy(res.instance_scores), want_s, rtol=1e-5, atol=1e-5)
+        assert res.pred_confmaps is not None and len(res.pred_paf_graph) == 4
+        assert res.pred_paf_graph[0].shape[0] == sum(p.shape[0] for p in peaks)
