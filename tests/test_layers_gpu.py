@@ -223,3 +223,52 @@ def test_apply_input_scale_matches_oracle(shape, scale):
     half = apply_input_scale(img.cuda().half(), scale)
     assert half.dtype == torch.float16
     close(npy(half.float()), want_fn(img.half().float().numpy(), scale), rtol=2e-3, atol=1e-3)
+
+
+def test_topdown_postproc_wide_frames_and_many_classes():
+    """More slots than a warp (I = 40) and more classes than a warp (K = 40): the strided loops of the select kernel and the
+    serial assignment path of the class kernel, against the oracle."""
+    from oracle import topdown as otd
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+    from tests.helpers import topdown_model
+
+    gen = torch.Generator().manual_seed(11)
+    B, I, H, W, crop_hw, Nn, K = 3, 40, 128, 160, (16, 24), 2, 40
+    cen = torch.rand((B, I, 2), generator=gen) * torch.tensor([W - 1.0, H - 1.0])
+    cen[torch.rand((B, I), generator=gen) < 0.15] = float("nan")
+    val = torch.rand((B, I), generator=gen)
+    img = (torch.rand((B, 1, H, W), generator=gen) * 255).to(torch.uint8)
+    gain = torch.rand((Nn, *crop_hw), generator=gen) * 0.5 + 0.5
+    pattern = torch.rand((Nn, *crop_hw), generator=gen) * 1e-3
+    cgain = torch.rand((K, *crop_hw), generator=gen) * 0.5 + 0.5
+    want = otd.stage_2(img, cen, val, None, crop_hw, lambda c: topdown_model(c, gain, pattern, cgain), nms=True, nms_threshold=0.1)
+    post = TopDownPostproc(crop_hw, centroid_nms=True, centroid_nms_threshold=0.1, return_class_vectors=True)
+    gd, pd, cd = gain.cuda(), pattern.cuda(), cgain.cuda()
+    o = post(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd, cd))
+    post.check()
+    eq(npy(o["valid_mask"]), want["valid"])
+    assert 0 < want["valid"].sum() < (~np.isnan(npy(cen)).any(-1)).sum()
+    eq(npy(o["pred_peak_values"]), want["vals"])
+    close(npy(o["pred_keypoints"]), want["kpts"], atol=1e-4)
+    eq(npy(o["pred_class_inds"]), want["class_inds"])
+    eq(npy(o["instance_tracking_scores"]), want["tracking"])
+    eq(npy(o["pred_class_vectors"]), want["class_vectors"])
+
+
+def test_topdown_select_degenerate_shapes_and_bad_class_vectors():
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+
+    post = TopDownPostproc((8, 8), n_nodes=2)
+    img = torch.zeros((0, 1, 16, 16), dtype=torch.uint8, device="cuda")
+    o = post(img, torch.zeros((0, 3, 2), device="cuda"), torch.zeros((0, 3), device="cuda"), lambda c: c.float())
+    assert tuple(o["pred_keypoints"].shape) == (0, 3, 2, 2) and tuple(o["valid_mask"].shape) == (0, 3)
+    img = torch.zeros((2, 1, 16, 16), dtype=torch.uint8, device="cuda")
+    o = post(img, torch.zeros((2, 0, 2), device="cuda"), torch.zeros((2, 0), device="cuda"), lambda c: c.float())
+    assert tuple(o["pred_keypoints"].shape) == (2, 0, 2, 2)
+    # a NaN class probability is an invalid cost matrix: ValueError, like scipy inside get_class_inds_from_vectors
+    cen = torch.tensor([[[8.0, 8.0], [4.0, 4.0]]], device="cuda")
+    model = lambda c: (c.float().repeat(1, 2, 1, 1) + 0.5, torch.full((c.shape[0], 3), float("nan"), device=c.device))
+    o = post(img[:1], cen, torch.tensor([[0.9, 0.8]], device="cuda"), model)
+    with pytest.raises(ValueError):
+        post.check()
+    assert (npy(o["pred_class_inds"]) == -1).all()
