@@ -1143,12 +1143,17 @@ extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W,
   static const bool use_ring = getenv("SNB_GLOBAL_RING") != nullptr;    // A/B: the persistent cp.async ring kernel
   const size_t ring_smem = (size_t)GP_STAGES * H * W * sizeof(float);
   if (vec && !force_generic && !use_ring && !no_ring && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
+    // A/B (SNB_GLOBAL_WARP_SMEM = bytes of unused dynamic shared memory per CTA): caps the resident warps per SM so that a
+    // launch whose planes would all be resident at once (cfg2: 22.5 per SM) runs in several waves and a wave's refinement
+    // epilogue overlaps the next wave's loads.  Measured on B200: WORSE at every cap (12-36 KB: 20.5-28.2 us vs 16.7 us) -
+    // the stream needs all ~22 warps x 4 KB in flight per SM more than it needs the epilogue hidden.  Default stays 0.
+    static const int pad_smem = getenv("SNB_GLOBAL_WARP_SMEM") ? atoi(getenv("SNB_GLOBAL_WARP_SMEM")) : 0;
     if (sh == W)
-      global_peaks_warp_kernel<8, true><<<(unsigned)planes, 32, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold, refine_size,
-                                                                        out_xy, out_val, lad);
+      global_peaks_warp_kernel<8, true><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
+                                                                               refine_size, out_xy, out_val, lad);
     else
-      global_peaks_warp_kernel<8, false><<<(unsigned)planes, 32, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold,
-                                                                         refine_size, out_xy, out_val, lad);
+      global_peaks_warp_kernel<8, false><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
+                                                                                refine_size, out_xy, out_val, lad);
   } else if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
     static bool attr_set = false;
     if (!attr_set) {
