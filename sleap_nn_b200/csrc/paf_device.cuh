@@ -353,112 +353,214 @@ struct AsmFrame {
   int inst_cap; float* oxy; float* oval; float* osc; int* n_inst_out; int* status;
 };
 
-__device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane) {
-  const int P = f.P, K = f.K;
-  for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
-  __syncwarp();
-  int n_order = 0;
-  for (int se = 0; se < f.n_sorted; ++se) {
-    const int e = f.sorted[se];
-    const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
-    const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
-    for (int m = m_lo; m < m_hi; ++m) {
-      if (f.m_edge[m] != e) continue;
-      if (!(f.m_score[m] >= f.min_line_scores)) continue;  // paf.py:993
-      const int sp = f.m_src[m], dp = f.m_dst[m];
-      if (sn < 0 || sn >= f.n_nodes || dn < 0 || dn >= f.n_nodes || sp < 0 || dp < 0 ||
-          sp >= f.ns[sn + 1] - f.ns[sn] || dp >= f.ns[dn + 1] - f.ns[dn]) {
-        if (lane == 0) atomicOr(f.status, SNB_STATUS_BAD_INDEX);
-        continue;
-      }
-      const int pa = f.np_[f.ns[sn] + sp], pb = f.np_[f.ns[dn] + dp];
-      const int ia = f.owner[pa], ib = f.owner[pb];
-      __syncwarp();  // every lane has read owner[] before lane 0 rewrites it below (WAR hazard found by racecheck)
-      if (ia < 0 && ib < 0) {
-        int mx = -1;
-        for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);
-        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
-        __syncwarp();
-        if (lane == 0) {
-          f.owner[pa] = mx + 1;
-          f.owner[pb] = mx + 1;
-          f.order[n_order] = pa;
-          if (pb != pa) f.order[n_order + 1] = pb;
-        }
-        n_order += (pb != pa) ? 2 : 1;
-      } else if (ia >= 0 && ib < 0) {
-        if (lane == 0) { f.owner[pb] = ia; f.order[n_order] = pb; }
-        n_order += 1;
-      } else if (ia >= 0 && ib >= 0) {
-        if (lane == 0) f.owner[pb] = ia;
-        __syncwarp();
-        if (ia != ib) {
-          for (int k = lane; k < f.n_nodes; k += 32) { f.fa[k] = 0; f.fb[k] = 0; }
-          __syncwarp();
-          for (int i = lane; i < P; i += 32) {
-            const int o = f.owner[i];
-            const int c = f.chan[i];
-            if (c >= 0 && c < f.n_nodes) {
-              if (o == ia) f.fa[c] = 1;
-              if (o == ib) f.fb[c] = 1;
-            }
-          }
-          __syncwarp();
-          int hit = 0;
-          for (int k = lane; k < f.n_nodes; k += 32) hit |= (f.fa[k] & f.fb[k]);
-          hit = __any_sync(FULL, hit);
-          if (!hit)
-            for (int i = lane; i < P; i += 32)
-              if (f.owner[i] == ib) f.owner[i] = ia;
+// One connection, applied by the whole warp exactly as the reference's loop body does (paf.py:754-789).  Used when
+// a chunk of an edge's connections cannot be applied together (a merge candidate, a repeated peak, a self edge).
+__device__ __forceinline__ void assemble_one(const AsmFrame& f, int lane, int pa, int pb, int& n_order) {
+  const int P = f.P;
+  const int ia = f.owner[pa], ib = f.owner[pb];
+  __syncwarp();  // every lane has read owner[] before lane 0 rewrites it below (WAR hazard found by racecheck)
+  if (ia < 0 && ib < 0) {
+    int mx = -1;
+    for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+    __syncwarp();
+    if (lane == 0) {
+      f.owner[pa] = mx + 1;
+      f.owner[pb] = mx + 1;
+      f.order[n_order] = pa;
+      if (pb != pa) f.order[n_order + 1] = pb;
+    }
+    n_order += (pb != pa) ? 2 : 1;
+  } else if (ia >= 0 && ib < 0) {
+    if (lane == 0) { f.owner[pb] = ia; f.order[n_order] = pb; }
+    n_order += 1;
+  } else if (ia >= 0 && ib >= 0) {
+    if (lane == 0) f.owner[pb] = ia;
+    __syncwarp();
+    if (ia != ib) {
+      for (int k = lane; k < f.n_nodes; k += 32) { f.fa[k] = 0; f.fb[k] = 0; }
+      __syncwarp();
+      for (int i = lane; i < P; i += 32) {
+        const int o = f.owner[i];
+        const int c = f.chan[i];
+        if (c >= 0 && c < f.n_nodes) {
+          if (o == ia) f.fa[c] = 1;
+          if (o == ib) f.fb[c] = 1;
         }
       }
       __syncwarp();
+      int hit = 0;
+      for (int k = lane; k < f.n_nodes; k += 32) hit |= (f.fa[k] & f.fb[k]);
+      hit = __any_sync(FULL, hit);
+      if (!hit)
+        for (int i = lane; i < P; i += 32)
+          if (f.owner[i] == ib) f.owner[i] = ia;
     }
   }
-  // instance sizes, min_instance_peaks filter, ascending-id compaction
+  __syncwarp();
+}
+
+// The greedy loop is sequential in the reference, but within ONE edge a proper matching touches every peak at most
+// once, so as long as no connection of a 32-wide chunk joins two existing instances ("both owned, different ids": the
+// only case that renames ids) the chunk's connections commute: each lane takes one connection, new ids are handed
+// out by a prefix count over the "neither owned" lanes (= max id so far + 1 + rank, exactly the sequential values;
+// the running maximum is kept in a register and re-scanned only after a fallback chunk), and the first-assignment
+// list is appended at prefix offsets.  Chunks with a merge candidate, a repeated peak or a self edge fall back to
+// assemble_one per connection.  ncu + clock64 stamps on busy frames (32 nodes, 8 animals): the one-connection-
+// at-a-time version spent 265 us of the tail's 348 us here, half of it in a lane-0 loop that accumulated the
+// instance scores with a global-memory read-modify-write per connection.
+__device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane) {
+  const int P = f.P, K = f.K;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
+  __syncwarp();
+  int n_order = 0, mx = -1;
+  for (int se = 0; se < f.n_sorted; ++se) {
+    const int e = f.sorted[se];
+    const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+    const bool nodes_ok = sn >= 0 && sn < f.n_nodes && dn >= 0 && dn < f.n_nodes;
+    const int s0 = nodes_ok ? f.ns[sn] : 0, d0 = nodes_ok ? f.ns[dn] : 0;
+    const int n_src = nodes_ok ? f.ns[sn + 1] - s0 : 0, n_dst = nodes_ok ? f.ns[dn + 1] - d0 : 0;
+    const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+    for (int mb = m_lo; mb < m_hi; mb += 32) {
+      const int m = mb + lane;
+      bool act = m < m_hi && f.m_edge[m] == e && (f.m_score[m] >= f.min_line_scores);  // paf.py:993
+      int pa = -1 - lane, pb = -1 - lane;  // distinct placeholders for __match_any_sync
+      if (act) {
+        const int sp = f.m_src[m], dp = f.m_dst[m];
+        if (sp < 0 || dp < 0 || sp >= n_src || dp >= n_dst) {
+          atomicOr(f.status, SNB_STATUS_BAD_INDEX);
+          act = false;
+        } else {
+          pa = f.np_[s0 + sp];
+          pb = f.np_[d0 + dp];
+        }
+      }
+      const unsigned am = __ballot_sync(FULL, act);
+      if (am == 0) continue;
+      const int ia = act ? f.owner[pa] : -1, ib = act ? f.owner[pb] : -1;
+      const bool c1 = act && ia < 0 && ib < 0, c2 = act && ia >= 0 && ib < 0;
+      const bool merge = act && ia >= 0 && ib >= 0 && ia != ib;
+      const unsigned same_a = __match_any_sync(FULL, pa), same_b = __match_any_sync(FULL, pb);  // both by ALL lanes
+      const bool repeated = __popc(same_a) > 1 || __popc(same_b) > 1;
+      __syncwarp();  // owner[] reads above happen before any write below
+      if (sn != dn && !__any_sync(FULL, merge || repeated)) {
+        const unsigned b1 = __ballot_sync(FULL, c1), b2 = __ballot_sync(FULL, c2);
+        const int off = n_order + 2 * __popc(b1 & lt) + __popc(b2 & lt);
+        if (c1) {
+          const int id = mx + 1 + __popc(b1 & lt);
+          f.owner[pa] = id;
+          f.owner[pb] = id;
+          f.order[off] = pa;
+          f.order[off + 1] = pb;
+        } else if (c2) {
+          f.owner[pb] = ia;
+          f.order[off] = pb;
+        }  // "both owned, same id": owner[pb] = ia is a no-op; "src free, dst owned": nothing (paf.py:754-789)
+        mx += __popc(b1);
+        n_order += 2 * __popc(b1) + __popc(b2);
+        __syncwarp();
+      } else {
+        unsigned todo = am;
+        while (todo) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
+          assemble_one(f, lane, __shfl_sync(FULL, pa, l), __shfl_sync(FULL, pb, l), n_order);
+        }
+        mx = -1;  // ids may have been renamed: re-scan the running maximum
+        for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+      }
+    }
+  }
+  // instance sizes, min_instance_peaks filter, ascending-id compaction (paf.py:791-818, :845-850)
   for (int i = lane; i < P; i += 32)
     if (f.owner[i] >= 0) atomicAdd(&f.id_count[f.owner[i]], 1);
   __syncwarp();
   int n_inst = 0;
-  if (lane == 0) {
-    for (int id = 0; id < P; ++id) {
-      const bool keep = f.id_count[id] > 0 && (f.min_instance_peaks <= 0 || f.id_count[id] >= f.min_instance_peaks);
-      f.id_rank[id] = keep ? n_inst++ : -1;
-    }
+  for (int i0 = 0; i0 < P; i0 += 32) {
+    const int id = i0 + lane;
+    const bool keep = id < P && f.id_count[id] > 0 && (f.min_instance_peaks <= 0 || f.id_count[id] >= f.min_instance_peaks);
+    const unsigned kb = __ballot_sync(FULL, keep);
+    if (id < P) f.id_rank[id] = keep ? n_inst + __popc(kb & lt) : -1;
+    n_inst += __popc(kb);
   }
-  n_inst = __shfl_sync(FULL, n_inst, 0);
   __syncwarp();
   if (n_inst > f.inst_cap) {
     if (lane == 0) { atomicOr(f.status, SNB_STATUS_INSTANCE_OVERFLOW); *f.n_inst_out = n_inst; }
     return;
   }
   for (int i = lane; i < n_inst * f.n_nodes; i += 32) { f.oxy[2 * i] = NAN; f.oxy[2 * i + 1] = NAN; f.oval[i] = NAN; }
-  for (int i = lane; i < n_inst; i += 32) f.osc[i] = 0.f;
-  __syncwarp();
-  if (lane == 0) {
-    *f.n_inst_out = n_inst;
+  if (lane == 0) *f.n_inst_out = n_inst;
+  // instance score = fp32 running sum of its connections' scores in visiting order (paf.py:853-865): lane r owns
+  // instance r and walks the connection list (uniform, broadcast loads), adding the ones that belong to it.  The
+  // connection -> instance map is precomputed in parallel into id_count[] (free by now) when it fits (K <= P);
+  // otherwise each step resolves it on the fly (a chain of four dependent loads).
+  int* m_rank = (K <= P) ? f.id_count : nullptr;
+  if (m_rank) {
+    __syncwarp();
+    for (int m = lane; m < K; m += 32) m_rank[m] = -1;
+    __syncwarp();
     for (int se = 0; se < f.n_sorted; ++se) {
       const int e = f.sorted[se];
       const int sn = f.edges[2 * e];
       if (sn < 0 || sn >= f.n_nodes) continue;
+      const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
       const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
-      for (int m = m_lo; m < m_hi; ++m) {
+      for (int m = m_lo + lane; m < m_hi; m += 32) {
         if (f.m_edge[m] != e || !(f.m_score[m] >= f.min_line_scores)) continue;
         const int sp = f.m_src[m];
-        if (sp < 0 || sp >= f.ns[sn + 1] - f.ns[sn]) continue;
-        const int o = f.owner[f.np_[f.ns[sn] + sp]];
-        if (o >= 0 && f.id_rank[o] >= 0) f.osc[f.id_rank[o]] = __fadd_rn(f.osc[f.id_rank[o]], f.m_score[m]);
+        if (sp < 0 || sp >= n_src) continue;
+        const int o = f.owner[f.np_[s0 + sp]];
+        m_rank[m] = (o >= 0) ? f.id_rank[o] : -1;
       }
     }
-    for (int t = 0; t < n_order; ++t) {
-      const int i = f.order[t];
+    __syncwarp();
+  }
+  for (int r0 = 0; r0 < n_inst; r0 += 32) {
+    const int r = r0 + lane;
+    float acc = 0.f;
+    for (int se = 0; se < f.n_sorted; ++se) {
+      const int e = f.sorted[se];
+      const int sn = f.edges[2 * e];
+      if (sn < 0 || sn >= f.n_nodes) continue;
+      const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
+      const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+      if (m_rank) {
+        for (int m = m_lo; m < m_hi; ++m)
+          if (f.m_edge[m] == e && m_rank[m] == r) acc = __fadd_rn(acc, f.m_score[m]);
+      } else {
+        for (int m = m_lo; m < m_hi; ++m) {
+          const float sc = f.m_score[m];
+          if (f.m_edge[m] != e || !(sc >= f.min_line_scores)) continue;
+          const int sp = f.m_src[m];
+          if (sp < 0 || sp >= n_src) continue;
+          const int o = f.owner[f.np_[s0 + sp]];
+          if (o >= 0 && f.id_rank[o] == r) acc = __fadd_rn(acc, sc);
+        }
+      }
+    }
+    if (r < n_inst) f.osc[r] = acc;
+  }
+  __syncwarp();  // the NaN fill above is ordered before the scatter below
+  // scatter in first-assignment order, later entries overwrite (paf.py:879-885): 32 entries per round, and inside a
+  // round only the LAST lane aiming at a slot writes
+  for (int t0 = 0; t0 < n_order; t0 += 32) {
+    const int t = t0 + lane;
+    long long slot = -1 - lane;
+    int i = 0;
+    if (t < n_order) {
+      i = f.order[t];
       const int r = f.id_rank[f.owner[i]];
-      if (r < 0) continue;
-      const long long slot = (long long)r * f.n_nodes + f.chan[i];
+      if (r >= 0) slot = (long long)r * f.n_nodes + f.chan[i];
+    }
+    const unsigned same = __match_any_sync(FULL, slot);
+    if (slot >= 0 && (same >> lane) == 1u) {  // no higher lane has the same slot
       f.oxy[2 * slot] = f.xy[2 * i];
       f.oxy[2 * slot + 1] = f.xy[2 * i + 1];
       f.oval[slot] = f.val[i];
     }
+    __syncwarp();
   }
 }
 
