@@ -383,3 +383,47 @@ def test_warp_lsap_structured_matcher_matches_scipy(pg):
         assert mc[b] == k
         eq(ms[b, :k], r.astype(np.int32)); eq(md[b, :k], c.astype(np.int32))
         eq(msc[b, :k], s[r, c])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_assembly_randomised_busy_frames_vs_oracle(pg, seed):
+    """The chunk-parallel greedy assembly against the (golden-pinned) oracle on inputs the hand-made cases do not
+    reach: up to 45 peaks per node (several 32-wide chunks per edge), skeletons with cross edges (instances met again
+    through another path: the merge / move-first branch and its fallback), proper matchings, partial matchings and,
+    every third case, matchings that reuse a peak (the repeated-peak fallback), int and fractional min_instance_peaks."""
+    from oracle import paf as opaf
+
+    g = np.random.default_rng(1000 + seed)
+    for case in range(12):
+        n_nodes = int(g.integers(3, 9))
+        edges = [(int(g.integers(0, k)), k) for k in range(1, n_nodes)]          # a random tree ...
+        for _ in range(int(g.integers(0, 3))):                                   # ... plus cross edges
+            a, b = sorted(g.choice(n_nodes, 2, replace=False).tolist())
+            if (a, b) not in edges:
+                edges.append((a, b))
+        edges = [edges[i] for i in g.permutation(len(edges))]
+        n_per = g.integers(1, 46 if case % 4 == 0 else 9, n_nodes)
+        ch = np.concatenate([np.full(n, k) for k, n in enumerate(n_per)]).astype(np.int32)
+        ch = ch[g.permutation(len(ch))]
+        pk = g.uniform(0, 500, (len(ch), 2)).astype(np.float32)
+        pv = g.uniform(0.2, 1, len(ch)).astype(np.float32)
+        me, ms, md, msc = [], [], [], []
+        for k, (a, b) in enumerate(edges):
+            n_m = int(g.integers(0, min(n_per[a], n_per[b]) + 1))
+            if case % 3 == 2:   # not a matching: peaks may repeat
+                src, dst = g.integers(0, n_per[a], n_m), g.integers(0, n_per[b], n_m)
+            else:               # a proper (partial) matching, as the assignment produces
+                src, dst = g.permutation(n_per[a])[:n_m], g.permutation(n_per[b])[:n_m]
+            me += [k] * n_m; ms += src.tolist(); md += dst.tolist(); msc += g.uniform(0.0, 1.0, n_m).tolist()
+        if case % 2:            # the match list need not be grouped by edge at the API level
+            order = g.permutation(len(me))
+            me, ms, md, msc = ([x[i] for i in order] for x in (me, ms, md, msc))
+        et = [pg.EdgeType(a, b) for a, b in edges]
+        sorted_inds = pg.toposort_edges(et)
+        mip = [0, 3, 0.5][case % 3]
+        i32 = lambda x: torch.tensor(x, dtype=torch.int32)
+        args = (T(pk), T(pv), T(ch), i32(me), i32(ms), i32(md), torch.tensor(msc, dtype=torch.float32))
+        got = pg.group_instances_sample(*args, n_nodes, sorted_inds, et, mip, 0.25)
+        want = opaf.group_sample(*args, n_nodes, sorted_inds, edges, mip, 0.25)
+        for a_, b_ in zip(got, want):
+            eq(a_, b_)

@@ -277,3 +277,36 @@ def test_group_scored_batch_seam_matches_reference():
         close(npy(res.instance_scores), want_s, rtol=1e-5, atol=1e-5)
         assert res.pred_confmaps is not None and len(res.pred_paf_graph) == 4
         assert res.pred_paf_graph[0].shape[0] == sum(p.shape[0] for p in peaks)
+
+
+def test_fused_pipeline_busy_flies_frames_vs_oracle():
+    """cfg4 geometry (32 nodes / 31 edges / 8 animals per 1024^2 frame: 256 peaks, ~2 k candidates, 248 connections per
+    frame) through the fused 2-launch chain vs the oracle on the same maps: the busy-frame paths of the tail (4 peaks
+    refined at once, per-edge match ranges, chunk-parallel assembly)."""
+    from oracle import paf as opaf
+    from oracle import peaks as opeaks
+    from oracle.synth import split_by_sample
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    B, n_inst, Nn, hw, stride = 3, 8, 32, (1024, 1024), 2
+    edges = synthetic.chain_edges(Nn)
+    poses = synthetic.random_poses(5, B, n_inst, Nn, hw, edges, margin=200.0, step=24.0, min_limb=8.0, min_sep=10.0)
+    dev = torch.device("cuda")
+    cms, pafs = synthetic.render_batch(poses, hw, stride, edges, dev, seed=5)
+    pipe = BottomUpPostproc(Nn, edges, B, (512, 512), cms_stride=stride, pafs_stride=stride, peak_cap=512, cand_cap=4096,
+                            match_cap=512, inst_cap=32)
+    assert pipe.fused and pipe.launches_per_call == 2
+    res = pipe(cms, pafs)
+    inst, pv, sc = res.to_lists()
+    c_cpu, p_cpu = cms.cpu(), pafs.cpu()
+    pts, vals, si, ci = opeaks.local_peaks(c_cpu, 0.2, "integral")
+    eq(npy(res.n_peaks), np.bincount(npy(si), minlength=B).astype(np.int32))
+    peaks, pvs, pcs = (split_by_sample(x, si, B) for x in (pts * stride, vals, ci))
+    want = opaf.predict(p_cpu.permute(0, 2, 3, 1), peaks, pvs, pcs, edges, Nn, stride)
+    for b in range(B):
+        assert inst[b].shape == want[0][b].shape and inst[b].shape[0] == n_inst
+        eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
+        close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
+        eq(npy(pv[b]), npy(want[1][b]))
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-4)  # a sum of 31 line scores
