@@ -147,7 +147,8 @@ int snb_centered_bboxes(const float* centers, long long n, float half_h, float h
  * valid = no NaN coordinate; optional greedy centroid NMS per frame (descending value, IoU of crop_h x crop_w boxes
  * centred on the centroids > nms_threshold drops; frames with <= 1 valid centroid untouched); then the valid (b, i)
  * pairs in torch.nonzero order as a crop list.  centroids (B, I, 2) are in IMAGE space; eff_scale (B) or NULL takes them
- * to sized space (x eff) for the boxes.  Outputs: n_valid (1), frame_off (B+1), and with capacity B*I rows:
+ * to sized space (x eff) for the boxes.  Outputs: n_valid (3 ints: the crop count, then the crop height and width
+ * crop_bboxes would read off bbox 0, ops/crops.py:66-67), frame_off (B+1), and with capacity B*I rows:
  * sample_inds (int64), rows (= b*I + i), crop_bboxes (., 4, 2) = make_centered_bboxes in sized space, crop_topleft
  * (., 2), crop_eff (.); per slot: row_to_crop (B*I) (-1 = none), valid_mask (B, I) bytes, centroids_img (B, I, 2) =
  * (c x eff) / eff, full_bboxes (B, I, 4, 2) = box / eff or NaN.  Needs snb_topdown_select_smem_bytes(B, I) <= 200 KB. */

@@ -107,7 +107,8 @@ topdown_select_kernel(const float* __restrict__ cen, const float* __restrict__ c
       acc += s_off[b + 1];
       s_off[b + 1] = acc;
     }
-    *n_valid = acc;
+    n_valid[0] = acc;
+    if (acc == 0) { n_valid[1] = (int)(2.f * half_h); n_valid[2] = (int)(2.f * half_w); }
   }
   __syncthreads();
   for (int b = threadIdx.x; b <= B; b += TD_THREADS) frame_off[b] = s_off[b];
@@ -138,6 +139,12 @@ topdown_select_kernel(const float* __restrict__ cen, const float* __restrict__ c
           for (int t = 0; t < 8; ++t) {
             crop_bboxes[8 * (size_t)r + t] = bx[t];
             fb[t] = __fdiv_rn(bx[t], e);  // bboxes_img = bboxes / per_crop_eff_scale (topdown.py:272)
+          }
+          if (r == 0) {  // crop_bboxes reads the crop size off bbox 0 (ops/crops.py:66-67): int(|BL.y - TL.y|) + 1 - for a
+            // centroid whose +/- half lands in another binade that is one less than the configured size, and the
+            // reference then crops (and runs its network on) the smaller window; reproduced, not corrected
+            n_valid[1] = (int)fabsf(__fsub_rn(yb, yt)) + 1;
+            n_valid[2] = (int)fabsf(__fsub_rn(xr, xl)) + 1;
           }
           crop_topleft[2 * (size_t)r] = xl;
           crop_topleft[2 * (size_t)r + 1] = yt;
@@ -205,7 +212,7 @@ extern "C" int snb_topdown_select(const float* centroids, const float* centroid_
   if (B < 0 || I < 0 || crop_h <= 0 || crop_w <= 0) return SNB_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream_;
   if (B == 0 || I == 0) {
-    cudaMemsetAsync(n_valid, 0, sizeof(int), st);
+    cudaMemsetAsync(n_valid, 0, 3 * sizeof(int), st);
     if (frame_off) cudaMemsetAsync(frame_off, 0, sizeof(int) * (size_t)(B + 1), st);
     return SNB_OK;
   }

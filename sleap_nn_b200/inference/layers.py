@@ -289,7 +289,7 @@ class TopDownPostproc:
         cap = max(B * I, 1)
         i32 = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
         f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        out = dict(n_valid=i32(1), frame_off=i32(B + 1), sample_inds=torch.empty((cap,), dtype=torch.int64, device=dev),
+        out = dict(n_valid=i32(3), frame_off=i32(B + 1), sample_inds=torch.empty((cap,), dtype=torch.int64, device=dev),
                    rows=i32(cap), row_to_crop=i32(cap), crop_bboxes=f32(cap, 4, 2), crop_topleft=f32(cap, 2),
                    crop_eff=f32(cap), valid_mask=torch.empty((B, I), dtype=torch.uint8, device=dev),
                    centroids_img=f32(B, I, 2), full_bboxes=f32(B, I, 4, 2), centroid_vals=val)
@@ -309,8 +309,9 @@ class TopDownPostproc:
         dev = image.device
         B, I = int(centroids.shape[0]), int(centroids.shape[1])
         sel = self.select(centroids, centroid_vals, eff_scale)
-        n = int(sel["n_valid"].item())  # the one host sync: the crop tensor's batch dimension
-        ch, cw = self.crop_size
+        # the one host sync: the crop tensor's batch dimension, and the crop size as crop_bboxes reads it off bbox 0
+        # (ops/crops.py:66-67; normally == crop_size, one less when fp32 rounding of the first box says so)
+        n, ch, cw = (int(v) for v in sel["n_valid"].tolist())
         st = lambda: N.stream_ptr(dev)
         res = dict(pred_centroids=sel["centroids_img"], pred_centroid_values=sel["centroid_vals"],
                    instance_scores=sel["centroid_vals"], valid_mask=sel["valid_mask"].bool())
@@ -331,6 +332,9 @@ class TopDownPostproc:
                 k4, v3 = self.stage2(cms, output_stride=output_stride, input_scale=input_scale)
                 kp, vals = k4.squeeze(1).contiguous(), v3.squeeze(1).contiguous()
                 if self.return_crops:
+                    if (ch, cw) != self.crop_size:  # the reference's scatter into (.., crop_h, crop_w) raises here too
+                        raise RuntimeError(f"shape mismatch: value tensor of shape [{n}, {Cn}, {ch}, {cw}] cannot be broadcast "
+                                           f"to indexing result of shape [{n}, {Cn}, {self.crop_size[0]}, {self.crop_size[1]}]")
                     full = torch.zeros((B * I, Cn, ch, cw), dtype=crops.dtype, device=dev)
                     full.index_copy_(0, sel["rows"][:n].long(), crops)  # topdown.py:293-303 (debug output)
                     res["crops"] = full.view(B, I, Cn, ch, cw)

@@ -78,7 +78,8 @@ def topdown_model(crops, gain, pattern, cgain=None):
     crops (n, 1, h, w) uint8 / float -> confmaps (n, N, h, w) [, class vectors (n, K)].  Every op is an exactly
     rounded elementwise fp32 op or a max, so CPU and CUDA runs see bit-identical maps."""
     x = crops.to(torch.float32) * 0.00390625  # 1 / 256: exact
-    cms = x * gain.unsqueeze(0) + pattern.unsqueeze(0)
+    h, w = x.shape[-2:]  # crop_bboxes reads the size off bbox 0: it can be one less than configured (ops/crops.py:66-67)
+    cms = x * gain[:, :h, :w].unsqueeze(0) + pattern[:, :h, :w].unsqueeze(0)
     if cgain is None:
         return cms
-    return cms, (x * cgain.unsqueeze(0)).amax(dim=(2, 3))
+    return cms, (x * cgain[:, :h, :w].unsqueeze(0)).amax(dim=(2, 3))

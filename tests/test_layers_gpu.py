@@ -184,7 +184,9 @@ def test_topdown_postproc_random_vs_oracle(seed, nms):
     cgain = torch.rand((K, *crop_hw), generator=gen) * 0.5 + 0.5
     want = otd.stage_2(img, cen, val, eff, crop_hw, lambda c: topdown_model(c, gain, pattern, cgain), nms=nms,
                        nms_threshold=0.2, output_stride=2, input_scale=0.5)
-    post = TopDownPostproc(crop_hw, centroid_nms=nms, centroid_nms_threshold=0.2, return_crops=True, return_class_vectors=True)
+    same_size = tuple(want["crops"].shape[-2:]) == crop_hw  # bbox 0 can round one short (ops/crops.py:66-67); the
+    post = TopDownPostproc(crop_hw, centroid_nms=nms, centroid_nms_threshold=0.2, return_crops=same_size,  # reference
+                           return_class_vectors=True)                                      # then cannot return crops
     gd, pd, cd = gain.cuda(), pattern.cuda(), cgain.cuda()
     o = post(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd, cd), eff_scale=eff.cuda(), output_stride=2,
              input_scale=0.5)
@@ -192,7 +194,8 @@ def test_topdown_postproc_random_vs_oracle(seed, nms):
     eq(npy(o["valid_mask"]), want["valid"])
     if nms:
         assert want["valid"].sum() < (~np.isnan(npy(cen)).any(-1)).sum(), "the case must exercise the suppression"
-    eq(npy(o["crops"]), want["crops"])
+    if same_size:
+        eq(npy(o["crops"]), want["crops"])
     eq(npy(o["pred_peak_values"]), want["vals"])
     close(npy(o["pred_keypoints"]), want["kpts"], atol=1e-4)
     close(npy(o["pred_crop_keypoints"]), want["crop_kpts"], atol=1e-4)
@@ -272,3 +275,30 @@ def test_topdown_select_degenerate_shapes_and_bad_class_vectors():
     with pytest.raises(ValueError):
         post.check()
     assert (npy(o["pred_class_inds"]) == -1).all()
+
+
+def test_topdown_crop_size_is_read_off_the_first_box_like_the_reference():
+    """crop_bboxes takes the crop size from bbox 0 as int(|BL.y - TL.y|) + 1 (ops/crops.py:66-67).  For a centroid whose
+    +/- half lands in another fp32 binade that is one less than the configured size; the reference then crops the smaller
+    window for EVERY crop of the batch.  Reproduced (and `return_crops` raises, as the reference's scatter does)."""
+    from oracle import topdown as otd
+    from sleap_nn_b200.inference.layers import TopDownPostproc
+    from tests.helpers import topdown_model
+
+    gen = torch.Generator().manual_seed(3)
+    crop_hw, Nn = (20, 28), 2
+    # y = 56.7: fl(fl(56.7 + 10) - 0.5) - fl(fl(56.7 - 10) + 0.5) = 18.999996 -> int() = 18 -> 19 rows
+    cen = torch.tensor([[[40.25, 56.7], [80.0, 30.0]]])
+    val = torch.tensor([[0.9, 0.8]])
+    img = (torch.rand((1, 1, 96, 120), generator=gen) * 255).to(torch.uint8)
+    gain = torch.rand((Nn, *crop_hw), generator=gen) * 0.5 + 0.5
+    pattern = torch.rand((Nn, *crop_hw), generator=gen) * 1e-3
+    want = otd.stage_2(img, cen, val, None, crop_hw, lambda c: topdown_model(c, gain, pattern))
+    assert want["crops"].shape[-2:] == (19, 28), "the case must exercise the short first box"
+    gd, pd = gain.cuda(), pattern.cuda()
+    o = TopDownPostproc(crop_hw)(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd))
+    eq(npy(o["pred_peak_values"]), want["vals"])
+    close(npy(o["pred_keypoints"]), want["kpts"], atol=1e-4)
+    eq(npy(o["instance_bboxes"]), want["bboxes"])
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        TopDownPostproc(crop_hw, return_crops=True)(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd))

@@ -121,3 +121,53 @@ def test_lsap_and_toposort_against_the_third_party_libraries(R):
     for edges in ([(0, 1), (1, 2), (1, 3)], [(2, 0), (0, 1), (0, 3), (3, 4)], [(0, 1), (2, 3)], [(0, 1), (0, 2), (1, 2)]):
         types = [R.paf.EdgeType(a, b) for a, b in edges]
         assert tuple(R.paf.toposort_edges(types)) == tuple(opaf.toposort_edge_order(edges))
+
+
+@pytest.mark.parametrize("seed,thr", [(0, 0.5), (1, 0.2), (2, 0.05)])
+def test_topdown_stage_b_and_stage_2_on_random_frames(R, seed, thr):
+    """oracle.topdown vs TopDownLayer._centroid_nms_mask / _run_stage_2 (unmodified reference methods, stand-in self)
+    on fresh random centroids: the NMS order / IoU arithmetic, the crop list, the lift and the per-frame classes."""
+    import types
+
+    from oracle import topdown as otd
+    from tests.helpers import topdown_model
+
+    TL = R.topdown.TopDownLayer
+    TM = R.topdown_multiclass.CenteredInstanceMultiClassLayer
+    P = R.preprocess_info.PreprocInfo
+    g = torch.Generator().manual_seed(300 + seed)
+    B, I, H, W, crop_hw, Nn, K = 5, 9, 96, 120, (20, 28), 3, 4
+    cen = torch.rand((B, I, 2), generator=g) * torch.tensor([W - 1.0, H - 1.0])
+    cen[torch.rand((B, I), generator=g) < 0.25] = float("nan")
+    cen[1] = float("nan")
+    val = torch.rand((B, I), generator=g)
+    eff = torch.rand((B,), generator=g) * 0.6 + 0.7
+    img = (torch.rand((B, 1, H, W), generator=g) * 255).to(torch.uint8)
+    gain = torch.rand((Nn, *crop_hw), generator=g) * 0.5 + 0.5
+    pattern = torch.rand((Nn, *crop_hw), generator=g) * 1e-3
+    cgain = torch.rand((K, *crop_hw), generator=g) * 0.5 + 0.5
+    cfg = types.SimpleNamespace(peak_threshold=0.2, effective_refinement="integral", integral_patch_size=5,
+                                return_confmaps=False, return_class_vectors=True)
+
+    def predict(crops):
+        cms, vec = topdown_model(crops, gain, pattern, cgain)
+        me2 = types.SimpleNamespace(postprocess_config=cfg, _extract_confmaps=lambda raw: raw["CenteredInstanceConfmapsHead"])
+        info = P(eff_scale=torch.ones(crops.shape[0]), input_scale=0.5, output_stride=2)
+        return TM.postprocess(me2, {"CenteredInstanceConfmapsHead": cms, "ClassVectorsHead": vec}, info)
+
+    inner = types.SimpleNamespace(predict=predict, postprocess_config=cfg)
+    me = types.SimpleNamespace(crop_size=crop_hw, centered_instance_layer=inner, return_crops=False, centroid_nms=True,
+                               centroid_nms_threshold=thr, _bbox_iou=TL._bbox_iou, _infer_n_nodes=lambda: Nn)
+    with ref_loader.reference_imports():
+        valid = ~torch.isnan(cen).any(dim=-1)
+        valid = valid & TL._centroid_nms_mask(me, cen, val, valid)
+        o = TL._run_stage_2(me, img, cen * eff.view(-1, 1, 1), val, valid, eff_scale=eff)
+    got = otd.stage_2(img, cen, val, eff, crop_hw, lambda c: topdown_model(c, gain, pattern, cgain), nms=True,
+                      nms_threshold=thr, output_stride=2, input_scale=0.5)
+    eq(got["valid"], npy(valid))
+    assert npy(valid).sum() < (~np.isnan(npy(cen)).any(-1)).sum() or thr >= 0.5
+    eq(got["kpts"], npy(o.pred_keypoints)); eq(got["crop_kpts"], npy(o.pred_crop_keypoints))
+    eq(got["vals"], npy(o.pred_peak_values)); eq(got["centroids"], npy(o.pred_centroids))
+    eq(got["bboxes"], npy(o.instance_bboxes))  # (return_crops is off: the reference itself raises when bbox 0 rounds short)
+    eq(got["class_inds"], npy(o.pred_class_inds)); eq(got["tracking"], npy(o.instance_tracking_scores))
+    eq(got["class_vectors"], npy(o.pred_class_vectors))
