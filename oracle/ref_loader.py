@@ -45,6 +45,7 @@ _HOT_FILES = [
     # stand-in `self` (the base classes resolve to stubs)
     ("sleap_nn.inference.layers.bottomup_multiclass", "sleap_nn/inference/layers/bottomup_multiclass.py"),
     # layer glue of the f2 row: postprocess / _run_stage_2 / _centroid_nms_mask are called with stand-in `self` objects
+    ("sleap_nn.inference.layers.bottomup", "sleap_nn/inference/layers/bottomup.py"),
     ("sleap_nn.inference.layers.centered_instance", "sleap_nn/inference/layers/centered_instance.py"),
     ("sleap_nn.inference.layers.single_instance", "sleap_nn/inference/layers/single_instance.py"),
     ("sleap_nn.inference.layers.centroid", "sleap_nn/inference/layers/centroid.py"),
@@ -209,6 +210,8 @@ def ref() -> types.SimpleNamespace:
             filters=full["sleap_nn.inference.filters"],
             ops_filters=full["sleap_nn.inference.ops.filters"],
             bottomup_multiclass=full["sleap_nn.inference.layers.bottomup_multiclass"],
+            bottomup=full["sleap_nn.inference.layers.bottomup"],
+            centroid=full["sleap_nn.inference.layers.centroid"],
             centered_instance=full["sleap_nn.inference.layers.centered_instance"],
             single_instance=full["sleap_nn.inference.layers.single_instance"],
             topdown=full["sleap_nn.inference.layers.topdown"],

@@ -171,3 +171,51 @@ def test_topdown_stage_b_and_stage_2_on_random_frames(R, seed, thr):
     eq(got["bboxes"], npy(o.instance_bboxes))  # (return_crops is off: the reference itself raises when bbox 0 rounds short)
     eq(got["class_inds"], npy(o.pred_class_inds)); eq(got["tracking"], npy(o.instance_tracking_scores))
     eq(got["class_vectors"], npy(o.pred_class_vectors))
+
+
+def test_layer_goldens_equal_the_layers_own_postprocess(R):
+    """The f1 / f2 goldens were composed from the reference's ops in the order its layers call them; here the layers' OWN
+    `postprocess` methods (unmodified classes, stand-in `self`) are run on the same inputs and must reproduce them."""
+    import types
+
+    from tests.helpers import T, golden
+
+    P = R.preprocess_info.PreprocInfo
+    cfg = lambda **kw: types.SimpleNamespace(peak_threshold=0.2, effective_refinement="integral", integral_patch_size=5,
+                                             return_confmaps=False, return_pafs=False, return_paf_graph=False, **kw)
+    # ---- f2: CentroidLayer.postprocess / CenteredInstanceLayer.postprocess vs ref_f2_layers.npz
+    d = golden("ref_f2_layers.npz")
+    CL, CI = R.centroid.CentroidLayer, R.centered_instance.CenteredInstanceLayer
+    for tag in ("dyn", "top3", "pad7"):
+        mi = int(d[f"cen_{tag}_max"])
+        me = types.SimpleNamespace(postprocess_config=cfg(max_instances=None), max_instances=None if mi < 0 else mi,
+                                   _extract_confmaps=lambda raw: raw["x"], _infer_max_instances=CL._infer_max_instances)
+        info = P(eff_scale=T(d["cen_eff"]), input_scale=float(d[f"cen_{tag}_scale"]), output_stride=int(d["cen_stride"]))
+        o = CL.postprocess(me, {"x": T(d["cen_cms"])}, info)
+        eq(npy(o.pred_centroids), d[f"cen_{tag}_xy"])
+        eq(npy(o.pred_centroid_values), d[f"cen_{tag}_val"])
+    me = types.SimpleNamespace(postprocess_config=cfg(), _extract_confmaps=lambda raw: raw["x"])
+    o = CI.postprocess(me, {"x": T(d["ci_cms"])}, P(eff_scale=T(d["ci_eff"]), input_scale=float(d["ci_scale"]), output_stride=2))
+    eq(npy(o.pred_keypoints), d["ci_xy"])
+    eq(npy(o.pred_peak_values), d["ci_val"])
+    # ---- f1: BottomUpLayer.postprocess (= _score_pafs_on_gpu + group_scored_batch) vs ref_f1_outputs.npz
+    p, f1 = golden("ref_pipeline_tree.npz"), golden("ref_f1_outputs.npz")
+    BU = R.bottomup.BottomUpLayer
+    edges, n_nodes, stride = p["edges"].tolist(), int(p["n_nodes"]), int(p["stride"])
+    scorer = R.paf.PAFScorer(part_names=[str(i) for i in range(n_nodes)], edges=[(str(a), str(b)) for a, b in edges],
+                             pafs_stride=stride, min_instance_peaks=int(p["min_instance_peaks"]))
+    raw = {"MultiInstanceConfmapsHead": T(p["cms"]), "PartAffinityFieldsHead": T(p["pafs"])}
+    for tag in f1["cases"].tolist():
+        mi = int(f1[f"{tag}_max_instances"])
+        skip = bool(f1[f"{tag}_skip"])
+        me = types.SimpleNamespace(postprocess_config=cfg(max_instances=None), cms_output_stride=stride, paf_scorer=scorer,
+                                   max_instances=None if mi < 0 else mi,
+                                   max_peaks_per_node=int(f1["max_node_peaks"]) - 1 if skip else None)
+        me._score_pafs_on_gpu = lambda r, i, me=me: BU._score_pafs_on_gpu(me, r, i)
+        me.grouping_params = lambda me=me: BU.grouping_params(me)
+        info = P(eff_scale=T(f1[f"{tag}_eff"]), input_scale=float(f1[f"{tag}_input_scale"]))
+        with ref_loader.reference_imports():
+            o = BU.postprocess(me, raw, info)
+        eq(npy(o.pred_keypoints), f1[f"{tag}_kpts"])
+        eq(npy(o.pred_peak_values), f1[f"{tag}_vals"])
+        eq(npy(o.instance_scores), f1[f"{tag}_scores"])
