@@ -42,6 +42,9 @@ extern "C" {
 #define SNB_STATUS_BAD_INDEX 32         /* an index argument pointed outside its table           */
 #define SNB_STATUS_MATCH_OVERFLOW 64    /* a frame had more matches than `match_cap`             */
 #define SNB_STATUS_LSAP_INVALID 128     /* scipy would raise "matrix contains invalid numeric entries" (NaN / -inf cost) */
+#define SNB_STATUS_ASM_MISMATCH 256     /* make_predicted_instances' sanity assert would fail (ops/paf.py:873): a scored   */
+                                        /* connection whose two peaks ended up in different instances                      */
+#define SNB_STATUS_ASM_MISSING 512      /* ... or whose destination peak is in no (kept) instance: KeyError there          */
 
 int snb_abi_version(void);
 

@@ -316,10 +316,12 @@ def build_instances(peaks_by_node, vals_by_node, conn_by_edge, owner):
     ids = sorted(set(owner.values()))
     rank = {inst: i for i, inst in enumerate(ids)}
     scores = np.zeros(len(ids), dtype=np.float32)
-    for (sn, _dn), conns in conn_by_edge:
-        for sp, _dp, sc in conns:
+    for (sn, dn), conns in conn_by_edge:
+        for sp, dp, sc in conns:
             if (sn, int(sp)) in owner:
                 scores[rank[owner[(sn, int(sp))]]] += np.float32(sc)
+                # the reference's sanity check (paf.py:866-873): KeyError if the destination is in no kept instance
+                assert owner[(sn, int(sp))] == owner[(dn, int(dp))]
     n_nodes = len(peaks_by_node)
     pts = np.full((len(ids), n_nodes, 2), np.nan, dtype=np.float32)
     pv = np.full((len(ids), n_nodes), np.nan, dtype=np.float32)

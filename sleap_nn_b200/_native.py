@@ -26,6 +26,8 @@ STATUS_INSTANCE_OVERFLOW = 16
 STATUS_BAD_INDEX = 32
 STATUS_MATCH_OVERFLOW = 64
 STATUS_LSAP_INVALID = 128
+STATUS_ASM_MISMATCH = 256
+STATUS_ASM_MISSING = 512
 
 _i, _ll, _f, _p = C.c_int, C.c_longlong, C.c_float, C.c_void_p
 _ip, _llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)

@@ -496,27 +496,39 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   // instance r and walks the connection list (uniform, broadcast loads), adding the ones that belong to it.  The
   // connection -> instance map is precomputed in parallel into id_count[] (free by now) when it fits (K <= P);
   // otherwise each step resolves it on the fly (a chain of four dependent loads).
+  // The same pass replays the reference's sanity check (ops/paf.py:866-873): a visited connection whose source is in a
+  // kept instance must have its destination in the SAME instance - otherwise the reference raises (AssertionError, or
+  // KeyError when the destination is in no kept instance).  Only improper matchings fed to the grouping API get there.
   int* m_rank = (K <= P) ? f.id_count : nullptr;
+  __syncwarp();
   if (m_rank) {
-    __syncwarp();
     for (int m = lane; m < K; m += 32) m_rank[m] = -1;
     __syncwarp();
-    for (int se = 0; se < f.n_sorted; ++se) {
-      const int e = f.sorted[se];
-      const int sn = f.edges[2 * e];
-      if (sn < 0 || sn >= f.n_nodes) continue;
-      const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
-      const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
-      for (int m = m_lo + lane; m < m_hi; m += 32) {
-        if (f.m_edge[m] != e || !(f.m_score[m] >= f.min_line_scores)) continue;
-        const int sp = f.m_src[m];
-        if (sp < 0 || sp >= n_src) continue;
-        const int o = f.owner[f.np_[s0 + sp]];
-        m_rank[m] = (o >= 0) ? f.id_rank[o] : -1;
+  }
+  for (int se = 0; se < f.n_sorted; ++se) {
+    const int e = f.sorted[se];
+    const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+    if (sn < 0 || sn >= f.n_nodes) continue;
+    const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
+    const bool dn_ok = dn >= 0 && dn < f.n_nodes;
+    const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
+    const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+    for (int m = m_lo + lane; m < m_hi; m += 32) {
+      if (f.m_edge[m] != e || !(f.m_score[m] >= f.min_line_scores)) continue;
+      const int sp = f.m_src[m], dp = f.m_dst[m];
+      if (sp < 0 || sp >= n_src) continue;
+      const int o = f.owner[f.np_[s0 + sp]];
+      const int rk = (o >= 0) ? f.id_rank[o] : -1;
+      if (m_rank) m_rank[m] = rk;
+      if (rk >= 0 && dp >= 0 && dp < n_dst) {
+        const int od = f.owner[f.np_[d0 + dp]];
+        const int rd = (od >= 0) ? f.id_rank[od] : -1;
+        if (rd < 0) atomicOr(f.status, SNB_STATUS_ASM_MISSING);
+        else if (rd != rk) atomicOr(f.status, SNB_STATUS_ASM_MISMATCH);
       }
     }
-    __syncwarp();
   }
+  __syncwarp();
   for (int r0 = 0; r0 < n_inst; r0 += 32) {
     const int r = r0 + lane;
     float acc = 0.f;

@@ -99,6 +99,10 @@ def _status_check(status: torch.Tensor, what: str) -> None:
         raise ValueError("cost matrix is infeasible")  # scipy's message, paf.py:589
     if s & N.STATUS_BAD_INDEX:
         raise IndexError(f"{what}: index out of range")
+    if s & N.STATUS_ASM_MISMATCH:  # make_predicted_instances' sanity assert (paf.py:866-873)
+        raise AssertionError("both peaks of a connection should have been assigned to the same instance")
+    if s & N.STATUS_ASM_MISSING:   # ... its dict lookup of a destination peak that is in no kept instance
+        raise KeyError("destination peak of a scored connection is not assigned to an instance")
     if s:
         raise RuntimeError(f"{what}: device status 0x{s:x}")
 
@@ -624,6 +628,8 @@ def _assemble_raw(chan, edges, me, ms, md, msc, n_nodes, min_instance_peaks, dev
         "snb_assemble",
     )
     w = ws.cpu().numpy()
+    # assign_connections_to_instances has no sanity check of its own: that one lives in make_predicted_instances
+    status &= ~(N.STATUS_ASM_MISMATCH | N.STATUS_ASM_MISSING)
     _status_check(status, "assign_connections_to_instances")
     owner, order, id_count, id_rank = w[:P], w[P:2 * P], w[2 * P:3 * P], w[3 * P:4 * P]
     kept = np.array([o if (o >= 0 and id_rank[o] >= 0) else -1 for o in owner])

@@ -85,6 +85,10 @@ class BottomUpResult:
         status = int(self.status.item())
         if status:
             self.status.zero_()  # sticky bits are reported once
+        if status & N.STATUS_ASM_MISMATCH:  # the reference's own sanity assert (ops/paf.py:866-873)
+            raise AssertionError("both peaks of a connection should have been assigned to the same instance")
+        if status & N.STATUS_ASM_MISSING:
+            raise KeyError("destination peak of a scored connection is not assigned to an instance")
         if status & N.STATUS_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
         if status:
@@ -379,6 +383,10 @@ class BottomUpHostStream:
         self._busy[k] = False
         h = self._host[k]
         status = int(h["status"][0])
+        if status & N.STATUS_ASM_MISMATCH:  # the reference's own sanity assert (ops/paf.py:866-873)
+            raise AssertionError("both peaks of a connection should have been assigned to the same instance")
+        if status & N.STATUS_ASM_MISSING:
+            raise KeyError("destination peak of a scored connection is not assigned to an instance")
         if status & N.STATUS_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
         if status:
