@@ -400,7 +400,10 @@ __global__ void interp1d_kernel(const float* __restrict__ x, int x_rows, const f
   }
   if (isnan(q)) lo = n;
   const int k = min(max(lo - 1, 0), n - 2);
-  const float slope = __fdiv_rn(__fsub_rn(yr[k + 1], yr[k]), __fadd_rn(1.1920928955078125e-07f, __fsub_rn(xr[k + 1], xr[k])));
+  // Reference quirk (utils.py:112-124): with ONE row of knots x the slope table is treated as flat and indexed by k
+  // alone, i.e. every row takes ROW 0's slopes even when y has several rows (the intercept y[k] is still the row's own).
+  const float* ys = (x_rows == 1) ? y : yr;
+  const float slope = __fdiv_rn(__fsub_rn(ys[k + 1], ys[k]), __fadd_rn(1.1920928955078125e-07f, __fsub_rn(xr[k + 1], xr[k])));
   out[i] = __fadd_rn(yr[k], __fmul_rn(slope, __fsub_rn(q, xr[k])));
 }
 

@@ -162,3 +162,158 @@ def test_targets_fuzz_nan_points_and_degenerate_edges(R):
         src, dst = pts[0][:, e[:, 0]], pts[0][:, e[:, 1]]
         close(npy(otgt.multi_pafs(oxv, oyv, src, dst, sigma)), npy(R.edge_maps.make_multi_pafs(xv, yv, src, dst, sigma)),
               rtol=1e-5, atol=1e-6)
+
+
+def test_match_candidates_fuzz_incl_nan_scores(R):
+    """match_candidates_sample on full src x dst candidate grids with random scores, some NaN (cost +inf): same matches,
+    and ValueError("cost matrix is infeasible") exactly where the reference (scipy) raises."""
+    from oracle.paf import lsap_jv
+
+    n_raised = 0
+    for seed in range(60):
+        g = torch.Generator().manual_seed(400 + seed)
+        n_nodes = int(torch.randint(2, 6, (1,), generator=g))
+        edges = [(k - 1, k) for k in range(1, n_nodes)]
+        ch = torch.randint(0, n_nodes, (int(torch.randint(2, 16, (1,), generator=g)),), generator=g).to(torch.int32)
+        ei, epi = R.paf.get_connection_candidates(ch, torch.tensor(edges, dtype=torch.int32), n_nodes)
+        sc = torch.rand((ei.numel(),), generator=g) * 2 - 0.5
+        if seed % 3 == 0 and ei.numel():
+            sc[torch.rand((ei.numel(),), generator=g) < 0.3] = float("nan")
+        try:
+            want = R.paf.match_candidates_sample(ei, epi, sc, len(edges))
+        except ValueError as err:
+            n_raised += 1
+            with pytest.raises(ValueError, match=str(err)):
+                opaf.match_sample(ei, epi, sc, len(edges), solver=lsap_jv)
+            continue
+        for solver in (None, lsap_jv):  # scipy (what the reference calls) and the restatement the kernels follow
+            got = opaf.match_sample(ei, epi, sc, len(edges), solver=solver)
+            for a_, b_ in zip(got, want):
+                eq(npy(a_), npy(b_))
+    assert n_raised > 0
+
+
+def test_identity_grouping_fuzz(R):
+    """group_class_peaks / classify_peaks_from_maps / get_class_inds_from_vectors on random probabilities (rows need not
+    sum to one, more peaks than classes and the reverse)."""
+    from oracle import identity as oid
+
+    for seed in range(40):
+        g = torch.Generator().manual_seed(500 + seed)
+        S, C, K = (int(v) for v in torch.randint(1, 5, (3,), generator=g))
+        P_ = int(torch.randint(0, 20, (1,), generator=g))
+        probs = torch.rand((P_, K), generator=g)
+        si = torch.randint(0, S, (P_,), generator=g).to(torch.int32)
+        ci = torch.randint(0, C, (P_,), generator=g).to(torch.int32)
+        for a_, b_ in zip(oid.group_class_peaks(probs, si, ci, S, C), R.identity.group_class_peaks(probs, si, ci, S, C)):
+            eq(npy(a_), npy(b_))
+        Hc, Wc = 9, 13
+        maps = torch.rand((S, K, Hc, Wc), generator=g)
+        pts = torch.rand((P_, 2), generator=g) * torch.tensor([Wc + 4.0, Hc + 4.0]) - 2.0  # some land outside: clamped
+        vals = torch.rand((P_,), generator=g)
+        want = R.identity.classify_peaks_from_maps(maps, pts, vals, si, ci, C)
+        got = oid.classify_peaks_from_maps(maps, pts, vals, si, ci, C)
+        for a_, b_ in zip(got, want):
+            eq(npy(a_), npy(b_))
+        vec = torch.rand((int(torch.randint(1, 9, (1,), generator=g)), K), generator=g)
+        for a_, b_ in zip(oid.class_inds_from_vectors(vec), R.identity.get_class_inds_from_vectors(vec)):
+            eq(npy(a_), npy(b_))
+
+
+def test_filter_pipeline_fuzz(R):
+    """FilterPipeline.apply on random padded outputs with NaN slots, every filter on, both overlap methods.  Decisions that
+    hinge on a mean (nanmean reduction order, OKS) are compared through the surviving-slot pattern with a retry margin:
+    a case is skipped when a statistic sits within 1e-6 of its threshold."""
+    from oracle import filters as ofil
+
+    FC, FP, Out = R.filters.FilterConfig, R.filters.FilterPipeline, R.outputs.Outputs
+    n_checked = 0
+    for seed in range(60):
+        g = torch.Generator().manual_seed(600 + seed)
+        B, I, Nn = 2, int(torch.randint(1, 7, (1,), generator=g)), int(torch.randint(2, 6, (1,), generator=g))
+        k = torch.rand((B, I, Nn, 2), generator=g) * 60
+        if seed % 2:
+            k[:, 1:] = k[:, :1] + torch.randn((B, I - 1, Nn, 2), generator=g) * 3  # overlapping instances
+        v = torch.rand((B, I, Nn), generator=g)
+        s = torch.rand((B, I), generator=g)
+        drop = torch.rand((B, I, Nn), generator=g) < 0.2
+        k[drop] = float("nan"); v[drop] = float("nan")
+        cfgd = dict(min_peak_value=[0.0, 0.15][seed % 2], min_instance_score=[0.0, 0.2][(seed // 2) % 2],
+                    min_mean_node_score=[0.0, 0.3][(seed // 4) % 2], min_visible_nodes=[0, 2][(seed // 8) % 2],
+                    min_visible_node_fraction=[0.0, 0.5][(seed // 3) % 2], overlapping=bool(seed % 3),
+                    overlapping_threshold=0.3, overlapping_method=["iou", "oks"][(seed // 5) % 2], min_centroid_distance=0.0)
+        want = FP(config=FC(**cfgd)).apply(Out(pred_keypoints=k, pred_peak_values=v, instance_scores=s))
+        got = ofil.apply(cfgd, kpts=k.numpy(), vals=v.numpy(), scores=s.numpy())
+        same = (np.isnan(got[0]) == np.isnan(npy(want.pred_keypoints))).all()
+        if not same:
+            # tolerate only threshold-adjacent decisions: perturb the thresholds by 1e-6 both ways and require a match
+            ok = False
+            for eps in (-1e-6, 1e-6):
+                c2 = dict(cfgd, min_mean_node_score=max(cfgd["min_mean_node_score"] + eps, 0.0),
+                          overlapping_threshold=cfgd["overlapping_threshold"] + eps)
+                g2 = ofil.apply(c2, kpts=k.numpy(), vals=v.numpy(), scores=s.numpy())
+                ok = ok or (np.isnan(g2[0]) == np.isnan(npy(want.pred_keypoints))).all()
+            assert ok, (seed, cfgd)
+            continue
+        close(got[0], npy(want.pred_keypoints)); close(got[1], npy(want.pred_peak_values)); close(got[2], npy(want.instance_scores))
+        n_checked += 1
+    assert n_checked > 50
+
+
+def test_dataset_target_wrappers_fuzz(R):
+    """generate_confmaps / generate_multiconfmaps / generate_pafs / generate_class_maps (the datasets' call sites) on random
+    frames: the num_instances slice, is_centroids, the in-image instance filter, flatten_channels, sigma x stride."""
+    from oracle import identity as oid
+
+    for seed in range(16):
+        g = torch.Generator().manual_seed(700 + seed)
+        h, w = 48, 64
+        I, N = int(torch.randint(1, 5, (1,), generator=g)), int(torch.randint(2, 5, (1,), generator=g))
+        inst = torch.rand((1, I, N, 2), generator=g) * torch.tensor([w + 16.0, h + 16.0]) - 8.0   # some nodes outside
+        if seed % 3 == 0:
+            inst[0, 0, 1] = float("nan")
+        n_use = int(torch.randint(0, I + 1, (1,), generator=g))
+        stride, sigma = [1, 2, 4][seed % 3], [1.0, 1.5, 3.0][seed % 3]
+        tol = dict(rtol=1e-5, atol=FLT_MIN)
+        close(npy(otgt.generate_multiconfmaps(inst, (h, w), n_use, sigma, stride)),
+              npy(R.confidence_maps.generate_multiconfmaps(inst, (h, w), n_use, sigma, stride)), **tol)
+        close(npy(otgt.generate_multiconfmaps(inst[:, :, 0, :], (h, w), n_use, sigma, stride, is_centroids=True)),
+              npy(R.confidence_maps.generate_multiconfmaps(inst[:, :, 0, :], (h, w), n_use, sigma, stride, is_centroids=True)), **tol)
+        close(npy(otgt.generate_confmaps(inst[:, 0], (h, w), sigma, stride)),
+              npy(R.confidence_maps.generate_confmaps(inst[:, 0], (h, w), sigma, stride)), **tol)
+        edges = torch.tensor([(k - 1, k) for k in range(1, N)])
+        for flat in (False, True):
+            close(npy(otgt.generate_pafs(inst, (h, w), sigma, stride, edges, flat)),
+                  npy(R.edge_maps.generate_pafs(inst, (h, w), sigma, stride, edges, flat)), rtol=1e-5, atol=1e-6)
+        if n_use > 0:
+            tracks = torch.randint(-1, 3, (n_use,), generator=g).to(torch.float32)
+            close(npy(oid.generate_class_maps(inst, (h, w), n_use, tracks, 3, 0.2, sigma, stride)),
+                  npy(R.data_identity.generate_class_maps(inst, (h, w), n_use, tracks, 3, 0.2, sigma, stride)), rtol=1e-6, atol=1e-7)
+
+
+def interp_cases():
+    """(x, y, xnew) triples shared with tests/test_paf_gpu.py::test_interp1d_vs_oracle."""
+    for seed in range(24):
+        g = torch.Generator().manual_seed(800 + seed)
+        M, n_k, n_q = 5, int(torch.randint(2, 6, (1,), generator=g)), 7
+        x = torch.sort(torch.rand((M, n_k), generator=g) * 10, dim=1).values
+        y = torch.randn((M, n_k), generator=g)
+        xq = torch.rand((M, n_q), generator=g) * 14 - 2          # inside and outside the knots: extrapolation
+        if seed % 4 == 1:
+            x, y = x[0], y[0]                                    # one shared knot row, several query rows (flattened)
+        elif seed % 4 == 2:
+            x, y, xq = x[0], y[0], xq[0]                         # all 1-D
+        elif seed % 4 == 3:
+            x = x[:1]                                            # x broadcast over the rows of y
+        yield x, y, xq
+
+
+def test_interp1d_fuzz(R):
+    """interp1d with 2..5 knots, every broadcasting mode, query points inside and outside the knot range."""
+    from oracle.interp import interp1d
+
+    for x, y, xq in interp_cases():
+        want = R.interp.interp1d(x, y, xq)
+        got = interp1d(x, y, xq)
+        assert tuple(got.shape) == tuple(want.shape)
+        eq(npy(got), npy(want))

@@ -432,3 +432,18 @@ def test_assembly_randomised_busy_frames_vs_oracle(pg, seed):
         got = pg.group_instances_sample(*args, n_nodes, sorted_inds, et, mip, 0.25)
         for a_, b_ in zip(got, want):
             eq(a_, b_)
+
+
+def test_interp1d_vs_oracle():
+    """Every broadcasting mode of interp1d (incl. the reference's flat-slope quirk for one row of knots) and queries outside
+    the knots, against the oracle that tests/test_oracle_fuzz_vs_reference.py pins to the live reference."""
+    from oracle.interp import interp1d as want_fn
+    from sleap_nn_b200.inference.utils import interp1d
+    from tests.test_oracle_fuzz_vs_reference import interp_cases
+
+    for x, y, xq in interp_cases():
+        want = want_fn(x, y, xq)
+        got = interp1d(x, y, xq)
+        assert tuple(got.shape) == tuple(want.shape)
+        eq(npy(got), npy(want))
+        eq(npy(interp1d(x.cuda(), y.cuda(), xq.cuda())), npy(want))
