@@ -317,3 +317,36 @@ def test_interp1d_fuzz(R):
         got = interp1d(x, y, xq)
         assert tuple(got.shape) == tuple(want.shape)
         eq(npy(got), npy(want))
+
+
+def test_bottomup_multiclass_layer_fuzz(R):
+    """BottomUpMultiClassLayer.postprocess (unmodified class, stand-in self) vs the oracle on random small frames: noisy
+    confidence maps (several peaks per node, some frames empty), random class maps, scales and instance caps."""
+    import types
+
+    from oracle import identity as oid
+
+    L = R.bottomup_multiclass.BottomUpMultiClassLayer
+    P = R.preprocess_info.PreprocInfo
+    for seed in range(24):
+        g = torch.Generator().manual_seed(900 + seed)
+        B, Nn, K, H, W = 2, int(torch.randint(1, 4, (1,), generator=g)), int(torch.randint(1, 5, (1,), generator=g)), 24, 32
+        cms = torch.rand((B, Nn, H, W), generator=g) ** 6          # sparse bright pixels -> a few peaks per node
+        if seed % 5 == 0:
+            cms[1] = 0.0                                           # a frame without peaks
+        cs = [1, 2, 4][seed % 3]
+        class_maps = torch.softmax(torch.randn((B, K, H * 2 // cs, W * 2 // cs), generator=g), dim=1)
+        scale = [1.0, 0.5, 2.0][seed % 3]
+        eff = [torch.ones(B), torch.tensor([0.8, 1.25])][seed % 2]
+        cap = [None, 1, 2, 3][seed % 4]
+        cfg = types.SimpleNamespace(peak_threshold=0.3, effective_refinement="integral", integral_patch_size=5,
+                                    max_instances=None, return_confmaps=False, return_class_maps=False)
+        me = types.SimpleNamespace(postprocess_config=cfg, cms_output_stride=2, class_maps_output_stride=cs,
+                                   max_instances=cap, _cap_instances_by_score=L._cap_instances_by_score)
+        o = L.postprocess(me, {"MultiInstanceConfmapsHead": cms, "ClassMapsHead": class_maps}, P(eff_scale=eff, input_scale=scale))
+        inst, pv, sc, tr = oid.bottomup_multiclass_postprocess(cms, class_maps, 2, cs, scale, eff, cap, threshold=0.3)
+        eq(np.isnan(npy(inst)), np.isnan(npy(o.pred_keypoints)))
+        close(npy(inst), npy(o.pred_keypoints), atol=1e-5)
+        eq(npy(pv), npy(o.pred_peak_values))
+        close(npy(sc), npy(o.instance_scores), rtol=1e-6, atol=1e-7)   # nanmean reduction order (DESIGN.md)
+        close(npy(tr), npy(o.instance_tracking_scores), rtol=1e-6, atol=1e-7)
