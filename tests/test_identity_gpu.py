@@ -155,3 +155,23 @@ def test_bottomup_multiclass_layer_golden():
     post(cms, bad)
     with pytest.raises(ValueError):
         post.check()
+
+
+def test_bottomup_multiclass_layer_random_vs_oracle():
+    """The generator of tests/test_oracle_fuzz_vs_reference.py::test_bottomup_multiclass_layer_fuzz (which pins the oracle
+    to the unmodified reference layer) through the device path: several peaks per node, empty frames, K from 1 to 4,
+    class-map strides 1 / 2 / 4, scales, instance caps."""
+    from oracle import identity as oid
+    from sleap_nn_b200.inference.layers import BottomUpMultiClassPostproc
+    from tests.test_oracle_fuzz_vs_reference import multiclass_cases
+
+    for cms, class_maps, cs, scale, eff, cap in multiclass_cases():
+        want = oid.bottomup_multiclass_postprocess(cms, class_maps, 2, cs, scale, eff, cap, threshold=0.3)
+        post = BottomUpMultiClassPostproc(0.3, "integral", 5, cms_output_stride=2, class_maps_output_stride=cs, max_instances=cap)
+        k, v, s, t = post(cms.cuda(), class_maps.cuda(), input_scale=scale, eff_scale=eff)
+        post.check()
+        eq(np.isnan(npy(k)), np.isnan(npy(want[0])))
+        close(npy(k), npy(want[0]), atol=1e-4)
+        eq(npy(v), npy(want[1]))
+        close(npy(s), npy(want[2]), rtol=1e-6, atol=1e-7)
+        close(npy(t), npy(want[3]), rtol=1e-6, atol=1e-7)

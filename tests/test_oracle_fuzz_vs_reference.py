@@ -319,15 +319,8 @@ def test_interp1d_fuzz(R):
         eq(npy(got), npy(want))
 
 
-def test_bottomup_multiclass_layer_fuzz(R):
-    """BottomUpMultiClassLayer.postprocess (unmodified class, stand-in self) vs the oracle on random small frames: noisy
-    confidence maps (several peaks per node, some frames empty), random class maps, scales and instance caps."""
-    import types
-
-    from oracle import identity as oid
-
-    L = R.bottomup_multiclass.BottomUpMultiClassLayer
-    P = R.preprocess_info.PreprocInfo
+def multiclass_cases():
+    """Random small frames for the multi-class bottom-up layer, shared with tests/test_identity_gpu.py."""
     for seed in range(24):
         g = torch.Generator().manual_seed(900 + seed)
         B, Nn, K, H, W = 2, int(torch.randint(1, 4, (1,), generator=g)), int(torch.randint(1, 5, (1,), generator=g)), 24, 32
@@ -339,6 +332,19 @@ def test_bottomup_multiclass_layer_fuzz(R):
         scale = [1.0, 0.5, 2.0][seed % 3]
         eff = [torch.ones(B), torch.tensor([0.8, 1.25])][seed % 2]
         cap = [None, 1, 2, 3][seed % 4]
+        yield cms, class_maps, cs, scale, eff, cap
+
+
+def test_bottomup_multiclass_layer_fuzz(R):
+    """BottomUpMultiClassLayer.postprocess (unmodified class, stand-in self) vs the oracle on random small frames: noisy
+    confidence maps (several peaks per node, some frames empty), random class maps, scales and instance caps."""
+    import types
+
+    from oracle import identity as oid
+
+    L = R.bottomup_multiclass.BottomUpMultiClassLayer
+    P = R.preprocess_info.PreprocInfo
+    for cms, class_maps, cs, scale, eff, cap in multiclass_cases():
         cfg = types.SimpleNamespace(peak_threshold=0.3, effective_refinement="integral", integral_patch_size=5,
                                     max_instances=None, return_confmaps=False, return_class_maps=False)
         me = types.SimpleNamespace(postprocess_config=cfg, cms_output_stride=2, class_maps_output_stride=cs,
