@@ -414,10 +414,11 @@ def run_ours(args, rank: int, world: int):
                              if hs.last_zero_copy else "copied to the device every step")},
             "gpu_launches": pipes[0].launches_per_call * args.steps, "host_issue_us_per_step": host_issue_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 335590000, "kernel": "local_peaks_detect_vec4<4,1,6>", "peak_source": which,
+                         "traffic": 338793984, "kernel": "local_peaks_detect_vec4<4,1,6>", "peak_source": which,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "avg_launch_ms": avg_detect_ms,
                          "how": "CUDA events recorded by the C ABI right around the kernel, kernel running alone, "
-                                "rotating 872 MB batches; traffic from ncu (profiles/)",
+                                "rotating 872 MB batches; traffic = dram__bytes_read.sum 335598848 + dram__bytes_write.sum 3195136 per "
+                                "launch from one ncu --set full capture (profiles/r1_d_detect_tail_ncu_raw.txt)",
                          "in_situ_avg_launch_ms": insitu_ms,
                          "in_situ_note": "same events inside the timed region; inflated when two streams overlap two detect kernels",
                          "whole_step_frac": (ALGO_BYTES_PER_FRAME * B / (ms_total / args.steps / 1e3) / 1e9) / peak},
