@@ -998,13 +998,10 @@ extern "C" int snb_local_peaks_detect(const float* cms, int B, int C, int H, int
   if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, st);
   if (contiguous && use_bulk) {
     const size_t smem = (size_t)BULK_STAGES * BULK_STAGE_FLOATS * 4 + BULK_STAGES * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(local_peaks_detect_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-          cudaSuccess)
-        return SNB_ERR_CUDA_LAUNCH;
-      attr_set = true;
-    }
+    // per launch, not cached in a static: the attribute is per DEVICE and one process may drive several GPUs
+    if (cudaFuncSetAttribute(local_peaks_detect_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return SNB_ERR_CUDA_LAUNCH;
     const long long n_elems = rows * W;
     const long long n_chunks = (n_elems + BULK_STAGE_FLOATS - 1) / BULK_STAGE_FLOATS;
     const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 3);  // 3 CTAs x 64 KB per SM
@@ -1155,13 +1152,10 @@ extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W,
       global_peaks_warp_kernel<8, false><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
                                                                                 refine_size, out_xy, out_val, lad);
   } else if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
-          cudaSuccess)
-        return SNB_ERR_CUDA_LAUNCH;
-      attr_set = true;
-    }
+    // per launch, not cached in a static: the attribute is per DEVICE and one process may drive several GPUs
+    if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
+        cudaSuccess)
+      return SNB_ERR_CUDA_LAUNCH;
     int per_sm = (int)((220 * 1024) / (ring_smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
     const long long want = (long long)sm_count() * per_sm;

@@ -310,3 +310,39 @@ def test_fused_pipeline_busy_flies_frames_vs_oracle():
         close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
         eq(npy(pv[b]), npy(want[1][b]))
         close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-4)  # a sum of 31 line scores
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """Inputs on cuda:1 while cuda:0 is the current device: kernels run on the input's device and stream, results come
+    back on that device and equal the cuda:0 results (per-device function attributes, workspaces and tables)."""
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.data.confidence_maps import make_multi_confmaps
+    from sleap_nn_b200.inference import peak_finding as pf
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    B, n_inst, Nn, hw, stride = 4, 2, 5, (512, 512), 2
+    edges = synthetic.chain_edges(Nn)
+    poses = synthetic.random_poses(9, B, n_inst, Nn, hw, edges, margin=60.0, step=24.0)
+    d0, d1 = torch.device("cuda", 0), torch.device("cuda", 1)
+    torch.cuda.set_device(d0)
+    cms0, pafs0 = synthetic.render_batch(poses, hw, stride, edges, d0, seed=9)
+    cms1, pafs1 = cms0.to(d1), pafs0.to(d1)
+    a, b = pf.find_local_peaks(cms0, 0.2, "integral"), pf.find_local_peaks(cms1, 0.2, "integral")
+    for x, y in zip(a, b):
+        assert y.device == d1
+        eq(npy(x), npy(y))
+    g0, g1 = pf.find_global_peaks(cms0[:, :, :100, :100], 0.2, "integral"), pf.find_global_peaks(cms1[:, :, :100, :100], 0.2, "integral")
+    assert g1[0].device == d1
+    eq(npy(g0[0]), npy(g1[0])); eq(npy(g0[1]), npy(g1[1]))
+    r0 = BottomUpPostproc(Nn, edges, B, tuple(cms0.shape[-2:]), cms_stride=stride, pafs_stride=stride, device=d0)(cms0, pafs0)
+    r1 = BottomUpPostproc(Nn, edges, B, tuple(cms1.shape[-2:]), cms_stride=stride, pafs_stride=stride, device=d1)(cms1, pafs1)
+    assert r1.instances.device == d1 and torch.cuda.current_device() == 0
+    for x, y in zip(r0.to_lists(), r1.to_lists()):
+        for u, v in zip(x, y):
+            eq(npy(u), npy(v))
+    xv, yv = torch.arange(0, 64, dtype=torch.float32), torch.arange(0, 48, dtype=torch.float32)
+    pts = torch.rand((1, 2, 3, 2)) * 40
+    t0, t1 = make_multi_confmaps(pts.to(d0), xv, yv, 2.0), make_multi_confmaps(pts.to(d1), xv, yv, 2.0)
+    assert t1.device == d1
+    eq(npy(t0), npy(t1))
