@@ -26,6 +26,15 @@ def _as_f32_cuda(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t
 
 
+def _threshold_for(dtype: torch.dtype, threshold: float) -> float:
+    """`cms > threshold` compares in the TENSOR's dtype (the python scalar is cast to it): for fp16 / bf16 maps the
+    threshold is first rounded to that dtype.  The up-cast values are exact, so comparing them with the rounded threshold
+    in fp32 reproduces the reference's decisions (an element equal to a threshold that rounds UP must not pass)."""
+    if dtype in (torch.float16, torch.bfloat16):
+        return float(torch.tensor(float(threshold), dtype=dtype))
+    return float(threshold)
+
+
 def _next_pow2(n: int) -> int:
     p = 1
     while p < n:
@@ -64,6 +73,7 @@ def _local_peaks(cms: torch.Tensor, threshold: float, refine_size: int):
         raise ValueError(f"cms must be (samples, channels, height, width), got {tuple(cms.shape)}")
     dev = N.compute_device(cms)
     out_dev, out_dtype = cms.device, cms.dtype
+    threshold = _threshold_for(cms.dtype, threshold)
     x = _as_f32_cuda(cms, dev)
     B = x.shape[0]
     if x.numel() == 0:
@@ -125,6 +135,7 @@ def _global_peaks(cms: torch.Tensor, threshold: float, refine_size: int):
         raise ValueError(f"cms must be (samples, channels, height, width), got {tuple(cms.shape)}")
     dev = N.compute_device(cms)
     out_dev, out_dtype = cms.device, cms.dtype
+    threshold = _threshold_for(cms.dtype, threshold)
     x = _as_f32_cuda(cms, dev)
     B, Cn, H, W = x.shape
     if H == 0 or W == 0:

@@ -225,3 +225,34 @@ def test_full_size_properties(pf):
     assert (npy(vals) == np.float32(0.9)).all()
     ipts = np.asarray([[t[2], t[1]] for t in got], np.float32)
     close(npy(pts), ipts, atol=2e-3)  # symmetric 3x3 blob on a <=1e-3 noise floor: offsets ~ noise only
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("thr", [0.3, 0.2, 0.7])
+def test_half_precision_maps_threshold_in_the_maps_dtype(pf, opeaks, dt, thr):
+    """fp16 / bf16 maps: `cms > threshold` and `max < threshold` compare in the maps' dtype (0.3 rounds UP to 0.30005 in
+    fp16, 0.2 rounds DOWN to 0.19995), so an element equal to the ROUNDED threshold decides differently from a comparison
+    with the fp32 threshold.  Integer results and values follow the reference exactly (the oracle runs the same torch ops on
+    the half tensor); refined coordinates are computed in fp32 on the exact up-cast values, where the reference accumulates
+    in the maps' dtype (differs by up to 4e-4 px fp16 / 3e-3 px bf16)."""
+    g = torch.Generator().manual_seed(21)
+    cms = torch.rand((2, 3, 40, 48), generator=g).to(dt)
+    edge = torch.tensor(thr, dtype=dt)
+    cms[0, 0, 8:13, 8:13] = 0.05
+    cms[0, 0, 10, 10] = edge                      # an isolated local maximum exactly AT the rounded threshold
+    cms[1, 2] = torch.minimum(cms[1, 2], edge)
+    cms[1, 2, 5, 7] = edge                        # a plane whose maximum IS the rounded threshold
+    want = opeaks.local_peaks_rough(cms, thr)
+    got = pf.find_local_peaks_rough(cms.cuda(), threshold=thr)
+    assert got[1].dtype == dt
+    for a, b in zip(got, want):
+        eq(npy(a.float()), npy(b.float()))
+    gw = opeaks.global_peaks_rough(cms, thr)
+    gg = pf.find_global_peaks_rough(cms.cuda(), threshold=thr)
+    eq(npy(gg[0]), npy(gw[0]))
+    eq(npy(gg[1].float()), npy(gw[1].float()))
+    ri = pf.find_local_peaks(cms.cuda(), threshold=thr, refinement="integral")
+    wi = opeaks.local_peaks(cms, thr, "integral", 5)
+    for a, b in zip(ri[1:], wi[1:]):
+        eq(npy(a.float()), npy(b.float()))
+    close(npy(ri[0]), npy(wi[0].float()), atol=5e-3)
