@@ -356,3 +356,32 @@ def test_bottomup_multiclass_layer_fuzz(R):
         eq(npy(pv), npy(o.pred_peak_values))
         close(npy(sc), npy(o.instance_scores), rtol=1e-6, atol=1e-7)   # nanmean reduction order
         close(npy(tr), npy(o.instance_tracking_scores), rtol=1e-6, atol=1e-7)
+
+
+def test_labels_level_nms_cores_fuzz(R):
+    """_nms_greedy_iou / _nms_greedy_oks / _compute_oks / _compute_iou_one_to_many (ops/filters.py:336-495, float64 numpy)
+    on random instances with NaN nodes and NaN scores."""
+    from oracle import filters as ofil
+
+    OF = R.ops_filters
+    for seed in range(60):
+        g = np.random.default_rng(1100 + seed)
+        n, nn = int(g.integers(0, 9)), int(g.integers(1, 6))
+        pts = [g.uniform(0, 50, (nn, 2)) + (0 if seed % 2 else g.uniform(0, 4)) for _ in range(n)]
+        if seed % 2 and n > 1:
+            pts = [pts[0] + g.normal(0, 2.0, (nn, 2)) for _ in range(n)]       # heavy overlap
+        for p in pts:
+            p[g.random(nn) < 0.2] = np.nan
+        scores = g.uniform(0, 1, n)
+        # (no exact score ties: `scores.argsort()[::-1]` is numpy's default introsort / AVX-512 sort, whose order of equal
+        #  keys is platform dependent - measured here: [0, 1] where the classic insertion-sort path gives [1, 0]; the
+        #  kernels document "equal keys by descending index", the classic behaviour, and parity is defined on tie-free input)
+        if n > 1 and seed % 5 == 0:
+            scores[-1] = np.nan
+        thr = float(g.uniform(0.05, 0.7))
+        boxes = np.array([ofil.instance_bbox64(p) for p in pts]).reshape(n, 4)
+        assert OF._nms_greedy_iou(boxes, scores, thr) == ofil.nms_greedy64(pts, scores, thr, "iou")
+        assert OF._nms_greedy_oks(pts, scores, thr) == ofil.nms_greedy64(pts, scores, thr, "oks")
+        for i in range(min(n, 3)):
+            for j in range(min(n, 3)):
+                close(ofil.oks64(pts[i], pts[j]), OF._compute_oks(pts[i], pts[j]), rtol=1e-12, atol=1e-15)
