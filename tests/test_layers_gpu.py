@@ -302,3 +302,26 @@ def test_topdown_crop_size_is_read_off_the_first_box_like_the_reference():
     eq(npy(o["instance_bboxes"]), want["bboxes"])
     with pytest.raises(RuntimeError, match="shape mismatch"):
         TopDownPostproc(crop_hw, return_crops=True)(img.cuda(), cen.cuda(), val.cuda(), lambda c: topdown_model(c, gd, pd))
+
+
+def test_single_stage_layers_random_vs_oracle():
+    """CentroidPostproc / CenteredInstancePostproc / SingleInstancePostproc on the generator that pins oracle.layers to
+    the unmodified reference layers: inferred and fixed max_instances, every ladder step, empty frames."""
+    from oracle import layers as olay
+    from sleap_nn_b200.inference.layers import CenteredInstancePostproc, CentroidPostproc, SingleInstancePostproc
+    from tests.test_oracle_fuzz_vs_reference import single_stage_cases
+
+    for cms, stride, scale, eff, cap in single_stage_cases():
+        want_xy, want_val = olay.centroid_postprocess(cms[:, :1], stride, scale, eff, cap, threshold=0.25)
+        xy, val = CentroidPostproc(0.25, "integral", 5, max_instances=cap)(cms[:, :1].cuda(), output_stride=stride,
+                                                                           input_scale=scale, eff_scale=eff)
+        assert tuple(xy.shape) == want_xy.shape
+        eq(np.isnan(npy(xy)), np.isnan(want_xy))
+        close(npy(xy), want_xy, atol=1e-4)
+        eq(npy(val), want_val)
+        wk, wv = olay.global_postprocess(cms, stride, scale, eff, threshold=0.25)
+        for post in (CenteredInstancePostproc(0.25, "integral", 5), SingleInstancePostproc(0.25, "integral", 5)):
+            k, v = post(cms.cuda(), output_stride=stride, input_scale=scale, eff_scale=eff)
+            eq(np.isnan(npy(k)), np.isnan(wk))
+            close(npy(k), wk, atol=1e-4)
+            eq(npy(v), wv)

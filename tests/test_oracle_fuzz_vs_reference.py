@@ -385,3 +385,42 @@ def test_labels_level_nms_cores_fuzz(R):
         for i in range(min(n, 3)):
             for j in range(min(n, 3)):
                 close(ofil.oks64(pts[i], pts[j]), OF._compute_oks(pts[i], pts[j]), rtol=1e-12, atol=1e-15)
+
+
+def single_stage_cases():
+    """Random confidence maps for the centroid / centred-instance / single-instance layers, shared with the GPU tests."""
+    for seed in range(24):
+        g = torch.Generator().manual_seed(1200 + seed)
+        B, C = int(torch.randint(1, 5, (1,), generator=g)), int(torch.randint(1, 4, (1,), generator=g))
+        cms = torch.rand((B, C, 28, 36), generator=g) ** 5
+        if seed % 6 == 0:
+            cms[0] = 0.0
+        stride = [1, 2, 4][seed % 3]
+        scale = [1.0, 0.5, 1.5][(seed // 3) % 3]
+        eff = torch.ones(B) if seed % 2 else torch.rand((B,), generator=g) * 0.6 + 0.7
+        cap = [None, 1, 3, 40][seed % 4]
+        yield cms, stride, scale, eff, cap
+
+
+def test_single_stage_layers_fuzz(R):
+    """CentroidLayer / CenteredInstanceLayer / SingleInstanceLayer .postprocess (unmodified classes, stand-in self) vs
+    oracle.layers on random maps: inferred and fixed max_instances (top-k truncation, NaN padding), every ladder step."""
+    import types
+
+    from oracle import layers as olay
+
+    P = R.preprocess_info.PreprocInfo
+    CL, CI, SI = R.centroid.CentroidLayer, R.centered_instance.CenteredInstanceLayer, R.single_instance.SingleInstanceLayer
+    for cms, stride, scale, eff, cap in single_stage_cases():
+        cfg = types.SimpleNamespace(peak_threshold=0.25, effective_refinement="integral", integral_patch_size=5,
+                                    return_confmaps=False, max_instances=None)
+        info = P(eff_scale=eff, input_scale=scale, output_stride=stride)
+        me = types.SimpleNamespace(postprocess_config=cfg, max_instances=cap, _extract_confmaps=lambda raw: raw["x"],
+                                   _infer_max_instances=CL._infer_max_instances)
+        o = CL.postprocess(me, {"x": cms[:, :1]}, info)
+        xy, val = olay.centroid_postprocess(cms[:, :1], stride, scale, eff, cap, threshold=0.25)
+        eq(xy, npy(o.pred_centroids)); eq(val, npy(o.pred_centroid_values))
+        for layer in (CI, SI):
+            o = layer.postprocess(me, {"x": cms}, info)
+            k, v = olay.global_postprocess(cms, stride, scale, eff, threshold=0.25)
+            eq(k, npy(o.pred_keypoints)); eq(v, npy(o.pred_peak_values))
