@@ -241,3 +241,17 @@ def test_c_program_drives_the_library_without_torch(tmp_path):
 
     r = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0 and "C ABI demo: OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_shim_tables_name_real_entry_points():
+    """The name -> C-ABI entry point tables of the two re-export shims stay truthful."""
+    from sleap_nn_b200 import _native as N
+    from sleap_nn_b200.inference import paf_grouping, peak_finding
+
+    entries = [e for e in paf_grouping._BACKED_BY.values() if e] + [e for _, e in peak_finding._BACKED_BY.values()]
+    for entry in entries:
+        for sym in entry.split(" + "):
+            assert sym in N.SIGNATURES, sym
+    for mod in (paf_grouping, peak_finding):
+        for name in mod.__all__:
+            assert callable(getattr(mod, name)) or isinstance(getattr(mod, name), type)
