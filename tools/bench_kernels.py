@@ -108,7 +108,7 @@ def k7_cfg4(dev, iters, bf16=False):
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
-    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_rows_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
+    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_rows2_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
          {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
