@@ -328,6 +328,8 @@ class TopDownPostproc:
                                               N.ptr(status), st()), "snb_crop_bboxes")
                 raw = model(crops)
                 cms, class_vectors = raw if isinstance(raw, (tuple, list)) else (raw, None)
+                if cms.dtype != torch.float32:  # an autocast network hands back fp16 / bf16 maps: exact up-cast
+                    cms = cms.float()
                 Nn = int(cms.shape[1])
                 k4, v3 = self.stage2(cms, output_stride=output_stride, input_scale=input_scale)
                 kp, vals = k4.squeeze(1).contiguous(), v3.squeeze(1).contiguous()
