@@ -1,4 +1,4 @@
-import ctypes as C, os, sys, json
+import ctypes as C, sys
 sys.path.insert(0, '/root/repo')
 import torch
 from sleap_nn_b200 import _native as N

@@ -5,7 +5,6 @@ files import at module top but the hot path never touches (omegaconf, sleap_io),
 reference modules the filter tests need, and provides the two asset fixtures of tests/fixtures/inference.py.
 """
 import importlib.util
-import os
 import sys
 import types
 from pathlib import Path
