@@ -1,10 +1,13 @@
-import ctypes as C, sys
-sys.path.insert(0, '/root/repo')
+"""Probe: how much of K2's 16.8 us at cfg2 is the stream itself (all planes below threshold), how much the refinement
+epilogue adds, and what a plain copy of the same 85 MB achieves at this size.  Scratch tool; numbers quoted in DESIGN.md."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
 from sleap_nn_b200 import _native as N
 from sleap_nn_b200.data.utils import make_grid_vectors
 from sleap_nn_b200.data.confidence_maps import _confmaps
-sys.path.insert(0, '/root/repo/tools')
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
 from bench_kernels import timed
 dev = torch.device("cuda", 0)
 B, Cn, H, W = 256, 13, 80, 80
