@@ -7,6 +7,8 @@
 // built WITHOUT --use_fast_math and with -ftz=false -prec-div=true -prec-sqrt=true.
 #pragma once
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -31,6 +33,125 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
                : "l"(p));
   return r;
 }
+
+// ---- element types of the maps (ABI v5: SNB_DTYPE_*).  Under autocast the backbone emits fp16 / bf16 heads
+// (layers/backends/torch_backend.py:125-146 casts them back with .float()); every value of those types is exactly
+// representable in fp32, so reading them natively and up-casting in registers gives bit-identical results to the
+// reference's .float() + fp32 ops while moving half the bytes.
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short u) { return __uint_as_float((unsigned)u << 16); }
+__device__ __forceinline__ float f16_bits_to_float(unsigned short u) { return __half2float(__ushort_as_half(u)); }
+
+// One element of a tensor whose type is only known at run time (the latency-bound kernels: O(#peaks) taps).
+// `dt` is warp-uniform, so the branch does not diverge.
+__device__ __forceinline__ float ld_elem(const void* base, long long idx, int dt) {
+  if (dt == SNB_DTYPE_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(base) + idx);
+  return dt == SNB_DTYPE_F16 ? f16_bits_to_float(u) : bf16_bits_to_float(u);
+}
+__host__ __device__ __forceinline__ int dtype_size(int dt) { return dt == SNB_DTYPE_F32 ? 4 : 2; }
+
+// Compile-time element traits for the streaming kernels: PER16 elements per 128-bit load.
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int PER16 = 4, DT = SNB_DTYPE_F32;
+  struct Thr { float f; };
+  static __device__ __forceinline__ Thr make_thr(float thr) { return Thr{thr}; }
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&e)[4]) {
+    e[0] = __uint_as_float(v.x); e[1] = __uint_as_float(v.y); e[2] = __uint_as_float(v.z); e[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ bool any_gt(const uint4& v, const Thr& t) {
+    return (__uint_as_float(v.x) > t.f) || (__uint_as_float(v.y) > t.f) || (__uint_as_float(v.z) > t.f) ||
+           (__uint_as_float(v.w) > t.f);
+  }
+  // maximum of the vector with NaN propagation (max.NaN: a NaN sticks)
+  static __device__ __forceinline__ float vmax_nan(const uint4& v) {
+    float a, b, r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(a) : "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(b) : "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+  }
+  static __device__ __forceinline__ float load1(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ uint4 neg_inf() {
+    const unsigned u = 0xff800000u;
+    return make_uint4(u, u, u, u);
+  }
+};
+template <> struct Elem<__half> {
+  static constexpr int PER16 = 8, DT = SNB_DTYPE_F16;
+  // `v > thr` for a half v and an fp32 thr  <=>  v > (thr rounded DOWN to half): no half lies in (rd(thr), thr].
+  struct Thr { float f; __half2 h2; };
+  static __device__ __forceinline__ Thr make_thr(float thr) {
+    const __half h = __float2half_rd(thr);
+    return Thr{thr, __halves2half2(h, h)};
+  }
+  static __device__ __forceinline__ __half2 h2(unsigned u) { return *reinterpret_cast<const __half2*>(&u); }
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&e)[8]) {
+    const float2 a = __half22float2(h2(v.x)), b = __half22float2(h2(v.y)), c = __half22float2(h2(v.z)),
+                 d = __half22float2(h2(v.w));
+    e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = d.x; e[7] = d.y;
+  }
+  static __device__ __forceinline__ bool any_gt(const uint4& v, const Thr& t) {
+    // __hmax2 returns the non-NaN operand: a NaN element never passes `v > thr`, so ignoring it is exact
+    const __half2 m = __hmax2(__hmax2(h2(v.x), h2(v.y)), __hmax2(h2(v.z), h2(v.w)));
+    return __hgt2_mask(m, t.h2) != 0u;
+  }
+  static __device__ __forceinline__ float vmax_nan(const uint4& v) {
+    const __half2 m = __hmax2_nan(__hmax2_nan(h2(v.x), h2(v.y)), __hmax2_nan(h2(v.z), h2(v.w)));
+    const float2 f = __half22float2(m);
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(f.x), "f"(f.y));
+    return r;
+  }
+  static __device__ __forceinline__ float load1(const __half* p) {
+    return f16_bits_to_float(__ldg(reinterpret_cast<const unsigned short*>(p)));
+  }
+  static __device__ __forceinline__ uint4 neg_inf() {
+    const unsigned u = 0xfc00fc00u;
+    return make_uint4(u, u, u, u);
+  }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int PER16 = 8, DT = SNB_DTYPE_BF16;
+  struct Thr { float f; __nv_bfloat162 h2; };
+  static __device__ __forceinline__ Thr make_thr(float thr) {
+    const __nv_bfloat16 h = __float2bfloat16_rd(thr);
+    return Thr{thr, __halves2bfloat162(h, h)};
+  }
+  static __device__ __forceinline__ __nv_bfloat162 h2(unsigned u) { return *reinterpret_cast<const __nv_bfloat162*>(&u); }
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&e)[8]) {
+    // bf16 -> fp32 is a 16-bit shift
+    e[0] = __uint_as_float(v.x << 16); e[1] = __uint_as_float(v.x & 0xffff0000u);
+    e[2] = __uint_as_float(v.y << 16); e[3] = __uint_as_float(v.y & 0xffff0000u);
+    e[4] = __uint_as_float(v.z << 16); e[5] = __uint_as_float(v.z & 0xffff0000u);
+    e[6] = __uint_as_float(v.w << 16); e[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ bool any_gt(const uint4& v, const Thr& t) {
+    const __nv_bfloat162 m = __hmax2(__hmax2(h2(v.x), h2(v.y)), __hmax2(h2(v.z), h2(v.w)));
+    return __hgt2_mask(m, t.h2) != 0u;
+  }
+  static __device__ __forceinline__ float vmax_nan(const uint4& v) {
+    const __nv_bfloat162 m = __hmax2_nan(__hmax2_nan(h2(v.x), h2(v.y)), __hmax2_nan(h2(v.z), h2(v.w)));
+    const unsigned u = *reinterpret_cast<const unsigned*>(&m);
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(__uint_as_float(u << 16)), "f"(__uint_as_float(u & 0xffff0000u)));
+    return r;
+  }
+  static __device__ __forceinline__ float load1(const __nv_bfloat16* p) {
+    return bf16_bits_to_float(__ldg(reinterpret_cast<const unsigned short*>(p)));
+  }
+  static __device__ __forceinline__ uint4 neg_inf() {
+    const unsigned u = 0xff80ff80u;
+    return make_uint4(u, u, u, u);
+  }
+};
 
 __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
