@@ -160,14 +160,18 @@ def time_cpu_port(cms_cpu, pafs_cpu, edges, frames_per_call: int, calls: int, wa
     return frames_per_call * calls / dt, dt / calls
 
 
-def make_inputs(dev, n_batches: int, seed0: int):
+DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def make_inputs(dev, n_batches: int, seed0: int, dtype=torch.float32):
     from sleap_nn_b200 import synthetic
 
     edges = synthetic.chain_edges(N_NODES)
     out = []
     for i in range(n_batches):
         poses = synthetic.random_poses(seed0 + i, B, N_INST, N_NODES, IMG_HW, edges)
-        out.append(synthetic.render_batch(poses, IMG_HW, STRIDE, edges, dev, seed=seed0 + i))
+        cms, pafs = synthetic.render_batch(poses, IMG_HW, STRIDE, edges, dev, seed=seed0 + i)
+        out.append((cms.to(dtype), pafs.to(dtype)))  # f16 / bf16: the heads an autocast backbone emits, read natively
     return edges, out
 
 
@@ -238,7 +242,10 @@ def run_ours(args, rank: int, world: int):
 
         host_cpus = None if args.no_numa_bind else bind_host_to_gpu(local)
     n_bufs, n_streams = args.buffers, args.streams
-    edges, inputs = make_inputs(dev, n_bufs, seed0=100 * (rank + 1))
+    dtype = DTYPES[args.dtype]
+    esz = 4 if dtype == torch.float32 else 2
+    algo_bytes_per_frame = esz * N_NODES * 512 * 512
+    edges, inputs = make_inputs(dev, n_bufs, seed0=100 * (rank + 1), dtype=dtype)
     # `--streams` pipeline instances, each with its own tables: instance i's detect kernel runs on the
     # (single) detect stream, its per-frame tail on the high-priority tail stream, so tail(i) overlaps
     # detect(i+1) and the step time tends to the HBM time of the confidence maps.
@@ -341,7 +348,7 @@ def run_ours(args, rank: int, world: int):
     def detect_only(i, evs=None):
         cms = inputs[i % n_bufs][0]
         sb_, sc_, sh_, sw_ = cms.stride()
-        NN.check(NN.lib.snb_local_peaks_detect(NN.ptr(cms), B, N_NODES, 512, 512, sb_, sc_, sh_, sw_, 0.2,
+        NN.check(NN.lib.snb_local_peaks_detect_t(NN.ptr(cms), NN.dtype_code(cms.dtype), B, N_NODES, 512, 512, sb_, sc_, sh_, sw_, 0.2,
                                                pipe0.caps["peak_cap"], NN.ptr(pipe0.buf["frame_count"]),
                                                NN.ptr(pipe0.buf["keys"]), evs[0].cuda_event if evs else None,
                                                evs[1].cuda_event if evs else None, NN.stream_ptr(dev)), "detect")
@@ -362,7 +369,7 @@ def run_ours(args, rank: int, world: int):
 
     hs = BottomUpHostStream(lambda: BottomUpPostproc(N_NODES, edges, B, (512, 512), cms_stride=STRIDE, pafs_stride=STRIDE,
                                                      device=dev, keep_tables=True), depth=args.e2e_depth,
-                            zero_copy_pafs=not args.copy_pafs)
+                            zero_copy_pafs=not args.copy_pafs, zero_copy_cms=args.zero_copy_cms)
     for i in range(3):
         hs.submit(*host[i % len(host)])
     hs.drain()
@@ -396,11 +403,11 @@ def run_ours(args, rank: int, world: int):
         peak, which = measured_peaks()
         avg_detect_ms = sum(iso_ms) / len(iso_ms)
         insitu_ms = sum(detect_ms) / len(detect_ms)
-        achieved = ALGO_BYTES_PER_FRAME * B / (avg_detect_ms / 1e3) / 1e9
+        achieved = algo_bytes_per_frame * B / (avg_detect_ms / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": args.dtype, "data": "synthetic",
             "config": dict(WORKLOAD, parallelism=f"frame-sharded x{world}, no collective", streams=n_streams,
                            input_batches=n_bufs, l2="inputs larger than L2: each batch is 872 MB and batches rotate",
                            tail="fused per-frame tail kernel" + (" on a high-priority second stream" if tail_stream is not None else ""),
@@ -408,24 +415,26 @@ def run_ours(args, rank: int, world: int):
                            launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "in_flight": args.e2e_depth,
+                    "cms": ("streamed by the detect kernel straight from pinned host memory (zero-copy)"
+                            if getattr(hs, "last_zero_copy_cms", False) else "cudaMemcpyAsync pinned host -> HBM staging buffer"),
                     "host_cpus_rank0": ("all" if host_cpus is None else f"{len(host_cpus)} CPUs local to the GPU"),
                     "pafs": ("sampled in place from pinned host memory (zero-copy): "
-                             f"{paf_sector_bytes} B of 32-byte sectors per step instead of {host[0][1].numel() * 4} B"
+                             f"{paf_sector_bytes} B of 32-byte sectors per step instead of {host[0][1].numel() * esz} B"
                              if hs.last_zero_copy else "copied to the device every step")},
             "gpu_launches": pipes[0].launches_per_call * args.steps, "host_issue_us_per_step": host_issue_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": 338793984, "kernel": "local_peaks_detect_vec4<4,1,6>", "peak_source": which,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * B, "avg_launch_ms": avg_detect_ms,
+                         "algorithmic_bytes_per_launch": algo_bytes_per_frame * B, "avg_launch_ms": avg_detect_ms,
                          "how": "CUDA events recorded by the C ABI right around the kernel, kernel running alone, "
                                 "rotating 872 MB batches; traffic = dram__bytes_read.sum 335598848 + dram__bytes_write.sum 3195136 per "
                                 "launch from one ncu --set full capture (profiles/r1_d_detect_tail_ncu_raw.txt)",
                          "in_situ_avg_launch_ms": insitu_ms,
                          "in_situ_note": "same events inside the timed region; inflated when two streams overlap two detect kernels",
-                         "whole_step_frac": (ALGO_BYTES_PER_FRAME * B / (ms_total / args.steps / 1e3) / 1e9) / peak},
+                         "whole_step_frac": (algo_bytes_per_frame * B / (ms_total / args.steps / 1e3) / 1e9) / peak},
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            cms_cpu, pafs_cpu = inputs[0][0][:16].cpu(), inputs[0][1][:16].cpu()
+            cms_cpu, pafs_cpu = inputs[0][0][:16].float().cpu(), inputs[0][1][:16].float().cpu()
             fps, per_call = time_cpu_port(cms_cpu, pafs_cpu, edges, 16, args.cpu_calls)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{args.cpu_calls} x 16 frames of the same cfg3 batch ({per_call:.2f} s/call), "
@@ -442,6 +451,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=list(DTYPES),
+                    help="element type of the maps: f32 (the reference's, default) or the f16 / bf16 heads of an autocast backbone")
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--buffers", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=100)
@@ -454,6 +465,8 @@ def main():
                          "launch per replay; measured slower at N=1: the graph's three chains run in lockstep, see DESIGN.md)")
     ap.add_argument("--tail-stream", dest="tail_stream", action="store_true",
                     help="one detect stream + one high-priority tail stream instead of one stream per pipeline instance")
+    ap.add_argument("--zero-copy-cms", action="store_true",
+                    help="e2e: the detect kernel streams the pinned host confidence maps itself (no cudaMemcpy + HBM staging)")
     ap.add_argument("--copy-pafs", action="store_true", help="e2e: stage the PAF tensor in HBM instead of sampling it in place")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--lean", action="store_true", help="do not write candidate / match tables to global memory")

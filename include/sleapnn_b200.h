@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SNB_ABI_VERSION 4
+#define SNB_ABI_VERSION 5
 
 #define SNB_OK 0
 #define SNB_ERR_BAD_ARG (-1)
@@ -45,6 +45,16 @@ extern "C" {
 #define SNB_STATUS_ASM_MISMATCH 256     /* make_predicted_instances' sanity assert would fail (ops/paf.py:873): a scored   */
                                         /* connection whose two peaks ended up in different instances                      */
 #define SNB_STATUS_ASM_MISSING 512      /* ... or whose destination peak is in no (kept) instance: KeyError there          */
+
+/* ABI v5: element type of the confidence-map / PAF tensors.  Under autocast the reference's backbone emits fp16 heads
+ * and casts them back with .float() before any of these ops run (inference/layers/backends/torch_backend.py:125-146).
+ * Every fp16 / bf16 value is exact in fp32, so the *_t entry points read the half tensors in place, up-cast in
+ * registers and compute exactly what the fp32 ops compute on the .float() copy - without that copy's extra read +
+ * write of the largest tensors.  The threshold stays an fp32 number (pass the dtype-rounded threshold to get the
+ * semantics of calling the reference ops directly on a half tensor, where torch compares in the tensor's dtype). */
+#define SNB_DTYPE_F32 0
+#define SNB_DTYPE_F16 1
+#define SNB_DTYPE_BF16 2
 
 int snb_abi_version(void);
 
@@ -85,6 +95,20 @@ int snb_local_peaks_finalize(const float* cms, int B, int C, int H, int W, long 
                              long long sw, int refine_size, float xy_scale, int cap, const int* frame_count,
                              uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status, void* stream);
 
+/* ABI v5: the same three entry points for fp32 / fp16 / bf16 maps (dtype = SNB_DTYPE_*; strides in elements of
+ * that type).  The fp32-only names above are kept and forward here with SNB_DTYPE_F32. */
+int snb_local_peaks_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                      long long sh, long long sw, float threshold, int refine_size, float xy_scale, int cap,
+                      int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan, int* status,
+                      void* stream);
+int snb_local_peaks_detect_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                             long long sh, long long sw, float threshold, int cap, int* frame_count, uint32_t* keys,
+                             void* ev_begin, void* ev_end, void* stream);
+int snb_local_peaks_finalize_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                               long long sh, long long sw, int refine_size, float xy_scale, int cap,
+                               const int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
+                               int* status, void* stream);
+
 /* Padded table -> the reference's concatenated (points, vals, sample_inds, channel_inds). */
 int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val, const int* chan,
                    float* o_xy, float* o_val, int* o_sample, int* o_chan, void* stream);
@@ -118,6 +142,11 @@ typedef struct snb_coord_ladder {
 int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
                         long long sw, float threshold, int refine_size, void* workspace,
                         const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream);
+
+/* ABI v5: snb_global_peaks_ex for fp32 / fp16 / bf16 maps (ladder may be NULL). */
+int snb_global_peaks_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                       long long sh, long long sw, float threshold, int refine_size, void* workspace,
+                       const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream);
 
 /* CentroidLayer.postprocess after find_local_peaks (layers/centroid.py:196-258) on the padded table written by
  * snb_local_peaks (whose xy_scale already applied the stride): / input_scale, per-frame top max_instances by value
@@ -209,6 +238,14 @@ int snb_paf_score(const float* pafs, long long pb, long long py, long long px, l
                   int n_nodes, int n_edges, const int* node_start, const int* node_peaks, const int* edge_off,
                   const int* cand_start, int cand_stride, int max_cand_per_frame, int* cand_edge,
                   long long* cand_epi, float* cand_score, int* status, void* stream);
+
+/* ABI v5: snb_paf_score on an fp32 / fp16 / bf16 PAF tensor (dtype = SNB_DTYPE_*, strides in elements). */
+int snb_paf_score_t(const void* pafs, int dtype, long long pb, long long py, long long px, long long pc, int H, int W,
+                    const float* t_table, int n_points, float stride, float max_edge_length, float penalty_weight,
+                    const float* peak_xy, const int* frame_start, int frame_stride, int B, const int* edges,
+                    int n_nodes, int n_edges, const int* node_start, const int* node_peaks, const int* edge_off,
+                    const int* cand_start, int cand_stride, int max_cand_per_frame, int* cand_edge,
+                    long long* cand_epi, float* cand_score, int* status, void* stream);
 
 /* make_line_subs (paf.py:133-234): out (M,n_points,2,3) int32 [row,col,channel]. */
 int snb_line_subs(const float* peaks, long long n_peaks, const long long* epi, const int* edge_inds, long long M,
@@ -444,10 +481,10 @@ int snb_instance_stats_f64(const double* pts, const double* point_scores, long l
  *   asm_ws B*4*peak_cap int32 | inst_xy B*inst_cap*C*2 | inst_val B*inst_cap*C | inst_score B*inst_cap
  *   n_inst B | status 1 (zeroed by the caller). */
 typedef struct snb_bottomup_args {
-  const float* cms;
+  const void* cms; /* (B, C, H, W), element type cms_dtype (ABI v5; fp32 when 0) */
   int B, C, H, W;
   long long cms_sb, cms_sc, cms_sh, cms_sw;
-  const float* pafs; /* (B, paf_H, paf_W, 2*n_edges) view, element strides below */
+  const void* pafs; /* (B, paf_H, paf_W, 2*n_edges) view, element strides below, element type pafs_dtype */
   int paf_H, paf_W;
   long long paf_sb, paf_sy, paf_sx, paf_sc;
   const int* edges; /* (n_edges, 2) node ids */
@@ -511,6 +548,9 @@ typedef struct snb_bottomup_args {
   float* out_kpts;      /* (B, max_instances, C, 2) */
   float* out_vals;      /* (B, max_instances, C) */
   float* out_scores;    /* (B, max_instances) */
+  /* ---- ABI v5: SNB_DTYPE_* of the two input tensors (0 = fp32).  Half-precision heads are read in place. */
+  int cms_dtype;
+  int pafs_dtype;
 } snb_bottomup_args;
 
 #define SNB_FLAG_UNFUSED_TAIL 1 /* chain the stand-alone kernels instead of the fused per-frame tail */

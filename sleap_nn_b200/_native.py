@@ -15,6 +15,9 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SLEAPNN_B200_LIB", os.path.join(_HERE, "lib", "libsleapnn_b200.so"))
 
+EXPECTED_ABI = 5  # include/sleapnn_b200.h SNB_ABI_VERSION this binding was written against
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
+
 OK = 0
 ERRORS = {-1: "bad argument", -2: "unsupported configuration", -3: "CUDA launch failed"}
 
@@ -39,10 +42,14 @@ SIGNATURES = {
     "snb_local_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_local_peaks_detect": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
     "snb_local_peaks_finalize": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
+    "snb_local_peaks_t": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
+    "snb_local_peaks_detect_t": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
+    "snb_local_peaks_finalize_t": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p, _p, _p, _p, _p, _p, _p],
     "snb_pack_peaks": [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "snb_global_peaks_workspace": [_i, _i, _i, _i, _ip, _ip, _llp],
     "snb_global_peaks": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p],
     "snb_global_peaks_ex": [_p, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
+    "snb_global_peaks_t": [_p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _f, _i, _p, _p, _p, _p, _p],
     "snb_peaks_topk": [_p, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p],
     "snb_coord_ladder_apply": [_p, _ll, _ll, _p, _p, _p],
     "snb_bilinear_resize": [_p, _i, _ll, _i, _i, _ll, _ll, _ll, _i, _i, _p, _p],
@@ -55,6 +62,8 @@ SIGNATURES = {
     "snb_paf_prepare": [_p, _p, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p],
     "snb_paf_score": [_p, _ll, _ll, _ll, _ll, _i, _i, _p, _i, _f, _f, _f, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p,
                       _i, _i, _p, _p, _p, _p, _p],
+    "snb_paf_score_t": [_p, _i, _ll, _ll, _ll, _ll, _i, _i, _p, _i, _f, _f, _f, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p, _p,
+                        _i, _i, _p, _p, _p, _p, _p],
     "snb_line_subs": [_p, _ll, _p, _p, _ll, _p, _i, _f, _i, _i, _p, _p, _p],
     "snb_paf_gather": [_p, _ll, _ll, _ll, _i, _i, _i, _p, _ll, _p, _p, _p],
     "snb_score_lines": [_p, _p, _ll, _p, _ll, _i, _f, _f, _p, _p, _p],
@@ -119,6 +128,7 @@ class BottomUpArgs(C.Structure):
         ("tail_stream", _p), ("ev_handoff", _p), ("ev_tail_done", _p), ("flags", _i),
         ("max_peaks_per_node", _i), ("skip_flag", _p), ("max_instances", _i), ("input_scale", _f),
         ("eff_scale", _p), ("out_kpts", _p), ("out_vals", _p), ("out_scores", _p),
+        ("cms_dtype", _i), ("pafs_dtype", _i),
     ]
 
 
@@ -156,7 +166,10 @@ def _load() -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = C.c_int
     for name, argtypes in RETURNS_LONGLONG.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
         fn.argtypes = argtypes
         fn.restype = C.c_longlong
     return lib
@@ -164,6 +177,9 @@ def _load() -> C.CDLL:
 
 lib = _load()
 ABI_VERSION = lib.snb_abi_version()
+if ABI_VERSION != EXPECTED_ABI:  # a stale / foreign .so called with these argtypes would corrupt memory silently
+    raise NativeLibraryError(f"{LIB_PATH} reports ABI v{ABI_VERSION}, this binding needs v{EXPECTED_ABI}: rebuild it "
+                             "(sleap_nn_b200/csrc/build.sh)")
 if lib.snb_bottomup_args_size() != C.sizeof(BottomUpArgs):
     raise NativeLibraryError(
         f"snb_bottomup_args layout mismatch: library {lib.snb_bottomup_args_size()} bytes, binding {C.sizeof(BottomUpArgs)}")
@@ -177,6 +193,17 @@ def check(rc: int, what: str) -> None:
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+_DTYPES = {torch.float32: DTYPE_F32, torch.float16: DTYPE_F16, torch.bfloat16: DTYPE_BF16}
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    """SNB_DTYPE_* of a map tensor the kernels read natively (fp32 / fp16 / bf16)."""
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise TypeError(f"confidence maps / PAFs must be float32, float16 or bfloat16, got {dtype}") from None
 
 
 def stream_ptr(device: torch.device) -> int:

@@ -45,6 +45,11 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ float fmax_nan(float a, float b) {  // maximum that PROPAGATES NaN (torch.max semantics)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
 __device__ __forceinline__ float bf16_bits_to_float(unsigned short u) { return __uint_as_float((unsigned)u << 16); }
 __device__ __forceinline__ float f16_bits_to_float(unsigned short u) { return __half2float(__ushort_as_half(u)); }
 
@@ -56,6 +61,10 @@ __device__ __forceinline__ float ld_elem(const void* base, long long idx, int dt
   return dt == SNB_DTYPE_F16 ? f16_bits_to_float(u) : bf16_bits_to_float(u);
 }
 __host__ __device__ __forceinline__ int dtype_size(int dt) { return dt == SNB_DTYPE_F32 ? 4 : 2; }
+// address of element `off` of a run-time typed tensor
+__device__ __forceinline__ const void* elem_ptr(const void* base, long long off, int dt) {
+  return reinterpret_cast<const char*>(base) + off * dtype_size(dt);
+}
 
 // Compile-time element traits for the streaming kernels: PER16 elements per 128-bit load.
 template <typename T> struct Elem;
@@ -169,7 +178,7 @@ __device__ __forceinline__ int div_up(int a, int b) { return (a + b - 1) / b; }
 // taps outside the image read 0 (ops/crops.py:97-99).  Grid = arange(s) - (s-1)/2
 // (ops/peaks.py:174).  Sums are accumulated in fp64 and rounded once to fp32 before the
 // fp32 division that the reference performs (ops/peaks.py:84-85); 0/0 -> NaN as there.
-__device__ __forceinline__ void integral_refine(const float* __restrict__ plane, int H, int W, long long sh,
+__device__ __forceinline__ void integral_refine(const void* __restrict__ plane, int dt, int H, int W, long long sh,
                                                 long long sw, float px, float py, int size, float* ox,
                                                 float* oy) {
   const float half_f = 0.5f * (float)size;           // box / 2 (python float, exact in fp32 for int size)
@@ -188,7 +197,7 @@ __device__ __forceinline__ void integral_refine(const float* __restrict__ plane,
     for (int i = 0; i < size; ++i) {
       const int xx = x0 + i;
       float p = 0.f;
-      if (yin && xx >= 0 && xx < W) p = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+      if (yin && xx >= 0 && xx < W) p = ld_elem(plane, (long long)yy * sh + (long long)xx * sw, dt);
       const float gx = g0 + (float)i;
       z += (double)p;
       sx += (double)__fmul_rn(gx, p);
@@ -203,8 +212,8 @@ __device__ __forceinline__ void integral_refine(const float* __restrict__ plane,
 // Warp-cooperative variant: the size x size taps are spread over the 32 lanes (one DRAM/L2 round
 // trip instead of size^2 serial ones); fp64 partial sums are combined by shuffles.  All lanes
 // return the same offsets.
-template <bool GLOBAL_MEM = true>  // false: `plane` points into shared memory (plain loads, not ld.global.nc)
-__device__ __forceinline__ void integral_refine_warp(const float* __restrict__ plane, int H, int W, long long sh,
+template <bool GLOBAL_MEM = true>  // false: `plane` points into shared memory (fp32, plain loads, not ld.global.nc)
+__device__ __forceinline__ void integral_refine_warp(const void* __restrict__ plane, int dt, int H, int W, long long sh,
                                                      long long sw, float px, float py, int size, int lane, float* ox,
                                                      float* oy) {
   const float half_f = 0.5f * (float)size;
@@ -220,8 +229,8 @@ __device__ __forceinline__ void integral_refine_warp(const float* __restrict__ p
     const int yy = y0 + j, xx = x0 + i;
     float p = 0.f;
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-      const float* q = plane + (long long)yy * sh + (long long)xx * sw;
-      p = GLOBAL_MEM ? __ldg(q) : *q;
+      const long long q = (long long)yy * sh + (long long)xx * sw;
+      p = GLOBAL_MEM ? ld_elem(plane, q, dt) : reinterpret_cast<const float*>(plane)[q];
     }
     z += (double)p;
     sx += (double)__fmul_rn(g0 + (float)i, p);
@@ -242,9 +251,10 @@ __device__ __forceinline__ void integral_refine_warp(const float* __restrict__ p
 // peaks (busy frames: hundreds of peaks per frame) pays one memory round trip per Q peaks instead of one per peak.
 // Same arithmetic as integral_refine_warp.  plane[q] == nullptr marks an unused slot (offsets returned as 0).
 template <int Q>
-__device__ __forceinline__ void integral_refine_warp_multi(const float* const (&plane)[Q], int H, int W, long long sh,
-                                                           long long sw, const float (&px)[Q], const float (&py)[Q],
-                                                           int size, int lane, float (&ox)[Q], float (&oy)[Q]) {
+__device__ __forceinline__ void integral_refine_warp_multi(const void* const (&plane)[Q], int dt, int H, int W,
+                                                           long long sh, long long sw, const float (&px)[Q],
+                                                           const float (&py)[Q], int size, int lane, float (&ox)[Q],
+                                                           float (&oy)[Q]) {
   const float half_f = 0.5f * (float)size;
   const int half_i = size / 2;
   const float g0 = -0.5f * (float)(size - 1);
@@ -263,7 +273,7 @@ __device__ __forceinline__ void integral_refine_warp_multi(const float* const (&
     for (int q = 0; q < Q; ++q) {
       const int yy = y0[q] + j, xx = x0[q] + i;
       p[q] = 0.f;
-      if (plane[q] && yy >= 0 && yy < H && xx >= 0 && xx < W) p[q] = __ldg(plane[q] + (long long)yy * sh + (long long)xx * sw);
+      if (plane[q] && yy >= 0 && yy < H && xx >= 0 && xx < W) p[q] = ld_elem(plane[q], (long long)yy * sh + (long long)xx * sw, dt);
     }
     const float gx = g0 + (float)i, gy = g0 + (float)j;
 #pragma unroll

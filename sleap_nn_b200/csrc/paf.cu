@@ -434,10 +434,24 @@ extern "C" int snb_paf_score(const float* pafs, long long pb, long long py, long
                              const int* node_peaks, const int* edge_off, const int* cand_start, int cand_stride,
                              int max_cand_per_frame, int* cand_edge, long long* cand_epi, float* cand_score,
                              int* status, void* stream_) {
+  return snb_paf_score_t(pafs, SNB_DTYPE_F32, pb, py, px, pc, H, W, t_table, n_points, stride, max_edge_length,
+                         penalty_weight, peak_xy, frame_start, frame_stride, B, edges, n_nodes, n_edges, node_start,
+                         node_peaks, edge_off, cand_start, cand_stride, max_cand_per_frame, cand_edge, cand_epi,
+                         cand_score, status, stream_);
+}
+
+extern "C" int snb_paf_score_t(const void* pafs, int dtype, long long pb, long long py, long long px, long long pc,
+                               int H, int W, const float* t_table, int n_points, float stride, float max_edge_length,
+                               float penalty_weight, const float* peak_xy, const int* frame_start, int frame_stride,
+                               int B, const int* edges, int n_nodes, int n_edges, const int* node_start,
+                               const int* node_peaks, const int* edge_off, const int* cand_start, int cand_stride,
+                               int max_cand_per_frame, int* cand_edge, long long* cand_epi, float* cand_score,
+                               int* status, void* stream_) {
   if (B < 0 || n_edges < 0 || max_cand_per_frame < 0) return SNB_ERR_BAD_ARG;
+  if (dtype != SNB_DTYPE_F32 && dtype != SNB_DTYPE_F16 && dtype != SNB_DTYPE_BF16) return SNB_ERR_BAD_ARG;
   if (B == 0 || n_edges == 0 || max_cand_per_frame == 0) return SNB_OK;
   if (B > 65535) return SNB_ERR_UNSUPPORTED;
-  ScoreArgs a{pafs, pb, py, px, pc, H, W, t_table, n_points, stride, max_edge_length, penalty_weight};
+  ScoreArgs a{pafs, dtype, pb, py, px, pc, H, W, t_table, n_points, stride, max_edge_length, penalty_weight};
   dim3 grid((max_cand_per_frame + 127) / 128, B);
   paf_score_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(a, peak_xy, frame_start, frame_stride, edges, n_nodes,
                                                            n_edges, node_start, node_peaks, edge_off, cand_start,

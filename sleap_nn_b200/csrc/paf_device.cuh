@@ -39,7 +39,8 @@ __device__ __forceinline__ int line_coord(float src, float dst, float t, float s
 }
 
 struct ScoreArgs {
-  const float* pafs;        // may be null: enumerate candidates only
+  const void* pafs;         // may be null: enumerate candidates only
+  int dt;                   // SNB_DTYPE_* of the PAF tensor
   long long pb, py, px, pc; // element strides of the (B, H, W, 2E) view
   int H, W;
   const float* t;           // n_points linspace table
@@ -55,7 +56,7 @@ __device__ __forceinline__ float score_candidate(const ScoreArgs& a, int b, int 
   const float vx = __fsub_rn(dx, sx), vy = __fsub_rn(dy, sy);
   const float len = sqrtf(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
   const float ux = __fdiv_rn(vx, len), uy = __fdiv_rn(vy, len);
-  const float* fb = a.pafs + (long long)b * a.pb + (long long)(2 * k) * a.pc;
+  const void* fb = elem_ptr(a.pafs, (long long)b * a.pb + (long long)(2 * k) * a.pc, a.dt);
   double acc = 0.0;
   for (int p0 = 0; p0 < a.n_points; p0 += 8) {  // 16 independent gathers in flight
     float fx[8], fy[8];
@@ -66,9 +67,9 @@ __device__ __forceinline__ float score_candidate(const ScoreArgs& a, int b, int 
         const float t = a.t[p];  // global or shared memory
         const int col = line_coord(sx, dx, t, a.stride, a.W - 1);
         const int row = line_coord(sy, dy, t, a.stride, a.H - 1);
-        const float* q = fb + (long long)row * a.py + (long long)col * a.px;
-        fx[u] = __ldg(q);
-        fy[u] = __ldg(q + a.pc);
+        const long long q = (long long)row * a.py + (long long)col * a.px;
+        fx[u] = ld_elem(fb, q, a.dt);
+        fy[u] = ld_elem(fb, q + a.pc, a.dt);
       }
     }
 #pragma unroll

@@ -29,8 +29,9 @@ namespace snb {
 // Peaks are appended to the frame's key list; key = (y*W + x)*C + c orders them the way
 // torch.where over (B,H,W,C) does (ops/peaks.py:211-217).
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ bool is_strict_max(const float* __restrict__ plane, int H, int W, long long sh,
-                                              long long sw, int y, int x, float v) {
+template <typename T>
+__device__ __forceinline__ bool is_strict_max(const T* __restrict__ plane, int H, int W, long long sh, long long sw,
+                                              int y, int x, float v) {
   bool ok = true;
 #pragma unroll
   for (int dy = -1; dy <= 1; ++dy) {
@@ -40,7 +41,7 @@ __device__ __forceinline__ bool is_strict_max(const float* __restrict__ plane, i
     for (int dx = -1; dx <= 1; ++dx) {
       const int xx = x + dx;
       if ((dy == 0 && dx == 0) || xx < 0 || xx >= W) continue;
-      const float nb = __ldg(plane + (long long)yy * sh + (long long)xx * sw);
+      const float nb = Elem<T>::load1(plane + (long long)yy * sh + (long long)xx * sw);
       ok = ok && (v > nb);
     }
   }
@@ -50,61 +51,65 @@ __device__ __forceinline__ bool is_strict_max(const float* __restrict__ plane, i
 __device__ __forceinline__ void emit_peak(int* __restrict__ frame_count, uint32_t* __restrict__ keys, int cap,
                                           int b, int C, int W, int c, int y, int x) {
   const int pos = atomicAdd(frame_count + b, 1);
-  if (pos < cap) keys[(long long)b * cap + pos] = (uint32_t)((y * W + x) * C + c);
+  // unsigned 32-bit math: the host guarantees H*W*C < 2^32, which a signed int would overflow above 2^31
+  if (pos < cap) keys[(long long)b * cap + pos] = ((uint32_t)y * (uint32_t)W + (uint32_t)x) * (uint32_t)C + (uint32_t)c;
 }
 
-template <int UNROLL, int ROWS, int MIN_BLOCKS>
+template <typename T, int UNROLL, int ROWS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
-local_peaks_detect_vec4(const float* __restrict__ cms, int n_rows, int C, int H, int W, long long sb, long long sc,
-                        long long sh, float thr, int cap, int* __restrict__ frame_count,
-                        uint32_t* __restrict__ keys) {
+local_peaks_detect_vec(const T* __restrict__ cms, int n_rows, int C, int H, int W, long long sb, long long sc,
+                       long long sh, float thr, int cap, int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
   // One warp owns ROWS consecutive map rows per iteration and issues all of their 128-bit loads
   // (ROWS * UNROLL per lane) before looking at any value: that is the memory-level parallelism
-  // that keeps HBM busy.  32-bit index math (the host guarantees n_rows < 2^31).
+  // that keeps HBM busy.  32-bit index math (the host guarantees n_rows < 2^31).  A 128-bit load holds
+  // PER = 4 fp32 or 8 fp16 / bf16 elements; half-precision maps are compared on their exact fp32 values.
+  constexpr int PER = Elem<T>::PER16;
+  const typename Elem<T>::Thr tv = Elem<T>::make_thr(thr);
   const int lane = lane_id();
   const int warps_per_block = blockDim.x >> 5;
-  const int W4 = W >> 2;
+  const int WV = W / PER;
   const int stride_rows = gridDim.x * warps_per_block * ROWS;
   for (int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * ROWS; row0 < n_rows; row0 += stride_rows) {
-    const float* rowp[ROWS];
+    const T* rowp[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int row = min(row0 + r, n_rows - 1);
       const int y = row % H, pc = row / H;
       rowp[r] = cms + (long long)(pc / C) * sb + (long long)(pc % C) * sc + (long long)y * sh;
     }
-    for (int x4 = lane; x4 < W4; x4 += 32 * UNROLL) {
-      float4 v[ROWS][UNROLL];
+    for (int xv = lane; xv < WV; xv += 32 * UNROLL) {
+      uint4 v[ROWS][UNROLL];
 #pragma unroll
       for (int r = 0; r < ROWS; ++r)
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int xx4 = x4 + 32 * u;
-          if (xx4 < W4) v[r][u] = ldg_stream4(rowp[r] + 4 * xx4);
+          const int xxv = xv + 32 * u;
+          if (xxv < WV) v[r][u] = ldg_stream16(rowp[r] + PER * xxv);
         }
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
         if (row0 + r >= n_rows) break;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const int xx4 = x4 + 32 * u;
-          if (xx4 >= W4) continue;
-          const float e[4] = {v[r][u].x, v[r][u].y, v[r][u].z, v[r][u].w};
-          if (!((e[0] > thr) || (e[1] > thr) || (e[2] > thr) || (e[3] > thr))) continue;
+          const int xxv = xv + 32 * u;
+          if (xxv >= WV) continue;
+          if (!Elem<T>::any_gt(v[r][u], tv)) continue;
+          float e[PER];
+          Elem<T>::unpack(v[r][u], e);
           const int row = row0 + r;  // rare path: recover (b, c, y) for this row
           const int y = row % H, pc = row / H;
           const int c = pc % C, b = pc / C;
-          const float* plane = cms + (long long)b * sb + (long long)c * sc;
+          const T* plane = cms + (long long)b * sb + (long long)c * sc;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < PER; ++k) {
             // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same
             // 128-bit word are already in registers, and a strict maximum must beat them too (same `v > nb`
             // predicate, so NaN neighbours reject as in the reference).  On a blob's row only the ridge pixel
             // (and at most the word-boundary pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads
             // on busy maps (cfg4: 256 blobs per frame).
-            if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == 3 || e[k] > e[k + 1])) {
-              const int x = 4 * xx4 + k;
-              if (is_strict_max(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+            if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == PER - 1 || e[k] > e[k + 1])) {
+              const int x = PER * xxv + k;
+              if (is_strict_max<T>(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
             }
           }
         }
@@ -113,9 +118,10 @@ local_peaks_detect_vec4(const float* __restrict__ cms, int n_rows, int C, int H,
   }
 }
 
-// Generic-stride scalar variant (non-contiguous views, W % 4 != 0, unaligned base).
+// Generic-stride scalar variant (non-contiguous views, W not a multiple of the vector width, unaligned base).
+template <typename T>
 __global__ void __launch_bounds__(256)
-local_peaks_detect_scalar(const float* __restrict__ cms, int B, int C, int H, int W, long long sb, long long sc,
+local_peaks_detect_scalar(const T* __restrict__ cms, int B, int C, int H, int W, long long sb, long long sc,
                           long long sh, long long sw, float thr, int cap, int* __restrict__ frame_count,
                           uint32_t* __restrict__ keys) {
   const long long n = (long long)B * C * H * W;
@@ -126,18 +132,18 @@ local_peaks_detect_scalar(const float* __restrict__ cms, int B, int C, int H, in
     r /= H;
     const int c = (int)(r % C);
     const int b = (int)(r / C);
-    const float* plane = cms + (long long)b * sb + (long long)c * sc;
-    const float v = __ldg(plane + (long long)y * sh + (long long)x * sw);
-    if (v > thr && is_strict_max(plane, H, W, sh, sw, y, x, v)) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
+    const T* plane = cms + (long long)b * sb + (long long)c * sc;
+    const float v = Elem<T>::load1(plane + (long long)y * sh + (long long)x * sw);
+    if (v > thr && is_strict_max<T>(plane, H, W, sh, sw, y, x, v)) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
   }
 }
 
+#ifdef SNB_AB_VARIANTS
 // ----------------------------------------------------------------------------------------
-// K1a, contiguous tensors: bulk-async streaming detect.  The maps are one flat array; each
-// persistent CTA walks it in 16 KB chunks through a ring of shared-memory stages filled by
-// cp.async.bulk (1-D TMA) and signalled by mbarriers, so ~64 KB per CTA are in flight with no
-// registers tied up and a few instructions per 16 bytes (LDS.128 + 4 compares).  Only a value
-// above the threshold leaves the streaming path (neighbour test through L2, see is_strict_max).
+// A/B only (-DSNB_AB_VARIANTS, tools/): K1a for contiguous fp32 tensors as a bulk-async ring.  The maps are one flat
+// array; each persistent CTA walks it in 16 KB chunks through a ring of shared-memory stages filled by
+// cp.async.bulk (1-D TMA) and signalled by mbarriers.  Only a value above the threshold leaves the streaming path.
+// The refill of a stage is issued by thread 0 right after the CTA-wide barrier that frees it.
 // ----------------------------------------------------------------------------------------
 constexpr int BULK_STAGE_FLOATS = 4096;  // 16 KB
 constexpr int BULK_STAGES = 4;
@@ -191,7 +197,7 @@ local_peaks_detect_bulk(const float* __restrict__ cms, long long n_elems, int C,
         const float* plane = cms + pc * plane_elems;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (e[k] > thr && is_strict_max(plane, H, W, W, 1, y, x0 + k, e[k]))
+          if (e[k] > thr && is_strict_max<float>(plane, H, W, W, 1, y, x0 + k, e[k]))
             emit_peak(frame_count, keys, cap, b, C, W, c, y, x0 + k);
       }
     }
@@ -202,6 +208,7 @@ local_peaks_detect_bulk(const float* __restrict__ cms, long long n_elems, int C,
     }
   }
 }
+#endif  // SNB_AB_VARIANTS
 
 // ----------------------------------------------------------------------------------------
 // K1b: per-frame finalize.  One CTA per frame: bitonic-sort the frame's keys in shared
@@ -229,7 +236,7 @@ __device__ __forceinline__ void bitonic_sort_smem(uint32_t* s, int n_pow2) {
 }
 
 __global__ void __launch_bounds__(256)
-local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+local_peaks_finalize(const void* __restrict__ cms, int dt, int C, int H, int W, long long sb, long long sc, long long sh,
                      long long sw, int refine_size, float xy_scale, int cap, int keys_presorted,
                      const int* __restrict__ frame_count, uint32_t* __restrict__ keys, float* __restrict__ out_xy,
                      float* __restrict__ out_val, int* __restrict__ out_chan, int* __restrict__ status) {
@@ -250,7 +257,7 @@ local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long lo
     for (int i = threadIdx.x; i < n; i += blockDim.x) gk[i] = skeys[i];  // keep sorted keys for callers
     sorted = skeys;
   }
-  const float* frame = cms + (long long)b * sb;
+  const void* frame = elem_ptr(cms, (long long)b * sb, dt);
   const int lane = lane_id(), warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   for (int i = warp; i < n; i += n_warps) {  // one warp per peak: the patch taps are fetched in parallel
     const uint32_t key = sorted[i];
@@ -258,11 +265,11 @@ local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long lo
     const uint32_t yx = key / (uint32_t)C;
     const int x = (int)(yx % (uint32_t)W);
     const int y = (int)(yx / (uint32_t)W);
-    const float* plane = frame + (long long)c * sc;
+    const void* plane = elem_ptr(frame, (long long)c * sc, dt);
     float fx = (float)x, fy = (float)y;
     if (refine_size > 0) {
       float ox, oy;
-      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, lane, &ox, &oy);
+      integral_refine_warp(plane, dt, H, W, sh, sw, fx, fy, refine_size, lane, &ox, &oy);
       fx = __fadd_rn(fx, ox);  // ops/peaks.py:258
       fy = __fadd_rn(fy, oy);
     }
@@ -274,7 +281,7 @@ local_peaks_finalize(const float* __restrict__ cms, int C, int H, int W, long lo
       const long long o = (long long)b * cap + i;
       out_xy[2 * o] = fx;
       out_xy[2 * o + 1] = fy;
-      out_val[o] = __ldg(plane + (long long)y * sh + (long long)x * sw);
+      out_val[o] = ld_elem(plane, (long long)y * sh + (long long)x * sw, dt);
       out_chan[o] = c;
     }
   }
@@ -373,8 +380,8 @@ __device__ __forceinline__ void write_global_peak(const Ladder& lad, int plane_i
 
 // Shared epilogue: thread 0 holds the CTA's Best `r`; publish it, let the plane's last CTA combine the
 // chunk partials, then warp 0 of that CTA applies the threshold and the integral refinement.
-__device__ __forceinline__ void global_peaks_finish(Best r, const float* __restrict__ plane, int plane_id, int chunk,
-                                                    int n_chunks, int H, int W, long long sh, long long sw, float thr,
+__device__ __forceinline__ void global_peaks_finish(Best r, const void* __restrict__ plane, int dt, int plane_id,
+                                                    int chunk, int n_chunks, int H, int W, long long sh, long long sw, float thr,
                                                     int refine_size, float* __restrict__ part_v,
                                                     int* __restrict__ part_xy, unsigned* __restrict__ tickets,
                                                     float* __restrict__ out_xy, float* __restrict__ out_val,
@@ -411,7 +418,7 @@ __device__ __forceinline__ void global_peaks_finish(Best r, const float* __restr
     float fx = low ? NAN : (float)b.x, fy = low ? NAN : (float)b.y;
     if (!low && refine_size > 0) {
       float ox, oy;
-      integral_refine_warp(plane, H, W, sh, sw, fx, fy, refine_size, threadIdx.x, &ox, &oy);
+      integral_refine_warp(plane, dt, H, W, sh, sw, fx, fy, refine_size, threadIdx.x, &ox, &oy);
       fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
       fy = __fadd_rn(fy, oy);
     }
@@ -419,16 +426,18 @@ __device__ __forceinline__ void global_peaks_finish(Best r, const float* __restr
   }
 }
 
-// Generic variant: any strides, any chunk size; one associative (v, x, y) merge per element.
+// Generic variant: any strides, any chunk size, any element type; one associative (v, x, y) merge per element.
+template <typename T>
 __global__ void __launch_bounds__(256)
-global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+global_peaks_kernel(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                     long long sw, int vec_ok, int rows_per_chunk, int n_chunks, float thr, int refine_size,
                     float* __restrict__ part_v, int* __restrict__ part_xy, unsigned* __restrict__ tickets,
                     float* __restrict__ out_xy, float* __restrict__ out_val, Ladder lad) {
+  constexpr int PER = Elem<T>::PER16;
   const int plane_id = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x % n_chunks;
   const int b = plane_id / C, c = plane_id % C;
-  const float* plane = cms + (long long)b * sb + (long long)c * sc;
+  const T* plane = cms + (long long)b * sb + (long long)c * sc;
   const int y0 = chunk * rows_per_chunk;
   const int y1 = min(H, y0 + rows_per_chunk);
   Best acc{-INFINITY, 0x7fffffff, 0x7fffffff};
@@ -439,21 +448,20 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
     any = true;
   };
   if (vec_ok) {
-    const int W4 = W >> 2;
-    const int n4 = (y1 - y0) * W4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-      const int y = y0 + i / W4, x4 = i % W4;
-      const float4 v = ldg_stream4(plane + (long long)y * sh + 4 * x4);
-      take(v.x, 4 * x4, y);
-      take(v.y, 4 * x4 + 1, y);
-      take(v.z, 4 * x4 + 2, y);
-      take(v.w, 4 * x4 + 3, y);
+    const int WV = W / PER;
+    const int nv = (y1 - y0) * WV;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const int y = y0 + i / WV, xv = i % WV;
+      float e[PER];
+      Elem<T>::unpack(ldg_stream16(plane + (long long)y * sh + PER * xv), e);
+#pragma unroll
+      for (int k = 0; k < PER; ++k) take(e[k], PER * xv + k, y);
     }
   } else {
     const int n = (y1 - y0) * W;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int y = y0 + i / W, x = i % W;
-      take(__ldg(plane + (long long)y * sh + (long long)x * sw), x, y);
+      take(Elem<T>::load1(plane + (long long)y * sh + (long long)x * sw), x, y);
     }
   }
   if (!any) acc = Best{-INFINITY, 0x7fffffff, 0x7fffffff};  // -inf loses to every real element
@@ -465,8 +473,8 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
   Best r = s_best[0];
   if (threadIdx.x == 0)
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = best_merge(r, s_best[w]);
-  global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, sw, thr, refine_size, part_v, part_xy, tickets,
-                      out_xy, out_val, s_best, &s_last, lad, C);
+  global_peaks_finish(r, plane, Elem<T>::DT, plane_id, chunk, n_chunks, H, W, sh, sw, thr, refine_size, part_v, part_xy,
+                      tickets, out_xy, out_val, s_best, &s_last, lad, C);
 }
 
 // Register-resident variant (the product path for vectorisable planes whose chunk is <= V*1024 elements).
@@ -475,40 +483,40 @@ global_peaks_kernel(const float* __restrict__ cms, int C, int H, int W, long lon
 // pass 1 is one FMNMX per element (+ NaN detection), the CTA agrees on the maximum m, pass 2 looks for
 // elements equal to m (a rare branch) and reduces min(x), min(y) - the reference's two independent arg-maxes
 // (ops/peaks.py:103-111).  A chunk that contains a NaN takes the exact generic merge over the same registers.
-template <int V>
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
-global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+global_peaks_regs_kernel(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                          int rows_per_chunk, int n_chunks, float thr, int refine_size, float* __restrict__ part_v,
                          int* __restrict__ part_xy, unsigned* __restrict__ tickets, float* __restrict__ out_xy,
                          float* __restrict__ out_val, Ladder lad) {
+  constexpr int PER = Elem<T>::PER16;
   const int plane_id = blockIdx.x / n_chunks;
   const int chunk = blockIdx.x % n_chunks;
   const int b = plane_id / C, c = plane_id % C;
-  const float* plane = cms + (long long)b * sb + (long long)c * sc;
+  const T* plane = cms + (long long)b * sb + (long long)c * sc;
   const int y0 = chunk * rows_per_chunk;
   const int y1 = min(H, y0 + rows_per_chunk);
-  const int W4 = W >> 2;
-  const int n4 = (y1 - y0) * W4;
+  const int WV = W / PER;
+  const int nv = (y1 - y0) * WV;
   const bool contig = (sh == W);
-  const float* base = plane + (long long)y0 * sh;
-  float4 v[V];
+  const T* base = plane + (long long)y0 * sh;
+  uint4 v[V];
 #pragma unroll
   for (int u = 0; u < V; ++u) {
     const int i = threadIdx.x + u * 256;
-    if (i < n4) {
-      const float* p = contig ? base + 4LL * i : base + (long long)(i / W4) * sh + 4 * (i % W4);
-      v[u] = ldg_stream4(p);
+    if (i < nv) {
+      const T* p = contig ? base + (long long)PER * i : base + (long long)(i / WV) * sh + PER * (i % WV);
+      v[u] = ldg_stream16(p);
     } else {
-      v[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);  // loses to (or ties harmlessly with) real data
+      v[u] = Elem<T>::neg_inf();  // loses to (or ties harmlessly with) real data
     }
   }
+  // max.NaN: a NaN anywhere in the thread's values makes m NaN
   float m = -INFINITY;
-  bool has_nan = false;
 #pragma unroll
-  for (int u = 0; u < V; ++u) {
-    m = fmaxf(m, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
-    has_nan = has_nan || (v[u].x != v[u].x) || (v[u].y != v[u].y) || (v[u].z != v[u].z) || (v[u].w != v[u].w);
-  }
+  for (int u = 0; u < V; ++u) m = fmax_nan(m, Elem<T>::vmax_nan(v[u]));
+  const bool has_nan = (m != m);
+  if (has_nan) m = -INFINITY;
   __shared__ float s_m[8];
   __shared__ int s_x[8], s_y[8];
   __shared__ Best s_best[8];
@@ -526,11 +534,12 @@ global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, lon
 #pragma unroll
     for (int u = 0; u < V; ++u) {
       const int i = threadIdx.x + u * 256;
-      if (i < n4) {
-        const int y = y0 + i / W4, x = 4 * (i % W4);
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      if (i < nv) {
+        const int y = y0 + i / WV, x = PER * (i % WV);
+        float e[PER];
+        Elem<T>::unpack(v[u], e);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < PER; ++k) {
           const Best o{e[k], x + k, y};
           acc = any ? best_merge(acc, o) : o;
           any = true;
@@ -551,11 +560,15 @@ global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, lon
     int bx = 0x7fffffff, by = 0x7fffffff;
 #pragma unroll
     for (int u = 0; u < V; ++u) {
-      if (v[u].x == m || v[u].y == m || v[u].z == m || v[u].w == m) {  // rare
+      if (Elem<T>::vmax_nan(v[u]) == m) {  // rare
         const int i = threadIdx.x + u * 256;
-        if (i < n4) {
-          const int y = y0 + i / W4, x = 4 * (i % W4);
-          const int k = (v[u].x == m) ? 0 : ((v[u].y == m) ? 1 : ((v[u].z == m) ? 2 : 3));  // first match = min x
+        if (i < nv) {
+          const int y = y0 + i / WV, x = PER * (i % WV);
+          float e[PER];
+          Elem<T>::unpack(v[u], e);
+          int k = PER - 1;
+#pragma unroll
+          for (int q = PER - 2; q >= 0; --q) k = (e[q] == m) ? q : k;  // first match = min x
           bx = min(bx, x + k);
           by = min(by, y);
         }
@@ -574,11 +587,12 @@ global_peaks_regs_kernel(const float* __restrict__ cms, int C, int H, int W, lon
     }
     r = Best{m, bx, by};
   }
-  global_peaks_finish(r, plane, plane_id, chunk, n_chunks, H, W, sh, 1, thr, refine_size, part_v, part_xy, tickets,
-                      out_xy, out_val, s_best, &s_last, lad, C);
+  global_peaks_finish(r, plane, Elem<T>::DT, plane_id, chunk, n_chunks, H, W, sh, 1, thr, refine_size, part_v, part_xy,
+                      tickets, out_xy, out_val, s_best, &s_last, lad, C);
 }
 
-// Persistent ring variant (the product path for planes that fit one shared-memory stage, e.g. cfg2's 80x80
+#ifdef SNB_AB_VARIANTS
+// A/B only (-DSNB_AB_VARIANTS): persistent ring variant for fp32 planes that fit one shared-memory stage (cfg2's 80x80
 // crops).  With one CTA per small plane the loads are in flight for only about a third of a CTA's life (the
 // rest is reductions + the refinement's dependent taps), which capped K2 at ~54 % of the HBM roofline.  Here a
 // persistent CTA walks planes p, p + grid, ... through a 3-stage shared-memory ring filled by cp.async
@@ -678,7 +692,7 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
       float fx = low ? NAN : (float)b.x, fy = low ? NAN : (float)b.y;
       if (!low && refine_size > 0) {
         float ox, oy;
-        integral_refine_warp<false>(st, H, W, W, 1, fx, fy, refine_size, lane, &ox, &oy);
+        integral_refine_warp<false>(st, SNB_DTYPE_F32, H, W, W, 1, fx, fy, refine_size, lane, &ox, &oy);
         fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
         fy = __fadd_rn(fy, oy);
       }
@@ -688,6 +702,7 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
   }
   cp_async_wait<0>();
 }
+#endif  // SNB_AB_VARIANTS
 
 // Warp-per-plane variant (the product path for small vectorisable planes, e.g. cfg2's 80x80 crops).  The ring
 // kernel above still spends five CTA-wide barriers and a serial warp-0 refinement per plane, during which the
@@ -699,36 +714,32 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
 // tie inside one lane's sequence or a NaN (max.NaN poisons the running maximum) sends the warp to the exact
 // generic merge.  One 32-thread CTA per plane, so
 // the hardware scheduler spreads the planes evenly over the 148 SMs (cfg2: 22.5 planes per SM, all resident).
-__device__ __forceinline__ float fmax_nan(float a, float b) {
-  float r;
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-  return r;
-}
 
-template <int U, bool CONTIG>
+template <typename T, int U, bool CONTIG>
 __global__ void __launch_bounds__(32)
-global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                          float thr, int refine_size, float* __restrict__ out_xy, float* __restrict__ out_val,
                          Ladder lad) {
+  constexpr int PER = Elem<T>::PER16;
   const int p = blockIdx.x, lane = threadIdx.x;
-  const float* plane = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
-  const int W4 = W >> 2, n4 = H * W4;
+  const T* plane = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
+  const int WV = W / PER, nv = H * WV;
   // Load cursor of this lane: 128-bit load number `li` = lane + 32 * (loads issued so far); for strided planes the
   // (row, column) pair is advanced incrementally (no integer division in the loop).
-  int li = lane, ly = lane / W4, lx4 = lane - ly * W4;
-  const int dy32 = 32 / W4, dx32 = 32 - dy32 * W4;
-  auto load_next = [&]() -> float4 {
-    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    if (li < n4) v = ldg_stream4(CONTIG ? plane + 4LL * li : plane + (long long)ly * sh + 4 * lx4);
+  int li = lane, ly = lane / WV, lxv = lane - ly * WV;
+  const int dy32 = 32 / WV, dx32 = 32 - dy32 * WV;
+  auto load_next = [&]() -> uint4 {
+    uint4 v = Elem<T>::neg_inf();
+    if (li < nv) v = ldg_stream16(CONTIG ? plane + (long long)PER * li : plane + (long long)ly * sh + PER * lxv);
     li += 32;
     if (!CONTIG) {
       ly += dy32;
-      lx4 += dx32;
-      if (lx4 >= W4) { lx4 -= W4; ++ly; }
+      lxv += dx32;
+      if (lxv >= WV) { lxv -= WV; ++ly; }
     }
     return v;
   };
-  float4 buf[U];
+  uint4 buf[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) buf[u] = load_next();
   // Per lane, branch-free: running maximum m (max.NaN: a NaN sticks), the number kbest of the FIRST load that
@@ -736,12 +747,12 @@ global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, lon
   float m = -INFINITY;
   int kbest = 0, k = 0;
   bool tie = false;
-  for (int base = 0; base < n4; base += 32 * U) {
+  for (int base = 0; base < nv; base += 32 * U) {
 #pragma unroll
     for (int u = 0; u < U; ++u, ++k) {
-      const float4 v = buf[u];
+      const uint4 v = buf[u];
       buf[u] = load_next();
-      const float mx = fmax_nan(fmax_nan(v.x, v.y), fmax_nan(v.z, v.w));
+      const float mx = Elem<T>::vmax_nan(v);
       const bool up = mx > m;
       tie = up ? false : (tie || mx == m);
       kbest = up ? k : kbest;
@@ -764,7 +775,7 @@ global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, lon
       bool any = false;
       for (int i = lane; i < H * W; i += 32) {
         const int y = i / W, x = i - y * W;
-        const Best o{__ldg(plane + (long long)y * sh + x), x, y};
+        const Best o{Elem<T>::load1(plane + (long long)y * sh + x), x, y};
         acc = any ? best_merge(acc, o) : o;
         any = true;
       }
@@ -773,10 +784,13 @@ global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, lon
       int bx = 0x7fffffff, by = 0x7fffffff;
       if (holder) {  // re-read the one 16-byte word that held the maximum (an L2 hit) to find the element
         const int i = lane + 32 * kbest;
-        const int y = i / W4, x4 = i - y * W4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(plane + (long long)y * sh + 4 * x4));
-        const int e = (v.x == gm) ? 0 : ((v.y == gm) ? 1 : ((v.z == gm) ? 2 : 3));  // first match = min x of the word
-        bx = 4 * x4 + e;
+        const int y = i / WV, xv = i - y * WV;
+        float e[PER];
+        Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(plane + (long long)y * sh + PER * xv)), e);
+        int q = PER - 1;
+#pragma unroll
+        for (int j = PER - 2; j >= 0; --j) q = (e[j] == gm) ? j : q;  // first match = min x of the word
+        bx = PER * xv + q;
         by = y;
       }
 #pragma unroll
@@ -792,7 +806,7 @@ global_peaks_warp_kernel(const float* __restrict__ cms, int C, int H, int W, lon
   float fx = low ? NAN : (float)r.x, fy = low ? NAN : (float)r.y;
   if (!low && refine_size > 0) {
     float ox, oy;
-    integral_refine_warp(plane, H, W, sh, 1, fx, fy, refine_size, lane, &ox, &oy);
+    integral_refine_warp(plane, Elem<T>::DT, H, W, sh, 1, fx, fy, refine_size, lane, &ox, &oy);
     fx = __fadd_rn(fx, ox);  // ops/peaks.py:179
     fy = __fadd_rn(fy, oy);
   }
@@ -967,83 +981,132 @@ static inline int grid_for(long long work_items, int per_block, int max_blocks) 
 
 using namespace snb;
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device (cached per device: one process may drive several, possibly different, GPUs).
 static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sm_count <= 0)
-      g_sm_count = 148;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
-  return g_sm_count;
+  return cache[dev];
 }
 
-// K1a: zero the per-frame counters and run the streaming detect kernel.  ev_begin / ev_end are
-// optional cudaEvent_t handles recorded right around the kernel (in-situ timing for benchmarks).
-extern "C" int snb_local_peaks_detect(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
-                                      long long sh, long long sw, float threshold, int cap, int* frame_count,
-                                      uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0) return SNB_ERR_BAD_ARG;
-  if ((double)H * W * C >= 4294967295.0) return SNB_ERR_UNSUPPORTED;
-  if (B == 0) return SNB_OK;
-  if (cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
-  const bool vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
-                   (((uintptr_t)cms) % 16 == 0);
+static inline bool dtype_ok(int dt) { return dt == SNB_DTYPE_F32 || dt == SNB_DTYPE_F16 || dt == SNB_DTYPE_BF16; }
+
+// 128-bit vector path: unit column stride, row length / strides multiples of the vector width, 16-byte aligned base.
+static inline bool vec_ok_for(const void* p, int dt, int W, long long sb, long long sc, long long sh, long long sw) {
+  const int per = 16 / dtype_size(dt);
+  return (sw == 1) && (W % per == 0) && (sh % per == 0) && (sc % per == 0) && (sb % per == 0) && (((uintptr_t)p) % 16 == 0);
+}
+
+template <typename T>
+static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                         long long sw, float threshold, int cap, int* frame_count, uint32_t* keys, cudaStream_t st) {
+  constexpr int PER = Elem<T>::PER16;
+  const bool vec = vec_ok_for(cms, Elem<T>::DT, W, sb, sc, sh, sw);
   const long long rows = (long long)B * C * H;
-  const bool contiguous = vec && sh == W && sc == (long long)H * W && sb == (long long)C * H * W;
-  // The cp.async.bulk ring is opt-in: on B200 it reaches only ~2.4 TB/s here (bulk copies issued
-  // from one SM are served with little overlap), the LDG.128 grid-stride kernel ~5.6 TB/s alone.
-  static const bool use_bulk = getenv("SNB_DETECT_BULK") != nullptr;
-  if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, st);
-  if (contiguous && use_bulk) {
-    const size_t smem = (size_t)BULK_STAGES * BULK_STAGE_FLOATS * 4 + BULK_STAGES * sizeof(uint64_t);
-    // per launch, not cached in a static: the attribute is per DEVICE and one process may drive several GPUs
-    if (cudaFuncSetAttribute(local_peaks_detect_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return SNB_ERR_CUDA_LAUNCH;
-    const long long n_elems = rows * W;
-    const long long n_chunks = (n_elems + BULK_STAGE_FLOATS - 1) / BULK_STAGE_FLOATS;
-    const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 3);  // 3 CTAs x 64 KB per SM
-    local_peaks_detect_bulk<<<grid, BULK_THREADS, smem, st>>>(cms, n_elems, C, H, W, threshold, cap, frame_count, keys);
-  } else if (vec && rows < 0x7fffffffLL) {
-    // grid-stride kernel, 8 warps per CTA; the variant (loads in flight per lane, CTAs per SM) is
-    // picked by row length.  SNB_DETECT_VARIANT overrides it for A/B profiling.
-    static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
+#ifdef SNB_AB_VARIANTS
+  if constexpr (Elem<T>::DT == SNB_DTYPE_F32) {
+    // A/B: the cp.async.bulk ring (tools/detect_variants.py); the LDG.128 kernel is the product
+    const bool contiguous = vec && sh == W && sc == (long long)H * W && sb == (long long)C * H * W;
+    static const bool use_bulk = getenv("SNB_DETECT_BULK") != nullptr;
+    if (contiguous && use_bulk) {
+      const size_t smem = (size_t)BULK_STAGES * BULK_STAGE_FLOATS * 4 + BULK_STAGES * sizeof(uint64_t);
+      if (cudaFuncSetAttribute(local_peaks_detect_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      const long long n_elems = rows * W;
+      const long long n_chunks = (n_elems + BULK_STAGE_FLOATS - 1) / BULK_STAGE_FLOATS;
+      const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * 3);  // 3 CTAs x 64 KB per SM
+      local_peaks_detect_bulk<<<grid, BULK_THREADS, smem, st>>>(cms, n_elems, C, H, W, threshold, cap, frame_count, keys);
+      return SNB_OK;
+    }
+  }
+#endif
+  if (vec && rows < 0x7fffffffLL) {
+    // grid-stride kernel, 8 warps per CTA; the variant (128-bit loads in flight per lane, CTAs per SM) is picked by
+    // the number of 128-bit vectors per row.  One row per warp with 4 loads per lane for >= 128 vectors (fp32 W >= 512,
+    // half W >= 1024), 40 registers -> 6 CTAs = 48 warps per SM, and a NON-persistent grid so the hardware CTA
+    // scheduler balances the SMs: measured on B200, cfg3 fp32 batch: 53.1 us = 6.3 TB/s.  Rows of 64..127 vectors
+    // (half-precision cfg3 maps: 512 x 2 B = 1 KB) take two rows of two loads each so that a lane still has
+    // 4 x 16 B in flight.
     const int n_rows = (int)rows;
-    int variant = (W >= 512) ? 0 : (W >= 256 ? 1 : 2);
+    const int vecs = W / PER;
+    int variant = (vecs >= 128) ? 0 : (vecs >= 64 ? (PER == 8 ? 6 : 1) : 2);
+#ifdef SNB_AB_VARIANTS
+    static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
     if (forced >= 0) variant = forced;
-    // One row per warp (4 x 128-bit loads per lane for W = 512), 40 registers -> 6 CTAs = 48 warps per
-    // SM, and a NON-persistent grid so the hardware CTA scheduler balances the SMs: measured on B200,
-    // cfg3 batch: 53.1 us = 6.3 TB/s.  Persistent / deeper-unrolled variants were slower (57-95 us).
-#define SNB_DETECT(U, R, MB, CTAS)                                                                             \
-  local_peaks_detect_vec4<U, R, MB><<<grid_for((rows + R - 1) / R, 8, sm_count() * CTAS), 256, 0, st>>>(        \
+#endif
+#define SNB_DETECT(U, R, MB, CTAS)                                                                              \
+  local_peaks_detect_vec<T, U, R, MB><<<grid_for((rows + R - 1) / R, 8, sm_count() * CTAS), 256, 0, st>>>(       \
       cms, n_rows, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys)
     switch (variant) {
-      case 0: SNB_DETECT(4, 1, 6, 100000); break;  // default for W >= 512
-      case 1: SNB_DETECT(2, 1, 8, 100000); break;  // W in [256, 512)
+      case 0: SNB_DETECT(4, 1, 6, 100000); break;  // >= 128 vectors per row
+      case 1: SNB_DETECT(2, 1, 8, 100000); break;  // 64..127 vectors per row (fp32)
+      case 6: SNB_DETECT(2, 2, 6, 100000); break;  // 64..127 vectors per row (fp16 / bf16): two rows per warp
       case 2: SNB_DETECT(1, 4, 6, 100000); break;  // narrow maps: four rows of one load each
+#ifdef SNB_AB_VARIANTS
       case 3: SNB_DETECT(4, 1, 4, 4); break;       // A/B: persistent single wave, 60 registers (57.1 us)
       case 4: SNB_DETECT(4, 2, 4, 4); break;       // A/B: 8 loads per lane (66.6 us)
-      default: SNB_DETECT(4, 4, 2, 2); break;      // A/B: 16 loads per lane, 2 CTAs / SM (95.1 us)
+      case 5: SNB_DETECT(4, 4, 2, 2); break;       // A/B: 16 loads per lane, 2 CTAs / SM (95.1 us)
+      case 7: SNB_DETECT(2, 4, 4, 100000); break;  // A/B: four rows of two loads
+#endif
+      default: return SNB_ERR_BAD_ARG;
     }
 #undef SNB_DETECT
   } else {
     const int grid = grid_for(rows * W, 256 * 4, sm_count() * 16);
-    local_peaks_detect_scalar<<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys);
+    local_peaks_detect_scalar<T><<<grid, 256, 0, st>>>(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys);
   }
+  return SNB_OK;
+}
+
+// K1a: zero the per-frame counters and run the streaming detect kernel.  ev_begin / ev_end are
+// optional cudaEvent_t handles recorded right around the kernel (in-situ timing for benchmarks).
+extern "C" int snb_local_peaks_detect_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb,
+                                        long long sc, long long sh, long long sw, float threshold, int cap,
+                                        int* frame_count, uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || !dtype_ok(dtype)) return SNB_ERR_BAD_ARG;
+  if ((double)H * W * C >= 4294967295.0) return SNB_ERR_UNSUPPORTED;
+  if (B == 0) return SNB_OK;
+  if (cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+  if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, st);
+  int rc;
+  switch (dtype) {
+    case SNB_DTYPE_F16:
+      rc = launch_detect((const __half*)cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, st);
+      break;
+    case SNB_DTYPE_BF16:
+      rc = launch_detect((const __nv_bfloat16*)cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, st);
+      break;
+    default:
+      rc = launch_detect((const float*)cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, st);
+  }
+  if (rc != SNB_OK) return rc;
   if (ev_end) cudaEventRecord((cudaEvent_t)ev_end, st);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
 
+extern "C" int snb_local_peaks_detect(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
+                                      long long sh, long long sw, float threshold, int cap, int* frame_count,
+                                      uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
+  return snb_local_peaks_detect_t(cms, SNB_DTYPE_F32, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys,
+                                  ev_begin, ev_end, stream_);
+}
+
 // K1b: per-frame key sort + value + integral refinement -> padded peak table.
-extern "C" int snb_local_peaks_finalize(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
-                                        long long sh, long long sw, int refine_size, float xy_scale, int cap,
-                                        const int* frame_count, uint32_t* keys, float* out_xy, float* out_val,
-                                        int* out_chan, int* status, void* stream_) {
+extern "C" int snb_local_peaks_finalize_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb,
+                                          long long sc, long long sh, long long sw, int refine_size, float xy_scale,
+                                          int cap, const int* frame_count, uint32_t* keys, float* out_xy, float* out_val,
+                                          int* out_chan, int* status, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || refine_size < 0) return SNB_ERR_BAD_ARG;
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || refine_size < 0 || !dtype_ok(dtype)) return SNB_ERR_BAD_ARG;
   if (B == 0) return SNB_OK;
   int n2 = 1;
   while (n2 < cap) n2 <<= 1;
@@ -1064,23 +1127,39 @@ extern "C" int snb_local_peaks_finalize(const float* cms, int B, int C, int H, i
         cudaSuccess)
       return SNB_ERR_CUDA_LAUNCH;
   }
-  local_peaks_finalize<<<B, 256, presorted ? 0 : smem, st>>>(cms, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap,
-                                                            presorted, frame_count, keys, out_xy, out_val, out_chan,
-                                                            status);
+  local_peaks_finalize<<<B, 256, presorted ? 0 : smem, st>>>(cms, dtype, C, H, W, sb, sc, sh, sw, refine_size, xy_scale,
+                                                            cap, presorted, frame_count, keys, out_xy, out_val,
+                                                            out_chan, status);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
+}
+
+extern "C" int snb_local_peaks_finalize(const float* cms, int B, int C, int H, int W, long long sb, long long sc,
+                                        long long sh, long long sw, int refine_size, float xy_scale, int cap,
+                                        const int* frame_count, uint32_t* keys, float* out_xy, float* out_val,
+                                        int* out_chan, int* status, void* stream_) {
+  return snb_local_peaks_finalize_t(cms, SNB_DTYPE_F32, B, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap,
+                                    frame_count, keys, out_xy, out_val, out_chan, status, stream_);
+}
+
+extern "C" int snb_local_peaks_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                                 long long sh, long long sw, float threshold, int refine_size, float xy_scale, int cap,
+                                 int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
+                                 int* status, void* stream_) {
+  if (refine_size < 0) return SNB_ERR_BAD_ARG;
+  const int rc = snb_local_peaks_detect_t(cms, dtype, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys,
+                                          nullptr, nullptr, stream_);
+  if (rc != SNB_OK) return rc;
+  return snb_local_peaks_finalize_t(cms, dtype, B, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap, frame_count,
+                                    keys, out_xy, out_val, out_chan, status, stream_);
 }
 
 extern "C" int snb_local_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
                                long long sw, float threshold, int refine_size, float xy_scale, int cap,
                                int* frame_count, uint32_t* keys, float* out_xy, float* out_val, int* out_chan,
                                int* status, void* stream_) {
-  if (refine_size < 0) return SNB_ERR_BAD_ARG;
-  const int rc = snb_local_peaks_detect(cms, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, nullptr,
-                                        nullptr, stream_);
-  if (rc != SNB_OK) return rc;
-  return snb_local_peaks_finalize(cms, B, C, H, W, sb, sc, sh, sw, refine_size, xy_scale, cap, frame_count, keys,
-                                  out_xy, out_val, out_chan, status, stream_);
+  return snb_local_peaks_t(cms, SNB_DTYPE_F32, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, xy_scale, cap,
+                           frame_count, keys, out_xy, out_val, out_chan, status, stream_);
 }
 
 extern "C" int snb_pack_peaks(const int* frame_count, int B, int cap, const float* xy, const float* val,
@@ -1106,23 +1185,79 @@ extern "C" int snb_global_peaks_workspace(int B, int C, int H, int W, int* rows_
   return SNB_OK;
 }
 
-extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
-                                long long sw, float threshold, int refine_size, void* workspace, float* out_xy,
-                                float* out_val, void* stream_) {
-  return snb_global_peaks_ex(cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, workspace, nullptr, out_xy, out_val,
-                             stream_);
+template <typename T>
+static int launch_global_peaks(const T* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                               long long sw, float threshold, int refine_size, int rpc, int nc, unsigned* tickets,
+                               float* part_v, int* part_xy, const Ladder& lad, float* out_xy, float* out_val,
+                               cudaStream_t st) {
+  constexpr int PER = Elem<T>::PER16;
+  const long long planes = (long long)B * C;
+  const int vec = vec_ok_for(cms, Elem<T>::DT, W, sb, sc, sh, sw) ? 1 : 0;
+  const long long chunkv = ((long long)rpc * W) / PER;  // 128-bit loads per chunk
+  const unsigned grid = (unsigned)(planes * nc);
+  bool force_generic = false, no_warp = false;
+  int pad_smem = 0;
+#ifdef SNB_AB_VARIANTS
+  // A/B (tools/k2_probe.py): SNB_GLOBAL_GENERIC = the first, merge-per-element kernel; SNB_GLOBAL_NO_RING = one CTA per
+  // plane with the values in registers; SNB_GLOBAL_RING = the persistent cp.async ring; SNB_GLOBAL_WARP_SMEM = bytes of
+  // unused dynamic shared memory per warp CTA (caps residency: measured WORSE at every cap, 20.5-28.2 us vs 16.7 us).
+  static const bool e_generic = getenv("SNB_GLOBAL_GENERIC") != nullptr;
+  static const bool e_no_ring = getenv("SNB_GLOBAL_NO_RING") != nullptr;
+  static const bool e_ring = getenv("SNB_GLOBAL_RING") != nullptr;
+  static const int e_pad = getenv("SNB_GLOBAL_WARP_SMEM") ? atoi(getenv("SNB_GLOBAL_WARP_SMEM")) : 0;
+  force_generic = e_generic;
+  no_warp = e_no_ring || e_ring;
+  pad_smem = e_pad;
+  if constexpr (Elem<T>::DT == SNB_DTYPE_F32) {
+    const size_t ring_smem = (size_t)GP_STAGES * H * W * sizeof(float);
+    if (vec && e_ring && !force_generic && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
+      if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
+          cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      int per_sm = (int)((220 * 1024) / (ring_smem + 1024));
+      per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+      const long long want = (long long)sm_count() * per_sm;
+      const unsigned rgrid = (unsigned)(planes < want ? planes : want);
+      global_peaks_ring_kernel<<<rgrid, 256, ring_smem, st>>>(cms, (int)planes, C, H, W, sb, sc, sh, threshold,
+                                                             refine_size, out_xy, out_val, lad);
+      return SNB_OK;
+    }
+  }
+#endif
+  if (vec && !force_generic && !no_warp && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
+    // small planes (cfg2's 80x80 crops): one warp per plane, no barrier anywhere
+    if (sh == W)
+      global_peaks_warp_kernel<T, 8, true><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
+                                                                                  refine_size, out_xy, out_val, lad);
+    else
+      global_peaks_warp_kernel<T, 8, false><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
+                                                                                   refine_size, out_xy, out_val, lad);
+  } else if (vec && !force_generic && chunkv <= 8 * 256) {
+#define SNB_GP(V)                                                                                                      \
+  global_peaks_regs_kernel<T, V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \
+                                                       part_xy, tickets, out_xy, out_val, lad)
+    if (chunkv <= 2 * 256) SNB_GP(2);
+    else if (chunkv <= 4 * 256) SNB_GP(4);
+    else SNB_GP(8);
+#undef SNB_GP
+  } else {
+    global_peaks_kernel<T><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold, refine_size,
+                                                 part_v, part_xy, tickets, out_xy, out_val, lad);
+  }
+  return SNB_OK;
 }
 
-extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
-                                   long long sw, float threshold, int refine_size, void* workspace,
-                                   const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream_) {
+extern "C" int snb_global_peaks_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc,
+                                  long long sh, long long sw, float threshold, int refine_size, void* workspace,
+                                  const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  if (!dtype_ok(dtype)) return SNB_ERR_BAD_ARG;
   Ladder lad{1.f, 1.f, nullptr, nullptr, nullptr, nullptr};
   if (ladder) lad = Ladder{ladder->stride, ladder->input_scale, ladder->eff_scale, ladder->crop_offset, ladder->eff_scale2,
                            ladder->scatter};
   int rpc, nc;
   long long nbytes;
-  const int rc = snb_global_peaks_workspace(B, C, H, W, &rpc, &nc, &nbytes);
+  int rc = snb_global_peaks_workspace(B, C, H, W, &rpc, &nc, &nbytes);
   if (rc != SNB_OK) return rc;
   if (B == 0) return SNB_OK;
   const long long planes = (long long)B * C;
@@ -1131,51 +1266,36 @@ extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W,
   unsigned* tickets = (unsigned*)workspace;
   float* part_v = (float*)(tickets + planes);
   int* part_xy = (int*)(part_v + planes * nc);
-  const int vec = (sw == 1) && (W % 4 == 0) && (sh % 4 == 0) && (sc % 4 == 0) && (sb % 4 == 0) &&
-                  (((uintptr_t)cms) % 16 == 0);
-  static const bool force_generic = getenv("SNB_GLOBAL_GENERIC") != nullptr;  // A/B: the first, merge-per-element kernel
-  const long long chunk4 = ((long long)rpc * W) >> 2;  // 128-bit loads per chunk
-  const unsigned grid = (unsigned)(planes * nc);
-  static const bool no_ring = getenv("SNB_GLOBAL_NO_RING") != nullptr;  // A/B: one CTA per plane, values in registers
-  static const bool use_ring = getenv("SNB_GLOBAL_RING") != nullptr;    // A/B: the persistent cp.async ring kernel
-  const size_t ring_smem = (size_t)GP_STAGES * H * W * sizeof(float);
-  if (vec && !force_generic && !use_ring && !no_ring && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
-    // A/B (SNB_GLOBAL_WARP_SMEM = bytes of unused dynamic shared memory per CTA): caps the resident warps per SM so that a
-    // launch whose planes would all be resident at once (cfg2: 22.5 per SM) runs in several waves and a wave's refinement
-    // epilogue overlaps the next wave's loads.  Measured on B200: WORSE at every cap (12-36 KB: 20.5-28.2 us vs 16.7 us) -
-    // the stream needs all ~22 warps x 4 KB in flight per SM more than it needs the epilogue hidden.  Default stays 0.
-    static const int pad_smem = getenv("SNB_GLOBAL_WARP_SMEM") ? atoi(getenv("SNB_GLOBAL_WARP_SMEM")) : 0;
-    if (sh == W)
-      global_peaks_warp_kernel<8, true><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
-                                                                               refine_size, out_xy, out_val, lad);
-    else
-      global_peaks_warp_kernel<8, false><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
-                                                                                refine_size, out_xy, out_val, lad);
-  } else if (vec && !force_generic && !no_ring && nc == 1 && ring_smem <= 96 * 1024 && planes < 0x7fffffffLL) {
-    // per launch, not cached in a static: the attribute is per DEVICE and one process may drive several GPUs
-    if (cudaFuncSetAttribute(global_peaks_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
-        cudaSuccess)
-      return SNB_ERR_CUDA_LAUNCH;
-    int per_sm = (int)((220 * 1024) / (ring_smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
-    const long long want = (long long)sm_count() * per_sm;
-    const unsigned rgrid = (unsigned)(planes < want ? planes : want);
-    global_peaks_ring_kernel<<<rgrid, 256, ring_smem, st>>>(cms, (int)planes, C, H, W, sb, sc, sh, threshold, refine_size,
-                                                           out_xy, out_val, lad);
-  } else if (vec && !force_generic && chunk4 <= 8 * 256) {
-#define SNB_GP(V)                                                                                                   \
-  global_peaks_regs_kernel<V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \
-                                                    part_xy, tickets, out_xy, out_val, lad)
-    if (chunk4 <= 2 * 256) SNB_GP(2);
-    else if (chunk4 <= 4 * 256) SNB_GP(4);
-    else SNB_GP(8);
-#undef SNB_GP
-  } else {
-    global_peaks_kernel<<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, sw, vec, rpc, nc, threshold, refine_size,
-                                              part_v, part_xy, tickets, out_xy, out_val, lad);
+  switch (dtype) {
+    case SNB_DTYPE_F16:
+      rc = launch_global_peaks((const __half*)cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, rpc, nc, tickets,
+                               part_v, part_xy, lad, out_xy, out_val, st);
+      break;
+    case SNB_DTYPE_BF16:
+      rc = launch_global_peaks((const __nv_bfloat16*)cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, rpc, nc,
+                               tickets, part_v, part_xy, lad, out_xy, out_val, st);
+      break;
+    default:
+      rc = launch_global_peaks((const float*)cms, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, rpc, nc, tickets,
+                               part_v, part_xy, lad, out_xy, out_val, st);
   }
+  if (rc != SNB_OK) return rc;
   SNB_LAUNCH_CHECK();
   return SNB_OK;
+}
+
+extern "C" int snb_global_peaks_ex(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                                   long long sw, float threshold, int refine_size, void* workspace,
+                                   const snb_coord_ladder* ladder, float* out_xy, float* out_val, void* stream_) {
+  return snb_global_peaks_t(cms, SNB_DTYPE_F32, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, workspace, ladder,
+                            out_xy, out_val, stream_);
+}
+
+extern "C" int snb_global_peaks(const float* cms, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                                long long sw, float threshold, int refine_size, void* workspace, float* out_xy,
+                                float* out_val, void* stream_) {
+  return snb_global_peaks_t(cms, SNB_DTYPE_F32, B, C, H, W, sb, sc, sh, sw, threshold, refine_size, workspace, nullptr,
+                            out_xy, out_val, stream_);
 }
 
 extern "C" int snb_crop_bboxes(const void* images, int elem_size, int S, int C, int H, int W, long long sb,

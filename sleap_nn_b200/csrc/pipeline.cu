@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
 
   SNB_STAMP(0);
   // ---- 2. value + integral refinement, one warp per peak (taps fetched in parallel)
-  const float* frame = a.cms + (long long)b * a.cms_sb;
+  const int cdt = a.cms_dtype;
+  const void* frame = elem_ptr(a.cms, (long long)b * a.cms_sb, cdt);
   constexpr int RQ = 4;  // peaks refined together by one warp (their taps are all in flight at once)
   for (int i0 = warp * RQ; i0 < n; i0 += n_warps * RQ) {
-    const float* plane[RQ];
+    const void* plane[RQ];
     float fx[RQ], fy[RQ], ox[RQ], oy[RQ];
     int cc[RQ], xi[RQ], yi[RQ];
 #pragma unroll
@@ -141,11 +142,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
         cc[q] = (int)(key % (uint32_t)a.C);
         const uint32_t yx = key / (uint32_t)a.C;
         xi[q] = (int)(yx % (uint32_t)a.W); yi[q] = (int)(yx / (uint32_t)a.W);
-        plane[q] = frame + (long long)cc[q] * a.cms_sc;
+        plane[q] = elem_ptr(frame, (long long)cc[q] * a.cms_sc, cdt);
         fx[q] = (float)xi[q]; fy[q] = (float)yi[q];
       }
     }
-    if (a.refine_size > 0) integral_refine_warp_multi<RQ>(plane, a.H, a.W, a.cms_sh, a.cms_sw, fx, fy, a.refine_size, lane, ox, oy);
+    if (a.refine_size > 0) integral_refine_warp_multi<RQ>(plane, cdt, a.H, a.W, a.cms_sh, a.cms_sw, fx, fy, a.refine_size, lane, ox, oy);
     if (lane < RQ) {  // lane q finishes peak i0 + q
 #pragma unroll
       for (int q = 0; q < RQ; ++q) {
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
         if (a.refine_size > 0) { x = __fadd_rn(x, ox[q]); y = __fadd_rn(y, oy[q]); }
         if (a.cms_stride != 1.0f) { x = __fmul_rn(x, a.cms_stride); y = __fmul_rn(y, a.cms_stride); }
         const int i = i0 + q;
-        const float v = __ldg(plane[q] + (long long)yi[q] * a.cms_sh + (long long)xi[q] * a.cms_sw);
+        const float v = ld_elem(plane[q], (long long)yi[q] * a.cms_sh + (long long)xi[q] * a.cms_sw, cdt);
         s_xy[2 * i] = x; s_xy[2 * i + 1] = y; s_val[i] = v; s_chan[i] = cc[q];
         const long long o = (long long)b * a.peak_cap + i;
         a.peak_xy[2 * o] = x; a.peak_xy[2 * o + 1] = y; a.peak_val[o] = v; a.peak_chan[o] = cc[q];
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   SNB_STAMP(2);
   // ---- 4. PAF line scores, one thread per candidate
   if (cand_ok) {
-    ScoreArgs sa{a.pafs, a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc, a.paf_H, a.paf_W, s_t, a.n_points,
+    ScoreArgs sa{a.pafs, a.pafs_dtype, a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc, a.paf_H, a.paf_W, s_t, a.n_points,
                  a.pafs_stride, a.max_edge_length, a.dist_penalty_weight};
     for (int m = tid; m < M; m += TAIL_THREADS) {
       int k, ps, pd;
@@ -410,8 +411,6 @@ bottomup_outputs_kernel(const int* __restrict__ n_inst, const float* __restrict_
 
 using namespace snb;
 
-extern "C" int snb_local_peaks_detect(const float*, int, int, int, int, long long, long long, long long, long long,
-                                      float, int, int*, uint32_t*, void*, void*, void*);
 
 extern "C" long long snb_bottomup_tail_smem_bytes(int peak_cap, int n_nodes, int n_edges, int cand_cap, int match_cap,
                                                   int n_sorted, int n_points) {
@@ -430,9 +429,9 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
   // buffers of this pipeline instance may still be read by its previous tail
   if (a->tail_stream && a->ev_tail_done) cudaStreamWaitEvent(st, (cudaEvent_t)a->ev_tail_done, 0);
   if (a->skip_flag && cudaMemsetAsync(a->skip_flag, 0, sizeof(int), st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
-  int rc = snb_local_peaks_detect(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
-                                  a->peak_threshold, a->peak_cap, a->frame_count, a->keys, a->ev_detect_begin,
-                                  a->ev_detect_end, stream);
+  int rc = snb_local_peaks_detect_t(a->cms, a->cms_dtype, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh,
+                                    a->cms_sw, a->peak_threshold, a->peak_cap, a->frame_count, a->keys,
+                                    a->ev_detect_begin, a->ev_detect_end, stream);
   if (rc != SNB_OK) return rc;
   if (a->tail_stream) {
     if (!a->ev_handoff) return SNB_ERR_BAD_ARG;
@@ -477,15 +476,13 @@ extern "C" int snb_bottomup_outputs(const int* n_inst, const float* inst_xy, con
 }
 
 // Stand-alone kernels chained on one stream (large capacities, or SNB_FLAG_UNFUSED_TAIL for tests).
-extern "C" int snb_local_peaks_finalize(const float*, int, int, int, int, long long, long long, long long, long long,
-                                        int, float, int, const int*, uint32_t*, float*, float*, int*, int*, void*);
 
 static int unfused_tail(const snb_bottomup_args* a, void* stream) {
   const int n_nodes = a->C;
   if (!a->node_start || !a->cand_edge || !a->m_edge) return SNB_ERR_BAD_ARG;  // needs the global tables
-  int rc = snb_local_peaks_finalize(a->cms, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
-                                    a->refine_size, a->cms_stride, a->peak_cap, a->frame_count, a->keys, a->peak_xy,
-                                    a->peak_val, a->peak_chan, a->status, stream);
+  int rc = snb_local_peaks_finalize_t(a->cms, a->cms_dtype, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh,
+                                      a->cms_sw, a->refine_size, a->cms_stride, a->peak_cap, a->frame_count, a->keys,
+                                      a->peak_xy, a->peak_val, a->peak_chan, a->status, stream);
   if (rc != SNB_OK) return rc;
   rc = snb_paf_prepare(a->peak_chan, nullptr, a->peak_cap, a->frame_count, a->B, a->edges, n_nodes, a->n_edges,
                        a->node_start, a->node_peaks, a->edge_off, a->match_off, stream);
@@ -496,7 +493,7 @@ static int unfused_tail(const snb_bottomup_args* a, void* stream) {
                                                                        a->max_peaks_per_node, a->skip_flag);
     SNB_LAUNCH_CHECK();
   }
-  rc = snb_paf_score(a->pafs, a->paf_sb, a->paf_sy, a->paf_sx, a->paf_sc, a->paf_H, a->paf_W, a->t_table, a->n_points,
+  rc = snb_paf_score_t(a->pafs, a->pafs_dtype, a->paf_sb, a->paf_sy, a->paf_sx, a->paf_sc, a->paf_H, a->paf_W, a->t_table, a->n_points,
                      a->pafs_stride, a->max_edge_length, a->dist_penalty_weight, a->peak_xy, nullptr, a->peak_cap,
                      a->B, a->edges, n_nodes, a->n_edges, a->node_start, a->node_peaks, a->edge_off, nullptr,
                      a->cand_cap, a->cand_cap, a->cand_edge, a->cand_epi, a->cand_score, a->status, stream);

@@ -45,15 +45,23 @@ class CentroidPostproc:
 
     def __call__(self, confmaps: torch.Tensor, output_stride: int = 1, input_scale: float = 1.0,
                  eff_scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        if not confmaps.is_cuda or confmaps.dtype != torch.float32:
-            raise TypeError("CentroidPostproc expects an fp32 CUDA tensor")
+        if not confmaps.is_cuda or confmaps.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise TypeError("CentroidPostproc expects an fp32 / fp16 / bf16 CUDA tensor")
         dev, B = confmaps.device, int(confmaps.shape[0])
         with torch.cuda.device(dev):
             count, xy, val, _chan, status, cap = local_peaks_padded(confmaps.detach(), self.peak_threshold,
                                                                     self.refine_size, float(output_stride), self.peak_cap)
             max_inst = self.max_instances
             if not max_inst:
-                max_inst = int(count.clamp(max=cap).max().item()) if B else 0
+                # this path synchronises anyway (`_infer_max_instances`): a frame with more peaks than the table holds is
+                # re-run with room for it, like ops.peaks._local_peaks, so the result never depends on which peaks the
+                # overflowing table happened to keep
+                worst = int(count.max().item()) if B else 0
+                if worst > cap:
+                    self.peak_cap = 1 << (worst - 1).bit_length()
+                    count, xy, val, _chan, status, cap = local_peaks_padded(
+                        confmaps.detach(), self.peak_threshold, self.refine_size, float(output_stride), self.peak_cap)
+                max_inst = min(worst, cap)
             max_inst = max(int(max_inst), 1)  # always at least one slot (centroid.py:222-223)
             o_xy = torch.empty((B, max_inst, 2), dtype=torch.float32, device=dev)
             o_val = torch.empty((B, max_inst), dtype=torch.float32, device=dev)
@@ -64,6 +72,15 @@ class CentroidPostproc:
                                          N.ptr(eff), N.ptr(o_xy), N.ptr(o_val), N.stream_ptr(dev)), "snb_peaks_topk")
         self.last_status = status  # SNB_STATUS_PEAK_OVERFLOW if a frame had more than peak_cap peaks
         return o_xy, o_val
+
+    def check(self) -> None:
+        """Synchronises: raises if a frame of the last call had more peaks than `peak_cap` (with a fixed `max_instances`
+        nothing is read back during the call, so which peaks an overflowing table kept - and therefore the top-k - would
+        depend on arrival order; the reference has no such limit).  Re-run with a larger `peak_cap`."""
+        st = getattr(self, "last_status", None)
+        if st is not None and int(st.item()) & N.STATUS_PEAK_OVERFLOW:
+            st.zero_()
+            raise RuntimeError(f"CentroidPostproc: a frame had more than peak_cap={self.peak_cap} peaks; raise peak_cap")
 
 
 class CenteredInstancePostproc:
@@ -78,14 +95,15 @@ class CenteredInstancePostproc:
 
     def __init__(self, peak_threshold: float = 0.2, refinement: Optional[str] = "integral", integral_patch_size: int = 5):
         self.peak_threshold, self.refine_size = float(peak_threshold), _refine_size(refinement, integral_patch_size)
-        self._ws = None
+        self._ws = {}  # (device, stream) -> ticket / partials workspace: two calls in flight on different streams
+        #                must not share the self-resetting tickets of the chunked kernels
 
     def __call__(self, confmaps: torch.Tensor, output_stride: int = 1, input_scale: float = 1.0,
                  eff_scale: Optional[torch.Tensor] = None, crop_topleft: Optional[torch.Tensor] = None,
                  per_crop_eff_scale: Optional[torch.Tensor] = None, scatter_rows: Optional[torch.Tensor] = None,
                  out_shape: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        if not confmaps.is_cuda or confmaps.dtype != torch.float32:
-            raise TypeError("CenteredInstancePostproc expects an fp32 CUDA tensor")
+        if not confmaps.is_cuda or confmaps.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise TypeError("CenteredInstancePostproc expects an fp32 / fp16 / bf16 CUDA tensor")
         dev = confmaps.device
         n, Cn, H, W = (int(v) for v in confmaps.shape)
         with torch.cuda.device(dev):
@@ -102,15 +120,19 @@ class CenteredInstancePostproc:
                 rpc, nch, nbytes = C.c_int(), C.c_int(), C.c_longlong()
                 N.check(N.lib.snb_global_peaks_workspace(n, Cn, H, W, C.byref(rpc), C.byref(nch), C.byref(nbytes)), "workspace")
                 need = (nbytes.value + 3) // 4
-                if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
-                    self._ws = torch.zeros((need,), dtype=torch.int32, device=dev)  # tickets self-reset after each use
+                ws_key = (dev.index, N.stream_ptr(dev))
+                ws = self._ws.get(ws_key)
+                if ws is None or ws.numel() < need:
+                    if len(self._ws) >= 16:
+                        self._ws.clear()
+                    ws = self._ws[ws_key] = torch.zeros((need,), dtype=torch.int32, device=dev)  # tickets self-reset after each use
                 lad, keep = make_ladder(dev, n, stride=float(output_stride), input_scale=float(input_scale),
                                         eff_scale=eff_scale, crop_offset=crop_topleft, eff_scale2=per_crop_eff_scale,
                                         scatter=scatter_rows)
                 x = confmaps.detach()
-                N.check(N.lib.snb_global_peaks_ex(N.ptr(x), n, Cn, H, W, *x.stride(), self.peak_threshold, self.refine_size,
-                                                  N.ptr(self._ws), C.byref(lad), N.ptr(kpts), N.ptr(vals), N.stream_ptr(dev)),
-                        "snb_global_peaks_ex")
+                N.check(N.lib.snb_global_peaks_t(N.ptr(x), N.dtype_code(x.dtype), n, Cn, H, W, *x.stride(), self.peak_threshold,
+                                                 self.refine_size, N.ptr(ws), C.byref(lad), N.ptr(kpts), N.ptr(vals),
+                                                 N.stream_ptr(dev)), "snb_global_peaks_t")
                 del keep
         if scatter_rows is not None:
             return kpts.view(out_shape[0], out_shape[1], Cn, 2), vals.view(out_shape[0], out_shape[1], Cn)
@@ -328,8 +350,8 @@ class TopDownPostproc:
                                               N.ptr(status), st()), "snb_crop_bboxes")
                 raw = model(crops)
                 cms, class_vectors = raw if isinstance(raw, (tuple, list)) else (raw, None)
-                if cms.dtype != torch.float32:  # an autocast network hands back fp16 / bf16 maps: exact up-cast
-                    cms = cms.float()
+                if cms.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                    cms = cms.float()  # fp16 / bf16 maps of an autocast network are read natively by the kernel
                 Nn = int(cms.shape[1])
                 k4, v3 = self.stage2(cms, output_stride=output_stride, input_scale=input_scale)
                 kp, vals = k4.squeeze(1).contiguous(), v3.squeeze(1).contiguous()

@@ -149,13 +149,14 @@ def _score_frames(pafs: Optional[torch.Tensor], peaks: Sequence[torch.Tensor], c
             pb = py = px = pc = 0
             H = W = 1
         N.check(
-            N.lib.snb_paf_score(N.ptr(pafs), pb, py, px, pc, H, W, N.ptr(_t_table(n_points, dev)), int(n_points),
+            N.lib.snb_paf_score_t(N.ptr(pafs), N.dtype_code(pafs.dtype) if pafs is not None else 0, pb, py, px, pc, H, W,
+                                N.ptr(_t_table(n_points, dev)), int(n_points),
                                 float(stride), float(max_edge_length), float(weight),
                                 N.ptr(xy_f.data) if xy_f is not None else None, N.ptr(chan_f.start), 0, B,
                                 N.ptr(edges_t), int(n_nodes), E, N.ptr(node_start), N.ptr(node_peaks),
                                 N.ptr(edge_off), N.ptr(cand_start), 0, int(m_per.max()), N.ptr(cand_edge),
                                 N.ptr(cand_epi), N.ptr(cand_score), N.ptr(status), N.stream_ptr(dev)),
-            "snb_paf_score",
+            "snb_paf_score_t",
         )
     split = lambda t: [t[starts[b]:starts[b + 1]] for b in range(B)]
     return split(cand_edge), split(cand_epi), split(cand_score)
@@ -306,7 +307,8 @@ def score_paf_lines_batch(
     max_edge_length = max_edge_length_ratio * max(pafs.shape[-1], pafs.shape[-2], pafs.shape[-3]) * pafs_stride
     dev = N.compute_device(pafs, *list(peaks))
     out_dev = pafs.device
-    p = pafs.detach().to(device=dev, dtype=torch.float32)
+    # fp16 / bf16 PAFs (an autocast backbone) are sampled in place: the taps are exact in fp32, no up-cast copy
+    p = pafs.detach().to(device=dev) if pafs.dtype in N._DTYPES else pafs.detach().to(device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         e, ep, sc = _score_frames(p, list(peaks), list(peak_channel_inds), skeleton_edges, n_nodes, n_line_points,
                                   pafs_stride, max_edge_length, dist_penalty_weight, dev)

@@ -26,6 +26,17 @@ def _as_f32_cuda(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
     return t
 
 
+_NATIVE_DTYPES = (torch.float32, torch.float16, torch.bfloat16)
+
+
+def _as_map_cuda(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    """Confidence maps on the compute device IN THEIR OWN dtype when the kernels read it natively (fp32 / fp16 / bf16:
+    no up-cast copy of the largest tensor on the hot path); anything else (float64, ints) is converted to fp32."""
+    if t.dtype not in _NATIVE_DTYPES:
+        return t.to(device=dev, dtype=torch.float32)
+    return t if t.device == dev else t.to(device=dev)
+
+
 def _threshold_for(dtype: torch.dtype, threshold: float) -> float:
     """`cms > threshold` compares in the TENSOR's dtype (the python scalar is cast to it): for fp16 / bf16 maps the
     threshold is first rounded to that dtype.  The up-cast values are exact, so comparing them with the rounded threshold
@@ -47,7 +58,8 @@ def local_peaks_padded(cms: torch.Tensor, threshold: float, refine_size: int, xy
     """Run K1 and return the padded per-frame peak table (all on device, no host sync).
 
     Returns (frame_count (B,) i32, xy (B,cap,2) f32, val (B,cap) f32, chan (B,cap) i32,
-    status (1,) i32, cap).  `cms` must be a CUDA fp32 tensor (any strides).
+    status (1,) i32, cap).  `cms` must be a CUDA fp32 / fp16 / bf16 tensor (any strides); half-precision maps are
+    read in place and compared / refined on their exact fp32 values.
     """
     B, Cn, H, W = cms.shape
     cap = int(cap or DEFAULT_PEAK_CAP)
@@ -60,10 +72,10 @@ def local_peaks_padded(cms: torch.Tensor, threshold: float, refine_size: int, xy
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
     sb, sc, sh, sw = cms.stride()
     N.check(
-        N.lib.snb_local_peaks(N.ptr(cms), B, Cn, H, W, sb, sc, sh, sw, float(threshold), int(refine_size),
-                              float(xy_scale), cap, N.ptr(frame_count), N.ptr(keys), N.ptr(xy), N.ptr(val),
-                              N.ptr(chan), N.ptr(status), N.stream_ptr(dev)),
-        "snb_local_peaks",
+        N.lib.snb_local_peaks_t(N.ptr(cms), N.dtype_code(cms.dtype), B, Cn, H, W, sb, sc, sh, sw, float(threshold),
+                                int(refine_size), float(xy_scale), cap, N.ptr(frame_count), N.ptr(keys), N.ptr(xy),
+                                N.ptr(val), N.ptr(chan), N.ptr(status), N.stream_ptr(dev)),
+        "snb_local_peaks_t",
     )
     return frame_count[:B], xy, val, chan, status, cap
 
@@ -74,7 +86,7 @@ def _local_peaks(cms: torch.Tensor, threshold: float, refine_size: int):
     dev = N.compute_device(cms)
     out_dev, out_dtype = cms.device, cms.dtype
     threshold = _threshold_for(cms.dtype, threshold)
-    x = _as_f32_cuda(cms, dev)
+    x = _as_map_cuda(cms, dev)
     B = x.shape[0]
     if x.numel() == 0:
         z = torch.zeros
@@ -136,7 +148,7 @@ def _global_peaks(cms: torch.Tensor, threshold: float, refine_size: int):
     dev = N.compute_device(cms)
     out_dev, out_dtype = cms.device, cms.dtype
     threshold = _threshold_for(cms.dtype, threshold)
-    x = _as_f32_cuda(cms, dev)
+    x = _as_map_cuda(cms, dev)
     B, Cn, H, W = x.shape
     if H == 0 or W == 0:
         raise ValueError("find_global_peaks: empty spatial dimensions")
@@ -150,9 +162,9 @@ def _global_peaks(cms: torch.Tensor, threshold: float, refine_size: int):
             ws = torch.zeros(((nbytes.value + 3) // 4,), dtype=torch.int32, device=dev)
             sb, sc, sh, sw = x.stride()
             N.check(
-                N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, sb, sc, sh, sw, float(threshold), int(refine_size),
-                                       N.ptr(ws), N.ptr(pts), N.ptr(vals), N.stream_ptr(dev)),
-                "snb_global_peaks",
+                N.lib.snb_global_peaks_t(N.ptr(x), N.dtype_code(x.dtype), B, Cn, H, W, sb, sc, sh, sw, float(threshold),
+                                         int(refine_size), N.ptr(ws), None, N.ptr(pts), N.ptr(vals), N.stream_ptr(dev)),
+                "snb_global_peaks_t",
             )
     if out_dtype != torch.float32:
         vals = vals.to(out_dtype)

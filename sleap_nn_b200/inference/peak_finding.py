@@ -1,17 +1,22 @@
-"""`sleap_nn.inference.peak_finding`'s import path (inference/peak_finding.py:9-27): the names callers import from there,
-bound to the CUDA-backed implementations; the table names the C-ABI entry point behind each one."""
+"""`sleap_nn.inference.peak_finding`'s import path (inference/peak_finding.py:9-27): the names callers import from
+there, re-exported from the CUDA-backed implementations."""
 
-from sleap_nn_b200.inference.ops import crops as _crops
-from sleap_nn_b200.inference.ops import peaks as _peaks
+from sleap_nn_b200.inference.ops.crops import crop_bboxes  # snb_crop_bboxes
+from sleap_nn_b200.inference.ops.peaks import (
+    find_global_peaks,        # K2 + K3: snb_global_peaks_t
+    find_global_peaks_rough,
+    find_local_peaks,         # K1 + K3: snb_local_peaks_t + snb_pack_peaks
+    find_local_peaks_rough,
+    integral_regression,      # snb_integral_regression
+    morphological_dilation,   # snb_dilate8
+)
 
-_BACKED_BY = {
-    "find_local_peaks": (_peaks, "snb_local_peaks + snb_pack_peaks"),        # K1 + K3
-    "find_local_peaks_rough": (_peaks, "snb_local_peaks + snb_pack_peaks"),
-    "find_global_peaks": (_peaks, "snb_global_peaks"),                        # K2 + K3
-    "find_global_peaks_rough": (_peaks, "snb_global_peaks"),
-    "integral_regression": (_peaks, "snb_integral_regression"),
-    "morphological_dilation": (_peaks, "snb_dilate8"),
-    "crop_bboxes": (_crops, "snb_crop_bboxes"),
-}
-globals().update({name: getattr(mod, name) for name, (mod, _entry) in _BACKED_BY.items()})
-__all__ = sorted(_BACKED_BY)
+__all__ = [
+    "crop_bboxes",
+    "find_global_peaks",
+    "find_global_peaks_rough",
+    "find_local_peaks",
+    "find_local_peaks_rough",
+    "integral_regression",
+    "morphological_dilation",
+]

@@ -227,23 +227,33 @@ class BottomUpPostproc:
                  eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
         """Enqueue the chain on the current stream of `self.device`; returns padded device tensors.
 
-        cms (B, N, H, W) fp32 CUDA; pafs (B, 2E, Hp, Wp) or (B, Hp, Wp, 2E) fp32 CUDA, any strides.
+        cms (B, N, H, W) CUDA; pafs (B, 2E, Hp, Wp) or (B, Hp, Wp, 2E) CUDA, any strides; fp32, or the fp16 / bf16
+        heads of an autocast backbone, read in place: results are bit-identical to running on `cms.float()`,
+        `pafs.float()` (what torch_backend.py:140-146 does before the reference's ops), without that copy.
         `detect_events` = (torch.cuda.Event, torch.cuda.Event) recorded around the streaming
         detect kernel (for the benchmark's roofline figure).  `input_scale` / `eff_scale` (B,) are
         `PreprocInfo`'s scale factors, undone in the `.outputs()` tensors (streaming.py:190-196).
         """
+        # The C side launches on the CURRENT device: when the caller's current device is another GPU, switch for the
+        # duration of the call (otherwise the chain would run there, reaching the tables over peer access, unordered
+        # with this device's streams).
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):
+                return self.__call__(cms, pafs, detect_events, input_scale, eff_scale)
         # fast path: tensors this pipeline has already been launched on (a loop fed from a few fixed buffers, the
         # steady state of a streaming pipeline) - a filled copy of the argument block is kept per input, so only the
         # launch itself is left (~5 us of host time instead of ~25 us)
-        # (the block is a pure function of the key - pointers, strides, shapes, scale - so nothing is kept alive)
+        # (the block is a pure function of the key - pointers, strides, shapes, scale, knobs - so nothing is kept alive)
         key = (cms.data_ptr(), pafs.data_ptr(), cms.stride(), pafs.stride(), tuple(cms.shape), tuple(pafs.shape),
-               cms.dtype, pafs.dtype, input_scale)
+               cms.dtype, pafs.dtype, input_scale, self._knobs())
         hit = self._fast.get(key) if (detect_events is None and eff_scale is None) else None
         if hit is not None:
             N.check(N.lib.snb_bottomup_postproc(C.byref(hit[0]), N.stream_ptr(self.device)), "snb_bottomup_postproc")
             return hit[1]
-        if not (cms.is_cuda and pafs.is_cuda) or cms.dtype != torch.float32 or pafs.dtype != torch.float32:
-            raise TypeError("BottomUpPostproc expects fp32 CUDA tensors; use .run_host() for host buffers")
+        if not (cms.is_cuda and pafs.is_cuda) or cms.dtype not in N._DTYPES or pafs.dtype not in N._DTYPES:
+            raise TypeError("BottomUpPostproc expects fp32 / fp16 / bf16 CUDA tensors; use .run_host() for host buffers")
+        if cms.device != self.device or pafs.device != self.device:
+            raise ValueError(f"inputs live on {cms.device} / {pafs.device}, the pipeline's tables on {self.device}")
         if tuple(cms.shape) != (self.batch, self.n_nodes) + self.cms_hw:
             raise ValueError(f"cms shape {tuple(cms.shape)} does not match the pipeline's batch shape")
         if pafs.dim() != 4 or pafs.shape[0] != self.batch:
@@ -253,7 +263,7 @@ class BottomUpPostproc:
         elif pafs.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
         res = self._launch(N.ptr(cms), cms.stride(), N.ptr(pafs), tuple(pafs.shape), pafs.stride(), detect_events,
-                           input_scale, eff_scale)
+                           input_scale, eff_scale, cms.dtype, pafs.dtype)
         if detect_events is None and eff_scale is None:
             if len(self._fast) >= 16:
                 self._fast.clear()
@@ -262,10 +272,25 @@ class BottomUpPostproc:
             self._fast[key] = (block, res)
         return res
 
+    def _knobs(self):
+        """The scalar knobs a caller may change on a live object (the reference's PAFScorer is mutable the same way,
+        ops/paf.py:1208-1218); they are re-read on every launch and are part of the fast-path key."""
+        return (self.peak_threshold, self.refine_size, self.max_edge_length_ratio, self.dist_penalty_weight,
+                self.min_instance_peaks, self.min_line_scores, self.cms_stride, self.pafs_stride, self.max_peaks_per_node)
+
     def _launch(self, cms_ptr: int, cms_strides, pafs_ptr: int, pafs_shape, pafs_strides, detect_events=None,
-                input_scale: float = 1.0, eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
-        """Fill the argument block from raw device-visible pointers and enqueue the chain."""
+                input_scale: float = 1.0, eff_scale: Optional[torch.Tensor] = None,
+                cms_dtype: torch.dtype = torch.float32, pafs_dtype: torch.dtype = torch.float32) -> BottomUpResult:
+        """Fill the argument block from raw device-visible pointers and enqueue the chain (current device must be
+        `self.device`: every caller holds the guard)."""
         a = self._args
+        a.peak_threshold, a.refine_size = float(self.peak_threshold), int(self.refine_size)
+        a.cms_stride, a.pafs_stride = float(self.cms_stride), float(self.pafs_stride)
+        a.dist_penalty_weight = float(self.dist_penalty_weight)
+        a.min_instance_peaks, a.min_line_scores = int(self.min_instance_peaks), float(self.min_line_scores)
+        if self._skip_flag is not None:
+            a.max_peaks_per_node = int(self.max_peaks_per_node or 0)
+        a.cms_dtype, a.pafs_dtype = N.dtype_code(cms_dtype), N.dtype_code(pafs_dtype)
         if eff_scale is not None:
             eff_scale = eff_scale.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
             if eff_scale.numel() == 1 and self.batch != 1:
@@ -296,46 +321,70 @@ class BottomUpPostproc:
         return int(N.lib.snb_bottomup_launches_per_call(C.byref(self._args)))
 
     # ------------------------------------------------------------------ host-buffer path
-    def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor, zero_copy_pafs: bool = True):
-        """Host buffers in, per-sample CPU tensors out: H2D + chain + D2H.
+    def _launch_from_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor, zero_copy_pafs: bool = True,
+                          zero_copy_cms: bool = False) -> BottomUpResult:
+        """Enqueue copy + chain for one batch that lives in HOST memory, on the current stream of `self.device` (the
+        caller holds the device guard).  Sets `last_h2d_bytes`, `last_zero_copy`, `last_zero_copy_cms`.
 
-        The confidence maps are copied to the device (every element has to be looked at).  The PAF
-        tensor is only SAMPLED (n_points x 2 taps per candidate), so when `pafs_host` is pinned it is
-        read in place over PCIe through its device alias (`snb_host_device_pointer`) and only the
-        sampled sectors cross the link; an unpinned buffer is staged like the confidence maps.
-        `self.last_h2d_bytes` holds the bytes this call moved host -> device (copy + sampled sectors).
-        Returns (instances, peak_scores, instance_scores) lists like `PAFScorer.predict`.
+        The confidence maps are copied to a device staging buffer (every element has to be looked at) - or, with
+        `zero_copy_cms` and a pinned buffer, streamed by the detect kernel itself straight out of host memory through
+        the buffer's device alias (the kernel's 128-bit loads are the DMA: no staging write + re-read in HBM, same
+        bytes over PCIe).  The PAF tensor is only SAMPLED (n_points x 2 taps per candidate), so a pinned one is read in
+        place and only the sampled sectors cross the link; an unpinned buffer is staged like the confidence maps.
         """
-        if cms_host.dtype != torch.float32 or pafs_host.dtype != torch.float32:
-            raise TypeError("run_host expects fp32 host tensors")
+        if cms_host.dtype not in N._DTYPES or pafs_host.dtype not in N._DTYPES:
+            raise TypeError("host tensors must be float32, float16 or bfloat16")
         if pafs_host.dim() != 4 or pafs_host.shape[0] != self.batch:
             raise ValueError("pafs must be (B, 2E, H, W) or its (B, H, W, 2E) view")
+        if tuple(cms_host.shape) != (self.batch, self.n_nodes) + self.cms_hw:
+            raise ValueError(f"cms shape {tuple(cms_host.shape)} does not match the pipeline's batch shape")
         channels_first = pafs_host.shape[1] == 2 * self.n_edges and pafs_host.shape[-1] != 2 * self.n_edges
         if not channels_first and pafs_host.shape[-1] != 2 * self.n_edges:
             raise ValueError("pafs channel count must be 2 * n_edges")
         view = (lambda t: t.permute(0, 2, 3, 1)) if channels_first else (lambda t: t)
+
+        def alias_of(t):
+            p = C.c_void_p()
+            ok = t.is_pinned() and N.lib.snb_host_device_pointer(t.data_ptr(), C.byref(p)) == N.OK and p.value
+            return p.value if ok else None
+
+        cms_alias = alias_of(cms_host) if zero_copy_cms else None
+        if cms_alias is not None:
+            cms_ptr, cms_strides = cms_alias, cms_host.stride()
+        else:
+            st = getattr(self, "_stage_cms", None)
+            if st is None or st.shape != cms_host.shape or st.dtype != cms_host.dtype:
+                st = self._stage_cms = torch.empty(cms_host.shape, dtype=cms_host.dtype, device=self.device)
+            st.copy_(cms_host, non_blocking=True)
+            cms_ptr, cms_strides = N.ptr(st), st.stride()
+        paf_alias = alias_of(pafs_host) if zero_copy_pafs else None
+        if paf_alias is not None:
+            pv = view(pafs_host)
+            paf_ptr = paf_alias
+        else:  # stage in the host tensor's own memory order (a dense copy), then take the channels-last view
+            sp = getattr(self, "_stage_pafs", None)
+            if sp is None or sp.shape != pafs_host.shape or sp.dtype != pafs_host.dtype or sp.stride() != pafs_host.stride():
+                sp = self._stage_pafs = torch.empty_strided(tuple(pafs_host.shape), pafs_host.stride(),
+                                                            dtype=pafs_host.dtype, device=self.device)
+            sp.copy_(pafs_host, non_blocking=True)
+            pv = view(sp)
+            paf_ptr = N.ptr(pv)
+        res = self._launch(cms_ptr, cms_strides, paf_ptr, tuple(pv.shape), pv.stride(), None, 1.0, None,
+                           cms_host.dtype, pafs_host.dtype)
+        self.last_zero_copy, self.last_zero_copy_cms = paf_alias is not None, cms_alias is not None
+        self.last_h2d_bytes = (cms_host.numel() * cms_host.element_size()
+                               + (0 if paf_alias is not None else pafs_host.numel() * pafs_host.element_size()))
+        return res
+
+    def run_host(self, cms_host: torch.Tensor, pafs_host: torch.Tensor, zero_copy_pafs: bool = True,
+                 zero_copy_cms: bool = False):
+        """Host buffers in, per-sample CPU tensors out: H2D + chain + D2H (synchronous; `BottomUpHostStream` pipelines).
+
+        `self.last_h2d_bytes` holds the bytes this call moved host -> device (the maps, plus the PAF tensor when it
+        had to be staged).  Returns (instances, peak_scores, instance_scores) lists like `PAFScorer.predict`.
+        """
         with torch.cuda.device(self.device):
-            if not hasattr(self, "_stage_cms") or self._stage_cms.shape != cms_host.shape:
-                self._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
-            self._stage_cms.copy_(cms_host, non_blocking=True)
-            paf_alias = C.c_void_p()
-            zero_copy = bool(zero_copy_pafs and pafs_host.is_pinned() and N.lib.snb_host_device_pointer(
-                pafs_host.data_ptr(), C.byref(paf_alias)) == N.OK and paf_alias.value)
-            if zero_copy:
-                pv = view(pafs_host)
-                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), paf_alias.value,
-                                   tuple(pv.shape), pv.stride())
-            else:  # stage in the host tensor's own memory order (a dense copy), then take the channels-last view
-                if not hasattr(self, "_stage_pafs") or self._stage_pafs.shape != pafs_host.shape:
-                    self._stage_pafs = torch.empty_strided(tuple(pafs_host.shape), pafs_host.stride(), dtype=torch.float32,
-                                                           device=self.device)
-                self._stage_pafs.copy_(pafs_host, non_blocking=True)
-                pv = view(self._stage_pafs)
-                res = self._launch(N.ptr(self._stage_cms), self._stage_cms.stride(), N.ptr(pv), tuple(pv.shape), pv.stride())
-            out = res.to_lists()
-            self.last_h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
-            self.last_zero_copy = zero_copy
-            return out
+            return self._launch_from_host(cms_host, pafs_host, zero_copy_pafs, zero_copy_cms).to_lists()
 
 
 class BottomUpHostStream:
@@ -355,12 +404,12 @@ class BottomUpHostStream:
     Results are `(instances, peak_scores, instance_scores)` per-sample lists like `PAFScorer.predict`.
     """
 
-    def __init__(self, make_pipe, depth: int = 2, zero_copy_pafs: bool = True):
+    def __init__(self, make_pipe, depth: int = 2, zero_copy_pafs: bool = True, zero_copy_cms: bool = False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.pipes = [make_pipe() for _ in range(depth)]
         self.device = self.pipes[0].device
-        self.zero_copy_pafs = zero_copy_pafs
+        self.zero_copy_pafs, self.zero_copy_cms = zero_copy_pafs, zero_copy_cms
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
             self.done = [torch.cuda.Event() for _ in range(depth)]
@@ -405,28 +454,9 @@ class BottomUpHostStream:
         self._next = (k + 1) % len(self.pipes)
         out = self._collect(k) if self._busy[k] else None
         pipe, st = self.pipes[k], self.streams[k]
-        if cms_host.dtype != torch.float32 or pafs_host.dtype != torch.float32:
-            raise TypeError("BottomUpHostStream expects fp32 host tensors")
-        channels_first = pafs_host.shape[1] == 2 * pipe.n_edges and pafs_host.shape[-1] != 2 * pipe.n_edges
-        view = (lambda t: t.permute(0, 2, 3, 1)) if channels_first else (lambda t: t)
         h = self._result_buffers(k)
         with torch.cuda.device(self.device), torch.cuda.stream(st):
-            if not hasattr(pipe, "_stage_cms") or pipe._stage_cms.shape != cms_host.shape:
-                pipe._stage_cms = torch.empty(cms_host.shape, dtype=torch.float32, device=self.device)
-            pipe._stage_cms.copy_(cms_host, non_blocking=True)
-            alias = C.c_void_p()
-            zero_copy = bool(self.zero_copy_pafs and pafs_host.is_pinned() and N.lib.snb_host_device_pointer(
-                pafs_host.data_ptr(), C.byref(alias)) == N.OK and alias.value)
-            if zero_copy:
-                pv = view(pafs_host)
-                res = pipe._launch(N.ptr(pipe._stage_cms), pipe._stage_cms.stride(), alias.value, tuple(pv.shape), pv.stride())
-            else:
-                if not hasattr(pipe, "_stage_pafs") or pipe._stage_pafs.shape != pafs_host.shape:
-                    pipe._stage_pafs = torch.empty_strided(tuple(pafs_host.shape), pafs_host.stride(), dtype=torch.float32,
-                                                           device=self.device)
-                pipe._stage_pafs.copy_(pafs_host, non_blocking=True)
-                pv = view(pipe._stage_pafs)
-                res = pipe._launch(N.ptr(pipe._stage_cms), pipe._stage_cms.stride(), N.ptr(pv), tuple(pv.shape), pv.stride())
+            res = pipe._launch_from_host(cms_host, pafs_host, self.zero_copy_pafs, self.zero_copy_cms)
             res.wait(st)
             b = pipe.buf
             for name in ("n_inst", "status", "inst_xy", "inst_val", "inst_score"):
@@ -434,9 +464,9 @@ class BottomUpHostStream:
             b["status"].zero_()  # sticky bits are reported once (after the copy above, in stream order)
             self.done[k].record(st)
         self._busy[k] = True
-        self.h2d_bytes = cms_host.numel() * 4 + (0 if zero_copy else pafs_host.numel() * 4)
+        self.h2d_bytes = pipe.last_h2d_bytes
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in h.values())
-        self.last_zero_copy = zero_copy
+        self.last_zero_copy, self.last_zero_copy_cms = pipe.last_zero_copy, pipe.last_zero_copy_cms
         return out
 
     def drain(self):

@@ -182,7 +182,9 @@ class ShardRunner:
         n_local = self.stop - self.start
         n_padded = -(-n_local // pipe.batch) * pipe.batch if n_local else 0
         dev, Nn = pipe.device, pipe.n_nodes
-        self.rows_cap = int(rows_cap if rows_cap is not None else max(n_padded, 1) * min(pipe.caps["inst_cap"], 8))
+        # default: room for every frame filling its instance table (so the packed table cannot overflow before the
+        # per-frame one does); pass rows_cap to bound the memory of very long shards of sparse frames
+        self.rows_cap = int(rows_cap if rows_cap is not None else max(n_padded, 1) * pipe.caps["inst_cap"])
         with torch.cuda.device(dev):
             self.cursor = torch.zeros((3,), dtype=torch.int64, device=dev)
             self.o_xy = torch.empty((self.rows_cap, Nn, 2), dtype=torch.float32, device=dev)
@@ -193,6 +195,10 @@ class ShardRunner:
         self.launches = 0
 
     def run(self, source: Callable[[int, int], Tuple[torch.Tensor, torch.Tensor]]) -> "ShardRunner":
+        with torch.cuda.device(self.pipe.device):  # the C side launches on the CURRENT device
+            return self._run(source)
+
+    def _run(self, source):
         N, pipe = self._N, self.pipe
         for s, e in batch_ranges(self.start, self.stop, pipe.batch):
             cms, pafs = source(s, e)
@@ -219,8 +225,12 @@ class ShardRunner:
             self.pipe.buf["status"].zero_()
         if status & N.STATUS_LSAP_INFEASIBLE:
             raise ValueError("cost matrix is infeasible")
+        if status & N.STATUS_INSTANCE_OVERFLOW and int(cur[0]) > self.rows_cap:
+            raise RuntimeError(f"sharded bottom-up run produced {int(cur[0])} instances, more than rows_cap={self.rows_cap} "
+                               "(the packed per-rank table): pass a larger rows_cap to ShardRunner")
         if status:
-            raise RuntimeError(f"sharded bottom-up run overflowed a fixed-capacity table (status 0x{status:x})")
+            raise RuntimeError(f"sharded bottom-up run overflowed a fixed-capacity table (status 0x{status:x}): raise "
+                               "peak_cap / cand_cap / match_cap / inst_cap of the pipeline")
         rows, n_local = int(cur[0]), self.stop - self.start
         return PackedInstances(self.start, self.o_count[:n_local].clone(), self.o_frame[:rows], self.o_xy[:rows],
                                self.o_val[:rows], self.o_score[:rows])

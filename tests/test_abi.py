@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
     assert set(table) == set(decl), set(table) ^ set(decl)
     for name, argtypes in table.items():
         assert len(argtypes) == decl[name], f"{name}: ctypes arity {len(argtypes)} != header {decl[name]}"
-    assert N.ABI_VERSION == 4
+    assert N.ABI_VERSION == N.EXPECTED_ABI == 5
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -243,15 +243,18 @@ def test_c_program_drives_the_library_without_torch(tmp_path):
     assert r.returncode == 0 and "C ABI demo: OK" in r.stdout, r.stdout + r.stderr
 
 
-def test_shim_tables_name_real_entry_points():
-    """The name -> C-ABI entry point tables of the two re-export shims stay truthful."""
-    from sleap_nn_b200 import _native as N
+def test_shims_are_plain_reexports_of_the_reference_names():
+    """The two backward-compatibility import paths (inference/peak_finding.py:9-27, inference/paf_grouping.py:8-46) are
+    explicit re-exports (visible to static analysis), and every name is the ops-module object itself."""
     from sleap_nn_b200.inference import paf_grouping, peak_finding
+    from sleap_nn_b200.inference.ops import crops, paf, peaks
 
-    entries = [e for e in paf_grouping._BACKED_BY.values() if e] + [e for _, e in peak_finding._BACKED_BY.values()]
-    for entry in entries:
-        for sym in entry.split(" + "):
-            assert sym in N.SIGNATURES, sym
+    for name in peak_finding.__all__:
+        assert getattr(peak_finding, name) is getattr(crops if name == "crop_bboxes" else peaks, name)
+    for name in paf_grouping.__all__:
+        assert getattr(paf_grouping, name) is getattr(paf, name)
     for mod in (paf_grouping, peak_finding):
+        src = open(mod.__file__).read()
+        assert "globals()" not in src
         for name in mod.__all__:
             assert callable(getattr(mod, name)) or isinstance(getattr(mod, name), type)
