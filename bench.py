@@ -1,31 +1,39 @@
 #!/usr/bin/env python
 """Benchmark of the bottom-up post-processing hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f32|f16|bf16]
 
 Workload (`config.workload`): BASELINE cfg3 "bottom-up mice" - 1024x1024 frames, 5 nodes /
 4 edges, stride-2 confidence maps (64,5,512,512) + PAFs (64,8,512,512), batch 64, full peak +
 PAF grouping.  One STEP = one pass of the whole hot path (K1 peaks + refinement -> K4 line
 scores -> K5 assignment -> K6 assembly) over one batch of 64 synthetic frames.
 
-  value   frames/s with the maps already resident in HBM (as they are after the backbone),
-          batches pipelined over `--streams` CUDA streams, inputs rotated over several distinct
-          batches (each 872 MB > 126 MB L2, so nothing is served from cache);
-  e2e     the same metric through the public API with HOST buffers: per step a pinned-host ->
-          device copy of the maps and a device -> host read of the grouped instances;
-  roofline  the dominant kernel (streaming NMS detect) timed in situ with CUDA events recorded
-          around it inside the timed region; algorithmic bytes = 4*C*H*W*B per launch;
-  cpu_baseline  the CPU oracle (a port of the reference's op chain, torch CPU ops, all host
-          threads) on a bounded sample of the same frames.  N=1, rank 0 only.
+  value     frames/s with the maps already resident in HBM (as they are after the backbone),
+            batches pipelined over `--streams` CUDA streams, inputs rotated over several distinct
+            batches (each 872 MB > 126 MB L2, so nothing is served from cache);
+  e2e       the same metric through the public API with HOST buffers: per step a pinned-host ->
+            device copy of the maps and a device -> host read of the grouped instances;
+  roofline  the dominant kernel (streaming NMS detect) timed alone with CUDA events recorded by the
+            C ABI right around it; algorithmic bytes = esz*C*H*W*B per launch; `traffic` from the
+            committed ncu capture (profiles/traffic.json, keyed by kernel + hash of the source);
+  cpu_baseline  the reference's own unmodified files (staged under baseline/_ref by build(); kind
+            "reference") - or, where they are absent, the oracle port - on a bounded sample of the
+            same frames, all host threads and one thread, per stage.  N=1, rank 0 only;
+  parity    the GPU results of that same sample compared with the oracle's, in this run;
+  extra     (N=1) the other kernels / configs of BASELINE.json, each with algorithmic bytes,
+            average launch time and roofline fraction: K2 cfg2, the cfg4 chain, K7 / K8 cfg4
+            (8 frames and 1 frame per launch, fp32 and bf16), K1a on f16 maps;
+  gather    (N>1) the same steps through ShardRunner + the end-of-shard gather_packed collective.
 
-`--impl reference` times that CPU port alone (the reference is pure Python / ATen and cannot
-travel to the GPU box).  Multi-GPU: frames shard, no collective on the hot path;
-one process per GPU (torchrun), barrier + synchronize around the timed region, max over ranks.
+`--impl reference` times the reference's CPU implementation alone, on the same config, all 64
+frames per step.  Multi-GPU: frames shard, no collective on the hot path; one process per GPU
+(torchrun), barrier + synchronize around the timed region, max over ranks.
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -46,9 +54,15 @@ WORKLOAD = dict(
     batch=64, n_nodes=5, n_edges=4, n_instances=2, img_hw=[1024, 1024], stride=2, maps_hw=[512, 512],
 )
 B, N_NODES, N_INST, IMG_HW, STRIDE = 64, 5, 2, (1024, 1024), 2
-ALGO_BYTES_PER_FRAME = 4 * N_NODES * 512 * 512  # K1 reads every confidence-map element once
 METRIC, UNIT = "bottom-up post-proc frames/s", "frames/s"
+DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
 emit = lambda obj: print(json.dumps(obj), flush=True)  # replaced in main() by a writer on the saved stdout descriptor
+
+
+def shared_config(world: int, dtype: str = "f32"):
+    """The `config` object BOTH arms print (the driver compares them for `same_config`)."""
+    return dict(WORKLOAD, parallelism=f"frame-sharded x{world}, no collective on the hot path", dtype=dtype,
+                l2="inputs larger than L2: each batch is 872 MB (fp32) and batches rotate")
 
 
 def measured_peaks():
@@ -59,8 +73,21 @@ def measured_peaks():
         return 6650.0, "fallback"  # B200_PROFILING.md fallback
 
 
+def recorded_traffic(kernel: str):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), with whether the
+    capture was taken on the current source of the kernel (sha256 of csrc/peaks.cu)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f)[kernel]
+        with open(os.path.join(ROOT, "sleap_nn_b200", "csrc", "peaks.cu"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+        return rec["dram_bytes_read"] + rec["dram_bytes_write"], dict(rec, source_matches=(rec.get("source_sha16") == sha))
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
-    """SM clocks / throttle reasons of the job's GPUs sampled every 100 ms while the timed region runs.
+    """SM clocks / throttle reasons of the job's GPUs sampled while the timed region runs.
 
     In-process NVML (nvidia-ml-py) when available - a query costs microseconds and takes no driver-wide lock;
     falls back to spawning `nvidia-smi` (the recipe's clocks line).  Only rank 0 samples, for all GPUs of the job:
@@ -135,7 +162,7 @@ class ClockSampler:
                 "samples": self.n, "gpus": self.indices, "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
-# --------------------------------------------------------------------------- CPU port (oracle)
+# --------------------------------------------------------------------------- the CPU arms (test infrastructure)
 def oracle_postproc(cms_cpu, pafs_cpu, edges):
     """The reference's bottom-up post-processing chain, as restated by oracle/ (CPU, torch ops)."""
     from oracle import paf as opaf
@@ -148,19 +175,85 @@ def oracle_postproc(cms_cpu, pafs_cpu, edges):
     return opaf.predict(pafs_cpu.permute(0, 2, 3, 1), peaks, pvs, pcs, edges, N_NODES, STRIDE)
 
 
-def time_cpu_port(cms_cpu, pafs_cpu, edges, frames_per_call: int, calls: int, warm: int = 1):
-    torch.set_num_threads(os.cpu_count() or 1)
-    c, p = cms_cpu[:frames_per_call], pafs_cpu[:frames_per_call]
+class ReferenceChain:
+    """The UNMODIFIED reference files, exec'd in place by oracle/ref_loader.py from baseline/_ref (staged by build(),
+    git-ignored, travels with the snapshot) or, in the build container, from /root/reference.
+
+    One call = what BottomUpLayer runs after the backbone on one batch (layers/bottomup.py:95-236): find_local_peaks
+    (ops/peaks.py:221-259) -> x stride -> per-sample split -> PAFScorer.predict (ops/paf.py:1456-1532).
+    """
+
+    def __init__(self, edges):
+        self.root = None
+        for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+            if os.path.isfile(os.path.join(root, "sleap_nn", "inference", "ops", "paf.py")):
+                self.root = root
+                break
+        if self.root is None:
+            raise FileNotFoundError("no reference files (baseline/_ref not staged and /root/reference absent)")
+        os.environ["SLEAPNN_REFERENCE_ROOT"] = self.root
+        from oracle import ref_loader
+
+        self.R = ref_loader.ref()
+        names = [str(i) for i in range(N_NODES)]
+        self.scorer = self.R.paf.PAFScorer(part_names=names, edges=[(str(a), str(b)) for a, b in edges],
+                                           pafs_stride=STRIDE)
+        self.stage_s = {}
+
+    def __call__(self, cms, pafs, stages: bool = False):
+        R, sc = self.R, self.scorer
+        t = [time.perf_counter()]
+        pts, vals, si, ci = R.peaks.find_local_peaks(cms, threshold=0.2, refinement="integral", integral_patch_size=5)
+        pts = pts * STRIDE
+        peaks, pvals, pch = [], [], []
+        for b in range(cms.shape[0]):
+            mask = si == b
+            peaks.append(pts[mask]); pvals.append(vals[mask].to(torch.float32)); pch.append(ci[mask])
+        t.append(time.perf_counter())
+        view = pafs.permute(0, 2, 3, 1)
+        if not stages:
+            return sc.predict(view, peaks, pvals, pch)
+        e, ep, ls = sc.score_paf_lines(view, peaks, pch)
+        t.append(time.perf_counter())
+        m = sc.match_candidates(e, ep, ls)
+        t.append(time.perf_counter())
+        out = sc.group_instances(peaks, pvals, pch, *m)
+        t.append(time.perf_counter())
+        for name, a, b_ in zip(("find_local_peaks+split", "score_paf_lines", "match_candidates", "group_instances"),
+                               t[:-1], t[1:]):
+            self.stage_s[name] = b_ - a
+        return tuple(out) + (e, ep, ls)
+
+
+class PortChain:
+    """Fallback CPU arm when the reference files are nowhere to be found: oracle/, the port of the same chain."""
+
+    def __init__(self, edges):
+        self.edges, self.stage_s = edges, {}
+
+    def __call__(self, cms, pafs, stages: bool = False):
+        return oracle_postproc(cms, pafs, self.edges)
+
+
+def cpu_arm(edges):
+    """(callable(cms, pafs) -> predict-shaped tuple, kind, description)."""
+    try:
+        chain = ReferenceChain(edges)
+        where = os.path.relpath(chain.root, ROOT) if chain.root.startswith(ROOT) else chain.root
+        return chain, "reference", f"unmodified reference files exec'd from {where}"
+    except Exception as e:  # noqa: BLE001 - fall back to the port, and say why
+        return PortChain(edges), "port", f"oracle/ port (reference files unavailable: {type(e).__name__}: {e})"
+
+
+def time_cpu(fn, cms_cpu, pafs_cpu, calls: int, threads: int, warm: int = 1):
+    torch.set_num_threads(threads)
     for _ in range(warm):
-        oracle_postproc(c, p, edges)
+        fn(cms_cpu, pafs_cpu)
     t0 = time.perf_counter()
     for _ in range(calls):
-        oracle_postproc(c, p, edges)
+        fn(cms_cpu, pafs_cpu)
     dt = time.perf_counter() - t0
-    return frames_per_call * calls / dt, dt / calls
-
-
-DTYPES = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+    return cms_cpu.shape[0] * calls / dt, dt / calls
 
 
 def make_inputs(dev, n_batches: int, seed0: int, dtype=torch.float32):
@@ -177,59 +270,105 @@ def make_inputs(dev, n_batches: int, seed0: int, dtype=torch.float32):
 
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank: int):
+    """The reference's own CPU implementation on the host cores: same config, all 64 frames of a batch per step.
+    Inputs come from the oracle's CPU renderer, so this process never maps libsleapnn_b200.so."""
     if rank != 0:
         return
-    from sleap_nn_b200 import synthetic
+    from oracle import synth as osynth
 
-    frames_per_step = 16  # bounded sample of the workload: 16 of the batch's 64 frames per step
-    edges = synthetic.chain_edges(N_NODES)
-    if torch.cuda.is_available():
-        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
-        poses = synthetic.random_poses(1000, frames_per_step, N_INST, N_NODES, IMG_HW, edges)
-        cms, pafs = synthetic.render_batch(poses, IMG_HW, STRIDE, edges, dev, seed=1000)
-        cms_cpu, pafs_cpu = cms.cpu(), pafs.cpu()
-        del cms, pafs
-    else:  # CPU-only box: render with the oracle's own target code
-        from oracle import synth as osynth
-
-        poses = osynth.make_poses(1000, frames_per_step, N_INST, N_NODES, IMG_HW, edges=edges)
-        cms_cpu, pafs_cpu = osynth.render(poses, IMG_HW, STRIDE, edges, seed=1000)
-    torch.set_num_threads(os.cpu_count() or 1)
-    for _ in range(max(args.warmup - 1, 0)):
-        oracle_postproc(cms_cpu, pafs_cpu, edges)
+    edges = osynth.chain_edges(N_NODES)
+    poses = osynth.make_poses(1000, B, N_INST, N_NODES, IMG_HW, edges=edges)
+    cms_cpu, pafs_cpu = osynth.render(poses, IMG_HW, STRIDE, edges, seed=1000)
+    fn, kind, what = cpu_arm(edges)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = B
     t1 = time.perf_counter()
-    oracle_postproc(cms_cpu, pafs_cpu, edges)
+    fn(cms_cpu, pafs_cpu)
     t1 = time.perf_counter() - t1
-    # keep the whole --steps run within a few minutes whatever K the caller picks: halve the per-step sample if needed
-    while frames_per_step > 1 and t1 * args.steps > 150.0:
-        frames_per_step //= 2
+    # keep the whole --steps + --warmup run within a few minutes whatever K the caller picks
+    while frames > 1 and t1 * (args.steps + args.warmup) > 240.0:
+        frames //= 2
         t1 /= 2
-        cms_cpu, pafs_cpu = cms_cpu[:frames_per_step], pafs_cpu[:frames_per_step]
+    c, p = cms_cpu[:frames], pafs_cpu[:frames]
+    for _ in range(max(args.warmup - 1, 0)):
+        fn(c, p)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_postproc(cms_cpu, pafs_cpu, edges)
+        out = fn(c, p)
     dt = time.perf_counter() - t0
-    fps = frames_per_step * args.steps / dt
-    sample = f"{frames_per_step} frames/step of the cfg3 batch, {args.steps} steps, torch CPU ops, {torch.get_num_threads()} threads"
-    emit(({
+    fps = frames * args.steps / dt
+    n_inst = sum(len(x) for x in out[0])
+    fn(c, p, stages=True)
+    stages = dict(fn.stage_s)
+    fps1, _ = time_cpu(fn, cms_cpu[:8], pafs_cpu[:8], 2, 1, warm=1)
+    torch.set_num_threads(cores)
+    sample = (f"{frames} frames/step" + (" (the whole cfg3 batch)" if frames == B else " (reduced to fit the time budget)")
+              + f", {args.steps} steps, {what}, {cores} threads")
+    emit({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, frames_per_step=frames_per_step),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": shared_config(args.gpus),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "one_thread": {"value": fps1, "unit": UNIT, "sample": "2 x 8 frames, torch.set_num_threads(1)"},
+                         "stage_seconds_per_step": stages, "frames_per_step": frames,
+                         "instances_found_last_step": n_inst, "instances_planted_per_step": frames * N_INST},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference is pure Python/ATen with no native path and cannot be installed offline (needs sleap-io, "
-                "lightning, omegaconf): this arm times oracle/, the CPU port of its op chain, on the host cores; in the build "
-                "container (8 cores) the port runs this chain 2.9x FASTER than the unmodified reference files (99 vs 34 "
-                "frames/s), so the baseline errs in the reference's favour",
-    }))
+    })
+
+
+# --------------------------------------------------------------------------- extras (N = 1): the other BASELINE configs
+def run_extras(dev, iters: int):
+    """Per-kernel roofline lines for the BASELINE configs the headline does not cover, measured in THIS run (outside the
+    headline's timed region): CUDA events on the launching stream, rotating buffers larger than L2 (tools/bench_kernels.py)."""
+    from tools import bench_kernels as bk
+
+    bk.QUIET = True
+    out = {}
+    plan = [
+        ("k1_cfg3_f16", lambda: bk.k1_cfg3(dev, iters, torch.float16)),
+        ("k1_cfg3_bf16", lambda: bk.k1_cfg3(dev, iters, torch.bfloat16)),
+        ("k2_cfg2", lambda: bk.k2_cfg2(dev, iters)),
+        ("k2_cfg2_b1024", lambda: bk.k2_cfg2(dev, iters, 1024)),
+        ("k2_cfg2_f16", lambda: bk.k2_cfg2(dev, iters, 256, torch.float16)),
+        ("k7_cfg4_g8", lambda: bk.k7_cfg4(dev, iters)),
+        ("k7_cfg4_g8_bf16", lambda: bk.k7_cfg4(dev, iters, True)),
+        ("k7_cfg4_g1", lambda: bk.k7_cfg4(dev, iters, False, 1)),
+        ("k7_cfg4_g1_bf16", lambda: bk.k7_cfg4(dev, iters, True, 1)),
+        ("k8_cfg4_g8", lambda: bk.k8_cfg4(dev, iters, False, 8)),
+        ("k8_cfg4_g8_bf16", lambda: bk.k8_cfg4(dev, iters, True, 8)),
+        ("k8_cfg4_g1", lambda: bk.k8_cfg4(dev, iters, False, 1)),
+        ("k8_cfg4_g1_bf16", lambda: bk.k8_cfg4(dev, iters, True, 1)),
+    ]
+    if hasattr(bk, "targets_cfg4_fused"):
+        plan += [("targets_cfg4_fused_g1", lambda: bk.targets_cfg4_fused(dev, iters)),
+                 ("targets_cfg4_fused_g1_bf16", lambda: bk.targets_cfg4_fused(dev, iters, True))]
+    keep = ("kernel", "algorithmic_bytes_per_launch", "avg_launch_ms", "achieved_GBps", "frac")
+    for name, fn in plan:
+        try:
+            d = fn()
+            out[name] = {k: d[k] for k in keep}
+        except Exception as e:  # noqa: BLE001 - one failing config must not hide the others
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    try:
+        n0 = len(bk.RESULTS)
+        bk.chain_cfg4(dev, min(iters, 60))
+        for d in bk.RESULTS[n0:]:
+            out[d["bench"]] = {k: d[k] for k in d if k in keep + ("frames_per_s", "instances_found", "instances_planted")}
+    except Exception as e:  # noqa: BLE001
+        out["chain_cfg4"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------- our arm
 def run_ours(args, rank: int, world: int):
     import torch.distributed as dist
 
-    from sleap_nn_b200.pipeline import BottomUpPostproc
+    from sleap_nn_b200 import _native as NN
+    from sleap_nn_b200.pipeline import BottomUpHostStream, BottomUpPostproc
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -244,14 +383,15 @@ def run_ours(args, rank: int, world: int):
     n_bufs, n_streams = args.buffers, args.streams
     dtype = DTYPES[args.dtype]
     esz = 4 if dtype == torch.float32 else 2
-    algo_bytes_per_frame = esz * N_NODES * 512 * 512
+    algo_bytes_per_frame = esz * N_NODES * 512 * 512  # K1 reads every confidence-map element once
     edges, inputs = make_inputs(dev, n_bufs, seed0=100 * (rank + 1), dtype=dtype)
+    make_pipe = lambda **kw: BottomUpPostproc(N_NODES, edges, B, (512, 512), cms_stride=STRIDE, pafs_stride=STRIDE,
+                                              device=dev, **kw)
     # `--streams` pipeline instances, each with its own tables: instance i's detect kernel runs on the
     # (single) detect stream, its per-frame tail on the high-priority tail stream, so tail(i) overlaps
     # detect(i+1) and the step time tends to the HBM time of the confidence maps.
     tail_stream = torch.cuda.Stream(device=dev, priority=-1) if args.tail_stream else None
-    pipes = [BottomUpPostproc(N_NODES, edges, B, (512, 512), cms_stride=STRIDE, pafs_stride=STRIDE, device=dev,
-                              tail_stream=tail_stream, keep_tables=not args.lean) for _ in range(n_streams)]
+    pipes = [make_pipe(tail_stream=tail_stream, keep_tables=not args.lean) for _ in range(n_streams)]
     if tail_stream is not None:
         det = torch.cuda.Stream(device=dev)
         streams = [det for _ in range(n_streams)]
@@ -271,10 +411,20 @@ def run_ours(args, rank: int, world: int):
                 cms, pafs = inputs[i % n_bufs]
                 pipes[s](cms, pafs, detect_events=None if events is None else events[i])
 
-    # ---- correctness guard: the timed configuration must produce the planted animals
+    # ---- correctness guard on the timed configuration.  fp32: every planted animal comes back.  Half-precision maps:
+    # quantisation can turn a blob's top into a two-pixel plateau (no strict maximum - in the reference too), so the
+    # guard is that the natively-read chain equals the fp32 chain on the exact up-cast copy, bit for bit.
     res = pipes[0](*inputs[0])
-    inst, _, _ = res.to_lists()
-    assert sum(len(x) for x in inst) == B * N_INST, "pipeline did not recover the planted instances"
+    inst, _, sc0 = res.to_lists()
+    if dtype == torch.float32:
+        assert sum(len(x) for x in inst) == B * N_INST, "pipeline did not recover the planted instances"
+    else:
+        up = make_pipe()
+        inst32, _, sc32 = up(inputs[0][0].float(), inputs[0][1].float()).to_lists()
+        same_xy = all(a.shape == b_.shape and bool(((a == b_) | (a.isnan() & b_.isnan())).all()) for a, b_ in zip(inst, inst32))
+        assert same_xy and all(torch.equal(a, b_) for a, b_ in zip(sc0, sc32)), \
+            "native half-precision chain differs from the fp32 chain on the up-cast maps"
+        del up
 
     # ---- device-resident timed region (value).  Default: the eager multi-stream loop (one ctypes call per step).
     # --graph: rotations of the pipeline are captured in a CUDA graph and replayed (one host launch per replay).
@@ -328,19 +478,22 @@ def run_ours(args, rank: int, world: int):
         s.wait_stream(main)
     run_steps(len(ev), ev)
     torch.cuda.synchronize(dev)
-    ms_total = t_begin.elapsed_time(t_end)
+    ms_local = t_begin.elapsed_time(t_end)
+    ms_total = ms_local
     detect_ms = [a.elapsed_time(b) for a, b in ev]
+    per_rank_ms = [ms_local / args.steps]
     if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        t = torch.tensor([ms_local], device=dev)
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_ms = [float(g.item()) / args.steps for g in gathered]
+        ms_total = max(float(g.item()) for g in gathered)
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- the dominant kernel alone (same process, same inputs, rotating batches): roofline.achieved
-    from sleap_nn_b200 import _native as NN
-
     pipe0 = pipes[0]
-    iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 200))]
+    iso = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(min(max(args.steps, 50), 200))]
     for a_, b_ in iso:
         a_.record(main); b_.record(main)
     torch.cuda.synchronize(dev)
@@ -348,10 +501,10 @@ def run_ours(args, rank: int, world: int):
     def detect_only(i, evs=None):
         cms = inputs[i % n_bufs][0]
         sb_, sc_, sh_, sw_ = cms.stride()
-        NN.check(NN.lib.snb_local_peaks_detect_t(NN.ptr(cms), NN.dtype_code(cms.dtype), B, N_NODES, 512, 512, sb_, sc_, sh_, sw_, 0.2,
-                                               pipe0.caps["peak_cap"], NN.ptr(pipe0.buf["frame_count"]),
-                                               NN.ptr(pipe0.buf["keys"]), evs[0].cuda_event if evs else None,
-                                               evs[1].cuda_event if evs else None, NN.stream_ptr(dev)), "detect")
+        NN.check(NN.lib.snb_local_peaks_detect_t(NN.ptr(cms), NN.dtype_code(cms.dtype), B, N_NODES, 512, 512, sb_, sc_,
+                                                 sh_, sw_, 0.2, pipe0.caps["peak_cap"], NN.ptr(pipe0.buf["frame_count"]),
+                                                 NN.ptr(pipe0.buf["keys"]), evs[0].cuda_event if evs else None,
+                                                 evs[1].cuda_event if evs else None, NN.stream_ptr(dev)), "detect")
 
     for i in range(5):
         detect_only(i)
@@ -365,11 +518,12 @@ def run_ours(args, rank: int, world: int):
     # copied pinned-host -> device every step; the PAF tensor is only sampled (20 taps per candidate), so it is
     # read in place from pinned host memory over PCIe (zero-copy) and only the sampled 32-byte sectors cross the link.
     host = [(c.cpu().pin_memory(), p.cpu().pin_memory()) for c, p in inputs[: min(2, n_bufs)]]
-    from sleap_nn_b200.pipeline import BottomUpHostStream
-
-    hs = BottomUpHostStream(lambda: BottomUpPostproc(N_NODES, edges, B, (512, 512), cms_stride=STRIDE, pafs_stride=STRIDE,
-                                                     device=dev, keep_tables=True), depth=args.e2e_depth,
+    hs = BottomUpHostStream(lambda: make_pipe(keep_tables=True), depth=args.e2e_depth,
                             zero_copy_pafs=not args.copy_pafs, zero_copy_cms=args.zero_copy_cms)
+    want_per_host = []  # what each host batch must yield: exactly what the resident chain yields for it
+    for k in range(len(host)):
+        r_ = pipes[0](*inputs[k]).to_lists()
+        want_per_host.append(sum(len(x) for x in r_[0]))
     for i in range(3):
         hs.submit(*host[i % len(host)])
     hs.drain()
@@ -392,53 +546,118 @@ def run_ours(args, rank: int, world: int):
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3  # host clock: the region ends when the last result is unpacked on the host
     barrier()
-    assert n_got == e2e_steps * B * N_INST, "host path did not recover the planted instances"
+    assert n_got == sum(want_per_host[i % len(host)] for i in range(e2e_steps)), "host path lost instances"
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+    zero_copy_pafs, zero_copy_cms = hs.last_zero_copy, getattr(hs, "last_zero_copy_cms", False)
+    paf_host_bytes = host[0][1].numel() * esz
+    del hs, host
+
+    # ---- N > 1: the same steps through ShardRunner (results packed on the device, no host sync inside the shard) and
+    # the one collective of the design, the end-of-shard gather of the variable-length instance lists
+    gather = None
+    if world > 1:
+        from sleap_nn_b200 import sharding
+
+        total_frames = world * B * args.steps
+        src = lambda s, e: inputs[((s // B) % n_bufs)]
+        sharding.ShardRunner(pipes[0], total_frames, rank, world).run(src).finish()  # warm-up (pack kernel load)
+        runner = sharding.ShardRunner(pipes[0], total_frames, rank, world)
+        barrier()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        g0.record(main)
+        runner.run(src)
+        g1.record(main)
+        local_res = runner.finish()
+        merged = sharding.gather_packed(local_res)
+        g2.record(main)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([g0.elapsed_time(g1), g1.elapsed_time(g2)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        payload = merged.rows * (N_NODES * 2 * 4 + N_NODES * 4 + 4 + 4) + merged.n_frames * 4
+        gather = {"shard_run_ms": float(t[0]), "gather_ms": float(t[1]), "rows_gathered": merged.rows,
+                  "frames": merged.n_frames, "payload_bytes": payload,
+                  "frames_per_s_incl_pack_and_gather": total_frames / ((float(t[0]) + float(t[1])) / 1e3),
+                  "note": "ShardRunner on one stream: chain + snb_pack_instances per batch; then finish() (the one host "
+                          "sync) + gather_packed (all_gather of counts, then of the padded payloads, NCCL)"}
 
     if rank == 0:
         peak, which = measured_peaks()
         avg_detect_ms = sum(iso_ms) / len(iso_ms)
         insitu_ms = sum(detect_ms) / len(detect_ms)
         achieved = algo_bytes_per_frame * B / (avg_detect_ms / 1e3) / 1e9
+        kernel = {"f32": "local_peaks_detect_vec<float,4,1,6>", "f16": "local_peaks_detect_vec<__half,2,2,6>",
+                  "bf16": "local_peaks_detect_vec<__nv_bfloat16,2,2,6>"}[args.dtype]
+        traffic, traffic_rec = recorded_traffic(kernel)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": dict(WORKLOAD, parallelism=f"frame-sharded x{world}, no collective", streams=n_streams,
-                           input_batches=n_bufs, l2="inputs larger than L2: each batch is 872 MB and batches rotate",
-                           tail="fused per-frame tail kernel" + (" on a high-priority second stream" if tail_stream is not None else ""),
-                           intermediate_tables_written=not args.lean,
-                           launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop"),
+            "dtype": args.dtype, "data": "synthetic", "config": shared_config(world, args.dtype),
+            "run": dict(streams=n_streams, input_batches=n_bufs,
+                        tail="fused per-frame tail kernel" + (" on a high-priority second stream" if tail_stream is not None else ""),
+                        intermediate_tables_written=not args.lean,
+                        launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop",
+                        per_rank_ms_per_step={"min": min(per_rank_ms), "median": statistics.median(per_rank_ms),
+                                              "max": max(per_rank_ms), "all": per_rank_ms}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "in_flight": args.e2e_depth,
                     "cms": ("streamed by the detect kernel straight from pinned host memory (zero-copy)"
-                            if getattr(hs, "last_zero_copy_cms", False) else "cudaMemcpyAsync pinned host -> HBM staging buffer"),
+                            if zero_copy_cms else "cudaMemcpyAsync pinned host -> HBM staging buffer"),
                     "host_cpus_rank0": ("all" if host_cpus is None else f"{len(host_cpus)} CPUs local to the GPU"),
                     "pafs": ("sampled in place from pinned host memory (zero-copy): "
-                             f"{paf_sector_bytes} B of 32-byte sectors per step instead of {host[0][1].numel() * esz} B"
-                             if hs.last_zero_copy else "copied to the device every step")},
+                             f"{paf_sector_bytes} B of 32-byte sectors per step instead of {paf_host_bytes} B"
+                             if zero_copy_pafs else "copied to the device every step")},
             "gpu_launches": pipes[0].launches_per_call * args.steps, "host_issue_us_per_step": host_issue_us,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 338793984, "kernel": "local_peaks_detect_vec4<4,1,6>", "peak_source": which,
+                         "traffic": traffic, "traffic_record": traffic_rec, "kernel": kernel, "peak_source": which,
                          "algorithmic_bytes_per_launch": algo_bytes_per_frame * B, "avg_launch_ms": avg_detect_ms,
                          "how": "CUDA events recorded by the C ABI right around the kernel, kernel running alone, "
-                                "rotating 872 MB batches; traffic = dram__bytes_read.sum 335598848 + dram__bytes_write.sum 3195136 per "
-                                "launch from one ncu --set full capture (profiles/r1_d_detect_tail_ncu_raw.txt)",
+                                "rotating batches larger than L2; traffic = dram__bytes_read.sum + dram__bytes_write.sum per "
+                                "launch from the committed ncu --set full capture named in traffic_record",
                          "in_situ_avg_launch_ms": insitu_ms,
                          "in_situ_note": "same events inside the timed region; inflated when two streams overlap two detect kernels",
                          "whole_step_frac": (algo_bytes_per_frame * B / (ms_total / args.steps / 1e3) / 1e9) / peak},
             "clocks": clocks.summary(),
         }
+        if gather is not None:
+            line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
-            cms_cpu, pafs_cpu = inputs[0][0][:16].float().cpu(), inputs[0][1][:16].float().cpu()
-            fps, per_call = time_cpu_port(cms_cpu, pafs_cpu, edges, 16, args.cpu_calls)
-            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{args.cpu_calls} x 16 frames of the same cfg3 batch ({per_call:.2f} s/call), "
-                                              "oracle/ torch-CPU port of the reference chain"}
+            # the CPU arm on 16 frames of the batch the GPU just processed, and - for free - the parity of the two
+            n_chk = 16
+            cms_cpu, pafs_cpu = inputs[0][0][:n_chk].float().cpu(), inputs[0][1][:n_chk].float().cpu()
+            fn, kind, what = cpu_arm(edges)
+            cores = os.cpu_count() or 1
+            fps, per_call = time_cpu(fn, cms_cpu, pafs_cpu, args.cpu_calls, cores)
+            fps1, _ = time_cpu(fn, cms_cpu[:8], pafs_cpu[:8], 1, 1, warm=0)
+            torch.set_num_threads(cores)
+            fn(cms_cpu, pafs_cpu, stages=True)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{args.cpu_calls} x {n_chk} frames of the same cfg3 batch ({per_call:.2f} s/call), {what}",
+                                    "one_thread": {"value": fps1, "unit": UNIT, "sample": "8 frames, torch.set_num_threads(1)"},
+                                    "stage_seconds_per_call": dict(fn.stage_s)}
+            want = oracle_postproc(cms_cpu, pafs_cpu, edges)
+            got = pipes[0](*inputs[0]).to_lists()
+            max_px = max_sc = 0.0
+            same = True
+            for b in range(n_chk):
+                g_xy, w_xy = got[0][b], want[0][b]
+                g_pv, w_pv = got[1][b], want[1][b]  # peak values: bit-exact, NaN (a missing node) == NaN
+                ok = (g_xy.shape == w_xy.shape and bool((g_xy.isnan() == w_xy.isnan()).all())
+                      and bool(((g_pv == w_pv) | (g_pv.isnan() & w_pv.isnan())).all()))
+                same = same and ok
+                if ok and g_xy.numel():
+                    max_px = max(max_px, float((g_xy - w_xy).abs().nan_to_num(0.0).max()))
+                    max_sc = max(max_sc, float((got[2][b] - want[2][b]).abs().max()))
+            line["parity"] = {"parity_checked_frames": n_chk, "instances_and_peak_values_identical": same,
+                              "max_abs_px": max_px, "max_score_err": max_sc,
+                              "against": "oracle/ (the CPU restatement pinned to the reference's goldens) on the same maps"}
+            assert same and max_px <= 1e-4 and max_sc <= 1e-5, f"GPU result differs from the oracle: {line['parity']}"
+        if world == 1 and not args.no_extras:
+            torch.cuda.empty_cache()
+            line["extra"] = run_extras(dev, args.extra_iters)
         emit(line)
     if world > 1:
         dist.barrier()
@@ -457,8 +676,10 @@ def main():
     ap.add_argument("--buffers", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-depth", type=int, default=2, help="batches in flight in the host-buffer pipeline (BottomUpHostStream)")
-    ap.add_argument("--cpu-calls", type=int, default=8)
+    ap.add_argument("--cpu-calls", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` block (the other BASELINE configs)")
+    ap.add_argument("--extra-iters", type=int, default=100)
     ap.add_argument("--graph-repeats", type=int, default=20, help="rotations of the pipeline captured per CUDA graph")
     ap.add_argument("--graph", action="store_true",
                     help="replay CUDA graphs of --graph-repeats pipeline rotations instead of the eager launch loop (one host "
@@ -484,7 +705,7 @@ def main():
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU port)")
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     if world != args.gpus and world == 1 and args.gpus > 1:
         # convenience: `python bench.py --gpus N` re-launches itself under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",

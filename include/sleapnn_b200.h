@@ -551,9 +551,14 @@ typedef struct snb_bottomup_args {
   /* ---- ABI v5: SNB_DTYPE_* of the two input tensors (0 = fp32).  Half-precision heads are read in place. */
   int cms_dtype;
   int pafs_dtype;
+  /* SNB_FLAG_SELF_RESET_COUNTERS (fused tail only): frame_count must be all zero before the FIRST call; every call's
+   * tail copies frame b's true peak count to n_peaks[b] and zeroes frame_count[b] again, so the chain is exactly two
+   * kernel launches with no memset node in between. */
+  int* n_peaks;
 } snb_bottomup_args;
 
 #define SNB_FLAG_UNFUSED_TAIL 1 /* chain the stand-alone kernels instead of the fused per-frame tail */
+#define SNB_FLAG_SELF_RESET_COUNTERS 2 /* see snb_bottomup_args.n_peaks */
 
 /* The tail (everything after the streaming detect kernel) runs as ONE CTA per frame with all tables
  * in shared memory when snb_bottomup_tail_smem_bytes(...) <= 200 KB; the intermediate tables

@@ -103,6 +103,7 @@ SIGNATURES = {
 RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_class_inds_workspace_bytes": [_i, _i],
                    "snb_class_inds_grouped_workspace_bytes": [_i, _i, _i], "snb_topdown_select_smem_bytes": [_i, _i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
 FLAG_UNFUSED_TAIL = 1
+FLAG_SELF_RESET_COUNTERS = 2
 
 
 class BottomUpArgs(C.Structure):
@@ -128,7 +129,7 @@ class BottomUpArgs(C.Structure):
         ("tail_stream", _p), ("ev_handoff", _p), ("ev_tail_done", _p), ("flags", _i),
         ("max_peaks_per_node", _i), ("skip_flag", _p), ("max_instances", _i), ("input_scale", _f),
         ("eff_scale", _p), ("out_kpts", _p), ("out_vals", _p), ("out_scores", _p),
-        ("cms_dtype", _i), ("pafs_dtype", _i),
+        ("cms_dtype", _i), ("pafs_dtype", _i), ("n_peaks", _p),
     ]
 
 

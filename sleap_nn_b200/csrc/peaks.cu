@@ -57,60 +57,54 @@ __device__ __forceinline__ void emit_peak(int* __restrict__ frame_count, uint32_
 
 template <typename T, int UNROLL, int ROWS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
-local_peaks_detect_vec(const T* __restrict__ cms, int n_rows, int C, int H, int W, long long sb, long long sc,
-                       long long sh, float thr, int cap, int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
-  // One warp owns ROWS consecutive map rows per iteration and issues all of their 128-bit loads
-  // (ROWS * UNROLL per lane) before looking at any value: that is the memory-level parallelism
-  // that keeps HBM busy.  32-bit index math (the host guarantees n_rows < 2^31).  A 128-bit load holds
-  // PER = 4 fp32 or 8 fp16 / bf16 elements; half-precision maps are compared on their exact fp32 values.
+local_peaks_detect_vec(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
+                       float thr, int cap, int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
+  // grid = (row groups of a plane, C, B): a CTA's 8 warps own 8 * ROWS consecutive rows of ONE plane, so the plane
+  // and the row come straight from the block / warp index - no integer division anywhere (with a flat row index the
+  // div / mod by H and C was ~100 of a warp's ~165 instructions, and a warp only lives for one 2 KB step).  A warp
+  // issues all of its 128-bit loads (ROWS * UNROLL per lane per step) before looking at any value: that is the
+  // memory-level parallelism that keeps HBM busy.  A 128-bit load holds PER = 4 fp32 or 8 fp16 / bf16 elements;
+  // half-precision maps are compared on their exact fp32 values.
   constexpr int PER = Elem<T>::PER16;
-  const typename Elem<T>::Thr tv = Elem<T>::make_thr(thr);
   const int lane = lane_id();
-  const int warps_per_block = blockDim.x >> 5;
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int y0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (y0 >= H) return;
+  const T* plane = cms + (long long)b * sb + (long long)c * sc;
   const int WV = W / PER;
-  const int stride_rows = gridDim.x * warps_per_block * ROWS;
-  for (int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * ROWS; row0 < n_rows; row0 += stride_rows) {
-    const T* rowp[ROWS];
+  const typename Elem<T>::Thr tv = Elem<T>::make_thr(thr);
+  for (int xv = lane; xv < WV; xv += 32 * UNROLL) {
+    uint4 v[ROWS][UNROLL];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
-      const int row = min(row0 + r, n_rows - 1);
-      const int y = row % H, pc = row / H;
-      rowp[r] = cms + (long long)(pc / C) * sb + (long long)(pc % C) * sc + (long long)y * sh;
+      const T* rowp = plane + (long long)min(y0 + r, H - 1) * sh;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xxv = xv + 32 * u;
+        if (xxv < WV) v[r][u] = ldg_stream16(rowp + PER * xxv);
+      }
     }
-    for (int xv = lane; xv < WV; xv += 32 * UNROLL) {
-      uint4 v[ROWS][UNROLL];
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r) {
+      const int y = y0 + r;
+      if (y >= H) break;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          const int xxv = xv + 32 * u;
-          if (xxv < WV) v[r][u] = ldg_stream16(rowp[r] + PER * xxv);
-        }
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xxv = xv + 32 * u;
+        if (xxv >= WV) continue;
+        if (!Elem<T>::any_gt(v[r][u], tv)) continue;
+        float e[PER];  // rare path: a value above the threshold
+        Elem<T>::unpack(v[r][u], e);
 #pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        if (row0 + r >= n_rows) break;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-          const int xxv = xv + 32 * u;
-          if (xxv >= WV) continue;
-          if (!Elem<T>::any_gt(v[r][u], tv)) continue;
-          float e[PER];
-          Elem<T>::unpack(v[r][u], e);
-          const int row = row0 + r;  // rare path: recover (b, c, y) for this row
-          const int y = row % H, pc = row / H;
-          const int c = pc % C, b = pc / C;
-          const T* plane = cms + (long long)b * sb + (long long)c * sc;
-#pragma unroll
-          for (int k = 0; k < PER; ++k) {
-            // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same
-            // 128-bit word are already in registers, and a strict maximum must beat them too (same `v > nb`
-            // predicate, so NaN neighbours reject as in the reference).  On a blob's row only the ridge pixel
-            // (and at most the word-boundary pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads
-            // on busy maps (cfg4: 256 blobs per frame).
-            if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == PER - 1 || e[k] > e[k + 1])) {
-              const int x = PER * xxv + k;
-              if (is_strict_max<T>(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
-            }
+        for (int k = 0; k < PER; ++k) {
+          // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same
+          // 128-bit word are already in registers, and a strict maximum must beat them too (same `v > nb`
+          // predicate, so NaN neighbours reject as in the reference).  On a blob's row only the ridge pixel
+          // (and at most the word-boundary pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads
+          // on busy maps (cfg4: 256 blobs per frame).
+          if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == PER - 1 || e[k] > e[k + 1])) {
+            const int x = PER * xxv + k;
+            if (is_strict_max<T>(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
           }
         }
       }
@@ -1027,33 +1021,30 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
     }
   }
 #endif
-  if (vec && rows < 0x7fffffffLL) {
-    // grid-stride kernel, 8 warps per CTA; the variant (128-bit loads in flight per lane, CTAs per SM) is picked by
-    // the number of 128-bit vectors per row.  One row per warp with 4 loads per lane for >= 128 vectors (fp32 W >= 512,
+  if (vec && B <= 65535 && C <= 65535) {
+    // 8 warps per CTA; the variant (128-bit loads in flight per lane, rows per warp, CTAs per SM) is picked by the
+    // number of 128-bit vectors per row.  One row per warp with 4 loads per lane for >= 128 vectors (fp32 W >= 512,
     // half W >= 1024), 40 registers -> 6 CTAs = 48 warps per SM, and a NON-persistent grid so the hardware CTA
-    // scheduler balances the SMs: measured on B200, cfg3 fp32 batch: 53.1 us = 6.3 TB/s.  Rows of 64..127 vectors
-    // (half-precision cfg3 maps: 512 x 2 B = 1 KB) take two rows of two loads each so that a lane still has
-    // 4 x 16 B in flight.
-    const int n_rows = (int)rows;
+    // scheduler balances the SMs.  Rows of 64..127 vectors (half-precision cfg3 maps: 512 x 2 B = 1 KB) take two
+    // rows of two loads each so that a lane still has 4 x 16 B in flight.
     const int vecs = W / PER;
     int variant = (vecs >= 128) ? 0 : (vecs >= 64 ? (PER == 8 ? 6 : 1) : 2);
 #ifdef SNB_AB_VARIANTS
     static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
     if (forced >= 0) variant = forced;
 #endif
-#define SNB_DETECT(U, R, MB, CTAS)                                                                              \
-  local_peaks_detect_vec<T, U, R, MB><<<grid_for((rows + R - 1) / R, 8, sm_count() * CTAS), 256, 0, st>>>(       \
-      cms, n_rows, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys)
+#define SNB_DETECT(U, R, MB)                                                                                          \
+  local_peaks_detect_vec<T, U, R, MB><<<dim3((unsigned)((H + 8 * R - 1) / (8 * R)), (unsigned)C, (unsigned)B), 256, 0, st>>>( \
+      cms, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys)
     switch (variant) {
-      case 0: SNB_DETECT(4, 1, 6, 100000); break;  // >= 128 vectors per row
-      case 1: SNB_DETECT(2, 1, 8, 100000); break;  // 64..127 vectors per row (fp32)
-      case 6: SNB_DETECT(2, 2, 6, 100000); break;  // 64..127 vectors per row (fp16 / bf16): two rows per warp
-      case 2: SNB_DETECT(1, 4, 6, 100000); break;  // narrow maps: four rows of one load each
+      case 0: SNB_DETECT(4, 1, 6); break;  // >= 128 vectors per row
+      case 1: SNB_DETECT(2, 1, 8); break;  // 64..127 vectors per row (fp32)
+      case 6: SNB_DETECT(2, 2, 6); break;  // 64..127 vectors per row (fp16 / bf16): two rows per warp
+      case 2: SNB_DETECT(1, 4, 6); break;  // narrow maps: four rows of one load each
 #ifdef SNB_AB_VARIANTS
-      case 3: SNB_DETECT(4, 1, 4, 4); break;       // A/B: persistent single wave, 60 registers (57.1 us)
-      case 4: SNB_DETECT(4, 2, 4, 4); break;       // A/B: 8 loads per lane (66.6 us)
-      case 5: SNB_DETECT(4, 4, 2, 2); break;       // A/B: 16 loads per lane, 2 CTAs / SM (95.1 us)
-      case 7: SNB_DETECT(2, 4, 4, 100000); break;  // A/B: four rows of two loads
+      case 4: SNB_DETECT(4, 2, 4); break;  // A/B: 8 loads per lane
+      case 7: SNB_DETECT(2, 4, 4); break;  // A/B: four rows of two loads
+      case 8: SNB_DETECT(2, 1, 8); break;  // A/B: one row of two loads, 8 CTAs / SM
 #endif
       default: return SNB_ERR_BAD_ARG;
     }
@@ -1065,16 +1056,17 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
   return SNB_OK;
 }
 
-// K1a: zero the per-frame counters and run the streaming detect kernel.  ev_begin / ev_end are
-// optional cudaEvent_t handles recorded right around the kernel (in-situ timing for benchmarks).
-extern "C" int snb_local_peaks_detect_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb,
-                                        long long sc, long long sh, long long sw, float threshold, int cap,
-                                        int* frame_count, uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
+namespace snb {
+// K1a launcher shared with the fused pipeline (pipeline.cu): zero_counters = false when the caller guarantees that
+// frame_count is already zero (the fused tail resets it, SNB_FLAG_SELF_RESET_COUNTERS).
+int detect_launch(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                  long long sw, float threshold, int cap, int* frame_count, uint32_t* keys, void* ev_begin, void* ev_end,
+                  void* stream_, bool zero_counters) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (B < 0 || C <= 0 || H <= 0 || W <= 0 || cap <= 0 || !dtype_ok(dtype)) return SNB_ERR_BAD_ARG;
   if ((double)H * W * C >= 4294967295.0) return SNB_ERR_UNSUPPORTED;
   if (B == 0) return SNB_OK;
-  if (cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+  if (zero_counters && cudaMemsetAsync(frame_count, 0, sizeof(int) * B, st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
   if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, st);
   int rc;
   switch (dtype) {
@@ -1091,6 +1083,16 @@ extern "C" int snb_local_peaks_detect_t(const void* cms, int dtype, int B, int C
   if (ev_end) cudaEventRecord((cudaEvent_t)ev_end, st);
   SNB_LAUNCH_CHECK();
   return SNB_OK;
+}
+}  // namespace snb
+
+// K1a: zero the per-frame counters and run the streaming detect kernel.  ev_begin / ev_end are
+// optional cudaEvent_t handles recorded right around the kernel (in-situ timing for benchmarks).
+extern "C" int snb_local_peaks_detect_t(const void* cms, int dtype, int B, int C, int H, int W, long long sb,
+                                        long long sc, long long sh, long long sw, float threshold, int cap,
+                                        int* frame_count, uint32_t* keys, void* ev_begin, void* ev_end, void* stream_) {
+  return detect_launch(cms, dtype, B, C, H, W, sb, sc, sh, sw, threshold, cap, frame_count, keys, ev_begin, ev_end,
+                       stream_, true);
 }
 
 extern "C" int snb_local_peaks_detect(const float* cms, int B, int C, int H, int W, long long sb, long long sc,

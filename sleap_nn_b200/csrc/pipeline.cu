@@ -15,6 +15,10 @@
 
 namespace snb {
 
+int detect_launch(const void* cms, int dtype, int B, int C, int H, int W, long long sb, long long sc, long long sh,
+                  long long sw, float threshold, int cap, int* frame_count, uint32_t* keys, void* ev_begin, void* ev_end,
+                  void* stream_, bool zero_counters);  // peaks.cu
+
 struct TailLayout {
   int keys, xy, val, chan, ns, cursor, np, eo, mo, score, m_edge, m_src, m_dst, m_score, lsap, owner, order, idc, idr,
       flags, edges, sorted, ttab, total;
@@ -281,6 +285,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     assemble_frame_warp(f, lane);
   }
   SNB_STAMP(5);
+  // self-resetting peak counter: every thread read `total` before the first barrier above, so the counter can go back
+  // to zero for the next call's detect kernel (no memset node in the chain)
+  if ((a.flags & SNB_FLAG_SELF_RESET_COUNTERS) && tid == 0) {
+    a.n_peaks[b] = total;
+    a.frame_count[b] = 0;
+  }
 }
 
 // Padded per-frame instance tables -> packed rows appended at a DEVICE-side running offset, so that a
@@ -429,18 +439,21 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
   // buffers of this pipeline instance may still be read by its previous tail
   if (a->tail_stream && a->ev_tail_done) cudaStreamWaitEvent(st, (cudaEvent_t)a->ev_tail_done, 0);
   if (a->skip_flag && cudaMemsetAsync(a->skip_flag, 0, sizeof(int), st) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
-  int rc = snb_local_peaks_detect_t(a->cms, a->cms_dtype, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh,
-                                    a->cms_sw, a->peak_threshold, a->peak_cap, a->frame_count, a->keys,
-                                    a->ev_detect_begin, a->ev_detect_end, stream);
+  const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
+                                                      a->n_points);
+  const bool fused = !(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024;
+  const bool self_reset = (a->flags & SNB_FLAG_SELF_RESET_COUNTERS) != 0;
+  if (self_reset && (!fused || !a->n_peaks)) return SNB_ERR_BAD_ARG;  // only the fused tail resets the counters
+  int rc = detect_launch(a->cms, a->cms_dtype, a->B, a->C, a->H, a->W, a->cms_sb, a->cms_sc, a->cms_sh, a->cms_sw,
+                         a->peak_threshold, a->peak_cap, a->frame_count, a->keys, a->ev_detect_begin, a->ev_detect_end,
+                         stream, !self_reset);
   if (rc != SNB_OK) return rc;
   if (a->tail_stream) {
     if (!a->ev_handoff) return SNB_ERR_BAD_ARG;
     cudaEventRecord((cudaEvent_t)a->ev_handoff, st);
     cudaStreamWaitEvent(tail_st, (cudaEvent_t)a->ev_handoff, 0);
   }
-  const long long smem = snb_bottomup_tail_smem_bytes(a->peak_cap, a->C, a->n_edges, a->cand_cap, a->match_cap, a->n_sorted,
-                                                      a->n_points);
-  if (!(a->flags & SNB_FLAG_UNFUSED_TAIL) && smem <= 200 * 1024) {
+  if (fused) {
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(bottomup_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return SNB_ERR_CUDA_LAUNCH;

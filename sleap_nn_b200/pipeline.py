@@ -187,7 +187,16 @@ class BottomUpPostproc:
             a.lsap_ws = None
         a.ev_detect_begin = a.ev_detect_end = None
         a.flags = 0 if fused_tail else N.FLAG_UNFUSED_TAIL
+        a.n_peaks = None
         self.fused = int(N.lib.snb_bottomup_launches_per_call(C.byref(a))) == 2
+        if self.fused:
+            # self-resetting peak counters: the detect kernel counts into a zero-initialised scratch, the tail copies
+            # each frame's count to buf["frame_count"] (the result the caller reads) and zeroes the scratch again -
+            # the chain is exactly two kernel launches, no memset node
+            with torch.cuda.device(dev):
+                self._peak_counter = torch.zeros((B,), dtype=torch.int32, device=dev)
+            a.frame_count, a.n_peaks = N.ptr(self._peak_counter), N.ptr(self.buf["frame_count"])
+            a.flags |= N.FLAG_SELF_RESET_COUNTERS
         if self.fused and not keep_tables:  # optional outputs of the fused tail
             for k in ("node_start", "node_peaks", "edge_off", "match_off", "cand_edge", "cand_epi", "cand_score",
                       "m_edge", "m_src", "m_dst", "m_score", "m_count"):

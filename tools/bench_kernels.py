@@ -46,6 +46,9 @@ def timed(fn, iters, warm=10):
     return a.elapsed_time(b) / iters  # ms per launch
 
 
+RESULTS = []  # every line() of this process, in order (bench.py's `extra` block reads it)
+
+
 def line(name, kernel, algo_bytes, ms, units, unit_name, extra=None):
     peak, src = peak_gbs()
     ach = algo_bytes / (ms / 1e3) / 1e9
@@ -54,35 +57,73 @@ def line(name, kernel, algo_bytes, ms, units, unit_name, extra=None):
          f"{unit_name}_per_s": units / (ms / 1e3)}
     if extra:
         d.update(extra)
-    print(json.dumps(d), flush=True)
+    RESULTS.append(d)
+    if not QUIET:
+        print(json.dumps(d), flush=True)
+    return d
 
 
-def k2_cfg2(dev, iters):
-    """cfg2: find_global_peaks + integral refine on (256,13,80,80) crops."""
-    B, Cn, H, W = 256, 13, 80, 80
+QUIET = False
+
+
+def k2_cfg2(dev, iters, B=256, dtype=torch.float32):
+    """cfg2: find_global_peaks + integral refine on (B,13,80,80) centred-instance crops (B = 256 in BASELINE.json)."""
+    Cn, H, W = 13, 80, 80
     g = torch.Generator(device=dev).manual_seed(0)
     bufs = []
-    for _ in range(4):  # 4 x 85 MB > L2
+    esz = 4 if dtype == torch.float32 else 2
+    n_bufs = max(4, -(-400_000_000 // (esz * B * Cn * H * W)))  # rotate over > 3 x L2
+    from sleap_nn_b200.data.confidence_maps import _confmaps
+    for _ in range(n_bufs):
         pts = torch.rand((B, 1, Cn, 2), generator=g, device=dev) * 60 + 10
         xv, yv = make_grid_vectors(H, W, 1)
-        from sleap_nn_b200.data.confidence_maps import _confmaps
         cms = _confmaps(pts, xv, yv, 3.0, torch.float32, dev)
         cms += torch.rand(cms.shape, generator=g, device=dev) * 1e-3
-        bufs.append(cms)
+        bufs.append(cms.to(dtype))
     rpc, nch, nbytes = C.c_int(), C.c_int(), C.c_longlong()
     N.check(N.lib.snb_global_peaks_workspace(B, Cn, H, W, C.byref(rpc), C.byref(nch), C.byref(nbytes)), "ws")
     ws = torch.zeros(((nbytes.value + 3) // 4,), dtype=torch.int32, device=dev)
     pts_o = torch.empty((B, Cn, 2), device=dev)
     val_o = torch.empty((B, Cn), device=dev)
     st = N.stream_ptr(dev)
+    dt = N.dtype_code(dtype)
 
     def fn(i):
         x = bufs[i % len(bufs)]
-        N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), st), "k2")
+        N.check(N.lib.snb_global_peaks_t(N.ptr(x), dt, B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), None, N.ptr(pts_o),
+                                         N.ptr(val_o), st), "k2")
 
     ms = timed(fn, iters)
-    line("k2_cfg2", "global_peaks_warp_kernel", 4 * B * Cn * H * W, ms, B, "crops",
-         {"shape": [B, Cn, H, W], "valid_peaks": int((val_o > 0).sum())})
+    tag = ("" if B == 256 else f"_b{B}") + ("" if dtype == torch.float32 else "_" + str(dtype).split(".")[-1])
+    return line("k2_cfg2" + tag, "global_peaks_warp_kernel", esz * B * Cn * H * W, ms, B, "crops",
+                {"shape": [B, Cn, H, W], "dtype": str(dtype), "valid_peaks": int((val_o > 0).sum())})
+
+
+def k1_cfg3(dev, iters, dtype=torch.float32):
+    """cfg3 detect kernel alone on (64,5,512,512) maps of the given element type (rotating batches > L2)."""
+    Bn, Cn, H, W = 64, 5, 512, 512
+    g = torch.Generator(device=dev).manual_seed(1)
+    esz = 4 if dtype == torch.float32 else 2
+    bufs = [(torch.rand((Bn, Cn, H, W), generator=g, device=dev) * 0.15).to(dtype) for _ in range(4 if esz == 4 else 6)]
+    for x in bufs:  # a few hundred blobs per batch so that the rare path is exercised as in real maps
+        ys = torch.randint(2, H - 2, (Bn, Cn, 2), generator=g, device=dev)
+        xs = torch.randint(2, W - 2, (Bn, Cn, 2), generator=g, device=dev)
+        bi = torch.arange(Bn, device=dev)[:, None, None].expand_as(ys)
+        ci = torch.arange(Cn, device=dev)[None, :, None].expand_as(ys)
+        x[bi, ci, ys, xs] = 0.9
+    cap = 256
+    count = torch.empty((Bn,), dtype=torch.int32, device=dev)
+    keys = torch.empty((Bn * cap,), dtype=torch.int32, device=dev)
+    st, dt = N.stream_ptr(dev), N.dtype_code(dtype)
+
+    def fn(i):
+        x = bufs[i % len(bufs)]
+        N.check(N.lib.snb_local_peaks_detect_t(N.ptr(x), dt, Bn, Cn, H, W, *x.stride(), 0.2, cap, N.ptr(count), N.ptr(keys),
+                                               None, None, st), "k1")
+
+    ms = timed(fn, iters)
+    return line("k1_cfg3_" + str(dtype).split(".")[-1], "local_peaks_detect_vec", esz * Bn * Cn * H * W, ms, Bn, "frames",
+                {"shape": [Bn, Cn, H, W], "dtype": str(dtype), "note": "includes the 256-byte counter memset node"})
 
 
 def _flies_poses(n_frames, seed=0):
@@ -91,30 +132,31 @@ def _flies_poses(n_frames, seed=0):
                                          min_limb=8.0, min_sep=10.0)
 
 
-def k7_cfg4(dev, iters, bf16=False):
-    """cfg4 targets: make_multi_confmaps, 32 nodes, 8 instances, sigma 2.5 x stride 2, out 512x512."""
-    G = 8
+def k7_cfg4(dev, iters, bf16=False, G=8):
+    """cfg4 targets: make_multi_confmaps, 32 nodes, 8 instances, sigma 2.5 x stride 2, out (G,32,512,512) per launch
+    (G = 1 is the shape BottomUpDataset.__getitem__ issues, data/custom_datasets.py:1305-1327)."""
     edges, poses = _flies_poses(G)
     xv, yv = make_grid_vectors(1024, 1024, 2)
     xd, yd, pts = xv.to(dev), yv.to(dev), poses.to(dev).contiguous()
     dt = torch.bfloat16 if bf16 else torch.float32
-    outs = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(3)]
+    n_out = max(3, -(-400_000_000 // (G * 32 * 512 * 512 * (2 if bf16 else 4))))  # rotate over > 3 x L2
+    outs = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(n_out)]
     st = N.stream_ptr(dev)
     den = float(2 * (2.5 * 2) ** 2)
 
     def fn(i):
         N.check(N.lib.snb_confmaps(N.ptr(pts), G, 8, 32, N.ptr(xd), N.ptr(yd), 512, 512, den, int(bf16),
-                                   N.ptr(outs[i % 3]), st), "k7")
+                                   N.ptr(outs[i % n_out]), st), "k7")
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
-    line("k7_cfg4" + ("_bf16" if bf16 else ""), "confmaps_rows2_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
+    return line("k7_cfg4" + ("" if G == 8 else f"_g{G}") + ("_bf16" if bf16 else ""), "confmaps_rows2_kernel", esz * G * 32 * 512 * 512, ms, G, "frames",
          {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
 def k8_cfg4(dev, iters, bf16=False, G=1):
     """cfg4 targets: make_multi_pafs, 31 edges, 8 instances, sigma 2.5, out (G,31,2,512,512) per launch."""
-    n_sets = max(2, 4 // G)
+    n_sets = max(2, -(-400_000_000 // (G * 62 * 512 * 512 * (2 if bf16 else 4))))  # rotate over > 3 x L2
     edges, poses = _flies_poses(G * n_sets)
     e = torch.tensor(edges, dtype=torch.int64)
     xv, yv = make_grid_vectors(1024, 1024, 2)
@@ -134,7 +176,7 @@ def k8_cfg4(dev, iters, bf16=False, G=1):
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
-    line(f"k8_cfg4_g{G}" + ("_bf16" if bf16 else ""), "pafs_rows_kernel", esz * G * 31 * 2 * 512 * 512, ms, G, "frames",
+    return line(f"k8_cfg4_g{G}" + ("_bf16" if bf16 else ""), "pafs_rows_kernel", esz * G * 31 * 2 * 512 * 512, ms, G, "frames",
          {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
@@ -142,7 +184,7 @@ def memset_ref(dev, iters):
     """Reference point for the store-bound kernels: cudaMemsetAsync (torch zero_) of 268 MB, rotating buffers."""
     bufs = [torch.empty((268435456 // 4,), dtype=torch.float32, device=dev) for _ in range(3)]
     ms = timed(lambda i: bufs[i % 3].zero_(), iters)
-    line("memset_268MB", "cudaMemsetAsync (reference, not ours)", 268435456, ms, 1, "launches")
+    return line("memset_268MB", "cudaMemsetAsync (reference, not ours)", 268435456, ms, 1, "launches")
 
 
 def chain_cfg4(dev, iters, Bn=64, n_streams=None):
@@ -200,7 +242,11 @@ def chain_cfg4(dev, iters, Bn=64, n_streams=None):
     line("k1_cfg4", "local_peaks_detect_vec4 (in situ)", algo, det, Bn, "frames", {"frames_per_launch": Bn})
 
 
-ALL = {"k2_cfg2": k2_cfg2, "k7_cfg4": k7_cfg4, "k7_cfg4_bf16": lambda d, i: k7_cfg4(d, i, True),
+ALL = {"k7_cfg4_g1": lambda d, i: k7_cfg4(d, i, False, 1), "k7_cfg4_g1_bf16": lambda d, i: k7_cfg4(d, i, True, 1),
+       "k2_cfg2": k2_cfg2, "k2_cfg2_b1024": lambda d, i: k2_cfg2(d, i, 1024),
+       "k2_cfg2_f16": lambda d, i: k2_cfg2(d, i, 256, torch.float16),
+       "k1_cfg3_f32": k1_cfg3, "k1_cfg3_f16": lambda d, i: k1_cfg3(d, i, torch.float16),
+       "k1_cfg3_bf16": lambda d, i: k1_cfg3(d, i, torch.bfloat16), "k7_cfg4": k7_cfg4, "k7_cfg4_bf16": lambda d, i: k7_cfg4(d, i, True),
        "k8_cfg4": k8_cfg4, "k8_cfg4_g8": lambda d, i: k8_cfg4(d, i, False, 8),
        "k8_cfg4_bf16": lambda d, i: k8_cfg4(d, i, True), "k8_cfg4_g8_bf16": lambda d, i: k8_cfg4(d, i, True, 8),
        "memset_ref": memset_ref, "chain_cfg4": chain_cfg4}

@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Turn `ncu --set full` captures into profiles/traffic.json, the record bench.py reads `roofline.traffic` from.
+
+    python tools/ncu_traffic.py gpurun_out/detect_f32.ncu-rep [more.ncu-rep ...] [--round r2]
+
+For every distinct kernel in the reports: per-launch dram__bytes_read.sum / dram__bytes_write.sum / gpu__time_duration
+(median over the captured launches), registers, and the sha256 of csrc/peaks.cu at capture time (bench.py reports whether
+the capture matches the source it is running).  Kernel names are normalised to `name<template args>`.
+"""
+import csv
+import hashlib
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rows_of(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    return hdr, units, rows[2:]
+
+
+def to_bytes(v, unit):
+    x = float(v.replace(",", ""))
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def to_us(v, unit):
+    x = float(v.replace(",", ""))
+    return x * {"ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}.get(unit, 1)
+
+
+def short_name(full):
+    m = re.match(r"(?:void\s+)?(?:snb::)?([A-Za-z_0-9]+)(<.*>)?\(", full)
+    if not m:
+        return full
+    return m.group(1) + (m.group(2) or "").replace(" ", "").replace("(int)", "")
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    rnd = "r2"
+    if "--round" in sys.argv:
+        rnd = sys.argv[sys.argv.index("--round") + 1]
+        args = [a for a in args if a != rnd]
+    with open(os.path.join(ROOT, "sleap_nn_b200", "csrc", "peaks.cu"), "rb") as f:
+        sha = hashlib.sha256(f.read()).hexdigest()[:16]
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    rec = json.load(open(path)) if os.path.isfile(path) else {}
+    for rep in args:
+        hdr, units, rows = rows_of(rep)
+        col = {h: i for i, h in enumerate(hdr)}
+        by = {}
+        for r in rows:
+            by.setdefault(short_name(r[col["Kernel Name"]] if "Kernel Name" in col else r[4]), []).append(r)
+        for name, rs in by.items():
+            rd = [to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) for r in rs]
+            wr = [to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]]) for r in rs]
+            us = [to_us(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]]) for r in rs]
+            rec[name] = {"dram_bytes_read": statistics.median(rd), "dram_bytes_write": statistics.median(wr),
+                         "ncu_time_us": statistics.median(us), "launches_captured": len(rs),
+                         "registers": int(rs[0][col["launch__registers_per_thread"]]),
+                         "grid": rs[0][col["launch__grid_size"]], "block": rs[0][col["launch__block_size"]],
+                         "source_sha16": sha, "capture": f"profiles/{rnd}_{os.path.basename(rep)} (ncu --set full --clock-control none)"}
+            print(name, rec[name])
+    json.dump(rec, open(path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""Stage the reference's OWN hot-path unit tests for a run against this package (build container only).
+"""Stage UNMODIFIED reference files under baseline/_ref/ (build container only; `__graft_entry__.build()` calls this):
+
+  * the reference's OWN hot-path unit tests, for a run against this package (tests/test_reference_suite_gpu.py), and
+  * the hot-path source files themselves (the list `oracle/ref_loader.py` exec's in place), so that `bench.py`'s CPU arm
+    (`--impl reference`, `cpu_baseline`) times the reference's own implementation on the GPU box's host cores, where
+    /root/reference does not exist.
 
     python tools/ref_tests/stage.py            # copies into baseline/_ref/ (git-ignored, travels with gpurun)
     gpurun -- 'python tools/ref_tests/run.py'  # runs them on the GPU box through sleap_nn_b200.compat.install()
@@ -36,6 +41,31 @@ FILES = [
 ]
 
 
+def hot_path_sources():
+    """Relative paths of the reference source files oracle/ref_loader.py loads (kept in one place: its _HOT_FILES)."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+
+    return [rel for _name, rel in ref_loader._HOT_FILES]
+
+
+def stage(verbose: bool = True) -> int:
+    """Copy the files (byte for byte) from REF into baseline/_ref/; returns how many.  No-op when REF is absent."""
+    if not os.path.isdir(REF):
+        return 0
+    files = list(dict.fromkeys(FILES + hot_path_sources()))
+    for rel in files:
+        dst = os.path.join(DST, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, rel), dst)
+        os.chmod(dst, 0o644)
+    shutil.copyfile(os.path.join(ROOT, "tools", "ref_tests", "conftest_staged.py"), os.path.join(DST, "tests", "conftest.py"))
+    if verbose:
+        print(f"staged {len(files)} unmodified reference files under {DST}")
+    return len(files)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--clean", action="store_true")
@@ -46,13 +76,7 @@ def main():
         return
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not found: staging only works in the build container")
-    for rel in FILES:
-        dst = os.path.join(DST, rel)
-        os.makedirs(os.path.dirname(dst), exist_ok=True)
-        shutil.copyfile(os.path.join(REF, rel), dst)
-        os.chmod(dst, 0o644)
-    shutil.copyfile(os.path.join(ROOT, "tools", "ref_tests", "conftest_staged.py"), os.path.join(DST, "tests", "conftest.py"))
-    print(f"staged {len(FILES)} files under {DST}")
+    stage()
 
 
 if __name__ == "__main__":
