@@ -78,6 +78,8 @@ SIGNATURES = {
     "snb_pafs": [_p, _p, _i, _i, _i, _p, _p, _i, _i, _f, _i, _i, _p, _p],
     "snb_confmaps_ex": [_p, _i, _i, _i, _ll, _ll, _ll, _p, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
     "snb_pafs_from_instances": [_p, _i, _i, _i, _p, _i, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
+    "snb_bottomup_targets": [_p, _i, _i, _i, _p, _f, _f, _p, _i, _f, _f, _p, _p, _i, _i, _f, _p, _p, _i, _i, _f, _i, _p, _p,
+                             _p, _p],
     "snb_debug_neg_div": [_p, _ll, _f, _p, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],

@@ -25,6 +25,32 @@ namespace snb {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// ---- programmatic dependent launch (PDL, sm_90+).  Short one-wave kernels that are issued back to back on one stream
+// (per-frame target launches from a data loader, global-peak launches per crop batch) otherwise pay the full
+// launch + ramp latency after the previous kernel has drained.  A kernel launched through launch_pdl() may become
+// resident while the previous kernel's last wave is still running; it must call pdl_wait() before its first global
+// memory access (the wait returns when the previous grid has completed and its writes are visible, so there is no
+// hazard on inputs or outputs) and calls pdl_launch_dependents() first thing so that its own successor can do the same.
+// A predecessor that knows nothing about PDL simply releases its dependents when it exits.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   // 128-bit read-only streaming load; the confidence maps are read exactly once.
   float4 r;

@@ -55,7 +55,27 @@ __device__ __forceinline__ void emit_peak(int* __restrict__ frame_count, uint32_
   if (pos < cap) keys[(long long)b * cap + pos] = ((uint32_t)y * (uint32_t)W + (uint32_t)x) * (uint32_t)C + (uint32_t)c;
 }
 
-template <typename T, int UNROLL, int ROWS, int MIN_BLOCKS>
+// Rare path of the streaming kernel: one 128-bit word of row y holds a value above the threshold.
+template <typename T>
+__device__ __noinline__ void detect_word(const T* __restrict__ plane, float thr, int H, int W, long long sh, int y, int x0,
+                                         int b, int c, int C, int cap, int* __restrict__ frame_count,
+                                         uint32_t* __restrict__ keys) {
+  constexpr int PER = Elem<T>::PER16;
+  float e[PER];
+  Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(plane + (long long)y * sh + x0)), e);  // an L2 hit
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same 128-bit
+    // word are already in registers, and a strict maximum must beat them too (same `v > nb` predicate, so NaN
+    // neighbours reject as in the reference).  On a blob's row only the ridge pixel (and at most the word-boundary
+    // pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads on busy maps (cfg4: 256 blobs per frame).
+    if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == PER - 1 || e[k] > e[k + 1])) {
+      if (is_strict_max<T>(plane, H, W, sh, 1, y, x0 + k, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x0 + k);
+    }
+  }
+}
+
+template <typename T, int UNROLL, int ROWS, int MIN_BLOCKS, bool EXACT>
 __global__ void __launch_bounds__(256, MIN_BLOCKS)
 local_peaks_detect_vec(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
                        float thr, int cap, int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
@@ -65,50 +85,48 @@ local_peaks_detect_vec(const T* __restrict__ cms, int C, int H, int W, long long
   // issues all of its 128-bit loads (ROWS * UNROLL per lane per step) before looking at any value: that is the
   // memory-level parallelism that keeps HBM busy.  A 128-bit load holds PER = 4 fp32 or 8 fp16 / bf16 elements;
   // half-precision maps are compared on their exact fp32 values.
+  //
+  // The streaming step only records WHICH of its words hold a value above the threshold (one bit each); the words
+  // themselves are dead after that.  A lane with a non-zero mask (a few per thousand) hands its hot words to the
+  // out-of-line neighbour test, which re-reads them (L2 hits).  With the rare path consuming the loaded registers
+  // directly, the half-precision kernels (eight up-cast values per word) went past the 40-register budget of
+  // 6 CTAs / SM and ptxas spilled inside the streaming loop (0.52 of the roofline).
+  // EXACT: H is a multiple of the CTA's rows and the row a multiple of one step, so the loop carries no bounds test.
   constexpr int PER = Elem<T>::PER16;
   const int lane = lane_id();
   const int c = blockIdx.y, b = blockIdx.z;
   const int y0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
-  if (y0 >= H) return;
+  if (!EXACT && y0 >= H) return;
   const T* plane = cms + (long long)b * sb + (long long)c * sc;
   const int WV = W / PER;
+  const int n_rows = EXACT ? ROWS : min(ROWS, H - y0);
   const typename Elem<T>::Thr tv = Elem<T>::make_thr(thr);
+  const T* rowp[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) rowp[r] = plane + (long long)(y0 + (EXACT ? r : min(r, n_rows - 1))) * sh + PER * lane;
   for (int xv = lane; xv < WV; xv += 32 * UNROLL) {
     uint4 v[ROWS][UNROLL];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const T* rowp = plane + (long long)min(y0 + r, H - 1) * sh;
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int xxv = xv + 32 * u;
-        if (xxv < WV) v[r][u] = ldg_stream16(rowp + PER * xxv);
+        if (EXACT || xv + 32 * u < WV) v[r][u] = ldg_stream16(rowp[r] + PER * 32 * u);
+        else v[r][u] = Elem<T>::neg_inf();
       }
+    unsigned hot = 0;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if ((EXACT || r < n_rows) && Elem<T>::any_gt(v[r][u], tv)) hot |= 1u << (r * UNROLL + u);
+    while (hot) {  // rare
+      const int k = __ffs(hot) - 1;
+      hot &= hot - 1;
+      const int r = k / UNROLL, u = k - r * UNROLL;
+      detect_word<T>(plane, thr, H, W, sh, y0 + r, PER * (xv + 32 * u), b, c, C, cap, frame_count, keys);
     }
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const int y = y0 + r;
-      if (y >= H) break;
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int xxv = xv + 32 * u;
-        if (xxv >= WV) continue;
-        if (!Elem<T>::any_gt(v[r][u], tv)) continue;
-        float e[PER];  // rare path: a value above the threshold
-        Elem<T>::unpack(v[r][u], e);
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-          // Cheap exact pre-filter before the 8 neighbour loads: the horizontal neighbours that sit in the same
-          // 128-bit word are already in registers, and a strict maximum must beat them too (same `v > nb`
-          // predicate, so NaN neighbours reject as in the reference).  On a blob's row only the ridge pixel
-          // (and at most the word-boundary pixels) goes on to is_strict_max - ~3x fewer L1/L2 neighbour reads
-          // on busy maps (cfg4: 256 blobs per frame).
-          if (e[k] > thr && (k == 0 || e[k] > e[k - 1]) && (k == PER - 1 || e[k] > e[k + 1])) {
-            const int x = PER * xxv + k;
-            if (is_strict_max<T>(plane, H, W, sh, 1, y, x, e[k])) emit_peak(frame_count, keys, cap, b, C, W, c, y, x);
-          }
-        }
-      }
-    }
+    for (int r = 0; r < ROWS; ++r) rowp[r] += PER * 32 * UNROLL;
   }
 }
 
@@ -715,9 +733,11 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
                          float thr, int refine_size, float* __restrict__ out_xy, float* __restrict__ out_val,
                          Ladder lad) {
   constexpr int PER = Elem<T>::PER16;
+  pdl_launch_dependents();
   const int p = blockIdx.x, lane = threadIdx.x;
   const T* plane = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
   const int WV = W / PER, nv = H * WV;
+  pdl_wait();  // the maps may be the previous kernel's output
   // Load cursor of this lane: 128-bit load number `li` = lane + 32 * (loads issued so far); for strided planes the
   // (row, column) pair is advanced incrementally (no integer division in the loop).
   int li = lane, ly = lane / WV, lxv = lane - ly * WV;
@@ -738,9 +758,12 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
   for (int u = 0; u < U; ++u) buf[u] = load_next();
   // Per lane, branch-free: running maximum m (max.NaN: a NaN sticks), the number kbest of the FIRST load that
   // reached it, and whether a later load tied with it.
+  // The 16-byte word that holds the running maximum stays in registers too (four predicated moves per load): the
+  // epilogue then needs no re-read of that word, one dependent L2 round trip less at the end of a one-wave kernel.
   float m = -INFINITY;
   int kbest = 0, k = 0;
   bool tie = false;
+  uint4 vbest = Elem<T>::neg_inf();
   for (int base = 0; base < nv; base += 32 * U) {
 #pragma unroll
     for (int u = 0; u < U; ++u, ++k) {
@@ -750,6 +773,7 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
       const bool up = mx > m;
       tie = up ? false : (tie || mx == m);
       kbest = up ? k : kbest;
+      vbest.x = up ? v.x : vbest.x; vbest.y = up ? v.y : vbest.y; vbest.z = up ? v.z : vbest.z; vbest.w = up ? v.w : vbest.w;
       m = fmax_nan(m, mx);
     }
   }
@@ -776,11 +800,11 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
       r = best_warp(acc);
     } else {
       int bx = 0x7fffffff, by = 0x7fffffff;
-      if (holder) {  // re-read the one 16-byte word that held the maximum (an L2 hit) to find the element
+      if (holder) {  // the element inside the 16-byte word that held the maximum
         const int i = lane + 32 * kbest;
         const int y = i / WV, xv = i - y * WV;
         float e[PER];
-        Elem<T>::unpack(__ldg(reinterpret_cast<const uint4*>(plane + (long long)y * sh + PER * xv)), e);
+        Elem<T>::unpack(vbest, e);
         int q = PER - 1;
 #pragma unroll
         for (int j = PER - 2; j >= 0; --j) q = (e[j] == gm) ? j : q;  // first match = min x of the word
@@ -1033,9 +1057,16 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
     static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
     if (forced >= 0) variant = forced;
 #endif
-#define SNB_DETECT(U, R, MB)                                                                                          \
-  local_peaks_detect_vec<T, U, R, MB><<<dim3((unsigned)((H + 8 * R - 1) / (8 * R)), (unsigned)C, (unsigned)B), 256, 0, st>>>( \
-      cms, C, H, W, sb, sc, sh, threshold, cap, frame_count, keys)
+#define SNB_DETECT(U, R, MB)                                                                                     \
+  do {                                                                                                           \
+    const dim3 grid((unsigned)((H + 8 * R - 1) / (8 * R)), (unsigned)C, (unsigned)B);                            \
+    if (H % (8 * R) == 0 && vecs % (32 * U) == 0)                                                                \
+      local_peaks_detect_vec<T, U, R, MB, true><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold, cap,  \
+                                                                      frame_count, keys);                        \
+    else                                                                                                         \
+      local_peaks_detect_vec<T, U, R, MB, false><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, threshold, cap, \
+                                                                       frame_count, keys);                       \
+  } while (0)
     switch (variant) {
       case 0: SNB_DETECT(4, 1, 6); break;  // >= 128 vectors per row
       case 1: SNB_DETECT(2, 1, 8); break;  // 64..127 vectors per row (fp32)
@@ -1228,12 +1259,14 @@ static int launch_global_peaks(const T* cms, int B, int C, int H, int W, long lo
 #endif
   if (vec && !force_generic && !no_warp && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
     // small planes (cfg2's 80x80 crops): one warp per plane, no barrier anywhere
+    cudaError_t err;
     if (sh == W)
-      global_peaks_warp_kernel<T, 8, true><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
-                                                                                  refine_size, out_xy, out_val, lad);
+      err = launch_pdl(global_peaks_warp_kernel<T, 8, true>, dim3((unsigned)planes), dim3(32), (size_t)pad_smem, st, cms, C, H,
+                       W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);
     else
-      global_peaks_warp_kernel<T, 8, false><<<(unsigned)planes, 32, pad_smem, st>>>(cms, C, H, W, sb, sc, sh, threshold,
-                                                                                   refine_size, out_xy, out_val, lad);
+      err = launch_pdl(global_peaks_warp_kernel<T, 8, false>, dim3((unsigned)planes), dim3(32), (size_t)pad_smem, st, cms, C,
+                       H, W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);
+    if (err != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
   } else if (vec && !force_generic && chunkv <= 8 * 256) {
 #define SNB_GP(V)                                                                                                      \
   global_peaks_regs_kernel<T, V><<<grid, 256, 0, st>>>(cms, C, H, W, sb, sc, sh, rpc, nc, threshold, refine_size, part_v, \

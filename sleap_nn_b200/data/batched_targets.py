@@ -42,6 +42,7 @@ class BatchedTargets:
             raise N.NativeLibraryError("BatchedTargets needs a CUDA device: there is no CPU fallback")
         self.out_dtype = out_dtype
         self._grids: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._fused_ws: Dict[int, torch.Tensor] = {}  # CUDA stream -> chunk counter of the fused kernel (self-resetting)
 
     # ------------------------------------------------------------------ helpers
     def _grid(self, stride: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -170,10 +171,54 @@ class BatchedTargets:
 
     # ------------------------------------------------------------------ dataset-shaped entry points
     def bottomup(self, instances, num_instances, edge_inds, confmap_sigma=1.5, confmap_stride=2, paf_sigma=1.5,
-                 paf_stride=2) -> Dict[str, torch.Tensor]:
-        """BottomUpDataset.__getitem__ targets (custom_datasets.py:1305-1327), collated."""
+                 paf_stride=2, fused: bool = True) -> Dict[str, torch.Tensor]:
+        """BottomUpDataset.__getitem__ targets (custom_datasets.py:1305-1327), collated: confidence maps
+        (B, 1, N, h, w) and part-affinity fields (B, 2E, h', w').
+
+        Both targets come out of ONE launch (`snb_bottomup_targets`: a persistent grid over 32 KB chunks of both outputs),
+        so a single frame - the reference's granularity - fills the GPU; values are bit-identical to `multi_confmaps` +
+        `pafs`, which are used instead for shapes the fused kernel does not take (`fused=False` forces them)."""
+        if fused:
+            out = self._bottomup_fused(instances, num_instances, edge_inds, confmap_sigma, confmap_stride, paf_sigma, paf_stride)
+            if out is not None:
+                return out
         return {"confidence_maps": self.multi_confmaps(instances, num_instances, confmap_sigma, confmap_stride),
                 "part_affinity_fields": self.pafs(instances, edge_inds, paf_sigma, paf_stride, flatten_channels=True)}
+
+    def _bottomup_fused(self, instances, num_instances, edge_inds, confmap_sigma, confmap_stride, paf_sigma, paf_stride):
+        x = self._f32(instances)
+        x = x.reshape(x.shape[0], -1, x.shape[-2], 2)
+        B, I, Nn = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        e = torch.as_tensor(edge_inds).reshape(-1, 2).to(device=self.device, dtype=torch.int32).contiguous()
+        E = int(e.shape[0])
+        if E and (int(e.min()) < 0 or int(e.max()) >= Nn):
+            raise IndexError("edge_inds refers to a node outside the skeleton")
+        xv7, yv7 = self._grid(confmap_stride)
+        xv8, yv8 = self._grid(paf_stride)
+        h7, w7, h8, w8 = int(yv7.shape[0]), int(xv7.shape[0]), int(yv8.shape[0]), int(xv8.shape[0])
+        bf16 = self.out_dtype == torch.bfloat16
+        if B == 0 or w7 % (8 if bf16 else 4) or w8 % 4 or (bf16 and w7 > 1024):
+            return None
+        n_valid = self._counts(num_instances, B)
+        xmax = float(((self.img_hw[1] - 1) // paf_stride) * paf_stride)
+        ymax = float(((self.img_hw[0] - 1) // paf_stride) * paf_stride)
+        with torch.cuda.device(self.device):
+            st = N.stream_ptr(self.device)
+            ws = self._fused_ws.get(st)
+            if ws is None:
+                if len(self._fused_ws) >= 16:
+                    self._fused_ws.clear()
+                ws = self._fused_ws[st] = torch.zeros((4,), dtype=torch.int32, device=self.device)
+            cms = torch.empty((B, Nn, h7, w7), dtype=self.out_dtype, device=self.device)
+            pafs = torch.empty((B, E, 2, h8, w8), dtype=self.out_dtype, device=self.device)
+            sig7 = confmap_sigma * confmap_stride  # generate_multiconfmaps scales sigma by the stride, generate_pafs does not
+            rc = N.lib.snb_bottomup_targets(N.ptr(x), B, I, Nn, N.ptr(n_valid), 0.0, 0.0, N.ptr(e), E, xmax, ymax,
+                                            N.ptr(xv7), N.ptr(yv7), h7, w7, float(2 * sig7**2), N.ptr(xv8), N.ptr(yv8), h8, w8,
+                                            float(2 * paf_sigma**2), int(bf16), N.ptr(cms), N.ptr(pafs), N.ptr(ws), st)
+        if rc == -2:  # SNB_ERR_UNSUPPORTED: shapes / smem the fused kernel does not take
+            return None
+        N.check(rc, "snb_bottomup_targets")
+        return {"confidence_maps": cms.unsqueeze(1), "part_affinity_fields": pafs.reshape(B, 2 * E, h8, w8)}
 
     def bottomup_multiclass(self, instances, num_instances, class_inds, num_tracks, confmap_sigma=1.5, confmap_stride=2,
                             class_map_threshold=0.2, class_map_sigma=1.5, class_map_stride=2) -> Dict[str, torch.Tensor]:

@@ -489,8 +489,8 @@ class BottomUpHostStream:
 
 
 def capture_rotation(pipes: Sequence[BottomUpPostproc], inputs: Sequence[Tuple[torch.Tensor, torch.Tensor]],
-                     streams: Optional[Sequence[torch.cuda.Stream]] = None, repeats: int = 1
-                     ) -> Tuple[torch.cuda.CUDAGraph, int]:
+                     streams: Optional[Sequence[torch.cuda.Stream]] = None, repeats: int = 1,
+                     stagger_chains: bool = True) -> Tuple[torch.cuda.CUDAGraph, int]:
     """Capture one full rotation of a multi-stream pipeline into a CUDA graph.
 
     Step i runs `pipes[i % len(pipes)]` on `inputs[i % len(inputs)]` on `streams[i % len(pipes)]`, for
@@ -526,6 +526,15 @@ def capture_rotation(pipes: Sequence[BottomUpPostproc], inputs: Sequence[Tuple[t
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
+        # Stagger: chain k's FIRST detect kernel waits for chain k-1's first detect kernel (events recorded inside the
+        # capture around the detect launches).  Without it the chains start together and stay in lockstep - all
+        # detect kernels share HBM, then all tails run with HBM idle; offset by one detect pass, a tail always hides
+        # under another chain's detect pass, as it does in the eager loop through the host's launch cadence.
+        stagger = [(torch.cuda.Event(), torch.cuda.Event()) for _ in range(len(pipes))] if stagger_chains else []
+        for pair in stagger:  # torch creates the cudaEvent lazily on first record; the C side re-records them in the capture
+            for e in pair:
+                e.record(torch.cuda.current_stream(dev))
+        torch.cuda.synchronize(dev)
         with torch.cuda.graph(graph, stream=cap):
             origin = torch.cuda.current_stream(dev)
             uniq = list({id(s): s for s in streams}.values())
@@ -533,7 +542,12 @@ def capture_rotation(pipes: Sequence[BottomUpPostproc], inputs: Sequence[Tuple[t
                 s.wait_stream(origin)  # fork
             for i in range(n):
                 with torch.cuda.stream(streams[i % len(pipes)]):
-                    pipes[i % len(pipes)](*inputs[i % len(inputs)])
+                    if stagger and i < len(pipes):
+                        if i > 0 and streams[i] is not streams[i - 1]:
+                            streams[i].wait_event(stagger[i - 1][1])
+                        pipes[i](*inputs[i % len(inputs)], detect_events=stagger[i])
+                    else:
+                        pipes[i % len(pipes)](*inputs[i % len(inputs)])
             for s in uniq:
                 origin.wait_stream(s)  # join
     return graph, n

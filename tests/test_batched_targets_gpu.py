@@ -102,3 +102,49 @@ def test_batched_targets_full_size_properties():
                                   flatten_channels=True)
         assert torch.equal(pf[b], want)
     assert float(cm.max()) > 0.99 and float(cm.min()) == 0.0
+
+
+def _random_batch(seed, B, I, Nn, hw):
+    g = torch.Generator().manual_seed(seed)
+    inst = torch.rand((B, I, Nn, 2), generator=g) * torch.tensor([hw[1], hw[0]], dtype=torch.float32)
+    inst[0, 0, 0] = float("nan")                       # a missing keypoint
+    inst[-1, -1] = float("nan")                        # a missing instance
+    inst[0, -1, :, 0] += hw[1]                         # an instance entirely outside the image (generate_pafs drops it)
+    num = torch.randint(1, I + 1, (B,), generator=g)
+    return inst, num
+
+
+@pytest.mark.parametrize("hw,B,I,Nn,s7,s8", [((64, 96), 3, 2, 3, 2, 4), ((128, 160), 5, 6, 7, 2, 2), ((1024, 1024), 1, 8, 32, 2, 2),
+                                             ((256, 256), 9, 3, 5, 4, 2)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_fused_bottomup_targets_equal_the_two_kernels(hw, B, I, Nn, s7, s8, dt):
+    """snb_bottomup_targets (one persistent launch for both targets) == snb_confmaps_ex + snb_pafs_from_instances, bit for
+    bit, fp32 and bf16, single frames and batches, different strides per head; repeated launches reuse the self-resetting
+    chunk counter."""
+    bt = _bt(hw, out_dtype=dt)
+    inst, num = _random_batch(B * 7 + I, B, I, Nn, hw)
+    edges = [(k, k + 1) for k in range(Nn - 1)] or [(0, 0)]
+    sep = bt.bottomup(inst, num, edges, 2.5, s7, 2.5, s8, fused=False)
+    for rep in range(3):
+        fu = bt.bottomup(inst, num, edges, 2.5, s7, 2.5, s8, fused=True)
+        assert fu["confidence_maps"].dtype == dt and fu["confidence_maps"].shape == sep["confidence_maps"].shape
+        assert torch.equal(fu["confidence_maps"].view(torch.int16 if dt == torch.bfloat16 else torch.int32),
+                           sep["confidence_maps"].view(torch.int16 if dt == torch.bfloat16 else torch.int32)), rep
+        assert torch.equal(fu["part_affinity_fields"].view(torch.int16 if dt == torch.bfloat16 else torch.int32),
+                           sep["part_affinity_fields"].view(torch.int16 if dt == torch.bfloat16 else torch.int32)), rep
+    assert int(next(iter(bt._fused_ws.values())).abs().sum()) == 0  # the counter went back to zero
+
+
+def test_bf16_confmaps_separable_form_vs_exact_fp32():
+    """bf16 confidence maps use exp(-dx^2/den) * exp(-dy^2/den) (a table per instance and band): after rounding to bf16
+    they must sit within ONE bf16 ulp of the exactly-computed fp32 maps rounded to bf16, zeros where those are zero."""
+    hw = (1024, 1024)
+    inst, num = _random_batch(3, 2, 8, 32, hw)
+    exact = _bt(hw).multi_confmaps(inst, num, 2.5, 2)
+    b16 = _bt(hw, out_dtype=torch.bfloat16).multi_confmaps(inst, num, 2.5, 2)
+    want = exact.bfloat16()
+    a, b = b16.view(torch.int16).int(), want.view(torch.int16).int()
+    assert int((a - b).abs().max()) <= 1                     # adjacent bf16 values at most (bit patterns of non-negative floats)
+    big = exact > 1e-30
+    assert bool(((b16.float() - exact).abs()[big] <= exact[big] * 2.0 ** -8).all())
+    assert float((a != b).float().mean()) < 0.02             # and almost always the very same value

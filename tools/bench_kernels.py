@@ -180,6 +180,36 @@ def k8_cfg4(dev, iters, bf16=False, G=1):
          {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
+def targets_cfg4_fused(dev, iters, bf16=False, G=1):
+    """cfg4 targets of G frames (default ONE, the granularity of BottomUpDataset.__getitem__) in one launch:
+    confidence maps (G,32,512,512) + PAFs (G,62,512,512) through snb_bottomup_targets."""
+    from sleap_nn_b200.data.batched_targets import BatchedTargets
+    esz = 2 if bf16 else 4
+    per_launch = esz * G * (32 + 62) * 512 * 512
+    n_sets = max(3, -(-400_000_000 // per_launch))
+    edges, poses = _flies_poses(G * n_sets)
+    pd = poses.to(dev).reshape(n_sets, G, 8, 32, 2).contiguous()
+    bt = BatchedTargets((1024, 1024), device=dev, out_dtype=torch.bfloat16 if bf16 else torch.float32)
+    e = torch.tensor(edges, dtype=torch.int32, device=dev)
+    xv, yv = bt._grid(2)
+    ws = torch.zeros((4,), dtype=torch.int32, device=dev)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    cms = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
+    pafs = [torch.empty((G, 31, 2, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
+    st = N.stream_ptr(dev)
+    den7, den8 = float(2 * (2.5 * 2) ** 2), float(2 * 2.5 ** 2)
+
+    def fn(i):
+        k = i % n_sets
+        N.check(N.lib.snb_bottomup_targets(N.ptr(pd[k]), G, 8, 32, None, 0.0, 0.0, N.ptr(e), 31, 1022.0, 1022.0, N.ptr(xv),
+                                           N.ptr(yv), 512, 512, den7, N.ptr(xv), N.ptr(yv), 512, 512, den8, int(bf16),
+                                           N.ptr(cms[k]), N.ptr(pafs[k]), N.ptr(ws), st), "fused targets")
+
+    ms = timed(fn, iters)
+    return line(f"targets_cfg4_fused_g{G}" + ("_bf16" if bf16 else ""), "targets_fused_kernel", per_launch, ms, G, "frames",
+                {"frames_per_launch": G, "out_dtype": str(dt)})
+
+
 def memset_ref(dev, iters):
     """Reference point for the store-bound kernels: cudaMemsetAsync (torch zero_) of 268 MB, rotating buffers."""
     bufs = [torch.empty((268435456 // 4,), dtype=torch.float32, device=dev) for _ in range(3)]
@@ -242,7 +272,9 @@ def chain_cfg4(dev, iters, Bn=64, n_streams=None):
     line("k1_cfg4", "local_peaks_detect_vec4 (in situ)", algo, det, Bn, "frames", {"frames_per_launch": Bn})
 
 
-ALL = {"k7_cfg4_g1": lambda d, i: k7_cfg4(d, i, False, 1), "k7_cfg4_g1_bf16": lambda d, i: k7_cfg4(d, i, True, 1),
+ALL = {"targets_cfg4_fused": targets_cfg4_fused, "targets_cfg4_fused_bf16": lambda d, i: targets_cfg4_fused(d, i, True),
+       "targets_cfg4_fused_g8": lambda d, i: targets_cfg4_fused(d, i, False, 8),
+       "k7_cfg4_g1": lambda d, i: k7_cfg4(d, i, False, 1), "k7_cfg4_g1_bf16": lambda d, i: k7_cfg4(d, i, True, 1),
        "k2_cfg2": k2_cfg2, "k2_cfg2_b1024": lambda d, i: k2_cfg2(d, i, 1024),
        "k2_cfg2_f16": lambda d, i: k2_cfg2(d, i, 256, torch.float16),
        "k1_cfg3_f32": k1_cfg3, "k1_cfg3_f16": lambda d, i: k1_cfg3(d, i, torch.float16),
