@@ -564,8 +564,9 @@ def run_ours(args, rank: int, world: int):
 
         total_frames = world * B * args.steps
         src = lambda s, e: inputs[((s // B) % n_bufs)]
-        sharding.ShardRunner(pipes[0], total_frames, rank, world).run(src).finish()  # warm-up (pack kernel load)
-        runner = sharding.ShardRunner(pipes[0], total_frames, rank, world)
+        # warm-up: pack kernel load, and NCCL's lazy all_gather channel setup (first call only)
+        sharding.gather_packed(sharding.ShardRunner(pipes[0], world * B * 4, rank, world).run(src).finish())
+        runner = sharding.ShardRunner(pipes[0], total_frames, rank, world, rows_cap=(total_frames // world) * 8)
         barrier()
         g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         g0.record(main)

@@ -342,20 +342,20 @@ int snb_pafs_from_instances(const float* instances, int G, int I, int N, const i
                             float in_ymax, const float* xv, const float* yv, int h, int w, float den, int out_bf16,
                             void* out, void* stream);
 
-/* ABI v5: the per-frame targets of a bottom-up dataset item in ONE launch - generate_multiconfmaps
+/* ABI v5: both targets of a bottom-up dataset item in one call - generate_multiconfmaps
  * (data/confidence_maps.py:46-91, with the datasets' `[:, :num_instances]` slice = n_valid and filter_oob_points =
  * oob_w / oob_h, as snb_confmaps_ex) and generate_pafs (data/edge_maps.py:250-323, with its in-image instance filter =
  * in_xmax / in_ymax, as snb_pafs_from_instances) for G frames, each head on its own grid (stride).  instances:
- * (G, I, N, 2); out_cms (G, N, h_cm, w_cm); out_pafs (G, E, 2, h_paf, w_paf); fp32 or bf16.  A persistent grid claims
- * 32 KB chunks of both outputs from a counter, so a SINGLE frame (what Dataset.__getitem__ produces,
- * data/custom_datasets.py:1305-1327) fills the GPU as well as a batch does.  workspace: 16 bytes, all zero before the
- * first call, self-resetting; calls that may run concurrently (different streams) need separate workspaces.
- * Values are those of snb_confmaps_ex / snb_pafs_from_instances bit for bit.  SNB_ERR_UNSUPPORTED for row lengths that
- * are not a multiple of 4 (8 for bf16 maps) or unaligned buffers: call the two stand-alone entry points instead. */
+ * (G, I, N, 2); out_cms (G, N, h_cm, w_cm); out_pafs (G, E, 2, h_paf, w_paf); fp32 or bf16.
+ * The two kernels are enqueued back to back as a programmatic-dependent-launch pair: the field kernel depends on
+ * nothing the map kernel writes, starts while the map kernel is still running and shares the SMs with it, and ties its
+ * own completion to the map kernel's - so a SINGLE frame (what Dataset.__getitem__ produces,
+ * data/custom_datasets.py:1305-1327; 33.5 + 65 MB at cfg4 size, too little for either kernel alone to fill the GPU)
+ * runs close to the store roofline.  Values are those of snb_confmaps_ex / snb_pafs_from_instances bit for bit. */
 int snb_bottomup_targets(const float* instances, int G, int I, int N, const int* n_valid, float oob_w, float oob_h,
                          const int* edges, int E, float in_xmax, float in_ymax, const float* xv_cm, const float* yv_cm,
                          int h_cm, int w_cm, float den_cm, const float* xv_paf, const float* yv_paf, int h_paf, int w_paf,
-                         float den_paf, int out_bf16, void* out_cms, void* out_pafs, void* workspace, void* stream);
+                         float den_paf, int out_bf16, void* out_cms, void* out_pafs, void* stream);
 
 /* Test hook: K7 divides by the per-launch constant 2*sigma^2 with a hoisted-reciprocal sequence instead of a full
  * div.rn per pixel; fast[i] = that sequence, exact[i] = __fdiv_rn(-a[i], den).  The parity tests require them equal
@@ -574,6 +574,7 @@ typedef struct snb_bottomup_args {
 
 #define SNB_FLAG_UNFUSED_TAIL 1 /* chain the stand-alone kernels instead of the fused per-frame tail */
 #define SNB_FLAG_SELF_RESET_COUNTERS 2 /* see snb_bottomup_args.n_peaks */
+#define SNB_FLAG_NO_TAIL_CLUSTER 4     /* batches of <= 16 frames: one CTA per frame instead of a 4-CTA cluster (A/B, tests) */
 
 /* The tail (everything after the streaming detect kernel) runs as ONE CTA per frame with all tables
  * in shared memory when snb_bottomup_tail_smem_bytes(...) <= 200 KB; the intermediate tables

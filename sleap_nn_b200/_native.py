@@ -79,7 +79,7 @@ SIGNATURES = {
     "snb_confmaps_ex": [_p, _i, _i, _i, _ll, _ll, _ll, _p, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
     "snb_pafs_from_instances": [_p, _i, _i, _i, _p, _i, _f, _f, _p, _p, _i, _i, _f, _i, _p, _p],
     "snb_bottomup_targets": [_p, _i, _i, _i, _p, _f, _f, _p, _i, _f, _f, _p, _p, _i, _i, _f, _p, _p, _i, _i, _f, _i, _p, _p,
-                             _p, _p],
+                             _p],
     "snb_debug_neg_div": [_p, _ll, _f, _p, _p, _p],
     "snb_edge_distance": [_p, _p, _p, _i, _ll, _p, _p, _i, _i, _f, _p, _p],
     "snb_gaussian_pdf": [_p, _ll, _f, _p, _p],
@@ -106,6 +106,7 @@ RETURNS_LONGLONG = {"snb_lsap_workspace_bytes": [_i], "snb_class_inds_workspace_
                    "snb_class_inds_grouped_workspace_bytes": [_i, _i, _i], "snb_topdown_select_smem_bytes": [_i, _i], "snb_bottomup_tail_smem_bytes": [_i, _i, _i, _i, _i, _i, _i]}
 FLAG_UNFUSED_TAIL = 1
 FLAG_SELF_RESET_COUNTERS = 2
+FLAG_NO_TAIL_CLUSTER = 4
 
 
 class BottomUpArgs(C.Structure):

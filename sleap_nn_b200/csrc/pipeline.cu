@@ -11,7 +11,11 @@
 // tail of batch i overlaps the detect pass of batch i+1: the detect kernel is the only part that
 // moves real bytes, so the step time tends to the HBM time of the confidence maps.
 // If the capacities do not fit in shared memory the stand-alone kernels are chained instead.
+#include <cooperative_groups.h>
+
 #include "paf_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace snb {
 
@@ -61,20 +65,36 @@ __host__ __device__ inline TailLayout tail_layout(int peak_cap, int n_nodes, int
 }
 
 constexpr int TAIL_THREADS = 256;
+constexpr int SNB_TAIL_CLUSTER = 4;              // CTAs per frame in the small-batch regime
+constexpr int SNB_TAIL_CLUSTER_MAX_FRAMES = 16;  // ... used up to this batch size
 
 // Profiling build only (-DSNB_TAIL_TIMING, tools/tail_phases.py): thread 0 of every CTA stamps clock64() at
 // the phase boundaries into asm_ws (unused by the fused tail), 16 ints per frame.
 #ifdef SNB_TAIL_TIMING
 #define SNB_STAMP(k)                                                                       \
   do {                                                                                     \
-    if (threadIdx.x == 0 && a.asm_ws) a.asm_ws[blockIdx.x * 16 + (k)] = (int)(clock64() - t_start); \
+    if (threadIdx.x == 0 && R == 0 && a.asm_ws) a.asm_ws[b * 16 + (k)] = (int)(clock64() - t_start); \
   } while (0)
 #else
 #define SNB_STAMP(k) do {} while (0)
 #endif
 
+// CS = CTAs per frame.  CS = 1: one CTA owns a frame (the pipelined regime: with a batch of 64 the tail hides under the
+// next batch's detect pass and more CTAs per frame would only take SMs away from it).  CS = 4 (small batches, where one
+// CTA per frame leaves most of the GPU idle and the tail's LATENCY is what the caller waits for): a thread-block cluster
+// per frame.  Every CTA of the cluster keeps the frame's full table set in its own shared memory; the cheap, sequential
+// steps (key sort, grouping by node) are computed redundantly by each CTA, the expensive parallel ones are split -
+// refinement over peaks (results broadcast to all CTAs through distributed shared memory), line scores over candidates
+// (each score stored into the shared memory of the CTA that owns the candidate's edge), assignments over edges (matches
+// stored into CTA 0) - and CTA 0 runs the assembly.  Three cluster barriers in total.
+template <int CS>
 __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomup_args a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int R = CS > 1 ? (int)cluster.block_rank() : 0;  // this CTA's rank inside the frame's cluster
+  // peer(p, r): the same shared-memory location in CTA r of the cluster (CS == 1: the local one)
+  auto peer = [&](auto* p, int r) { return CS > 1 ? cluster.map_shared_rank(p, (unsigned)r) : p; };
+  auto cluster_sync = [&]() { if (CS > 1) cluster.sync(); else __syncthreads(); };
   const int n_warps = TAIL_THREADS / 32;
   const TailLayout L = tail_layout(a.peak_cap, a.C, a.n_edges, a.cand_cap, a.match_cap, n_warps, a.n_sorted, a.n_points);
   uint32_t* s_keys = (uint32_t*)(smem + L.keys);
@@ -92,7 +112,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   int* s_m_dst = (int*)(smem + L.m_dst);
   float* s_m_score = (float*)(smem + L.m_score);
 
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / CS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_nodes = a.C, E = a.n_edges;
 #ifdef SNB_TAIL_TIMING
   const long long t_start = clock64();
@@ -106,7 +126,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   for (int i = tid; i < a.n_sorted; i += TAIL_THREADS) s_sorted[i] = a.sorted_edges[i];
   for (int i = tid; i < a.n_points; i += TAIL_THREADS) s_t[i] = a.t_table[i];
   const int total = a.frame_count[b];
-  if (total > a.peak_cap && tid == 0) atomicOr(a.status, SNB_STATUS_PEAK_OVERFLOW);
+  if (CS > 1) cluster.sync();  // every CTA of the cluster is running before anyone touches a peer's shared memory
+  if (total > a.peak_cap && tid == 0 && R == 0) atomicOr(a.status, SNB_STATUS_PEAK_OVERFLOW);
   const int n = min(total, a.peak_cap);
 
   // ---- 1. order the frame's keys: ascending key == (y, x, channel) == torch.where order
@@ -133,7 +154,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   const int cdt = a.cms_dtype;
   const void* frame = elem_ptr(a.cms, (long long)b * a.cms_sb, cdt);
   constexpr int RQ = 4;  // peaks refined together by one warp (their taps are all in flight at once)
-  for (int i0 = warp * RQ; i0 < n; i0 += n_warps * RQ) {
+  for (int i0 = (R * n_warps + warp) * RQ; i0 < n; i0 += CS * n_warps * RQ) {
     const void* plane[RQ];
     float fx[RQ], fy[RQ], ox[RQ], oy[RQ];
     int cc[RQ], xi[RQ], yi[RQ];
@@ -160,13 +181,17 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
         if (a.cms_stride != 1.0f) { x = __fmul_rn(x, a.cms_stride); y = __fmul_rn(y, a.cms_stride); }
         const int i = i0 + q;
         const float v = ld_elem(plane[q], (long long)yi[q] * a.cms_sh + (long long)xi[q] * a.cms_sw, cdt);
-        s_xy[2 * i] = x; s_xy[2 * i + 1] = y; s_val[i] = v; s_chan[i] = cc[q];
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {  // every CTA of the cluster gets the refined peak
+          float* pxy = peer(s_xy, r);
+          pxy[2 * i] = x; pxy[2 * i + 1] = y; peer(s_val, r)[i] = v; peer(s_chan, r)[i] = cc[q];
+        }
         const long long o = (long long)b * a.peak_cap + i;
         a.peak_xy[2 * o] = x; a.peak_xy[2 * o + 1] = y; a.peak_val[o] = v; a.peak_chan[o] = cc[q];
       }
     }
   }
-  __syncthreads();
+  cluster_sync();
 
   SNB_STAMP(1);
   // ---- 3. group peaks by node, candidate / match offsets
@@ -175,18 +200,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     if (lane == 0) edge_offsets(s_edges, n_nodes, E, s_ns, s_eo, s_mo);
   }
   __syncthreads();
-  if (a.max_peaks_per_node > 0 && a.skip_flag) {  // layers/bottomup.py:128-148: batch-wide guard
+  if (a.max_peaks_per_node > 0 && a.skip_flag && R == 0) {  // layers/bottomup.py:128-148: batch-wide guard
     bool over = false;
     for (int k = tid; k < n_nodes; k += TAIL_THREADS) over = over || (s_ns[k + 1] - s_ns[k] > a.max_peaks_per_node);
     if (over) atomicOr(a.skip_flag, 1);
   }
   const int M = s_eo[E];
   const bool cand_ok = M <= a.cand_cap;
-  if (!cand_ok && tid == 0) atomicOr(a.status, SNB_STATUS_CAND_OVERFLOW);
+  if (!cand_ok && tid == 0 && R == 0) atomicOr(a.status, SNB_STATUS_CAND_OVERFLOW);
   const int K = s_mo[E];
   const int klimit = min(K, a.match_cap);
-  if (K > klimit && tid == 0) atomicOr(a.status, SNB_STATUS_MATCH_OVERFLOW);
-  if (a.node_start) {  // optional copies of the intermediate tables (the API-level 6-tuple)
+  if (K > klimit && tid == 0 && R == 0) atomicOr(a.status, SNB_STATUS_MATCH_OVERFLOW);
+  if (a.node_start && R == 0) {  // optional copies of the intermediate tables (the API-level 6-tuple)
     for (int i = tid; i <= n_nodes; i += TAIL_THREADS) a.node_start[(long long)b * (n_nodes + 1) + i] = s_ns[i];
     for (int i = tid; i < n; i += TAIL_THREADS) a.node_peaks[(long long)b * a.peak_cap + i] = s_np[i];
     for (int i = tid; i <= E; i += TAIL_THREADS) {
@@ -200,24 +225,28 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   if (cand_ok) {
     ScoreArgs sa{a.pafs, a.pafs_dtype, a.paf_sb, a.paf_sy, a.paf_sx, a.paf_sc, a.paf_H, a.paf_W, s_t, a.n_points,
                  a.pafs_stride, a.max_edge_length, a.dist_penalty_weight};
-    for (int m = tid; m < M; m += TAIL_THREADS) {
+    for (int m = R * TAIL_THREADS + tid; m < M; m += CS * TAIL_THREADS) {
       int k, ps, pd;
       decode_candidate(m, s_eo, E, s_ns, s_edges, s_np, &k, &ps, &pd);
       const float sc = score_candidate(sa, b, k, s_xy[2 * ps], s_xy[2 * ps + 1], s_xy[2 * pd], s_xy[2 * pd + 1]);
-      s_score[m] = sc;
+      peer(s_score, k % CS)[m] = sc;  // into the CTA that solves edge k's assignment
       if (a.cand_edge) {
         const long long o = (long long)b * a.cand_cap + m;
         a.cand_edge[o] = k; a.cand_epi[2 * o] = ps; a.cand_epi[2 * o + 1] = pd; a.cand_score[o] = sc;
       }
     }
   }
-  __syncthreads();
+  cluster_sync();
 
   SNB_STAMP(3);
   // ---- 5. per-edge optimal assignment, one warp per edge (scipy's algorithm; the scan over free columns runs
   //         one column per lane when the problem fits 32 x 32, else lane 0 solves it serially in global scratch)
   if (cand_ok) {
-    for (int k = warp; k < E; k += n_warps) {
+    int* r0_m_edge = peer(s_m_edge, 0);
+    int* r0_m_src = peer(s_m_src, 0);
+    int* r0_m_dst = peer(s_m_dst, 0);
+    float* r0_m_score = peer(s_m_score, 0);
+    for (int k = R + CS * warp; k < E; k += CS * n_warps) {  // edge k belongs to CTA k % CS
       const int s = s_edges[2 * k], d = s_edges[2 * k + 1];
       if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) continue;
       const int n_src = s_ns[s + 1] - s_ns[s], n_dst = s_ns[d + 1] - s_ns[d];
@@ -245,16 +274,20 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
       }
       if (!ok) {
         if (lane == 0) atomicOr(a.status, SNB_STATUS_LSAP_INFEASIBLE);
-        for (int r = lane; r < n_match; r += 32) { s_m_edge[o + r] = k; s_m_src[o + r] = -1; s_m_dst[o + r] = -1; s_m_score[o + r] = NAN; }
+        for (int r = lane; r < n_match; r += 32) { r0_m_edge[o + r] = k; r0_m_src[o + r] = -1; r0_m_dst[o + r] = -1; r0_m_score[o + r] = NAN; }
         continue;
       }
-      for (int r = lane; r < n_match; r += 32) {
-        s_m_edge[o + r] = k;
-        s_m_score[o + r] = sc[s_m_src[o + r] * n_dst + s_m_dst[o + r]];
+      __syncwarp();
+      for (int r = lane; r < n_match; r += 32) {  // the solver wrote (src, dst) locally; CTA 0 gets the finished match rows
+        const int ms = s_m_src[o + r], md = s_m_dst[o + r];
+        r0_m_edge[o + r] = k;
+        r0_m_score[o + r] = sc[ms * n_dst + md];
+        if (CS > 1) { r0_m_src[o + r] = ms; r0_m_dst[o + r] = md; }
       }
     }
   }
-  __syncthreads();
+  cluster_sync();
+  if (R != 0) return;  // nobody reads this CTA's shared memory any more; CTA 0 finishes the frame alone
   const int n_matches = cand_ok ? klimit : 0;
   if (a.m_edge) {
     for (int i = tid; i < n_matches; i += TAIL_THREADS) {
@@ -454,10 +487,32 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
     cudaStreamWaitEvent(tail_st, (cudaEvent_t)a->ev_handoff, 0);
   }
   if (fused) {
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(bottomup_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return SNB_ERR_CUDA_LAUNCH;
-    bottomup_tail_kernel<<<a->B, TAIL_THREADS, (size_t)smem, tail_st>>>(*a);
+    // Small batches: a 4-CTA cluster per frame (see bottomup_tail_kernel).  From 17 frames on, one CTA per frame - the
+    // regime where tails hide under the next batch's detect pass and extra CTAs would only take SMs away from it.
+    const bool use_cluster = a->B <= SNB_TAIL_CLUSTER_MAX_FRAMES && !(a->flags & SNB_FLAG_NO_TAIL_CLUSTER);
+    if (use_cluster) {
+      if (smem > 48 * 1024 && cudaFuncSetAttribute(bottomup_tail_kernel<SNB_TAIL_CLUSTER>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)a->B * SNB_TAIL_CLUSTER);
+      cfg.blockDim = dim3(TAIL_THREADS);
+      cfg.dynamicSmemBytes = (size_t)smem;
+      cfg.stream = tail_st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = SNB_TAIL_CLUSTER;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (cudaLaunchKernelEx(&cfg, bottomup_tail_kernel<SNB_TAIL_CLUSTER>, *a) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+    } else {
+      if (smem > 48 * 1024 &&
+          cudaFuncSetAttribute(bottomup_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      bottomup_tail_kernel<1><<<a->B, TAIL_THREADS, (size_t)smem, tail_st>>>(*a);
+    }
     SNB_LAUNCH_CHECK();
   } else {
     rc = unfused_tail(a, (void*)tail_st);

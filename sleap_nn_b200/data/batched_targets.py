@@ -42,7 +42,6 @@ class BatchedTargets:
             raise N.NativeLibraryError("BatchedTargets needs a CUDA device: there is no CPU fallback")
         self.out_dtype = out_dtype
         self._grids: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}
-        self._fused_ws: Dict[int, torch.Tensor] = {}  # CUDA stream -> chunk counter of the fused kernel (self-resetting)
 
     # ------------------------------------------------------------------ helpers
     def _grid(self, stride: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -175,9 +174,9 @@ class BatchedTargets:
         """BottomUpDataset.__getitem__ targets (custom_datasets.py:1305-1327), collated: confidence maps
         (B, 1, N, h, w) and part-affinity fields (B, 2E, h', w').
 
-        Both targets come out of ONE launch (`snb_bottomup_targets`: a persistent grid over 32 KB chunks of both outputs),
-        so a single frame - the reference's granularity - fills the GPU; values are bit-identical to `multi_confmaps` +
-        `pafs`, which are used instead for shapes the fused kernel does not take (`fused=False` forces them)."""
+        Both targets come out of ONE call (`snb_bottomup_targets`: the two kernels as a programmatic-dependent-launch
+        pair that share the SMs), so a single frame - the reference's granularity - fills the GPU; values are
+        bit-identical to `multi_confmaps` + `pafs` (`fused=False` issues those two calls instead)."""
         if fused:
             out = self._bottomup_fused(instances, num_instances, edge_inds, confmap_sigma, confmap_stride, paf_sigma, paf_stride)
             if out is not None:
@@ -197,24 +196,19 @@ class BatchedTargets:
         xv8, yv8 = self._grid(paf_stride)
         h7, w7, h8, w8 = int(yv7.shape[0]), int(xv7.shape[0]), int(yv8.shape[0]), int(xv8.shape[0])
         bf16 = self.out_dtype == torch.bfloat16
-        if B == 0 or w7 % (8 if bf16 else 4) or w8 % 4 or (bf16 and w7 > 1024):
+        if B == 0:
             return None
         n_valid = self._counts(num_instances, B)
         xmax = float(((self.img_hw[1] - 1) // paf_stride) * paf_stride)
         ymax = float(((self.img_hw[0] - 1) // paf_stride) * paf_stride)
         with torch.cuda.device(self.device):
             st = N.stream_ptr(self.device)
-            ws = self._fused_ws.get(st)
-            if ws is None:
-                if len(self._fused_ws) >= 16:
-                    self._fused_ws.clear()
-                ws = self._fused_ws[st] = torch.zeros((4,), dtype=torch.int32, device=self.device)
             cms = torch.empty((B, Nn, h7, w7), dtype=self.out_dtype, device=self.device)
             pafs = torch.empty((B, E, 2, h8, w8), dtype=self.out_dtype, device=self.device)
             sig7 = confmap_sigma * confmap_stride  # generate_multiconfmaps scales sigma by the stride, generate_pafs does not
             rc = N.lib.snb_bottomup_targets(N.ptr(x), B, I, Nn, N.ptr(n_valid), 0.0, 0.0, N.ptr(e), E, xmax, ymax,
                                             N.ptr(xv7), N.ptr(yv7), h7, w7, float(2 * sig7**2), N.ptr(xv8), N.ptr(yv8), h8, w8,
-                                            float(2 * paf_sigma**2), int(bf16), N.ptr(cms), N.ptr(pafs), N.ptr(ws), st)
+                                            float(2 * paf_sigma**2), int(bf16), N.ptr(cms), N.ptr(pafs), st)
         if rc == -2:  # SNB_ERR_UNSUPPORTED: shapes / smem the fused kernel does not take
             return None
         N.check(rc, "snb_bottomup_targets")

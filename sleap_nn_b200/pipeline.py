@@ -122,6 +122,9 @@ class BottomUpPostproc:
         fused_tail: run everything after the detect kernel as one CTA per frame with shared-memory
             tables (default; falls back automatically when the capacities do not fit).
         keep_tables: also write the intermediate tables (candidates, matches) to global memory.
+        tail_cluster: batches of <= 16 frames run the tail as a 4-CTA thread-block cluster per frame (refinement,
+            line scores and assignments split over the CTAs through distributed shared memory) - the latency of a lone
+            call instead of the throughput of a pipelined one; False keeps one CTA per frame (A/B, tests).
     """
 
     def __init__(self, n_nodes: int, edge_inds: Sequence[Tuple[int, int]], batch: int, cms_hw: Tuple[int, int],
@@ -132,7 +135,7 @@ class BottomUpPostproc:
                  cand_cap: int = 4096, match_cap: int = 512, inst_cap: int = 64, lsap_max_dim: int = 32,
                  device: Optional[torch.device] = None, tail_stream: Optional[torch.cuda.Stream] = None,
                  fused_tail: bool = True, keep_tables: bool = True, max_instances: Optional[int] = None,
-                 max_peaks_per_node: Optional[int] = None):
+                 max_peaks_per_node: Optional[int] = None, tail_cluster: bool = True):
         self.device = torch.device(device) if device is not None else N.compute_device()
         self.n_nodes, self.batch = int(n_nodes), int(batch)
         self.edge_inds = [(int(a), int(b)) for a, b in edge_inds]
@@ -187,6 +190,8 @@ class BottomUpPostproc:
             a.lsap_ws = None
         a.ev_detect_begin = a.ev_detect_end = None
         a.flags = 0 if fused_tail else N.FLAG_UNFUSED_TAIL
+        if not tail_cluster:
+            a.flags |= N.FLAG_NO_TAIL_CLUSTER
         a.n_peaks = None
         self.fused = int(N.lib.snb_bottomup_launches_per_call(C.byref(a))) == 2
         if self.fused:

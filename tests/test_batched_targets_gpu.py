@@ -118,9 +118,9 @@ def _random_batch(seed, B, I, Nn, hw):
                                              ((256, 256), 9, 3, 5, 4, 2)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_fused_bottomup_targets_equal_the_two_kernels(hw, B, I, Nn, s7, s8, dt):
-    """snb_bottomup_targets (one persistent launch for both targets) == snb_confmaps_ex + snb_pafs_from_instances, bit for
-    bit, fp32 and bf16, single frames and batches, different strides per head; repeated launches reuse the self-resetting
-    chunk counter."""
+    """snb_bottomup_targets (both targets as an overlapping programmatic-dependent-launch pair) == snb_confmaps_ex +
+    snb_pafs_from_instances, bit for bit, fp32 and bf16, single frames and batches, different strides per head; repeated
+    back-to-back calls (each pair's successor overlaps its tail) stay correct."""
     bt = _bt(hw, out_dtype=dt)
     inst, num = _random_batch(B * 7 + I, B, I, Nn, hw)
     edges = [(k, k + 1) for k in range(Nn - 1)] or [(0, 0)]
@@ -132,7 +132,6 @@ def test_fused_bottomup_targets_equal_the_two_kernels(hw, B, I, Nn, s7, s8, dt):
                            sep["confidence_maps"].view(torch.int16 if dt == torch.bfloat16 else torch.int32)), rep
         assert torch.equal(fu["part_affinity_fields"].view(torch.int16 if dt == torch.bfloat16 else torch.int32),
                            sep["part_affinity_fields"].view(torch.int16 if dt == torch.bfloat16 else torch.int32)), rep
-    assert int(next(iter(bt._fused_ws.values())).abs().sum()) == 0  # the counter went back to zero
 
 
 def test_bf16_confmaps_separable_form_vs_exact_fp32():

@@ -33,17 +33,57 @@ def peak_gbs():
         return 6650.0, "fallback"
 
 
+GRAPH = os.environ.get("SNB_BENCH_GRAPH", "1") != "0"
+
+
 def timed(fn, iters, warm=10):
+    """ms per launch of `iters` back-to-back launches on one stream, CUDA events around the whole run.
+
+    The launches are replayed from a CUDA graph (captured once, replayed warm) so that short kernels are timed at the
+    GPU's pace: issued one by one from this Python loop, a ctypes call + cudaLaunchKernelEx costs ~12 us of host time,
+    more than a single-frame target kernel runs.  SNB_BENCH_GRAPH=0 times the eager loop instead; both are reported
+    when they differ by more than 10 %."""
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(iters):
-        fn(i)
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters  # ms per launch
+
+    def run_eager():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(iters):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    eager = run_eager()
+    timed.last = {"eager_ms": eager, "graph_ms": None}
+    if not GRAPH:
+        return eager
+    try:
+        st = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                for i in range(iters):
+                    fn(i)
+            g.replay()
+            st.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            g.replay()
+            b.record(st)
+            st.synchronize()
+        ms = a.elapsed_time(b) / iters
+        timed.last["graph_ms"] = ms
+        return min(ms, eager)
+    except Exception as e:  # noqa: BLE001 - capture not possible for this launcher: keep the eager figure
+        timed.last["graph_error"] = f"{type(e).__name__}: {e}"
+        torch.cuda.synchronize()
+        return eager
+
+
+timed.last = {}
 
 
 RESULTS = []  # every line() of this process, in order (bench.py's `extra` block reads it)
@@ -55,6 +95,9 @@ def line(name, kernel, algo_bytes, ms, units, unit_name, extra=None):
     d = {"bench": name, "kernel": kernel, "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": ms,
          "achieved_GBps": ach, "peak_GBps": peak, "peak_source": src, "frac": ach / peak,
          f"{unit_name}_per_s": units / (ms / 1e3)}
+    if timed.last.get("graph_ms") is not None:
+        d["launch_loop"] = ("CUDA graph replay" if timed.last["graph_ms"] <= timed.last["eager_ms"] else "eager Python loop")
+        d["eager_loop_ms"], d["graph_replay_ms"] = timed.last["eager_ms"], timed.last["graph_ms"]
     if extra:
         d.update(extra)
     RESULTS.append(d)
@@ -85,13 +128,13 @@ def k2_cfg2(dev, iters, B=256, dtype=torch.float32):
     ws = torch.zeros(((nbytes.value + 3) // 4,), dtype=torch.int32, device=dev)
     pts_o = torch.empty((B, Cn, 2), device=dev)
     val_o = torch.empty((B, Cn), device=dev)
-    st = N.stream_ptr(dev)
+    st = lambda: N.stream_ptr(dev)  # the CURRENT stream at launch time (the capture stream during graph capture)
     dt = N.dtype_code(dtype)
 
     def fn(i):
         x = bufs[i % len(bufs)]
         N.check(N.lib.snb_global_peaks_t(N.ptr(x), dt, B, Cn, H, W, *x.stride(), 0.2, 5, N.ptr(ws), None, N.ptr(pts_o),
-                                         N.ptr(val_o), st), "k2")
+                                         N.ptr(val_o), st()), "k2")
 
     ms = timed(fn, iters)
     tag = ("" if B == 256 else f"_b{B}") + ("" if dtype == torch.float32 else "_" + str(dtype).split(".")[-1])
@@ -114,12 +157,12 @@ def k1_cfg3(dev, iters, dtype=torch.float32):
     cap = 256
     count = torch.empty((Bn,), dtype=torch.int32, device=dev)
     keys = torch.empty((Bn * cap,), dtype=torch.int32, device=dev)
-    st, dt = N.stream_ptr(dev), N.dtype_code(dtype)
+    st, dt = (lambda: N.stream_ptr(dev)), N.dtype_code(dtype)
 
     def fn(i):
         x = bufs[i % len(bufs)]
         N.check(N.lib.snb_local_peaks_detect_t(N.ptr(x), dt, Bn, Cn, H, W, *x.stride(), 0.2, cap, N.ptr(count), N.ptr(keys),
-                                               None, None, st), "k1")
+                                               None, None, st()), "k1")
 
     ms = timed(fn, iters)
     return line("k1_cfg3_" + str(dtype).split(".")[-1], "local_peaks_detect_vec", esz * Bn * Cn * H * W, ms, Bn, "frames",
@@ -141,12 +184,12 @@ def k7_cfg4(dev, iters, bf16=False, G=8):
     dt = torch.bfloat16 if bf16 else torch.float32
     n_out = max(3, -(-400_000_000 // (G * 32 * 512 * 512 * (2 if bf16 else 4))))  # rotate over > 3 x L2
     outs = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(n_out)]
-    st = N.stream_ptr(dev)
+    st = lambda: N.stream_ptr(dev)  # the CURRENT stream at launch time (the capture stream during graph capture)
     den = float(2 * (2.5 * 2) ** 2)
 
     def fn(i):
         N.check(N.lib.snb_confmaps(N.ptr(pts), G, 8, 32, N.ptr(xd), N.ptr(yd), 512, 512, den, int(bf16),
-                                   N.ptr(outs[i % n_out]), st), "k7")
+                                   N.ptr(outs[i % n_out]), st()), "k7")
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
@@ -166,13 +209,13 @@ def k8_cfg4(dev, iters, bf16=False, G=1):
     dsts = [pd[f][:, :, e[:, 1]].contiguous() for f in range(n_sets)]
     dt = torch.bfloat16 if bf16 else torch.float32
     outs = [torch.empty((G, 31, 2, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
-    st = N.stream_ptr(dev)
+    st = lambda: N.stream_ptr(dev)  # the CURRENT stream at launch time (the capture stream during graph capture)
     den = float(2 * 2.5 ** 2)
 
     def fn(i):
         k = i % n_sets
         N.check(N.lib.snb_pafs(N.ptr(srcs[k]), N.ptr(dsts[k]), G, 8, 31, N.ptr(xd), N.ptr(yd), 512, 512, den, 1,
-                               int(bf16), N.ptr(outs[k]), st), "k8")
+                               int(bf16), N.ptr(outs[k]), st()), "k8")
 
     ms = timed(fn, iters)
     esz = 2 if bf16 else 4
@@ -192,21 +235,20 @@ def targets_cfg4_fused(dev, iters, bf16=False, G=1):
     bt = BatchedTargets((1024, 1024), device=dev, out_dtype=torch.bfloat16 if bf16 else torch.float32)
     e = torch.tensor(edges, dtype=torch.int32, device=dev)
     xv, yv = bt._grid(2)
-    ws = torch.zeros((4,), dtype=torch.int32, device=dev)
     dt = torch.bfloat16 if bf16 else torch.float32
     cms = [torch.empty((G, 32, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
     pafs = [torch.empty((G, 31, 2, 512, 512), dtype=dt, device=dev) for _ in range(n_sets)]
-    st = N.stream_ptr(dev)
+    st = lambda: N.stream_ptr(dev)  # the CURRENT stream at launch time (the capture stream during graph capture)
     den7, den8 = float(2 * (2.5 * 2) ** 2), float(2 * 2.5 ** 2)
 
     def fn(i):
         k = i % n_sets
         N.check(N.lib.snb_bottomup_targets(N.ptr(pd[k]), G, 8, 32, None, 0.0, 0.0, N.ptr(e), 31, 1022.0, 1022.0, N.ptr(xv),
                                            N.ptr(yv), 512, 512, den7, N.ptr(xv), N.ptr(yv), 512, 512, den8, int(bf16),
-                                           N.ptr(cms[k]), N.ptr(pafs[k]), N.ptr(ws), st), "fused targets")
+                                           N.ptr(cms[k]), N.ptr(pafs[k]), st()), "fused targets")
 
     ms = timed(fn, iters)
-    return line(f"targets_cfg4_fused_g{G}" + ("_bf16" if bf16 else ""), "targets_fused_kernel", per_launch, ms, G, "frames",
+    return line(f"targets_cfg4_fused_g{G}" + ("_bf16" if bf16 else ""), "confmaps_rows2 / confmaps_sep + pafs_rows (PDL pair)", per_launch, ms, G, "frames",
                 {"frames_per_launch": G, "out_dtype": str(dt)})
 
 
