@@ -352,7 +352,17 @@ struct AsmFrame {
   int min_instance_peaks; float min_line_scores;
   int* owner; int* order; int* id_count; int* id_rank; unsigned char* fa; unsigned char* fb;
   int inst_cap; float* oxy; float* oval; float* osc; int* n_inst_out; int* status;
+  int* stamps = nullptr; long long t0 = 0;  // profiling build (-DSNB_TAIL_TIMING): clock64 stamps of the assembly's phases
+  // optional scratch (the fused tail lends its candidate-score table, free once the assignments are solved): with at
+  // least 2 * K + n_edges + n_sorted + inst_cap + 2 words the post-loop passes run flattened over the connections in
+  // visiting order instead of edge by edge (see assemble_frame_warp)
+  int* scratch = nullptr; int scratch_words = 0; int n_edges = 0;
 };
+#ifdef SNB_TAIL_TIMING
+#define SNB_ASM_STAMP(k) do { if (lane == 0 && f.stamps) f.stamps[(k)] = (int)(clock64() - f.t0); } while (0)
+#else
+#define SNB_ASM_STAMP(k) do {} while (0)
+#endif
 
 // One connection, applied by the whole warp exactly as the reference's loop body does (paf.py:754-789).  Used when
 // a chunk of an edge's connections cannot be applied together (a merge candidate, a repeated peak, a self edge).
@@ -416,13 +426,28 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
   __syncwarp();
   int n_order = 0, mx = -1;
-  for (int se = 0; se < f.n_sorted; ++se) {
-    const int e = f.sorted[se];
-    const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+  // per-edge header (edge id, node offsets, match range): a chain of three dependent loads.  The NEXT edge's header is
+  // fetched before the current edge's connections are applied, so the chain overlaps the body instead of heading it.
+  struct EdgeHdr { int e, s0, d0, n_src, n_dst, m_lo, m_hi; bool distinct; };
+  auto load_hdr = [&](int se) -> EdgeHdr {
+    EdgeHdr hd;
+    hd.e = f.sorted[se];
+    const int sn = f.edges[2 * hd.e], dn = f.edges[2 * hd.e + 1];
     const bool nodes_ok = sn >= 0 && sn < f.n_nodes && dn >= 0 && dn < f.n_nodes;
-    const int s0 = nodes_ok ? f.ns[sn] : 0, d0 = nodes_ok ? f.ns[dn] : 0;
-    const int n_src = nodes_ok ? f.ns[sn + 1] - s0 : 0, n_dst = nodes_ok ? f.ns[dn + 1] - d0 : 0;
-    const int m_lo = f.mo ? min(f.mo[e], K) : 0, m_hi = f.mo ? min(f.mo[e + 1], K) : K;
+    hd.s0 = nodes_ok ? f.ns[sn] : 0;
+    hd.d0 = nodes_ok ? f.ns[dn] : 0;
+    hd.n_src = nodes_ok ? f.ns[sn + 1] - hd.s0 : 0;
+    hd.n_dst = nodes_ok ? f.ns[dn + 1] - hd.d0 : 0;
+    hd.m_lo = f.mo ? min(f.mo[hd.e], K) : 0;
+    hd.m_hi = f.mo ? min(f.mo[hd.e + 1], K) : K;
+    hd.distinct = sn != dn;
+    return hd;
+  };
+  EdgeHdr nxt = f.n_sorted > 0 ? load_hdr(0) : EdgeHdr{};
+  for (int se = 0; se < f.n_sorted; ++se) {
+    const EdgeHdr hd = nxt;
+    if (se + 1 < f.n_sorted) nxt = load_hdr(se + 1);
+    const int e = hd.e, s0 = hd.s0, d0 = hd.d0, n_src = hd.n_src, n_dst = hd.n_dst, m_lo = hd.m_lo, m_hi = hd.m_hi;
     for (int mb = m_lo; mb < m_hi; mb += 32) {
       const int m = mb + lane;
       bool act = m < m_hi && f.m_edge[m] == e && (f.m_score[m] >= f.min_line_scores);  // paf.py:993
@@ -445,7 +470,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       const unsigned same_a = __match_any_sync(FULL, pa), same_b = __match_any_sync(FULL, pb);  // both by ALL lanes
       const bool repeated = __popc(same_a) > 1 || __popc(same_b) > 1;
       __syncwarp();  // owner[] reads above happen before any write below
-      if (sn != dn && !__any_sync(FULL, merge || repeated)) {
+      if (hd.distinct && !__any_sync(FULL, merge || repeated)) {
         const unsigned b1 = __ballot_sync(FULL, c1), b2 = __ballot_sync(FULL, c2);
         const int off = n_order + 2 * __popc(b1 & lt) + __popc(b2 & lt);
         if (c1) {
@@ -474,6 +499,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       }
     }
   }
+  SNB_ASM_STAMP(6);
   // instance sizes, min_instance_peaks filter, ascending-id compaction (paf.py:791-818, :845-850)
   for (int i = lane; i < P; i += 32)
     if (f.owner[i] >= 0) atomicAdd(&f.id_count[f.owner[i]], 1);
@@ -491,6 +517,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
     if (lane == 0) { atomicOr(f.status, SNB_STATUS_INSTANCE_OVERFLOW); *f.n_inst_out = n_inst; }
     return;
   }
+  SNB_ASM_STAMP(7);
   for (int i = lane; i < n_inst * f.n_nodes; i += 32) { f.oxy[2 * i] = NAN; f.oxy[2 * i + 1] = NAN; f.oval[i] = NAN; }
   if (lane == 0) *f.n_inst_out = n_inst;
   // instance score = fp32 running sum of its connections' scores in visiting order (paf.py:853-865): lane r owns
@@ -500,6 +527,93 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   // The same pass replays the reference's sanity check (ops/paf.py:866-873): a visited connection whose source is in a
   // kept instance must have its destination in the SAME instance - otherwise the reference raises (AssertionError, or
   // KeyError when the destination is in no kept instance).  Only improper matchings fed to the grouping API get there.
+  if (f.scratch && f.mo && f.scratch_words >= 2 * K + f.n_edges + f.n_sorted + n_inst + 2) {
+    // ---- flattened passes.  Connection m of edge e is visited at position voff[se(e)] + (m - mo[e]) (edges in
+    // `sorted` order, connections in list order).  One parallel pass over ALL connections resolves each one's instance
+    // rank and writes (rank, score) at its visiting position; the score sums then walk that list 32 positions at a
+    // time: lanes holding the same instance form a group (__match_any_sync) whose lowest lane adds the group's scores
+    // in lane (= visiting) order on top of the instance's running sum - the strict left-to-right fp32 sum of
+    // paf.py:853-865, without every lane scanning every connection (was 18.6 + 12.4 us of a busy frame's 53 us).
+    int* spos = f.scratch;                       // n_edges : position of edge e in `sorted`, -1 = never visited
+    int* voff = spos + f.n_edges;                // n_sorted + 1
+    int* vrank = voff + f.n_sorted + 1;          // K
+    float* vscore = reinterpret_cast<float*>(vrank + K);  // K
+    float* acc = vscore + K;                     // n_inst
+    for (int e = lane; e < f.n_edges; e += 32) spos[e] = -1;
+    for (int r = lane; r < n_inst; r += 32) acc[r] = 0.f;
+    __syncwarp();
+    int run = 0;
+    for (int s0 = 0; s0 < f.n_sorted; s0 += 32) {  // exclusive scan of the per-edge connection counts
+      const int se = s0 + lane;
+      int cnt = 0;
+      if (se < f.n_sorted) {
+        const int e = f.sorted[se];
+        spos[e] = se;
+        cnt = min(f.mo[e + 1], K) - min(f.mo[e], K);
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (se < f.n_sorted) voff[se] = run + inc - cnt;
+      run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) voff[f.n_sorted] = run;
+    const int n_vis = run;
+    __syncwarp();
+    for (int v = lane; v < n_vis; v += 32) vrank[v] = -1;
+    __syncwarp();
+    for (int m = lane; m < K; m += 32) {
+      const int e = f.m_edge[m];
+      if (e < 0 || e >= f.n_edges) continue;
+      const int se = spos[e];
+      if (se < 0) continue;
+      const int m_lo = min(f.mo[e], K), m_hi = min(f.mo[e + 1], K);
+      if (m < m_lo || m >= m_hi) continue;  // not in its edge's slice: never visited
+      const float sc = f.m_score[m];
+      if (!(sc >= f.min_line_scores)) continue;
+      const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+      if (sn < 0 || sn >= f.n_nodes) continue;
+      const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
+      const bool dn_ok = dn >= 0 && dn < f.n_nodes;
+      const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
+      const int sp = f.m_src[m], dp = f.m_dst[m];
+      if (sp < 0 || sp >= n_src) continue;
+      const int o = f.owner[f.np_[s0 + sp]];
+      const int rk = (o >= 0) ? f.id_rank[o] : -1;
+      const int pos = voff[se] + (m - m_lo);
+      vrank[pos] = rk;
+      vscore[pos] = sc;
+      if (rk >= 0 && dp >= 0 && dp < n_dst) {  // the reference's sanity check (ops/paf.py:866-873)
+        const int od = f.owner[f.np_[d0 + dp]];
+        const int rd = (od >= 0) ? f.id_rank[od] : -1;
+        if (rd < 0) atomicOr(f.status, SNB_STATUS_ASM_MISSING);
+        else if (rd != rk) atomicOr(f.status, SNB_STATUS_ASM_MISMATCH);
+      }
+    }
+    __syncwarp();
+    SNB_ASM_STAMP(8);
+    for (int v0 = 0; v0 < n_vis; v0 += 32) {
+      const int v = v0 + lane;
+      const int rk = v < n_vis ? vrank[v] : -1;
+      const float sc = v < n_vis ? vscore[v] : 0.f;
+      const unsigned peers = __match_any_sync(FULL, rk >= 0 ? rk : -1 - lane);
+      const bool leader = rk >= 0 && (__ffs(peers) - 1) == lane;
+      const unsigned any_valid = __ballot_sync(FULL, rk >= 0);
+      if (any_valid == 0) continue;
+      float a = leader ? acc[rk] : 0.f;
+      const int last = 31 - __clz(any_valid);
+      for (int k = __ffs(any_valid) - 1; k <= last; ++k) {
+        const float t = __shfl_sync(FULL, sc, k);
+        if (leader && ((peers >> k) & 1u)) a = __fadd_rn(a, t);
+      }
+      if (leader) acc[rk] = a;
+      __syncwarp();
+    }
+    for (int r = lane; r < n_inst; r += 32) f.osc[r] = acc[r];
+  } else {
   int* m_rank = (K <= P) ? f.id_count : nullptr;
   __syncwarp();
   if (m_rank) {
@@ -530,6 +644,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
     }
   }
   __syncwarp();
+  SNB_ASM_STAMP(8);
   for (int r0 = 0; r0 < n_inst; r0 += 32) {
     const int r = r0 + lane;
     float acc = 0.f;
@@ -555,6 +670,8 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
     }
     if (r < n_inst) f.osc[r] = acc;
   }
+  }  // edge-by-edge passes (no scratch)
+  SNB_ASM_STAMP(9);
   __syncwarp();  // the NaN fill above is ordered before the scatter below
   // scatter in first-assignment order, later entries overwrite (paf.py:879-885): 32 entries per round, and inside a
   // round only the LAST lane aiming at a slot writes

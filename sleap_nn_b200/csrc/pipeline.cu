@@ -315,6 +315,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     f.oval = a.inst_val + (long long)b * a.inst_cap * n_nodes;
     f.osc = a.inst_score + (long long)b * a.inst_cap;
     f.n_inst_out = a.n_inst + b; f.status = a.status;
+    f.scratch = reinterpret_cast<int*>(s_score);  // candidate scores are dead once the assignments are solved
+    f.scratch_words = a.cand_cap; f.n_edges = E;
+#ifdef SNB_TAIL_TIMING
+    f.stamps = a.asm_ws ? a.asm_ws + b * 16 : nullptr; f.t0 = t_start;
+#endif
     assemble_frame_warp(f, lane);
   }
   SNB_STAMP(5);

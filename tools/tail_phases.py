@@ -27,9 +27,14 @@ pipe = BottomUpPostproc(Nn, edges, Bn, (512, 512), device=dev, keep_tables=False
 for _ in range(3):
     res = pipe(cms, pafs)
 torch.cuda.synchronize()
-t = pipe.buf["asm_ws"][: Bn * 16].reshape(Bn, 16)[:, :6].cpu().double()
+raw = pipe.buf["asm_ws"][: Bn * 16].reshape(Bn, 16).cpu().double()
+t = raw[:, :6]
 d = torch.cat([t[:, :1], t[:, 1:] - t[:, :-1]], dim=1)
 names = ["sort", "refine", "group", "score", "match", "assemble"]
+sub = raw[:, [4, 6, 7, 8, 9, 5]]  # match end | greedy loop | compaction | NaN fill + rank pass | score sums | scatter (= assemble end)
+sd = sub[:, 1:] - sub[:, :-1]
+for k, nm in enumerate(["asm: greedy loop", "asm: count+compact", "asm: fill+rank pass", "asm: score sums", "asm: scatter"]):
+    print(f"{nm:20s} {float(sd[:, k].median()):10.0f} cycles  ~{float(sd[:, k].median()) / 1900.0:8.1f} us")
 mhz = 1900.0
 print(cfg, "peaks/frame", float(res.n_peaks.float().mean()), "instances/frame", float(res.n_instances.float().mean()))
 for k, nm in enumerate(names):
