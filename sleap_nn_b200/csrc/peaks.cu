@@ -1049,10 +1049,11 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
     // 8 warps per CTA; the variant (128-bit loads in flight per lane, rows per warp, CTAs per SM) is picked by the
     // number of 128-bit vectors per row.  One row per warp with 4 loads per lane for >= 128 vectors (fp32 W >= 512,
     // half W >= 1024), 40 registers -> 6 CTAs = 48 warps per SM, and a NON-persistent grid so the hardware CTA
-    // scheduler balances the SMs.  Rows of 64..127 vectors (half-precision cfg3 maps: 512 x 2 B = 1 KB) take two
-    // rows of two loads each so that a lane still has 4 x 16 B in flight.
+    // scheduler balances the SMs.  Rows of 64..127 vectors (fp32 W = 256; half-precision cfg3 maps: 512 x 2 B = 1 KB):
+    // one row of two loads per lane at 32 registers -> 8 CTAs = 64 warps per SM.  A/B on B200 for f16 cfg3 maps
+    // (profiles/r2_detect_ab.jsonl): (2 loads, 1 row, 8 CTAs) 28.9 us, (2, 2, 6) 30.8 us, (2, 4, 4) 33.0 us, (4, 1, 6) 34.9 us.
     const int vecs = W / PER;
-    int variant = (vecs >= 128) ? 0 : (vecs >= 64 ? (PER == 8 ? 6 : 1) : 2);
+    int variant = (vecs >= 128) ? 0 : (vecs >= 64 ? 1 : 2);
 #ifdef SNB_AB_VARIANTS
     static const int forced = getenv("SNB_DETECT_VARIANT") ? atoi(getenv("SNB_DETECT_VARIANT")) : -1;
     if (forced >= 0) variant = forced;
@@ -1069,10 +1070,10 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
   } while (0)
     switch (variant) {
       case 0: SNB_DETECT(4, 1, 6); break;  // >= 128 vectors per row
-      case 1: SNB_DETECT(2, 1, 8); break;  // 64..127 vectors per row (fp32)
-      case 6: SNB_DETECT(2, 2, 6); break;  // 64..127 vectors per row (fp16 / bf16): two rows per warp
+      case 1: SNB_DETECT(2, 1, 8); break;  // 64..127 vectors per row
       case 2: SNB_DETECT(1, 4, 6); break;  // narrow maps: four rows of one load each
 #ifdef SNB_AB_VARIANTS
+      case 6: SNB_DETECT(2, 2, 6); break;  // A/B: two rows of two loads
       case 4: SNB_DETECT(4, 2, 4); break;  // A/B: 8 loads per lane
       case 7: SNB_DETECT(2, 4, 4); break;  // A/B: four rows of two loads
       case 8: SNB_DETECT(2, 1, 8); break;  // A/B: one row of two loads, 8 CTAs / SM

@@ -82,6 +82,7 @@ def main():
     ap.add_argument("--oracle-sample", type=int, default=256,
                     help="frames per rank (seeded random sample) re-rendered and compared with the CPU oracle")
     ap.add_argument("--dump", default=os.path.join(ROOT, "gpurun_out"), help="directory for the offending-frame dumps")
+    ap.add_argument("--cpu-frames", type=int, default=64, help="frames of the CPU reference sample timed beside the sweep (0 = skip)")
     ap.add_argument("--as-rank", type=int, default=None,
                     help="single process only: run the shard (frame range AND seeds) that rank --as-rank of --as-world owns, "
                          "to reproduce one shard of a multi-GPU run on one GPU")
@@ -165,6 +166,22 @@ def main():
         maxs, sums = t.tolist(), nb.tolist()
     ms, worst, max_abs_px, max_score_err, gather_ms = maxs
     n_bad, n_checked, n_mismatch, n_off, n_off_checked, n_off_equal = (int(v) for v in sums)
+    cpu_ref = None
+    if (rank == 0 or emulate) and args.cpu_frames > 0:
+        # the reference's own CPU chain on a bounded sample of the same frames (BASELINE configs[4]: "... vs host-core CPU
+        # reference"): the unmodified files staged under baseline/_ref when present, else the oracle port
+        import bench
+
+        fn, kind, what = bench.cpu_arm(edges)
+        c, p = source(start, min(start + args.cpu_frames, stop))
+        c, p = c.cpu(), p.cpu()
+        torch.set_num_threads(os.cpu_count() or 1)
+        fn(c[:8], p[:8])
+        t_c = time.perf_counter()
+        fn(c, p)
+        t_c = time.perf_counter() - t_c
+        cpu_ref = {"frames_per_s": c.shape[0] / t_c, "kind": kind, "threads": torch.get_num_threads(), "what": what,
+                   "sample": f"{c.shape[0]} frames of the shard"}
     if rank == 0 or emulate:
         if emulate:
             args.frames = stop - start
@@ -178,7 +195,7 @@ def main():
             "offending_frames_where_oracle_gives_the_same_result": n_off_equal,
             "oracle_checked_frames": n_checked, "oracle_mismatching_frames": n_mismatch,
             "oracle_max_abs_px": max_abs_px, "oracle_max_score_err": max_score_err,
-            "gather_ms": gather_ms, "launches_per_rank": runner.launches,
+            "gather_ms": gather_ms, "launches_per_rank": runner.launches, "cpu_reference": cpu_ref,
         }), flush=True)
         # parity: every frame looked at (all offenders up to 64 per rank + the random sample) equals the oracle - same
         # instance count and order, keypoints within 1e-4 px, scores within 1e-5; an offending frame is then a property of
