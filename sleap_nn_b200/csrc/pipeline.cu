@@ -67,6 +67,7 @@ __host__ __device__ inline TailLayout tail_layout(int peak_cap, int n_nodes, int
 constexpr int TAIL_THREADS = 256;
 constexpr int SNB_TAIL_CLUSTER = 4;              // CTAs per frame in the small-batch regime
 constexpr int SNB_TAIL_CLUSTER_MAX_FRAMES = 16;  // ... used up to this batch size
+constexpr int SNB_TAIL_CLUSTER_MIN_EDGES = 8;    // ... and from this many skeleton edges on
 
 // Profiling build only (-DSNB_TAIL_TIMING, tools/tail_phases.py): thread 0 of every CTA stamps clock64() at
 // the phase boundaries into asm_ws (unused by the fused tail), 16 ints per frame.
@@ -494,7 +495,11 @@ extern "C" int snb_bottomup_postproc(const snb_bottomup_args* a, void* stream) {
   if (fused) {
     // Small batches: a 4-CTA cluster per frame (see bottomup_tail_kernel).  From 17 frames on, one CTA per frame - the
     // regime where tails hide under the next batch's detect pass and extra CTAs would only take SMs away from it.
-    const bool use_cluster = a->B <= SNB_TAIL_CLUSTER_MAX_FRAMES && !(a->flags & SNB_FLAG_NO_TAIL_CLUSTER);
+    // ... and only for skeletons with enough edges to split: measured on B200 (tools/latency_small_batch.py), batch 8:
+    // 32 nodes / 31 edges with 8 animals 143 -> 85 us, but 5 nodes / 4 edges with 2 animals 35 -> 43 us (three cluster
+    // barriers cost more than four edges' worth of parallelism returns).
+    const bool use_cluster = a->B <= SNB_TAIL_CLUSTER_MAX_FRAMES && a->n_edges >= SNB_TAIL_CLUSTER_MIN_EDGES &&
+                             !(a->flags & SNB_FLAG_NO_TAIL_CLUSTER);
     if (use_cluster) {
       if (smem > 48 * 1024 && cudaFuncSetAttribute(bottomup_tail_kernel<SNB_TAIL_CLUSTER>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

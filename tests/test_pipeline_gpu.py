@@ -346,3 +346,49 @@ def test_second_device_in_the_same_process():
     t0, t1 = make_multi_confmaps(pts.to(d0), xv, yv, 2.0), make_multi_confmaps(pts.to(d1), xv, yv, 2.0)
     assert t1.device == d1
     eq(npy(t0), npy(t1))
+
+
+@pytest.mark.parametrize("B", [1, 5, 16])
+def test_cluster_tail_equals_single_cta_tail_and_oracle(B):
+    """Small batches of skeletons with >= 8 edges run the tail as a 4-CTA cluster per frame (refined peaks, line scores and
+    matches exchanged through distributed shared memory): every table must equal the one-CTA-per-frame tail's bit for
+    bit, and the instances the oracle's."""
+    from oracle import paf as opaf
+    from oracle import peaks as opeaks
+    from oracle.synth import split_by_sample
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    n_inst, Nn, hw, stride = 4, 12, (384, 384), 2
+    edges = synthetic.chain_edges(Nn)
+    poses = synthetic.random_poses(40 + B, B, n_inst, Nn, hw, edges, margin=90.0, step=20.0, min_limb=8.0, min_sep=10.0)
+    cms, pafs = synthetic.render_batch(poses, hw, stride, edges, torch.device("cuda"), seed=B)
+    kw = dict(cms_stride=stride, pafs_stride=stride, peak_cap=256, cand_cap=2048, match_cap=256, inst_cap=32)
+    clu = BottomUpPostproc(Nn, edges, B, (192, 192), **kw)
+    one = BottomUpPostproc(Nn, edges, B, (192, 192), tail_cluster=False, **kw)
+    r_c, r_o = clu(cms, pafs), one(cms, pafs)
+    torch.cuda.synchronize()
+    npk, nin = npy(one.buf["frame_count"]), npy(one.buf["n_inst"])
+    eq(npy(clu.buf["frame_count"]), npk); eq(npy(clu.buf["n_inst"]), nin); eq(npy(clu.buf["m_count"]), npy(one.buf["m_count"]))
+    for b in range(B):
+        for k in ("peak_xy", "peak_val", "peak_chan"):
+            eq(npy(clu.buf[k][b, : npk[b]]), npy(one.buf[k][b, : npk[b]]))
+        for k in ("inst_xy", "inst_val", "inst_score"):
+            eq(npy(clu.buf[k][b, : nin[b]]), npy(one.buf[k][b, : nin[b]]))
+        mc = int(one.buf["m_count"][b])
+        o = b * one.caps["match_cap"]
+        for k in ("m_edge", "m_src", "m_dst", "m_score"):
+            eq(npy(clu.buf[k][o : o + mc]), npy(one.buf[k][o : o + mc]))
+        no = b * one.caps["cand_cap"]
+        nc = int(one.buf["edge_off"][b, -1])
+        eq(npy(clu.buf["cand_score"][no : no + nc]), npy(one.buf["cand_score"][no : no + nc]))
+    inst, pv, sc = r_c.to_lists()
+    pts, vals, si, ci = opeaks.local_peaks(cms.cpu(), 0.2, "integral")
+    peaks, pvs, pcs = (split_by_sample(x, si, B) for x in (pts * stride, vals, ci))
+    want = opaf.predict(pafs.cpu().permute(0, 2, 3, 1), peaks, pvs, pcs, edges, Nn, stride)
+    for b in range(B):
+        assert inst[b].shape == want[0][b].shape
+        eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
+        close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
+        eq(npy(pv[b]), npy(want[1][b]))
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-6)
