@@ -590,8 +590,8 @@ def run_ours(args, rank: int, world: int):
         avg_detect_ms = sum(iso_ms) / len(iso_ms)
         insitu_ms = sum(detect_ms) / len(detect_ms)
         achieved = algo_bytes_per_frame * B / (avg_detect_ms / 1e3) / 1e9
-        kernel = {"f32": "local_peaks_detect_vec<float,4,1,6>", "f16": "local_peaks_detect_vec<__half,2,1,8>",
-                  "bf16": "local_peaks_detect_vec<__nv_bfloat16,2,1,8>"}[args.dtype]
+        kernel = {"f32": "local_peaks_detect_vec<float,4,1,6,1>", "f16": "local_peaks_detect_vec<__half,2,1,8,1>",
+                  "bf16": "local_peaks_detect_vec<__nv_bfloat16,2,1,8,1>"}[args.dtype]  # <T, loads, rows, CTAs/SM, EXACT>
         traffic, traffic_rec = recorded_traffic(kernel)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -27,7 +27,7 @@ st = N.stream_ptr(dev)
 for thr, ref, label in ((0.2, 5, "refine 5x5"), (0.2, 0, "no refinement"), (5.0, 0, "all below threshold (stream + reductions only)")):
     def fn(i):
         x = bufs[i % 4]
-        N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), thr, ref, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), st), "k2")
+        N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), thr, ref, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), N.stream_ptr(dev)), "k2")
     print(label, round(timed(fn, 400) * 1e3, 2), "us")
 # a plain streaming read of the same bytes by torch (max over all) for reference
 print("torch.amax over the same 85 MB:", round(timed(lambda i: bufs[i % 4].amax(dim=(2, 3)), 200) * 1e3, 2), "us")

@@ -67,7 +67,9 @@ def main():
                          "ncu_time_us": statistics.median(us), "launches_captured": len(rs),
                          "registers": int(rs[0][col["launch__registers_per_thread"]]),
                          "grid": rs[0][col["launch__grid_size"]], "block": rs[0][col["launch__block_size"]],
-                         "source_sha16": sha, "capture": f"profiles/{rnd}_{os.path.basename(rep)} (ncu --set full --clock-control none)"}
+                         "source_sha16": sha,
+                         "capture": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_ncu_raw.txt") +
+                                    " (selected metrics of an ncu --set full --clock-control none capture)"}
             print(name, rec[name])
     json.dump(rec, open(path, "w"), indent=1, sort_keys=True)
 
