@@ -41,7 +41,7 @@ def test_fused_pipeline_matches_reference_golden(name):
             eq(np.isnan(npy(inst[b])), np.isnan(npy(want_inst[b])))
             close(npy(inst[b]), npy(want_inst[b]), atol=1e-4)
             eq(npy(pv[b]), npy(want_pv[b]))
-            close(npy(sc[b]), npy(want_sc[b]), rtol=1e-5, atol=1e-5)
+            close(npy(sc[b]), npy(want_sc[b]), rtol=1e-5, atol=1e-6)
     # fused and unfused tails must agree bit for bit on every table they both write
     a, u = variants["fused"], variants["unfused"]
     a(cms, pafs); u(cms, pafs)
@@ -91,7 +91,7 @@ def test_fused_pipeline_full_size_vs_oracle():
         eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
         close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
         eq(npy(pv[b]), npy(want[1][b]))
-        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-5)
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-6)
         # every planted animal is recovered within a pixel
         got = npy(inst[b])
         for a in range(n_inst):
@@ -145,7 +145,7 @@ def test_outputs_epilogue_matches_reference_group_scored_batch(fixed):
         eq(np.isnan(npy(k)), np.isnan(want_k))
         close(npy(k), want_k, atol=1e-4)
         eq(npy(v), want_v)
-        close(npy(s), want_s, rtol=1e-5, atol=1e-5)
+        close(npy(s), want_s, rtol=1e-5, atol=1e-6)
         if fixed:
             assert pipe.launches_per_call == 3 and res.pred_keypoints is k
 
@@ -274,7 +274,7 @@ def test_group_scored_batch_seam_matches_reference():
         eq(np.isnan(npy(res.pred_keypoints)), np.isnan(want_k))
         close(npy(res.pred_keypoints), want_k, atol=1e-4)
         eq(npy(res.pred_peak_values), want_v)
-        close(npy(res.instance_scores), want_s, rtol=1e-5, atol=1e-5)
+        close(npy(res.instance_scores), want_s, rtol=1e-5, atol=1e-6)
         assert res.pred_confmaps is not None and len(res.pred_paf_graph) == 4
         assert res.pred_paf_graph[0].shape[0] == sum(p.shape[0] for p in peaks)
 
@@ -309,7 +309,7 @@ def test_fused_pipeline_busy_flies_frames_vs_oracle():
         eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
         close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
         eq(npy(pv[b]), npy(want[1][b]))
-        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-4)  # a sum of 31 line scores
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-6)  # a sum of 31 line scores: observed |d| < 2e-5 on scores of ~30
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
