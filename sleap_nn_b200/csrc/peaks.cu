@@ -220,6 +220,81 @@ local_peaks_detect_bulk(const float* __restrict__ cms, long long n_elems, int C,
     }
   }
 }
+
+// A/B only: the same stream as a PRODUCER / CONSUMER bulk-async ring, the way TMA pipelines are meant to be built.
+// One elected thread of a dedicated producer warp keeps up to TMA_STAGES 16 KB bulk copies in flight per CTA and
+// refills a stage as soon as the four consumer warps have released it (an `empty` mbarrier per stage, one arrival per
+// consumer warp) - no CTA-wide barrier anywhere, unlike local_peaks_detect_bulk above, whose single refill thread sits
+// behind a __syncthreads() per chunk.  Any element type (the chunk is a flat byte range of a contiguous tensor).
+#ifndef SNB_TMA_STAGE_BYTES
+#define SNB_TMA_STAGE_BYTES 8192
+#endif
+#ifndef SNB_TMA_STAGES
+#define SNB_TMA_STAGES 8
+#endif
+constexpr int TMA_STAGE_BYTES = SNB_TMA_STAGE_BYTES;
+constexpr int TMA_STAGES = SNB_TMA_STAGES;
+constexpr int TMA_CONSUMER_WARPS = 4;
+constexpr int TMA_THREADS = 32 * (TMA_CONSUMER_WARPS + 1);
+
+template <typename T>
+__global__ void __launch_bounds__(TMA_THREADS)
+local_peaks_detect_tma(const T* __restrict__ cms, long long n_elems, int C, int H, int W, float thr, int cap,
+                       int* __restrict__ frame_count, uint32_t* __restrict__ keys) {
+  constexpr int PER = Elem<T>::PER16;
+  constexpr int STAGE_ELEMS = TMA_STAGE_BYTES / (int)sizeof(T);
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(tma_smem + (size_t)TMA_STAGES * TMA_STAGE_BYTES);
+  uint64_t* empty = full + TMA_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_chunks = (n_elems + STAGE_ELEMS - 1) / STAGE_ELEMS;
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, TMA_CONSUMER_WARPS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (warp == TMA_CONSUMER_WARPS) {  // ===== producer warp: one elected thread issues every bulk copy of this CTA
+    if (lane == 0) {
+      int it = 0;
+      for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+        const int s = it % TMA_STAGES;
+        if (it >= TMA_STAGES) mbar_wait(empty + s, (uint32_t)(((it / TMA_STAGES) - 1) & 1));
+        const long long e0 = chunk * STAGE_ELEMS;
+        const uint32_t bytes = (uint32_t)(min((long long)STAGE_ELEMS, n_elems - e0) * (long long)sizeof(T));
+        mbar_expect_tx(full + s, bytes);
+        bulk_g2s(tma_smem + (size_t)s * TMA_STAGE_BYTES, cms + e0, bytes, full + s);
+      }
+    }
+    return;
+  }
+  // ===== consumer warps: each owns a quarter of every stage
+  const typename Elem<T>::Thr tv = Elem<T>::make_thr(thr);
+  const long long plane_elems = (long long)H * W;
+  constexpr int VEC_PER_WARP = TMA_STAGE_BYTES / 16 / TMA_CONSUMER_WARPS;  // 256 x 16 B
+  int it = 0;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x, ++it) {
+    const int s = it % TMA_STAGES;
+    mbar_wait(full + s, (uint32_t)((it / TMA_STAGES) & 1));
+    const long long e0 = chunk * STAGE_ELEMS;
+    const int nv = (int)(min((long long)STAGE_ELEMS, n_elems - e0) / PER);
+    const uint4* buf = reinterpret_cast<const uint4*>(tma_smem + (size_t)s * TMA_STAGE_BYTES);
+#pragma unroll
+    for (int u = 0; u < VEC_PER_WARP / 32; ++u) {
+      const int iv = warp * VEC_PER_WARP + u * 32 + lane;
+      if (iv >= nv) break;
+      const uint4 v = buf[iv];
+      if (Elem<T>::any_gt(v, tv)) {  // rare: locate the word in (b, c, y, x) and run the neighbour test
+        const long long ebase = e0 + (long long)PER * iv;  // the row is a multiple of the vector: one row per word
+        const long long pc = ebase / plane_elems;
+        const int rem = (int)(ebase - pc * plane_elems);
+        const int y = rem / W, x0 = rem - y * W;
+        detect_word<T>(cms + pc * plane_elems, thr, H, W, W, y, x0, (int)(pc / C), (int)(pc % C), C, cap, frame_count, keys);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);  // this warp is done with the stage
+  }
+}
 #endif  // SNB_AB_VARIANTS
 
 // ----------------------------------------------------------------------------------------
@@ -1028,6 +1103,23 @@ static int launch_detect(const T* cms, int B, int C, int H, int W, long long sb,
   const bool vec = vec_ok_for(cms, Elem<T>::DT, W, sb, sc, sh, sw);
   const long long rows = (long long)B * C * H;
 #ifdef SNB_AB_VARIANTS
+  {
+    // A/B: producer / consumer bulk-async (TMA) ring, any element type, contiguous tensors (tools/detect_variants.py)
+    static const bool use_tma = getenv("SNB_DETECT_TMA") != nullptr;
+    static const int tma_ctas = getenv("SNB_DETECT_TMA_CTAS") ? atoi(getenv("SNB_DETECT_TMA_CTAS")) : 3;
+    const bool contiguous = vec && sh == W && sc == (long long)H * W && sb == (long long)C * H * W;
+    if (contiguous && use_tma) {
+      const size_t smem = (size_t)TMA_STAGES * TMA_STAGE_BYTES + 2 * TMA_STAGES * sizeof(uint64_t);
+      if (cudaFuncSetAttribute(local_peaks_detect_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess)
+        return SNB_ERR_CUDA_LAUNCH;
+      const long long n_elems = rows * W;
+      const long long n_chunks = (n_elems * (long long)sizeof(T) + TMA_STAGE_BYTES - 1) / TMA_STAGE_BYTES;
+      const int grid = (int)std::min<long long>(n_chunks, (long long)sm_count() * tma_ctas);
+      local_peaks_detect_tma<T><<<grid, TMA_THREADS, smem, st>>>(cms, n_elems, C, H, W, threshold, cap, frame_count, keys);
+      return SNB_OK;
+    }
+  }
   if constexpr (Elem<T>::DT == SNB_DTYPE_F32) {
     // A/B: the cp.async.bulk ring (tools/detect_variants.py); the LDG.128 kernel is the product
     const bool contiguous = vec && sh == W && sc == (long long)H * W && sb == (long long)C * H * W;

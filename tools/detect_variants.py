@@ -4,7 +4,7 @@
 Needs the A/B build of the library (the product build compiles the variants and their getenv switches out):
 
     SNB_LIB_NAME=libsleapnn_b200_ab.so SNB_NVCC_EXTRA=-DSNB_AB_VARIANTS bash sleap_nn_b200/csrc/build.sh
-    SLEAPNN_B200_LIB=sleap_nn_b200/lib/libsleapnn_b200_ab.so [SNB_DETECT_VARIANT=k | SNB_DETECT_BULK=1] \
+    SLEAPNN_B200_LIB=sleap_nn_b200/lib/libsleapnn_b200_ab.so [SNB_DETECT_VARIANT=k | SNB_DETECT_BULK=1 | SNB_DETECT_TMA=1] \
         python tools/detect_variants.py [f32|f16|bf16]
 
 Times the kernel alone on the bench's cfg3 batches (real blobs, rotating 6 batches > L2), CUDA events around 200 launches.
@@ -46,5 +46,8 @@ torch.cuda.synchronize()
 us = a.elapsed_time(b) / n * 1e3
 nbytes = B * 5 * 512 * 512 * inputs[0][0].element_size()
 print(json.dumps({"dtype": str(dt), "variant": os.environ.get("SNB_DETECT_VARIANT", "default"),
-                  "bulk_tma_ring": bool(os.environ.get("SNB_DETECT_BULK")), "us_per_launch_incl_memset": us,
+                  "bulk_ring_single_thread_refill": bool(os.environ.get("SNB_DETECT_BULK")),
+                  "tma_ring_producer_consumer": bool(os.environ.get("SNB_DETECT_TMA")),
+                  "tma_ctas_per_sm": os.environ.get("SNB_DETECT_TMA_CTAS", "3") if os.environ.get("SNB_DETECT_TMA") else None,
+                  "us_per_launch_incl_memset": us,
                   "GBps": nbytes / us / 1e3, "peaks_last_batch": int(fc.sum())}))
