@@ -390,12 +390,15 @@ def run_ours(args, rank: int, world: int):
     # `--streams` pipeline instances, each with its own tables: instance i's detect kernel runs on the
     # (single) detect stream, its per-frame tail on the high-priority tail stream, so tail(i) overlaps
     # detect(i+1) and the step time tends to the HBM time of the confidence maps.
-    tail_stream = torch.cuda.Stream(device=dev, priority=-1) if args.tail_stream else None
+    # default: one detect stream per pipeline instance + ONE shared high-priority tail stream (see PipelineRing);
+    # --graph needs single-stream pipelines, --tail-stream is the older one-detect-stream variant
+    tail_priority = not (args.no_tail_priority or args.graph or args.tail_stream)
+    tail_stream = torch.cuda.Stream(device=dev, priority=-1) if (args.tail_stream or tail_priority) else None
     pipes = [make_pipe(tail_stream=tail_stream, keep_tables=not args.lean) for _ in range(n_streams)]
-    if tail_stream is not None:
+    if args.tail_stream:
         det = torch.cuda.Stream(device=dev)
         streams = [det for _ in range(n_streams)]
-    else:
+    else:  # one detect stream per pipeline instance (default: plus ONE shared high-priority tail stream)
         streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     main = torch.cuda.current_stream(dev)
 
@@ -404,11 +407,20 @@ def run_ours(args, rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from sleap_nn_b200.pipeline import PipelineRing
+
+    ring = PipelineRing(pipes, streams) if not args.tail_stream else None
+
     def run_steps(n, events=None):
+        if events is None and ring is not None:  # the product's own multi-stream loop (staggered start, explicit streams)
+            ring.reset()
+            for i in range(n):
+                ring.submit(*inputs[i % n_bufs])
+            return
         for i in range(n):
             s = i % n_streams
+            cms, pafs = inputs[i % n_bufs]
             with torch.cuda.stream(streams[s]):
-                cms, pafs = inputs[i % n_bufs]
                 pipes[s](cms, pafs, detect_events=None if events is None else events[i])
 
     # ---- correctness guard on the timed configuration.  fp32: every planted animal comes back.  Half-precision maps:
@@ -535,10 +547,37 @@ def run_ours(args, rank: int, world: int):
     d2h = hs.d2h_bytes
     barrier()
     e2e_steps = min(args.steps, args.e2e_steps)
-    n_got = 0
+    # N > 1: the world * e2e_steps batches of the job sit in ONE queue and every rank pulls the next batch index when it
+    # has a free slot (a counter in torch.distributed's store, ~0.1 ms per pull against ~6 ms per batch) - what a
+    # multi-GPU predictor fed from host memory does.  On this pool's 8-GPU boxes the GPUs sit behind two host bridges
+    # of unequal speed (tools/h2d_scaling_probe.py: 20.8 vs 35.7 GB/s per GPU when all eight copy at once), and a fixed
+    # equal split is paced by the slow group.  --e2e-static keeps the fixed split.
+    queue = None
+    if world > 1 and not args.e2e_static:
+        try:
+            queue = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                queue.set("snb_e2e_next", "0")
+        except Exception:  # noqa: BLE001 - no store: fall back to the fixed split
+            queue = None
+    barrier()
+    total_steps = world * e2e_steps
+
+    def next_index(i):
+        if queue is None:
+            return i if i < e2e_steps else None
+        k = int(queue.add("snb_e2e_next", 1)) - 1
+        return k if k < total_steps else None
+
+    n_got, n_want, my_steps = 0, 0, 0
     t0 = time.perf_counter()
-    for i in range(e2e_steps):  # every step: H2D of its inputs, the chain, D2H of its results; `depth` steps in flight
-        out = hs.submit(*host[i % len(host)])
+    while True:  # every step: H2D of its inputs, the chain, D2H of its results; `depth` steps in flight
+        k = next_index(my_steps)
+        if k is None:
+            break
+        out = hs.submit(*host[k % len(host)])
+        n_want += want_per_host[k % len(host)]
+        my_steps += 1
         if out is not None:
             n_got += sum(len(x) for x in out[0])
     for out in hs.drain():
@@ -546,12 +585,16 @@ def run_ours(args, rank: int, world: int):
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3  # host clock: the region ends when the last result is unpacked on the host
     barrier()
-    assert n_got == sum(want_per_host[i % len(host)] for i in range(e2e_steps)), "host path lost instances"
+    assert n_got == n_want, "host path lost instances"
+    e2e_steps_per_rank = [my_steps]
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+        t = torch.tensor([e2e_ms, float(my_steps)], device=dev, dtype=torch.float64)
+        got = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(got, t)
+        e2e_ms = max(float(g[0]) for g in got)
+        e2e_steps_per_rank = [int(g[1]) for g in got]
+        assert sum(e2e_steps_per_rank) == total_steps
+    e2e_value = B * sum(e2e_steps_per_rank) / (e2e_ms / 1e3)
     zero_copy_pafs, zero_copy_cms = hs.last_zero_copy, getattr(hs, "last_zero_copy_cms", False)
     paf_host_bytes = host[0][1].numel() * esz
     del hs, host
@@ -598,13 +641,15 @@ def run_ours(args, rank: int, world: int):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": shared_config(world, args.dtype),
             "run": dict(streams=n_streams, input_batches=n_bufs,
-                        tail="fused per-frame tail kernel" + (" on a high-priority second stream" if tail_stream is not None else ""),
+                        tail="fused per-frame tail kernel" + (" on one shared high-priority stream" if tail_stream is not None else ""),
                         intermediate_tables_written=not args.lean,
                         launch=("CUDA graph: %d steps per replay, remainder eager" % per_replay) if graph is not None else "eager Python loop",
                         per_rank_ms_per_step={"min": min(per_rank_ms), "median": statistics.median(per_rank_ms),
                                               "max": max(per_rank_ms), "all": per_rank_ms}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "in_flight": args.e2e_depth,
+                    "steps_per_rank": e2e_steps_per_rank,
+                    "split": ("one shared batch queue, ranks pull" if (world > 1 and not args.e2e_static) else "fixed, equal per rank"),
                     "cms": ("streamed by the detect kernel straight from pinned host memory (zero-copy)"
                             if zero_copy_cms else "cudaMemcpyAsync pinned host -> HBM staging buffer"),
                     "host_cpus_rank0": ("all" if host_cpus is None else f"{len(host_cpus)} CPUs local to the GPU"),
@@ -687,8 +732,12 @@ def main():
                          "launch per replay; measured slower at N=1: the graph's three chains run in lockstep, see DESIGN.md)")
     ap.add_argument("--tail-stream", dest="tail_stream", action="store_true",
                     help="one detect stream + one high-priority tail stream instead of one stream per pipeline instance")
+    ap.add_argument("--no-tail-priority", dest="no_tail_priority", action="store_true",
+                    help="A/B: per-instance streams WITHOUT the shared high-priority tail stream (tails run on the detect streams)")
     ap.add_argument("--zero-copy-cms", action="store_true",
                     help="e2e: the detect kernel streams the pinned host confidence maps itself (no cudaMemcpy + HBM staging)")
+    ap.add_argument("--e2e-static", action="store_true",
+                    help="N>1 e2e: a fixed equal number of batches per rank instead of one shared batch queue")
     ap.add_argument("--copy-pafs", action="store_true", help="e2e: stage the PAF tensor in HBM instead of sampling it in place")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to the CPUs next to its GPU")
     ap.add_argument("--lean", action="store_true", help="do not write candidate / match tables to global memory")

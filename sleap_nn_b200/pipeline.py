@@ -238,7 +238,7 @@ class BottomUpPostproc:
 
     # ------------------------------------------------------------------ device-resident path
     def __call__(self, cms: torch.Tensor, pafs: torch.Tensor, detect_events=None, input_scale: float = 1.0,
-                 eff_scale: Optional[torch.Tensor] = None) -> BottomUpResult:
+                 eff_scale: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> BottomUpResult:
         """Enqueue the chain on the current stream of `self.device`; returns padded device tensors.
 
         cms (B, N, H, W) CUDA; pafs (B, 2E, Hp, Wp) or (B, Hp, Wp, 2E) CUDA, any strides; fp32, or the fp16 / bf16
@@ -247,13 +247,15 @@ class BottomUpPostproc:
         `detect_events` = (torch.cuda.Event, torch.cuda.Event) recorded around the streaming
         detect kernel (for the benchmark's roofline figure).  `input_scale` / `eff_scale` (B,) are
         `PreprocInfo`'s scale factors, undone in the `.outputs()` tensors (streaming.py:190-196).
+        `stream`: enqueue on this stream instead of the current one (saves the ~10 us `with torch.cuda.stream(...)`
+        costs a tight multi-stream launch loop per step).
         """
         # The C side launches on the CURRENT device: when the caller's current device is another GPU, switch for the
         # duration of the call (otherwise the chain would run there, reaching the tables over peer access, unordered
         # with this device's streams).
         if torch.cuda.current_device() != self.device.index:
             with torch.cuda.device(self.device):
-                return self.__call__(cms, pafs, detect_events, input_scale, eff_scale)
+                return self.__call__(cms, pafs, detect_events, input_scale, eff_scale, stream)
         # fast path: tensors this pipeline has already been launched on (a loop fed from a few fixed buffers, the
         # steady state of a streaming pipeline) - a filled copy of the argument block is kept per input, so only the
         # launch itself is left (~5 us of host time instead of ~25 us)
@@ -262,8 +264,12 @@ class BottomUpPostproc:
                cms.dtype, pafs.dtype, input_scale, self._knobs())
         hit = self._fast.get(key) if (detect_events is None and eff_scale is None) else None
         if hit is not None:
-            N.check(N.lib.snb_bottomup_postproc(C.byref(hit[0]), N.stream_ptr(self.device)), "snb_bottomup_postproc")
+            N.check(N.lib.snb_bottomup_postproc(C.byref(hit[0]), stream.cuda_stream if stream is not None
+                                                else N.stream_ptr(self.device)), "snb_bottomup_postproc")
             return hit[1]
+        if stream is not None:  # slow path (first call on these tensors): the ordinary current-stream route
+            with torch.cuda.stream(stream):
+                return self.__call__(cms, pafs, detect_events, input_scale, eff_scale, None)
         if not (cms.is_cuda and pafs.is_cuda) or cms.dtype not in N._DTYPES or pafs.dtype not in N._DTYPES:
             raise TypeError("BottomUpPostproc expects fp32 / fp16 / bf16 CUDA tensors; use .run_host() for host buffers")
         if cms.device != self.device or pafs.device != self.device:
@@ -491,6 +497,66 @@ class BottomUpHostStream:
             if self._busy[k]:
                 outs.append(self._collect(k))
         return outs
+
+
+class PipelineRing:
+    """Round-robin of `BottomUpPostproc` instances over their own CUDA streams: the throughput configuration.
+
+    With k instances the tail of one batch should hide under the detect pass of the next.  Left to itself it often does
+    not: the next batch's detect kernel (20 480 CTAs, ready long before) floods every SM the moment the previous detect
+    kernel drains, its CTAs keep refilling the register files, and the 64 tail CTAs (116 registers x 256 threads each)
+    find no room until that kernel's LAST wave - so the chain that waits for this tail starts late and the detect passes
+    end up strictly one after another with a launch bubble between them (52 us per cfg3 step; whether a process landed in
+    that state or in the good one depended on how its streams happened to map onto hardware queues).  Giving the tails a
+    HIGH-PRIORITY stream makes the block scheduler place them first: 44.4 us per step on every rank of every run,
+    with 2, 3 or 4 instances (`profiles/r2_tail_priority_ab.txt`).
+
+        ring = PipelineRing.build(3, n_nodes=N, edge_inds=edges, batch=B, cms_hw=(H, W), cms_stride=2, pafs_stride=2)
+        for cms, pafs in batches: res = ring.submit(cms, pafs); ...; res.wait()   # res.wait(): the tail ran on another stream
+
+    `PipelineRing(pipes, streams)` wraps pre-built instances instead; if those have no tail stream the ring staggers the
+    chains' first detect kernels after every `reset()` (events around the detect launches), which is what
+    `capture_rotation` does inside a CUDA graph, where cross-stream priorities are not available.
+    """
+
+    def __init__(self, pipes: Sequence["BottomUpPostproc"], streams: Optional[Sequence[torch.cuda.Stream]] = None):
+        if not pipes:
+            raise ValueError("need at least one pipeline")
+        self.pipes = list(pipes)
+        self.device = self.pipes[0].device
+        self._stagger = all(p.tail_stream is None for p in self.pipes)
+        with torch.cuda.device(self.device):
+            self.streams = list(streams) if streams is not None else [torch.cuda.Stream(device=self.device) for _ in self.pipes]
+            self._ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in self.pipes]
+            for pair in self._ev:  # torch creates the cudaEvent lazily on first record; the C side re-records them
+                for e in pair:
+                    e.record(torch.cuda.current_stream(self.device))
+        self._i = 0
+        self._fresh = len(self.pipes) if self._stagger else 0
+
+    @classmethod
+    def build(cls, n: int = 3, device: Optional[torch.device] = None, **pipe_kwargs) -> "PipelineRing":
+        """n instances sharing ONE high-priority tail stream, each with its own detect stream."""
+        dev = torch.device(device) if device is not None else N.compute_device()
+        with torch.cuda.device(dev):
+            tail = torch.cuda.Stream(device=dev, priority=-1)
+        return cls([BottomUpPostproc(device=dev, tail_stream=tail, **pipe_kwargs) for _ in range(int(n))])
+
+    def reset(self) -> None:
+        """The ring is idle: (stagger mode only) offset the chains again on the next submissions."""
+        self._fresh = len(self.pipes) if self._stagger else 0
+        self._i = 0
+
+    def submit(self, cms: torch.Tensor, pafs: torch.Tensor) -> "BottomUpResult":
+        k = self._i
+        self._i = (k + 1) % len(self.pipes)
+        if self._fresh > 0:
+            self._fresh -= 1
+            with torch.cuda.device(self.device), torch.cuda.stream(self.streams[k]):
+                if k > 0 and self.streams[k] is not self.streams[k - 1]:
+                    self.streams[k].wait_event(self._ev[k - 1][1])
+                return self.pipes[k](cms, pafs, detect_events=self._ev[k])
+        return self.pipes[k](cms, pafs, stream=self.streams[k])
 
 
 def capture_rotation(pipes: Sequence[BottomUpPostproc], inputs: Sequence[Tuple[torch.Tensor, torch.Tensor]],

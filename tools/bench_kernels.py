@@ -273,8 +273,10 @@ def chain_cfg4(dev, iters, Bn=64, n_streams=None):
     for s in range(2):  # 2 x 64 x (33.5 + 65.0 MB) = 12.6 GB
         edges, poses = _flies_poses(Bn, seed=s)
         inputs.append(synthetic.render_batch(poses, (1024, 1024), 2, edges, dev, seed=s))
+    tail = torch.cuda.Stream(device=dev, priority=-1)  # shared high-priority tail stream (see pipeline.PipelineRing)
     pipes = [BottomUpPostproc(32, edges, Bn, (512, 512), cms_stride=2, pafs_stride=2, device=dev, peak_cap=512,
-                              cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False) for _ in range(n_streams)]
+                              cand_cap=4096, match_cap=512, inst_cap=32, keep_tables=False, tail_stream=tail)
+             for _ in range(n_streams)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
     res = pipes[0](*inputs[0])
     inst, _, _ = res.to_lists()
@@ -297,11 +299,11 @@ def chain_cfg4(dev, iters, Bn=64, n_streams=None):
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record(main)
-    for s_ in streams:
+    for s_ in streams + [tail]:
         s_.wait_stream(main)
     for i in range(iters):
         step(i)
-    for s_ in streams:
+    for s_ in streams + [tail]:
         main.wait_stream(s_)
     t1.record(main)
     torch.cuda.synchronize()
