@@ -1,10 +1,20 @@
+#!/bin/bash
+# One gpurun call that regenerates the round's evidence:  gpurun --timeout 2400 -- 'bash tools/final_run.sh'
+# Bench numbers are never taken under ncu; the ncu passes below only feed profiles/ (run tools/ncu_traffic.py and
+# tools/ncu_summary.py on the results afterwards, WITHOUT editing csrc/peaks.cu in between: traffic.json keys on its hash).
 set -x
-python tools/sweep_cfg5.py > gpurun_out/r1d_cfg5_n1.json 2> gpurun_out/r1d_cfg5_n1.err; cat gpurun_out/r1d_cfg5_n1.json | cut -c1-600
-python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r1d_bench_ref.json 2>/dev/null
-python bench.py > gpurun_out/r1d_bench_n1.json 2> gpurun_out/r1d_bench_n1.err; cut -c1-400 gpurun_out/r1d_bench_n1.json
-python tools/bench_kernels.py > gpurun_out/r1d_bench_kernels.jsonl 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1d_bench_launches.csv python bench.py --steps 4 --warmup 3 --e2e-steps 2 --no-cpu-baseline > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/r1d_kernels_launches.csv python tools/bench_kernels.py --iters 3 --only k2_cfg2,k7_cfg4,k8_cfg4_g8 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"confmaps_rows2" -s 12 -c 1 -o gpurun_out/r1d_k7 python tools/bench_kernels.py --iters 3 --only k7_cfg4 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"local_peaks_detect|bottomup_tail" -s 8 -c 2 -o gpurun_out/r1d_cfg3 python tools/chain_once.py 8 > /dev/null 2>&1
-ls -la gpurun_out | tail -12
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_final_pytest.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.txt 2>&1
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_final_bench_ref.json 2> /dev/null
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_final_bench_s20.json 2> gpurun_out/r2_final_bench_s20.err
+python bench.py --steps 2000 --warmup 20 --no-extras > gpurun_out/r2_final_bench_f32.json 2> /dev/null
+python bench.py --steps 2000 --warmup 20 --no-extras --dtype f16 > gpurun_out/r2_final_bench_f16.json 2> /dev/null
+python bench.py --steps 2000 --warmup 20 --no-extras --graph > gpurun_out/r2_final_bench_graph.json 2> /dev/null
+for dt in f32 f16 bf16; do
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:local_peaks_detect -s 12 -c 3 -o gpurun_out/r2_detect_$dt -f python tools/bench_kernels.py --iters 10 --only k1_cfg3_$dt > /dev/null 2>&1
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"bottomup_tail|local_peaks_detect" -s 8 -c 4 -o gpurun_out/r2_bench_detect_tail -f python bench.py --steps 6 --warmup 3 --no-extras --no-cpu-baseline --streams 1 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:confmaps_sep -s 12 -c 1 -o gpurun_out/r2_k7_sep_bf16 -f python tools/bench_kernels.py --iters 4 --only k7_cfg4_bf16 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_bench_launches.csv python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out | tail -14

@@ -5,7 +5,8 @@
 
 For every distinct kernel in the reports: per-launch dram__bytes_read.sum / dram__bytes_write.sum / gpu__time_duration
 (median over the captured launches), registers, and the sha256 of csrc/peaks.cu at capture time (bench.py reports whether
-the capture matches the source it is running).  Kernel names are normalised to `name<template args>`.
+the capture matches the source it is running).  Kernel names are normalised to `name<template args>`.  Next to it, for
+every report, profiles/<report>_ncu_raw.txt: the selected metrics of each captured launch (`--raw-only` skips traffic.json).
 """
 import csv
 import hashlib
@@ -43,7 +44,32 @@ def short_name(full):
     return m.group(1) + (m.group(2) or "").replace(" ", "").replace("(int)", "")
 
 
+RAW_METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+               "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+               "launch__registers_per_thread", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size",
+               "launch__block_size", "launch__cluster_size", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+               "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "launch__occupancy_limit_registers",
+               "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "launch__occupancy_limit_blocks",
+               "smsp__inst_executed.sum", "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
+               "smsp__cycles_active.avg", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static"]
+
+
+def write_raw(rep, hdr, units, rows):
+    col = {h: i for i, h in enumerate(hdr)}
+    out = os.path.join(ROOT, "profiles", os.path.basename(rep).replace(".ncu-rep", "_ncu_raw.txt"))
+    with open(out, "w") as f:
+        for k, r in enumerate(rows):
+            if k:
+                f.write("---\n")
+            f.write(f"{'Kernel Name':<75} {r[col['Kernel Name']][:70]} \n")
+            for m in RAW_METRICS:
+                if m in col:
+                    f.write(f"{m:<75} {r[col[m]]} {units[col[m]]}\n")
+    return out
+
+
 def main():
+    raw_only = "--raw-only" in sys.argv
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     rnd = "r2"
     if "--round" in sys.argv:
@@ -56,6 +82,9 @@ def main():
     for rep in args:
         hdr, units, rows = rows_of(rep)
         col = {h: i for i, h in enumerate(hdr)}
+        print("wrote", write_raw(rep, hdr, units, rows))
+        if raw_only:
+            continue
         by = {}
         for r in rows:
             by.setdefault(short_name(r[col["Kernel Name"]] if "Kernel Name" in col else r[4]), []).append(r)
@@ -71,7 +100,8 @@ def main():
                          "capture": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_ncu_raw.txt") +
                                     " (selected metrics of an ncu --set full --clock-control none capture)"}
             print(name, rec[name])
-    json.dump(rec, open(path, "w"), indent=1, sort_keys=True)
+    if not raw_only:
+        json.dump(rec, open(path, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
