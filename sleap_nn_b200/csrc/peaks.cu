@@ -802,17 +802,42 @@ global_peaks_ring_kernel(const float* __restrict__ cms, int n_planes, int C, int
 // generic merge.  One 32-thread CTA per plane, so
 // the hardware scheduler spreads the planes evenly over the 148 SMs (cfg2: 22.5 planes per SM, all resident).
 
-template <typename T, int U, bool CONTIG>
-__global__ void __launch_bounds__(32)
-global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long long sb, long long sc, long long sh,
-                         float thr, int refine_size, float* __restrict__ out_xy, float* __restrict__ out_val,
-                         Ladder lad) {
+#ifdef SNB_AB_VARIANTS
+// A/B build only: globaltimer stamps of every plane's warp (start of streaming, end of streaming, end of epilogue),
+// read back by tools/k2_probe.py through snb_ab_k2_stamps
+constexpr int K2_STAMP_PLANES = 16384;
+__device__ unsigned long long g_k2_stamps[3 * K2_STAMP_PLANES];
+__device__ int g_k2_stamps_on = 0;
+__device__ __forceinline__ void k2_stamp(int p, int which, int lane) {
+  if (g_k2_stamps_on && lane == 0 && p < K2_STAMP_PLANES) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_k2_stamps[3 * p + which] = t;
+  }
+}
+#define SNB_K2_STAMP(p, which, lane) k2_stamp(p, which, lane)
+#else
+#define SNB_K2_STAMP(p, which, lane) ((void)0)
+#endif
+
+constexpr int GP_WARPS_PER_CTA = 1;    // planes (= warps) per CTA of the warp kernel
+constexpr int GP_LOADS_IN_FLIGHT = 8;  // 128-bit loads in flight per lane
+
+template <typename T, int U, bool CONTIG, int WPC>
+__global__ void __launch_bounds__(32 * WPC)
+global_peaks_warp_kernel(const T* __restrict__ cms, int planes, int C, int H, int W, long long sb, long long sc,
+                         long long sh, float thr, int refine_size, float* __restrict__ out_xy,
+                         float* __restrict__ out_val, Ladder lad) {
   constexpr int PER = Elem<T>::PER16;
   pdl_launch_dependents();
-  const int p = blockIdx.x, lane = threadIdx.x;
+  // WPC independent warps per CTA (no barrier, no shared memory): fewer, fatter CTAs only shorten the launch ramp of
+  // a one-wave grid
+  const int p = blockIdx.x * WPC + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= planes) return;
   const T* plane = cms + (long long)(p / C) * sb + (long long)(p % C) * sc;
   const int WV = W / PER, nv = H * WV;
   pdl_wait();  // the maps may be the previous kernel's output
+  SNB_K2_STAMP(p, 0, lane);
   // Load cursor of this lane: 128-bit load number `li` = lane + 32 * (loads issued so far); for strided planes the
   // (row, column) pair is advanced incrementally (no integer division in the loop).
   int li = lane, ly = lane / WV, lxv = lane - ly * WV;
@@ -855,6 +880,7 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
   // Warp: the plane maximum and the lanes that hold it.  Exactly one un-tied holder is the common case; several
   // holders still give min(x), min(y) exactly; a tie INSIDE a holder's own sequence (plateaus, saturated maps) or a
   // NaN sends the warp to the exact generic merge below.
+  SNB_K2_STAMP(p, 1, lane);
   float gm = m;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) gm = fmax_nan(gm, __shfl_xor_sync(FULL, gm, d));
@@ -904,6 +930,7 @@ global_peaks_warp_kernel(const T* __restrict__ cms, int C, int H, int W, long lo
     fy = __fadd_rn(fy, oy);
   }
   if (lane == 0) write_global_peak(lad, p, C, fx, fy, low ? 0.f : r.v, out_xy, out_val);
+  SNB_K2_STAMP(p, 2, lane);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1352,13 +1379,32 @@ static int launch_global_peaks(const T* cms, int B, int C, int H, int W, long lo
 #endif
   if (vec && !force_generic && !no_warp && (long long)H * W <= 16384 && planes < 0x7fffffffLL) {
     // small planes (cfg2's 80x80 crops): one warp per plane, no barrier anywhere
-    cudaError_t err;
-    if (sh == W)
-      err = launch_pdl(global_peaks_warp_kernel<T, 8, true>, dim3((unsigned)planes), dim3(32), (size_t)pad_smem, st, cms, C, H,
-                       W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);
-    else
-      err = launch_pdl(global_peaks_warp_kernel<T, 8, false>, dim3((unsigned)planes), dim3(32), (size_t)pad_smem, st, cms, C,
-                       H, W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);
+    cudaError_t err = cudaErrorInvalidValue;
+#define SNB_GPW(U_, WPC_)                                                                                              \
+  do {                                                                                                                 \
+    const dim3 g((unsigned)((planes + (WPC_) - 1) / (WPC_)));                                                          \
+    if (sh == W)                                                                                                       \
+      err = launch_pdl(global_peaks_warp_kernel<T, U_, true, WPC_>, g, dim3(32 * (WPC_)), (size_t)pad_smem, st, cms,   \
+                       (int)planes, C, H, W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);                \
+    else                                                                                                               \
+      err = launch_pdl(global_peaks_warp_kernel<T, U_, false, WPC_>, g, dim3(32 * (WPC_)), (size_t)pad_smem, st, cms,  \
+                       (int)planes, C, H, W, sb, sc, sh, threshold, refine_size, out_xy, out_val, lad);                \
+  } while (0)
+#ifdef SNB_AB_VARIANTS
+    // A/B: SNB_K2_WPC in {1,2,4,8} warps per CTA, SNB_K2_U in {4,5,6,8,12} loads in flight per lane
+    const int e_wpc = getenv("SNB_K2_WPC") ? atoi(getenv("SNB_K2_WPC")) : GP_WARPS_PER_CTA;
+    const int e_u = getenv("SNB_K2_U") ? atoi(getenv("SNB_K2_U")) : GP_LOADS_IN_FLIGHT;
+#define SNB_GPW_U(WPC_)                                                                                                \
+  do {                                                                                                                 \
+    if (e_u == 4) SNB_GPW(4, WPC_); else if (e_u == 5) SNB_GPW(5, WPC_); else if (e_u == 6) SNB_GPW(6, WPC_);          \
+    else if (e_u == 12) SNB_GPW(12, WPC_); else SNB_GPW(8, WPC_);                                                      \
+  } while (0)
+    if (e_wpc == 1) SNB_GPW_U(1); else if (e_wpc == 2) SNB_GPW_U(2); else if (e_wpc == 8) SNB_GPW_U(8); else SNB_GPW_U(4);
+#undef SNB_GPW_U
+#else
+    SNB_GPW(GP_LOADS_IN_FLIGHT, GP_WARPS_PER_CTA);
+#endif
+#undef SNB_GPW
     if (err != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
   } else if (vec && !force_generic && chunkv <= 8 * 256) {
 #define SNB_GP(V)                                                                                                      \
@@ -1501,3 +1547,17 @@ extern "C" int snb_coord_ladder_apply(const float* xy, long long n_samples, long
   SNB_LAUNCH_CHECK();
   return SNB_OK;
 }
+
+#ifdef SNB_AB_VARIANTS
+// A/B build only (not in include/sleapnn_b200.h): switch the K2 stamps on / off and copy them out.
+extern "C" int snb_ab_k2_stamps(int on, unsigned long long* host_out, int n_planes) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+  if (host_out && n_planes > 0) {
+    if (n_planes > snb::K2_STAMP_PLANES) n_planes = snb::K2_STAMP_PLANES;
+    if (cudaMemcpyFromSymbol(host_out, snb::g_k2_stamps, sizeof(unsigned long long) * 3 * (size_t)n_planes) != cudaSuccess)
+      return SNB_ERR_CUDA_LAUNCH;
+  }
+  if (cudaMemcpyToSymbol(snb::g_k2_stamps_on, &on, sizeof(int)) != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;
+  return SNB_OK;
+}
+#endif

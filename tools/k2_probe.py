@@ -34,3 +34,31 @@ print("torch.amax over the same 85 MB:", round(timed(lambda i: bufs[i % 4].amax(
 big = [torch.empty(85196800 // 4, device=dev) for _ in range(4)]
 dst = torch.empty(85196800 // 4, device=dev)
 print("torch copy 85 MB (r+w):", round(timed(lambda i: dst.copy_(big[i % 4]), 200) * 1e3, 2), "us")
+
+# ---- per-plane globaltimer stamps (A/B build only: SLEAPNN_B200_LIB=.../libsleapnn_b200_ab.so) ----
+if hasattr(N.lib, "snb_ab_k2_stamps"):
+    import json
+    import numpy as np
+    P = B * Cn
+    host = (C.c_ulonglong * (3 * P))()
+    for wpc in (1, 4):
+        os.environ["SNB_K2_WPC"] = str(wpc)
+        x = bufs[0]
+
+        def one(thr=0.2, ref=5):
+            N.check(N.lib.snb_global_peaks(N.ptr(x), B, Cn, H, W, *x.stride(), thr, ref, N.ptr(ws), N.ptr(pts_o), N.ptr(val_o), N.stream_ptr(dev)), "k2")
+
+        for _ in range(3):
+            one()
+        N.lib.snb_ab_k2_stamps(1, None, 0)
+        big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        big.zero_()  # flush L2, then ONE stamped launch, alone
+        torch.cuda.synchronize()
+        one()
+        N.lib.snb_ab_k2_stamps(0, host, P)
+        t = np.frombuffer(host, dtype=np.uint64).reshape(P, 3).astype(np.int64)
+        t0 = t[:, 0].min()
+        q = lambda a: [round(float(v) / 1e3, 2) for v in np.percentile(a, [0, 10, 50, 90, 100])]
+        print(json.dumps({"k2_stamps_us": {"wpc": wpc, "planes": P, "pct": [0, 10, 50, 90, 100],
+                                           "start": q(t[:, 0] - t0), "stream_end": q(t[:, 1] - t0), "end": q(t[:, 2] - t0),
+                                           "stream_dur": q(t[:, 1] - t[:, 0]), "epilogue_dur": q(t[:, 2] - t[:, 1])}}), flush=True)
