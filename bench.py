@@ -411,7 +411,7 @@ def run_ours(args, rank: int, world: int):
 
     from sleap_nn_b200.pipeline import PipelineRing
 
-    ring = PipelineRing(pipes, streams) if not args.tail_stream else None
+    ring = PipelineRing(pipes, streams, stagger=True if args.fill_stagger else None) if not args.tail_stream else None
 
     def run_steps(n, events=None):
         if events is None and ring is not None:  # the product's own multi-stream loop (staggered start, explicit streams)
@@ -736,6 +736,8 @@ def main():
                     help="one detect stream + one high-priority tail stream instead of one stream per pipeline instance")
     ap.add_argument("--no-tail-priority", dest="no_tail_priority", action="store_true",
                     help="A/B: per-instance streams WITHOUT the shared high-priority tail stream (tails run on the detect streams)")
+    ap.add_argument("--fill-stagger", dest="fill_stagger", action="store_true",
+                    help="A/B: after a sync the first detect kernels of the ring's chains start one after another instead of together")
     ap.add_argument("--zero-copy-cms", action="store_true",
                     help="e2e: the detect kernel streams the pinned host confidence maps itself (no cudaMemcpy + HBM staging)")
     ap.add_argument("--e2e-static", action="store_true",

@@ -357,6 +357,10 @@ struct AsmFrame {
   // least 2 * K + n_edges + n_sorted + inst_cap + 2 words the post-loop passes run flattened over the connections in
   // visiting order instead of edge by edge (see assemble_frame_warp)
   int* scratch = nullptr; int scratch_words = 0; int n_edges = 0;
+  // the match list is known to be a proper matching per edge (every peak at most once as a source and once as a
+  // destination of that edge) - true for the fused tail, whose assignments come from its own solver; the grouping
+  // entry points take arbitrary lists and leave it false (the chunk path then checks for repeated peaks itself)
+  bool proper = false;
 };
 #ifdef SNB_TAIL_TIMING
 #define SNB_ASM_STAMP(k) do { if (lane == 0 && f.stamps) f.stamps[(k)] = (int)(clock64() - f.t0); } while (0)
@@ -426,6 +430,142 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
   __syncwarp();
   int n_order = 0, mx = -1;
+  // ---- flat mode (scratch lent by the caller, matches grouped by edge).  A single warp issues in order, so every level
+  // of a dependent shared-memory chain (sorted -> edges -> ns, m_src -> np_ -> owner) stalls it for a full latency, and
+  // the edge-by-edge loop below spent ~750 cycles per edge mostly on such chains.  Here everything that does not depend
+  // on the evolving ownership is resolved for ALL connections in one parallel pre-pass:
+  //   qa[m]   source peak of connection m, or -1 when the loop never applies it / the sums never count it
+  //   qb[m]   destination peak, or -1
+  //   qpos[m] its position in visiting order (edges in `sorted` order, connections in list order), or -1
+  // so that the sequential part per edge is: read qa / qb (one level), read owner[] (second level), ballots, writes.
+  const bool flat = f.scratch && f.mo && f.scratch_words >= 5 * K + f.n_edges + f.n_sorted + f.inst_cap + 2;
+  int* spos = f.scratch;                        // n_edges : position of edge e in `sorted`, -1 = never visited
+  int* voff = spos + f.n_edges;                 // n_sorted + 1 : first visiting position of each sorted edge
+  int* vrank = voff + f.n_sorted + 1;           // K : instance rank at each visiting position
+  float* vscore = reinterpret_cast<float*>(vrank + K);  // K
+  int* qa = reinterpret_cast<int*>(vscore + K); // K
+  int* qb = qa + K;                             // K
+  int* qpos = qb + K;                           // K
+  float* acc = reinterpret_cast<float*>(qpos + K);  // inst_cap
+  int n_vis = 0;
+  if (flat) {
+    for (int e = lane; e < f.n_edges; e += 32) spos[e] = -1;
+    __syncwarp();
+    int run = 0;
+    for (int s0 = 0; s0 < f.n_sorted; s0 += 32) {  // exclusive scan of the per-edge connection counts
+      const int se = s0 + lane;
+      int cnt = 0;
+      if (se < f.n_sorted) {
+        const int e = f.sorted[se];
+        spos[e] = se;
+        cnt = min(f.mo[e + 1], K) - min(f.mo[e], K);
+      }
+      int inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (se < f.n_sorted) voff[se] = run + inc - cnt;
+      run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) voff[f.n_sorted] = run;
+    n_vis = run;
+    __syncwarp();
+    for (int m = lane; m < K; m += 32) {
+      int a = -1, b = -1, pos = -1;
+      const int e = f.m_edge[m];
+      if (e >= 0 && e < f.n_edges) {
+        const int se = spos[e];
+        const int m_lo = min(f.mo[e], K), m_hi = min(f.mo[e + 1], K);
+        if (se >= 0 && m >= m_lo && m < m_hi && (f.m_score[m] >= f.min_line_scores)) {  // visited, paf.py:993
+          const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+          const bool sn_ok = sn >= 0 && sn < f.n_nodes, dn_ok = dn >= 0 && dn < f.n_nodes;
+          const int s0 = sn_ok ? f.ns[sn] : 0, n_src = sn_ok ? f.ns[sn + 1] - s0 : 0;
+          const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
+          const int sp = f.m_src[m], dp = f.m_dst[m];
+          const bool sp_ok = sp >= 0 && sp < n_src, dp_ok = dp >= 0 && dp < n_dst;
+          // the loop applies a connection only when both nodes exist and both ranks are in range (anything else is
+          // reported); the score sums count it as soon as its source resolves
+          if (!(sn_ok && dn_ok && sp_ok && dp_ok)) atomicOr(f.status, SNB_STATUS_BAD_INDEX);
+          if (sp_ok) { a = f.np_[s0 + sp]; pos = voff[se] + (m - m_lo); }
+          if (dp_ok) b = f.np_[d0 + dp];
+          if (!(sn_ok && dn_ok)) b = -1;  // never applied; still counted through `a` when the source node exists
+        }
+      }
+      qa[m] = a;
+      qb[m] = b;
+      qpos[m] = pos;
+    }
+    __syncwarp();
+    // (A parallel formulation was tried here: on a forest visited parents first - what toposort_edges gives - instances
+    // are the trees of the destination -> source links, ids and order[] follow from scans over the visiting positions,
+    // owners from pointer jumping.  Bit-exact, but a lone warp pays ~400 cycles per pass over shared tables and the
+    // dozen passes cost what the 31 sequential edge steps cost: 14.4 K vs 15 K cycles at cfg4, 5 K vs 2.4 K at cfg3.)
+    for (int c0 = 0; c0 < f.n_sorted; c0 += 32) {
+      // headers of 32 sorted edges at a time, one per lane; the loop below fetches them by shuffle
+      int h_e = -1, h_lo = 0, h_hi = 0, h_distinct = 0;
+      if (c0 + lane < f.n_sorted) {
+        h_e = f.sorted[c0 + lane];
+        h_lo = min(f.mo[h_e], K);
+        h_hi = min(f.mo[h_e + 1], K);
+        h_distinct = f.edges[2 * h_e] != f.edges[2 * h_e + 1];
+      }
+      const int c1 = min(32, f.n_sorted - c0);
+      for (int j = 0; j < c1; ++j) {
+        const int e = __shfl_sync(FULL, h_e, j), m_lo = __shfl_sync(FULL, h_lo, j), m_hi = __shfl_sync(FULL, h_hi, j);
+        const bool distinct = __shfl_sync(FULL, h_distinct, j) != 0;
+        for (int mb = m_lo; mb < m_hi; mb += 32) {
+          const int m = mb + lane;
+          int pa = -1 - lane, pb = -1 - lane;  // distinct placeholders for __match_any_sync
+          bool act = false;
+          if (m < m_hi) {
+            const int a = qa[m], b = qb[m];
+            act = a >= 0 && b >= 0 && f.m_edge[m] == e;
+            if (act) { pa = a; pb = b; }
+          }
+          const unsigned am = __ballot_sync(FULL, act);
+          if (am == 0) continue;
+          const int ia = act ? f.owner[pa] : -1, ib = act ? f.owner[pb] : -1;
+          const bool k1 = act && ia < 0 && ib < 0, k2 = act && ia >= 0 && ib < 0;
+          const bool merge = act && ia >= 0 && ib >= 0 && ia != ib;
+          bool repeated = false;
+          if (!f.proper) {
+            const unsigned same_a = __match_any_sync(FULL, pa), same_b = __match_any_sync(FULL, pb);
+            repeated = __popc(same_a) > 1 || __popc(same_b) > 1;
+          }
+          __syncwarp();  // owner[] reads above happen before any write below
+          if (distinct && !__any_sync(FULL, merge || repeated)) {
+            const unsigned b1 = __ballot_sync(FULL, k1), b2 = __ballot_sync(FULL, k2);
+            const int off = n_order + 2 * __popc(b1 & lt) + __popc(b2 & lt);
+            if (k1) {
+              const int id = mx + 1 + __popc(b1 & lt);
+              f.owner[pa] = id;
+              f.owner[pb] = id;
+              f.order[off] = pa;
+              f.order[off + 1] = pb;
+            } else if (k2) {
+              f.owner[pb] = ia;
+              f.order[off] = pb;
+            }
+            mx += __popc(b1);
+            n_order += 2 * __popc(b1) + __popc(b2);
+            __syncwarp();
+          } else {
+            unsigned todo = am;
+            while (todo) {
+              const int l = __ffs(todo) - 1;
+              todo &= todo - 1;
+              assemble_one(f, lane, __shfl_sync(FULL, pa, l), __shfl_sync(FULL, pb, l), n_order);
+            }
+            mx = -1;  // ids may have been renamed: re-scan the running maximum
+            for (int i = lane; i < P; i += 32) mx = max(mx, f.owner[i]);
+            for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+          }
+        }
+      }
+    }
+  } else {
   // per-edge header (edge id, node offsets, match range): a chain of three dependent loads.  The NEXT edge's header is
   // fetched before the current edge's connections are applied, so the chain overlaps the body instead of heading it.
   struct EdgeHdr { int e, s0, d0, n_src, n_dst, m_lo, m_hi; bool distinct; };
@@ -467,8 +607,11 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       const int ia = act ? f.owner[pa] : -1, ib = act ? f.owner[pb] : -1;
       const bool c1 = act && ia < 0 && ib < 0, c2 = act && ia >= 0 && ib < 0;
       const bool merge = act && ia >= 0 && ib >= 0 && ia != ib;
-      const unsigned same_a = __match_any_sync(FULL, pa), same_b = __match_any_sync(FULL, pb);  // both by ALL lanes
-      const bool repeated = __popc(same_a) > 1 || __popc(same_b) > 1;
+      bool repeated = false;
+      if (!f.proper) {  // (warp-uniform) two match.any per chunk are a large part of an edge's ~1 100 cycles
+        const unsigned same_a = __match_any_sync(FULL, pa), same_b = __match_any_sync(FULL, pb);  // both by ALL lanes
+        repeated = __popc(same_a) > 1 || __popc(same_b) > 1;
+      }
       __syncwarp();  // owner[] reads above happen before any write below
       if (hd.distinct && !__any_sync(FULL, merge || repeated)) {
         const unsigned b1 = __ballot_sync(FULL, c1), b2 = __ballot_sync(FULL, c2);
@@ -499,6 +642,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       }
     }
   }
+  }  // edge-by-edge greedy loop (no scratch)
   SNB_ASM_STAMP(6);
   // instance sizes, min_instance_peaks filter, ascending-id compaction (paf.py:791-818, :845-850)
   for (int i = lane; i < P; i += 32)
@@ -527,67 +671,25 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   // The same pass replays the reference's sanity check (ops/paf.py:866-873): a visited connection whose source is in a
   // kept instance must have its destination in the SAME instance - otherwise the reference raises (AssertionError, or
   // KeyError when the destination is in no kept instance).  Only improper matchings fed to the grouping API get there.
-  if (f.scratch && f.mo && f.scratch_words >= 2 * K + f.n_edges + f.n_sorted + n_inst + 2) {
-    // ---- flattened passes.  Connection m of edge e is visited at position voff[se(e)] + (m - mo[e]) (edges in
-    // `sorted` order, connections in list order).  One parallel pass over ALL connections resolves each one's instance
-    // rank and writes (rank, score) at its visiting position; the score sums then walk that list 32 positions at a
-    // time: lanes holding the same instance form a group (__match_any_sync) whose lowest lane adds the group's scores
-    // in lane (= visiting) order on top of the instance's running sum - the strict left-to-right fp32 sum of
-    // paf.py:853-865, without every lane scanning every connection (was 18.6 + 12.4 us of a busy frame's 53 us).
-    int* spos = f.scratch;                       // n_edges : position of edge e in `sorted`, -1 = never visited
-    int* voff = spos + f.n_edges;                // n_sorted + 1
-    int* vrank = voff + f.n_sorted + 1;          // K
-    float* vscore = reinterpret_cast<float*>(vrank + K);  // K
-    float* acc = vscore + K;                     // n_inst
-    for (int e = lane; e < f.n_edges; e += 32) spos[e] = -1;
+  if (flat) {
+    // ---- flattened passes.  One parallel pass over ALL connections resolves each one's instance rank and writes
+    // (rank, score) at its visiting position; the score sums then walk that list 32 positions at a time: lanes holding
+    // the same instance form a group (__match_any_sync) whose lowest lane adds the group's scores in lane (= visiting)
+    // order on top of the instance's running sum - the strict left-to-right fp32 sum of paf.py:853-865, without every
+    // lane scanning every connection (was 18.6 + 12.4 us of a busy frame's 53 us).
     for (int r = lane; r < n_inst; r += 32) acc[r] = 0.f;
-    __syncwarp();
-    int run = 0;
-    for (int s0 = 0; s0 < f.n_sorted; s0 += 32) {  // exclusive scan of the per-edge connection counts
-      const int se = s0 + lane;
-      int cnt = 0;
-      if (se < f.n_sorted) {
-        const int e = f.sorted[se];
-        spos[e] = se;
-        cnt = min(f.mo[e + 1], K) - min(f.mo[e], K);
-      }
-      int inc = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += t;
-      }
-      if (se < f.n_sorted) voff[se] = run + inc - cnt;
-      run += __shfl_sync(FULL, inc, 31);
-    }
-    if (lane == 0) voff[f.n_sorted] = run;
-    const int n_vis = run;
-    __syncwarp();
     for (int v = lane; v < n_vis; v += 32) vrank[v] = -1;
     __syncwarp();
     for (int m = lane; m < K; m += 32) {
-      const int e = f.m_edge[m];
-      if (e < 0 || e >= f.n_edges) continue;
-      const int se = spos[e];
-      if (se < 0) continue;
-      const int m_lo = min(f.mo[e], K), m_hi = min(f.mo[e + 1], K);
-      if (m < m_lo || m >= m_hi) continue;  // not in its edge's slice: never visited
-      const float sc = f.m_score[m];
-      if (!(sc >= f.min_line_scores)) continue;
-      const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
-      if (sn < 0 || sn >= f.n_nodes) continue;
-      const int s0 = f.ns[sn], n_src = f.ns[sn + 1] - s0;
-      const bool dn_ok = dn >= 0 && dn < f.n_nodes;
-      const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
-      const int sp = f.m_src[m], dp = f.m_dst[m];
-      if (sp < 0 || sp >= n_src) continue;
-      const int o = f.owner[f.np_[s0 + sp]];
+      const int pos = qpos[m];
+      if (pos < 0) continue;  // never visited, or its source does not resolve
+      const int o = f.owner[qa[m]];
       const int rk = (o >= 0) ? f.id_rank[o] : -1;
-      const int pos = voff[se] + (m - m_lo);
       vrank[pos] = rk;
-      vscore[pos] = sc;
-      if (rk >= 0 && dp >= 0 && dp < n_dst) {  // the reference's sanity check (ops/paf.py:866-873)
-        const int od = f.owner[f.np_[d0 + dp]];
+      vscore[pos] = f.m_score[m];
+      const int b = qb[m];
+      if (rk >= 0 && b >= 0) {  // the reference's sanity check (ops/paf.py:866-873)
+        const int od = f.owner[b];
         const int rd = (od >= 0) ? f.id_rank[od] : -1;
         if (rd < 0) atomicOr(f.status, SNB_STATUS_ASM_MISSING);
         else if (rd != rk) atomicOr(f.status, SNB_STATUS_ASM_MISMATCH);

@@ -821,7 +821,12 @@ __device__ __forceinline__ void k2_stamp(int p, int which, int lane) {
 #endif
 
 constexpr int GP_WARPS_PER_CTA = 1;    // planes (= warps) per CTA of the warp kernel
-constexpr int GP_LOADS_IN_FLIGHT = 8;  // 128-bit loads in flight per lane
+// 128-bit loads in flight per lane.  Around one wave of warps (cfg2 batch 256: 3 328 planes on 148 SMs) a SHALLOW window
+// is faster - 4 -> 15.9-16.9 us, 5 -> 15.8-16.1, 6 -> 15.9-16.5, 8 -> 16.5-16.9, 10 -> 16.6, 12 -> 17.0 on two B200s
+// (fp16 maps: 5 -> 9.6, 8 -> 10.5) - while a sub-wave launch needs the deeper one to cover the latency (batch 64:
+// 8 -> 8.4 us, 5 -> 10.3); many waves do not care (batch 1 024: 50-51 us at every depth).  profiles/r2_sweep_small_launch.jsonl
+constexpr int GP_LOADS_IN_FLIGHT = 5;
+constexpr int GP_LOADS_IN_FLIGHT_SUBWAVE = 8;  // fewer than 16 planes per SM
 
 template <typename T, int U, bool CONTIG, int WPC>
 __global__ void __launch_bounds__(32 * WPC)
@@ -1393,16 +1398,18 @@ static int launch_global_peaks(const T* cms, int B, int C, int H, int W, long lo
 #ifdef SNB_AB_VARIANTS
     // A/B: SNB_K2_WPC in {1,2,4,8} warps per CTA, SNB_K2_U in {4,5,6,8,12} loads in flight per lane
     const int e_wpc = getenv("SNB_K2_WPC") ? atoi(getenv("SNB_K2_WPC")) : GP_WARPS_PER_CTA;
-    const int e_u = getenv("SNB_K2_U") ? atoi(getenv("SNB_K2_U")) : GP_LOADS_IN_FLIGHT;
+    const int e_u = getenv("SNB_K2_U") ? atoi(getenv("SNB_K2_U"))
+                                       : (planes < 16LL * sm_count() ? GP_LOADS_IN_FLIGHT_SUBWAVE : GP_LOADS_IN_FLIGHT);
 #define SNB_GPW_U(WPC_)                                                                                                \
   do {                                                                                                                 \
-    if (e_u == 4) SNB_GPW(4, WPC_); else if (e_u == 5) SNB_GPW(5, WPC_); else if (e_u == 6) SNB_GPW(6, WPC_);          \
-    else if (e_u == 12) SNB_GPW(12, WPC_); else SNB_GPW(8, WPC_);                                                      \
+    if (e_u == 4) SNB_GPW(4, WPC_); else if (e_u == 6) SNB_GPW(6, WPC_); else if (e_u == 8) SNB_GPW(8, WPC_);          \
+    else if (e_u == 10) SNB_GPW(10, WPC_); else if (e_u == 12) SNB_GPW(12, WPC_); else SNB_GPW(5, WPC_);               \
   } while (0)
     if (e_wpc == 1) SNB_GPW_U(1); else if (e_wpc == 2) SNB_GPW_U(2); else if (e_wpc == 8) SNB_GPW_U(8); else SNB_GPW_U(4);
 #undef SNB_GPW_U
 #else
-    SNB_GPW(GP_LOADS_IN_FLIGHT, GP_WARPS_PER_CTA);
+    if (planes < 16LL * sm_count()) SNB_GPW(GP_LOADS_IN_FLIGHT_SUBWAVE, GP_WARPS_PER_CTA);
+    else SNB_GPW(GP_LOADS_IN_FLIGHT, GP_WARPS_PER_CTA);
 #endif
 #undef SNB_GPW
     if (err != cudaSuccess) return SNB_ERR_CUDA_LAUNCH;

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   const int n_nodes = a.C, E = a.n_edges;
 #ifdef SNB_TAIL_TIMING
   const long long t_start = clock64();
+  unsigned long long g_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
 #endif
   // small read-only tables -> shared memory once (the sequential phases would otherwise pay an L2
   // round trip per dependent access)
@@ -318,12 +320,20 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
     f.n_inst_out = a.n_inst + b; f.status = a.status;
     f.scratch = reinterpret_cast<int*>(s_score);  // candidate scores are dead once the assignments are solved
     f.scratch_words = a.cand_cap; f.n_edges = E;
+    f.proper = true;  // the matches come from this kernel's own assignment solver
 #ifdef SNB_TAIL_TIMING
     f.stamps = a.asm_ws ? a.asm_ws + b * 16 : nullptr; f.t0 = t_start;
 #endif
     assemble_frame_warp(f, lane);
   }
   SNB_STAMP(5);
+#ifdef SNB_TAIL_TIMING
+  if (threadIdx.x == 0 && R == 0 && a.asm_ws) {  // wall time of the same span in ns (the SM clock is not fixed)
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    a.asm_ws[b * 16 + 10] = (int)(g_end - g_start);
+  }
+#endif
   // self-resetting peak counter: every thread read `total` before the first barrier above, so the counter can go back
   // to zero for the next call's detect kernel (no memset node in the chain)
   if ((a.flags & SNB_FLAG_SELF_RESET_COUNTERS) && tid == 0) {

@@ -135,7 +135,8 @@ class BottomUpPostproc:
                  cand_cap: int = 4096, match_cap: int = 512, inst_cap: int = 64, lsap_max_dim: int = 32,
                  device: Optional[torch.device] = None, tail_stream: Optional[torch.cuda.Stream] = None,
                  fused_tail: bool = True, keep_tables: bool = True, max_instances: Optional[int] = None,
-                 max_peaks_per_node: Optional[int] = None, tail_cluster: bool = True):
+                 max_peaks_per_node: Optional[int] = None, tail_cluster: bool = True,
+                 sorted_edge_inds: Optional[Sequence[int]] = None):
         self.device = torch.device(device) if device is not None else N.compute_device()
         self.n_nodes, self.batch = int(n_nodes), int(batch)
         self.edge_inds = [(int(a), int(b)) for a, b in edge_inds]
@@ -153,7 +154,14 @@ class BottomUpPostproc:
         self.min_line_scores = float(min_line_scores)
         self.caps = dict(peak_cap=int(peak_cap), cand_cap=int(cand_cap), match_cap=int(match_cap),
                          inst_cap=int(inst_cap), lsap_max_dim=int(lsap_max_dim))
-        self.sorted_edge_inds = toposort_edges([EdgeType(a, b) for a, b in self.edge_inds]) if self.n_edges else ()
+        # order in which the assembly visits the edges: the reference's PAFScorer.sorted_edge_inds (ops/paf.py:1230-1236,
+        # toposort_edges); an explicit order is for tests of the assembly's non-forest path
+        if sorted_edge_inds is not None:
+            self.sorted_edge_inds = tuple(int(e) for e in sorted_edge_inds)
+            if any(e < 0 or e >= self.n_edges for e in self.sorted_edge_inds):
+                raise ValueError("sorted_edge_inds must index edge_inds")
+        else:
+            self.sorted_edge_inds = toposort_edges([EdgeType(a, b) for a, b in self.edge_inds]) if self.n_edges else ()
         dev, B, Nn, E = self.device, self.batch, self.n_nodes, self.n_edges
         i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
         f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
@@ -519,12 +527,15 @@ class PipelineRing:
     `capture_rotation` does inside a CUDA graph, where cross-stream priorities are not available.
     """
 
-    def __init__(self, pipes: Sequence["BottomUpPostproc"], streams: Optional[Sequence[torch.cuda.Stream]] = None):
+    def __init__(self, pipes: Sequence["BottomUpPostproc"], streams: Optional[Sequence[torch.cuda.Stream]] = None,
+                 stagger: Optional[bool] = None):
         if not pipes:
             raise ValueError("need at least one pipeline")
         self.pipes = list(pipes)
         self.device = self.pipes[0].device
-        self._stagger = all(p.tail_stream is None for p in self.pipes)
+        # stagger: after reset(), chain k's first detect kernel waits for chain k-1's (default: only when the pipes have
+        # no tail stream; with one, it only shortens the fill of an idle ring, and measured slower over a short run: 52.8 vs 50.2 us per step over 20 steps, bench.py --fill-stagger)
+        self._stagger = all(p.tail_stream is None for p in self.pipes) if stagger is None else bool(stagger)
         with torch.cuda.device(self.device):
             self.streams = list(streams) if streams is not None else [torch.cuda.Stream(device=self.device) for _ in self.pipes]
             self._ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in self.pipes]

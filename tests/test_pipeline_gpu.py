@@ -312,6 +312,55 @@ def test_fused_pipeline_busy_flies_frames_vs_oracle():
         close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-6)  # a sum of 31 line scores: observed |d| < 2e-5 on scores of ~30
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["branching_tree", "children_first_order", "two_parents_all_edges"])
+def test_fused_pipeline_assembly_paths_vs_oracle(case):
+    """The tail's assembly has a parallel path for skeletons visited as a forest, parents first (instances = trees over
+    the peaks: what toposort_edges' order gives), and the reference's sequential loop for everything else.  Same maps
+    and the same visiting order through the oracle: a branching tree in the product's own order (forest path); the
+    same tree visited children first, and a node with two parents with every edge visited (the connections then break
+    the forest conditions - a destination used as a source earlier, a peak that is a destination twice - and the
+    sequential loop runs)."""
+    from oracle import paf as opaf
+    from oracle import peaks as opeaks
+    from oracle.synth import split_by_sample
+    from sleap_nn_b200 import synthetic
+    from sleap_nn_b200.pipeline import BottomUpPostproc
+
+    tree = [(0, 1), (0, 2), (1, 3), (1, 4), (2, 5), (5, 6), (5, 7)]
+    edges = tree + [(3, 7)] if case == "two_parents_all_edges" else tree
+    B, n_inst, Nn, hw, stride = 4, 4, 8, (512, 512), 2
+    poses = synthetic.random_poses(11, B, n_inst, Nn, hw, tree, margin=120.0, step=30.0, min_limb=10.0, min_sep=14.0)
+    dev = torch.device("cuda")
+    cms, pafs = synthetic.render_batch(poses, hw, stride, edges, dev, seed=11)
+    order = None
+    if case == "children_first_order":
+        order = tuple(reversed(BottomUpPostproc(Nn, edges, B, (256, 256)).sorted_edge_inds))
+    elif case == "two_parents_all_edges":
+        order = tuple(range(len(edges)))  # (5, 7) and (3, 7) are both visited
+    pipe = BottomUpPostproc(Nn, edges, B, (256, 256), cms_stride=stride, pafs_stride=stride, sorted_edge_inds=order)
+    assert pipe.fused
+    res = pipe(cms, pafs)
+    c_cpu, p_cpu = cms.cpu(), pafs.cpu()
+    pts, vals, si, ci = opeaks.local_peaks(c_cpu, 0.2, "integral")
+    peaks, pvs, pcs = (split_by_sample(x, si, B) for x in (pts * stride, vals, ci))
+    try:
+        want = opaf.predict(p_cpu.permute(0, 2, 3, 1), peaks, pvs, pcs, edges, Nn, stride, sorted_edge_inds=order)
+    except (AssertionError, KeyError) as e:  # the reference's own sanity check (ops/paf.py:866-873) rejects this order
+        with pytest.raises(type(e)):
+            res.to_lists()
+        return
+    inst, pv, sc = res.to_lists()
+    for b in range(B):
+        assert inst[b].shape == want[0][b].shape
+        eq(np.isnan(npy(inst[b])), np.isnan(npy(want[0][b])))
+        close(npy(inst[b]), npy(want[0][b]), atol=1e-4)
+        eq(npy(pv[b]), npy(want[1][b]))
+        close(npy(sc[b]), npy(want[2][b]), rtol=1e-5, atol=1e-6)
+    if case == "branching_tree":
+        assert all(x.shape[0] == n_inst for x in inst)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
 def test_second_device_in_the_same_process():
     """Inputs on cuda:1 while cuda:0 is the current device: kernels run on the input's device and stream, results come

@@ -36,7 +36,7 @@ def one(dev, name, Bn, Nn, n_inst, pipe_kw, pose_kw, cpu=True):
         res = pipe(*inputs[0])
         n_found = sum(len(x) for x in res.to_lists()[0])
         chain, det = [], []
-        for i in range(210):
+        for i in range(int(os.environ.get("SNB_LATENCY_CALLS", 210))):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for e in (d0, d1):
@@ -51,7 +51,7 @@ def one(dev, name, Bn, Nn, n_inst, pipe_kw, pose_kw, cpu=True):
                 det.append(d0.elapsed_time(d1) * 1e3)
         out[label] = {"chain_us": statistics.median(chain), "detect_us": statistics.median(det),
                       "tail_us": statistics.median(chain) - statistics.median(det), "instances_found": n_found}
-    if cpu:
+    if cpu and not os.environ.get("SNB_LATENCY_NO_CPU"):
         import bench
 
         bench.N_NODES, bench.STRIDE = Nn, 2

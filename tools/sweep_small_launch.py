@@ -88,10 +88,13 @@ def main():
             out("k7_cfg4_g1", env, with_env(env, lambda: bk.k7_cfg4(dev, iters, G=1)))
     if want("k2u"):
         for rep in range(2):
-            for u in (4, 5, 6, 8):
+            for u in (4, 5, 6, 8, 10):
                 env = {"SNB_K2_WPC": 1, "SNB_K2_U": u}
                 out("k2_cfg2", {**env, "rep": rep}, with_env(env, lambda: bk.k2_cfg2(dev, iters)))
                 out("k2_cfg2_f16", {**env, "rep": rep}, with_env(env, lambda: bk.k2_cfg2(dev, iters, dtype=torch.float16)))
+                if rep == 0:
+                    out("k2_cfg2_b1024", env, with_env(env, lambda: bk.k2_cfg2(dev, iters, B=1024)))
+                    out("k2_cfg2_b64", env, with_env(env, lambda: bk.k2_cfg2(dev, iters, B=64)))
     if want("k7g"):
         for bf16 in (False, True):
             for G in (1, 2, 4, 8):
@@ -104,6 +107,17 @@ def main():
                 out("k8_cfg4" + ("_bf16" if bf16 else ""), {"G": G, "rows": "wave_fit"}, bk.k8_cfg4(dev, iters, bf16=bf16, G=G))
                 env = {"SNB_PAF_RPB": 32}
                 out("k8_cfg4" + ("_bf16" if bf16 else ""), {**env, "G": G}, with_env(env, lambda: bk.k8_cfg4(dev, iters, bf16=bf16, G=G)))
+    if want("prod"):  # the library's own choices (no switch set)
+        for G in (1, 2, 4, 8):
+            for bf16 in (False, True):
+                out("k7_cfg4" + ("_bf16" if bf16 else ""), {"G": G, "rows": "product"}, bk.k7_cfg4(dev, iters, bf16=bf16, G=G))
+        for bf16 in (False, True):
+            for G in (1, 8):
+                out("targets_cfg4_fused" + ("_bf16" if bf16 else ""), {"G": G, "rows": "product"},
+                    bk.targets_cfg4_fused(dev, iters, bf16=bf16, G=G))
+        for B in (64, 256, 1024):
+            for dt in (torch.float32, torch.float16):
+                out("k2_cfg2_" + str(dt).split(".")[-1], {"B": B, "loads_in_flight": "product"}, bk.k2_cfg2(dev, iters, B=B, dtype=dt))
     if want("pair"):
         for r7 in (16, 32, 64):
             for r8 in (16, 19, 37):

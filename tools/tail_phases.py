@@ -34,8 +34,10 @@ names = ["sort", "refine", "group", "score", "match", "assemble"]
 sub = raw[:, [4, 6, 7, 8, 9, 5]]  # match end | greedy loop | compaction | NaN fill + rank pass | score sums | scatter (= assemble end)
 sd = sub[:, 1:] - sub[:, :-1]
 for k, nm in enumerate(["asm: greedy loop", "asm: count+compact", "asm: fill+rank pass", "asm: score sums", "asm: scatter"]):
-    print(f"{nm:20s} {float(sd[:, k].median()):10.0f} cycles  ~{float(sd[:, k].median()) / 1900.0:8.1f} us")
-mhz = 1900.0
+    print(f"{nm:20s} {float(sd[:, k].median()):10.0f} cycles  ~{float(sd[:, k].median()) / 1900.0:8.1f} us at 1.9 GHz")
+ns = float(raw[:, 10].median())  # globaltimer span of the same region (ns): the SM clock is not fixed
+mhz = float(t[:, 5].median()) / (ns / 1e3) if ns > 0 else 1900.0
+print(f"wall {ns / 1e3:.1f} us for {float(t[:, 5].median()):.0f} cycles -> SM clock {mhz:.0f} MHz during the tail")
 print(cfg, "peaks/frame", float(res.n_peaks.float().mean()), "instances/frame", float(res.n_instances.float().mean()))
 for k, nm in enumerate(names):
     c = float(d[:, k].median())
