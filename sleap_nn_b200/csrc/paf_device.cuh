@@ -424,11 +424,84 @@ __device__ __forceinline__ void assemble_one(const AsmFrame& f, int lane, int pa
 // assemble_one per connection.  ncu + clock64 stamps on busy frames (32 nodes, 8 animals): the one-connection-
 // at-a-time version spent 265 us of the tail's 348 us here, half of it in a lane-0 loop that accumulated the
 // instance scores with a global-memory read-modify-write per connection.
-__device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane) {
+// Does the lent scratch hold the flat-mode tables (spos, voff, vrank, vscore, qa, qb, qpos, acc)?
+__device__ __forceinline__ bool asm_flat_ok(const AsmFrame& f) {
+  return f.scratch && f.mo && f.scratch_words >= 5 * f.K + f.n_edges + f.n_sorted + f.inst_cap + 2;
+}
+
+// Flat-mode tables of the assembly (see assemble_frame_warp), shared with the CTA-wide pre-pass.
+// asm_scan_edges (one warp): spos[e] = position of edge e in `sorted` (-1 = never visited), voff[se] = first visiting
+// position of sorted edge se; returns the number of visiting positions.
+__device__ __forceinline__ int asm_scan_edges(const AsmFrame& f, int lane, int* spos, int* voff) {
+  const int K = f.K;
+  for (int e = lane; e < f.n_edges; e += 32) spos[e] = -1;
+  __syncwarp();
+  int run = 0;
+  for (int s0 = 0; s0 < f.n_sorted; s0 += 32) {  // exclusive scan of the per-edge connection counts
+    const int se = s0 + lane;
+    int cnt = 0;
+    if (se < f.n_sorted) {
+      const int e = f.sorted[se];
+      spos[e] = se;
+      cnt = min(f.mo[e + 1], K) - min(f.mo[e], K);
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (se < f.n_sorted) voff[se] = run + inc - cnt;
+    run += __shfl_sync(FULL, inc, 31);
+  }
+  if (lane == 0) voff[f.n_sorted] = run;
+  __syncwarp();
+  return run;
+}
+
+// asm_prepass: connections first, first + stride, ... -> (qa, qb, qpos).  Any group of threads; spos / voff complete.
+__device__ __forceinline__ void asm_prepass(const AsmFrame& f, int first, int stride, const int* spos, const int* voff,
+                                            int* qa, int* qb, int* qpos) {
+  const int K = f.K;
+  for (int m = first; m < K; m += stride) {
+    int a = -1, b = -1, pos = -1;
+    const int e = f.m_edge[m];
+    if (e >= 0 && e < f.n_edges) {
+      const int se = spos[e];
+      const int m_lo = min(f.mo[e], K), m_hi = min(f.mo[e + 1], K);
+      if (se >= 0 && m >= m_lo && m < m_hi && (f.m_score[m] >= f.min_line_scores)) {  // visited, paf.py:993
+        const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
+        const bool sn_ok = sn >= 0 && sn < f.n_nodes, dn_ok = dn >= 0 && dn < f.n_nodes;
+        const int s0 = sn_ok ? f.ns[sn] : 0, n_src = sn_ok ? f.ns[sn + 1] - s0 : 0;
+        const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
+        const int sp = f.m_src[m], dp = f.m_dst[m];
+        const bool sp_ok = sp >= 0 && sp < n_src, dp_ok = dp >= 0 && dp < n_dst;
+        // the loop applies a connection only when both nodes exist and both ranks are in range (anything else is
+        // reported); the score sums count it as soon as its source resolves
+        if (!(sn_ok && dn_ok && sp_ok && dp_ok)) atomicOr(f.status, SNB_STATUS_BAD_INDEX);
+        if (sp_ok) { a = f.np_[s0 + sp]; pos = voff[se] + (m - m_lo); }
+        if (dp_ok) b = f.np_[d0 + dp];
+        if (!(sn_ok && dn_ok)) b = -1;  // never applied; still counted through `a` when the source node exists
+      }
+    }
+    qa[m] = a;
+    qb[m] = b;
+    qpos[m] = pos;
+  }
+}
+
+// Hand-over from the sequential part of the assembly (one warp) to its CTA-wide finish (assemble_finish_cta): lives in
+// shared memory.  split == 1 means the warp stopped after the id compaction and everything after it is still to do.
+struct AsmSplit { int pre, split, n_inst, n_order, n_vis; };  // pre == 1: assemble_prepass_cta already ran
+
+__device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane, AsmSplit* hand = nullptr) {
   const int P = f.P, K = f.K;
   const unsigned lt = (1u << lane) - 1u;
-  for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
-  __syncwarp();
+  const bool pre = hand && hand->pre;  // owner / id_count initialised and the flat tables filled by the whole CTA
+  if (!pre) {
+    for (int i = lane; i < P; i += 32) { f.owner[i] = -1; f.id_count[i] = 0; }
+    __syncwarp();
+  }
   int n_order = 0, mx = -1;
   // ---- flat mode (scratch lent by the caller, matches grouped by edge).  A single warp issues in order, so every level
   // of a dependent shared-memory chain (sorted -> edges -> ns, m_src -> np_ -> owner) stalls it for a full latency, and
@@ -438,7 +511,7 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   //   qb[m]   destination peak, or -1
   //   qpos[m] its position in visiting order (edges in `sorted` order, connections in list order), or -1
   // so that the sequential part per edge is: read qa / qb (one level), read owner[] (second level), ballots, writes.
-  const bool flat = f.scratch && f.mo && f.scratch_words >= 5 * K + f.n_edges + f.n_sorted + f.inst_cap + 2;
+  const bool flat = asm_flat_ok(f);
   int* spos = f.scratch;                        // n_edges : position of edge e in `sorted`, -1 = never visited
   int* voff = spos + f.n_edges;                 // n_sorted + 1 : first visiting position of each sorted edge
   int* vrank = voff + f.n_sorted + 1;           // K : instance rank at each visiting position
@@ -449,55 +522,13 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
   float* acc = reinterpret_cast<float*>(qpos + K);  // inst_cap
   int n_vis = 0;
   if (flat) {
-    for (int e = lane; e < f.n_edges; e += 32) spos[e] = -1;
-    __syncwarp();
-    int run = 0;
-    for (int s0 = 0; s0 < f.n_sorted; s0 += 32) {  // exclusive scan of the per-edge connection counts
-      const int se = s0 + lane;
-      int cnt = 0;
-      if (se < f.n_sorted) {
-        const int e = f.sorted[se];
-        spos[e] = se;
-        cnt = min(f.mo[e + 1], K) - min(f.mo[e], K);
-      }
-      int inc = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += t;
-      }
-      if (se < f.n_sorted) voff[se] = run + inc - cnt;
-      run += __shfl_sync(FULL, inc, 31);
+    if (pre) {
+      n_vis = hand->n_vis;
+    } else {
+      n_vis = asm_scan_edges(f, lane, spos, voff);
+      asm_prepass(f, lane, 32, spos, voff, qa, qb, qpos);
+      __syncwarp();
     }
-    if (lane == 0) voff[f.n_sorted] = run;
-    n_vis = run;
-    __syncwarp();
-    for (int m = lane; m < K; m += 32) {
-      int a = -1, b = -1, pos = -1;
-      const int e = f.m_edge[m];
-      if (e >= 0 && e < f.n_edges) {
-        const int se = spos[e];
-        const int m_lo = min(f.mo[e], K), m_hi = min(f.mo[e + 1], K);
-        if (se >= 0 && m >= m_lo && m < m_hi && (f.m_score[m] >= f.min_line_scores)) {  // visited, paf.py:993
-          const int sn = f.edges[2 * e], dn = f.edges[2 * e + 1];
-          const bool sn_ok = sn >= 0 && sn < f.n_nodes, dn_ok = dn >= 0 && dn < f.n_nodes;
-          const int s0 = sn_ok ? f.ns[sn] : 0, n_src = sn_ok ? f.ns[sn + 1] - s0 : 0;
-          const int d0 = dn_ok ? f.ns[dn] : 0, n_dst = dn_ok ? f.ns[dn + 1] - d0 : 0;
-          const int sp = f.m_src[m], dp = f.m_dst[m];
-          const bool sp_ok = sp >= 0 && sp < n_src, dp_ok = dp >= 0 && dp < n_dst;
-          // the loop applies a connection only when both nodes exist and both ranks are in range (anything else is
-          // reported); the score sums count it as soon as its source resolves
-          if (!(sn_ok && dn_ok && sp_ok && dp_ok)) atomicOr(f.status, SNB_STATUS_BAD_INDEX);
-          if (sp_ok) { a = f.np_[s0 + sp]; pos = voff[se] + (m - m_lo); }
-          if (dp_ok) b = f.np_[d0 + dp];
-          if (!(sn_ok && dn_ok)) b = -1;  // never applied; still counted through `a` when the source node exists
-        }
-      }
-      qa[m] = a;
-      qb[m] = b;
-      qpos[m] = pos;
-    }
-    __syncwarp();
     // (A parallel formulation was tried here: on a forest visited parents first - what toposort_edges gives - instances
     // are the trees of the destination -> source links, ids and order[] follow from scans over the visiting positions,
     // owners from pointer jumping.  Bit-exact, but a lone warp pays ~400 cycles per pass over shared tables and the
@@ -662,6 +693,12 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
     return;
   }
   SNB_ASM_STAMP(7);
+  // a caller with a whole CTA at hand finishes from here with all of its warps (flat mode only, and only when the
+  // scratch also holds one word per output slot for the scatter)
+  if (hand && flat && f.scratch_words >= 5 * K + f.n_edges + f.n_sorted + f.inst_cap + 2 + f.inst_cap * f.n_nodes) {
+    if (lane == 0) { hand->n_inst = n_inst; hand->n_order = n_order; hand->n_vis = n_vis; hand->split = 1; }
+    return;
+  }
   for (int i = lane; i < n_inst * f.n_nodes; i += 32) { f.oxy[2 * i] = NAN; f.oxy[2 * i + 1] = NAN; f.oval[i] = NAN; }
   if (lane == 0) *f.n_inst_out = n_inst;
   // instance score = fp32 running sum of its connections' scores in visiting order (paf.py:853-865): lane r owns
@@ -793,6 +830,114 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane)
       f.oval[slot] = f.val[i];
     }
     __syncwarp();
+  }
+}
+
+// CTA-wide start of the assembly: ownership tables initialised and the flat-mode tables filled by all threads (one
+// connection per thread instead of eight rounds of one warp).  Every thread of the CTA calls it; the caller puts a
+// barrier between this and assemble_frame_warp(f, lane, hand).
+__device__ __forceinline__ void assemble_prepass_cta(const AsmFrame& f, AsmSplit* hand, int tid, int n_threads) {
+  if (!asm_flat_ok(f)) return;  // (uniform) the warp does everything itself
+  const int K = f.K;
+  int* spos = f.scratch;
+  int* voff = spos + f.n_edges;
+  int* qa = voff + f.n_sorted + 1 + 2 * K;
+  int* qb = qa + K;
+  int* qpos = qb + K;
+  if (tid < 32) {
+    const int n_vis = asm_scan_edges(f, tid, spos, voff);
+    if (tid == 0) hand->n_vis = n_vis;
+  }
+  for (int i = tid; i < f.P; i += n_threads) { f.owner[i] = -1; f.id_count[i] = 0; }
+  __syncthreads();
+  asm_prepass(f, tid, n_threads, spos, voff, qa, qb, qpos);
+  if (tid == 0) hand->pre = 1;
+}
+
+// CTA-wide finish of assemble_frame_warp (after the id compaction): NaN fill, the rank pass over all connections, the
+// score sums (still one warp: a strict left-to-right fp32 sum per instance) and the scatter.  Every thread of the CTA
+// calls it; `hand` was written by the warp that ran the sequential part and is visible (the caller put a barrier in
+// between).  The scatter's "later entries overwrite" (paf.py:879-885) becomes: per output slot the LAST position of the
+// first-assignment list aiming at it (atomicMax), then only that entry writes.
+__device__ __forceinline__ void assemble_finish_cta(const AsmFrame& f, const AsmSplit* hand, int tid, int n_threads) {
+  if (!hand->split) return;
+  const int K = f.K, n_inst = hand->n_inst, n_order = hand->n_order, n_vis = hand->n_vis;
+  const int lane = tid & 31, warp = tid >> 5;
+  int* vrank = f.scratch + f.n_edges + f.n_sorted + 1;
+  float* vscore = reinterpret_cast<float*>(vrank + K);
+  int* qa = reinterpret_cast<int*>(vscore + K);
+  int* qb = qa + K;
+  int* qpos = qb + K;
+  float* acc = reinterpret_cast<float*>(qpos + K);
+  int* last = reinterpret_cast<int*>(acc + f.inst_cap);  // inst_cap x n_nodes
+  const int n_slots = n_inst * f.n_nodes;
+  for (int i = tid; i < n_slots; i += n_threads) {
+    f.oxy[2 * i] = NAN;
+    f.oxy[2 * i + 1] = NAN;
+    f.oval[i] = NAN;
+    last[i] = -1;
+  }
+  if (tid == 0) *f.n_inst_out = n_inst;
+  for (int r = tid; r < n_inst; r += n_threads) acc[r] = 0.f;
+  for (int v = tid; v < n_vis; v += n_threads) vrank[v] = -1;
+  __syncthreads();
+  for (int m = tid; m < K; m += n_threads) {
+    const int pos = qpos[m];
+    if (pos < 0) continue;  // never visited, or its source does not resolve
+    const int o = f.owner[qa[m]];
+    const int rk = (o >= 0) ? f.id_rank[o] : -1;
+    vrank[pos] = rk;
+    vscore[pos] = f.m_score[m];
+    const int b = qb[m];
+    if (rk >= 0 && b >= 0) {  // the reference's sanity check (ops/paf.py:866-873)
+      const int od = f.owner[b];
+      const int rd = (od >= 0) ? f.id_rank[od] : -1;
+      if (rd < 0) atomicOr(f.status, SNB_STATUS_ASM_MISSING);
+      else if (rd != rk) atomicOr(f.status, SNB_STATUS_ASM_MISMATCH);
+    }
+  }
+  for (int t = tid; t < n_order; t += n_threads) {
+    const int i = f.order[t];
+    const int r = f.id_rank[f.owner[i]];
+    if (r >= 0) atomicMax(&last[r * f.n_nodes + f.chan[i]], t);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    SNB_ASM_STAMP(8);
+    for (int v0 = 0; v0 < n_vis; v0 += 32) {
+      const int v = v0 + lane;
+      const int rk = v < n_vis ? vrank[v] : -1;
+      const float sc = v < n_vis ? vscore[v] : 0.f;
+      const unsigned peers = __match_any_sync(FULL, rk >= 0 ? rk : -1 - lane);
+      const bool leader = rk >= 0 && (__ffs(peers) - 1) == lane;
+      const unsigned any_valid = __ballot_sync(FULL, rk >= 0);
+      if (any_valid == 0) continue;
+      float a = leader ? acc[rk] : 0.f;
+      const int last_lane = 31 - __clz(any_valid);
+      for (int k = __ffs(any_valid) - 1; k <= last_lane; ++k) {
+        const float t = __shfl_sync(FULL, sc, k);
+        if (leader && ((peers >> k) & 1u)) a = __fadd_rn(a, t);
+      }
+      if (leader) acc[rk] = a;
+      __syncwarp();
+    }
+    for (int r = lane; r < n_inst; r += 32) f.osc[r] = acc[r];
+    SNB_ASM_STAMP(9);
+  }
+  // the scatter runs on the other warps meanwhile (all of them when the CTA is a single warp)
+  const int w0 = n_threads > 32 ? 32 : 0;
+  if (tid >= w0) {
+    for (int t = tid - w0; t < n_order; t += n_threads - w0) {
+      const int i = f.order[t];
+      const int r = f.id_rank[f.owner[i]];
+      if (r < 0) continue;
+      const int slot = r * f.n_nodes + f.chan[i];
+      if (last[slot] == t) {
+        f.oxy[2 * slot] = f.xy[2 * i];
+        f.oxy[2 * slot + 1] = f.xy[2 * i + 1];
+        f.oval[slot] = f.val[i];
+      }
+    }
   }
 }
 

@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   }
 
   SNB_STAMP(4);
-  // ---- 6. greedy assembly by warp 0
-  if (warp == 0) {
+  // ---- 6. assembly: the sequential part (greedy loop, id compaction) by warp 0, the rest by the whole CTA
+  __shared__ AsmSplit s_hand;
+  if (tid == 0) { s_hand.split = 0; s_hand.pre = 0; }
+  __syncthreads();
+  {
     AsmFrame f;
     f.xy = s_xy; f.val = s_val; f.chan = s_chan; f.P = n;
     f.ns = s_ns; f.np_ = s_np; f.n_nodes = n_nodes;
@@ -324,7 +327,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
 #ifdef SNB_TAIL_TIMING
     f.stamps = a.asm_ws ? a.asm_ws + b * 16 : nullptr; f.t0 = t_start;
 #endif
-    assemble_frame_warp(f, lane);
+    assemble_prepass_cta(f, &s_hand, tid, TAIL_THREADS);
+    __syncthreads();
+    if (warp == 0) assemble_frame_warp(f, lane, &s_hand);
+    __syncthreads();
+    assemble_finish_cta(f, &s_hand, tid, TAIL_THREADS);
   }
   SNB_STAMP(5);
 #ifdef SNB_TAIL_TIMING
