@@ -492,7 +492,12 @@ __device__ __forceinline__ void asm_prepass(const AsmFrame& f, int first, int st
 
 // Hand-over from the sequential part of the assembly (one warp) to its CTA-wide finish (assemble_finish_cta): lives in
 // shared memory.  split == 1 means the warp stopped after the id compaction and everything after it is still to do.
-struct AsmSplit { int pre, split, n_inst, n_order, n_vis; };  // pre == 1: assemble_prepass_cta already ran
+struct AsmSplit {
+  int pre;        // assemble_prepass_cta ran: ownership tables initialised, flat tables filled
+  int forest;     // assemble_forest_cta produced owner[] / order[] / n_order: the sequential loop is skipped
+  int irregular;  // (scratch of assemble_forest_cta) some connection breaks the forest conditions
+  int split, n_inst, n_order, n_vis;
+};
 
 __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane, AsmSplit* hand = nullptr) {
   const int P = f.P, K = f.K;
@@ -529,11 +534,9 @@ __device__ __forceinline__ void assemble_frame_warp(const AsmFrame& f, int lane,
       asm_prepass(f, lane, 32, spos, voff, qa, qb, qpos);
       __syncwarp();
     }
-    // (A parallel formulation was tried here: on a forest visited parents first - what toposort_edges gives - instances
-    // are the trees of the destination -> source links, ids and order[] follow from scans over the visiting positions,
-    // owners from pointer jumping.  Bit-exact, but a lone warp pays ~400 cycles per pass over shared tables and the
-    // dozen passes cost what the 31 sequential edge steps cost: 14.4 K vs 15 K cycles at cfg4, 5 K vs 2.4 K at cfg3.)
-    for (int c0 = 0; c0 < f.n_sorted; c0 += 32) {
+    const bool forest = pre && hand->forest;  // owner[] / order[] already final (assemble_forest_cta)
+    if (forest) n_order = hand->n_order;
+    for (int c0 = 0; !forest && c0 < f.n_sorted; c0 += 32) {
       // headers of 32 sorted edges at a time, one per lane; the loop below fetches them by shuffle
       int h_e = -1, h_lo = 0, h_hi = 0, h_distinct = 0;
       if (c0 + lane < f.n_sorted) {
@@ -852,6 +855,121 @@ __device__ __forceinline__ void assemble_prepass_cta(const AsmFrame& f, AsmSplit
   __syncthreads();
   asm_prepass(f, tid, n_threads, spos, voff, qa, qb, qpos);
   if (tid == 0) hand->pre = 1;
+}
+
+constexpr int ASM_FOREST_MIN_EDGES = 12;  // visited edges from which assemble_forest_cta replaces the sequential loop
+
+// CTA-wide replacement of the sequential edge loop for the common case.  On a skeleton visited as a forest, parents
+// first (what toposort_edges' order gives), the loop only ever sees "neither owned" (a new instance) and "source owned,
+// destination free" (the destination joins): every peak is a destination at most once, before any use as a source,
+// and nothing is renamed.  The result is then a forest over the peaks (destination -> source links), an instance id =
+// the number of roots created earlier in visiting order, and order[] = per connection in visiting order [source if it
+// creates the instance], destination - scans over the visiting positions and pointer jumping instead of one dependent
+// step per edge.  The conditions are CHECKED on the frame's actual connections; anything else (a node with two visited
+// parents, children before parents, repeated edges, self edges, improper matchings) leaves hand->forest at 0 and the
+// sequential loop runs.  (As ONE warp this cost what the loop costs - ~400 cycles per pass; it pays with one peak /
+// connection per thread.)  Every thread of the CTA calls it, after assemble_prepass_cta and a barrier.
+__device__ __forceinline__ void assemble_forest_cta(const AsmFrame& f, AsmSplit* hand, int tid, int n_threads) {
+  const int K = f.K, P = f.P;
+  if (!hand->pre) return;  // (uniform)
+  // a dozen CTA barriers cost more than a short loop: 4 edges (cfg3) 2.4 K cycles sequentially, 5.8 K this way;
+  // 31 edges (cfg4) 15 K against 8 K
+  if (f.n_sorted < ASM_FOREST_MIN_EDGES) return;
+  const int n_vis = hand->n_vis;
+  if (f.scratch_words < 5 * K + f.n_edges + f.n_sorted + f.inst_cap + 2 + f.inst_cap * f.n_nodes + P) return;
+  constexpr int INF = 0x7fffffff;
+  int* spos = f.scratch;
+  int* vcre = f.scratch + f.n_edges + f.n_sorted + 1;   // (= vrank) per visiting position: creates an instance -> its id
+  int* vcnt = vcre + K;                                 // (= vscore) per visiting position: order[] entries -> offset
+  int* qa = vcnt + K;
+  int* qb = qa + K;
+  int* qpos = qb + K;
+  int* par2 = qpos + K + f.inst_cap + f.inst_cap * f.n_nodes;  // behind acc and the scatter's slot table
+  int* par = f.owner;        // destination -> source; roots: -2 - id; untouched: -1 (as initialised by the pre-pass)
+  int* dposv = f.id_rank;    // visiting position of the connection that has the peak as destination
+  int* sfirst = f.id_count;  // first visiting position with the peak as source
+  bool bad = n_vis > K;
+  for (int i = tid; i < P; i += n_threads) { dposv[i] = INF; sfirst[i] = INF; }
+  for (int v = tid; v < n_vis && v < K; v += n_threads) { vcre[v] = 0; vcnt[v] = 0; }
+  for (int se = tid; se < f.n_sorted; se += n_threads) bad |= spos[f.sorted[se]] != se;  // an edge listed twice
+  __syncthreads();
+  for (int m = tid; m < K; m += n_threads) {
+    const int a = qa[m], b = qb[m];
+    if (a < 0 || b < 0) continue;
+    const int pos = qpos[m], e = f.m_edge[m];
+    bad |= f.edges[2 * e] == f.edges[2 * e + 1];             // self edge
+    atomicMin(&sfirst[a], pos);
+    if (atomicMin(&dposv[b], pos) != INF) bad = true;        // a destination twice
+    par[b] = a;
+  }
+  __syncthreads();
+  for (int m = tid; m < K; m += n_threads) {
+    const int a = qa[m], b = qb[m];
+    if (a < 0 || b < 0) continue;
+    const int pos = qpos[m], da = dposv[a];
+    if (!(da == INF || da < pos)) bad = true;   // the source joins its own instance only later
+    if (!(sfirst[b] > pos)) bad = true;         // the destination was already used as a source
+    const int cre = (da == INF && sfirst[a] == pos) ? 1 : 0;
+    vcre[pos] = cre;
+    vcnt[pos] = 1 + cre;
+  }
+  if (__syncthreads_or(bad ? 1 : 0)) {  // not a forest: back to the initial state, the sequential loop takes over
+    for (int i = tid; i < P; i += n_threads) { f.owner[i] = -1; f.id_count[i] = 0; }
+    return;
+  }
+  if (tid < 32) {  // exclusive scans over the visiting positions: ids of the created instances, offsets into order[]
+    const int lane = tid;
+    int run_c = 0, run_o = 0;
+    for (int v0 = 0; v0 < n_vis; v0 += 32) {
+      const int v = v0 + lane;
+      const int c = v < n_vis ? vcre[v] : 0, o = v < n_vis ? vcnt[v] : 0;
+      int ic = c, io = o;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int tc = __shfl_up_sync(FULL, ic, d), to = __shfl_up_sync(FULL, io, d);
+        if (lane >= d) { ic += tc; io += to; }
+      }
+      if (v < n_vis) { vcre[v] = run_c + ic - c; vcnt[v] = run_o + io - o; }
+      run_c += __shfl_sync(FULL, ic, 31);
+      run_o += __shfl_sync(FULL, io, 31);
+    }
+    if (lane == 0) hand->n_order = run_o;
+  }
+  __syncthreads();
+  for (int m = tid; m < K; m += n_threads) {
+    const int a = qa[m], b = qb[m];
+    if (a < 0 || b < 0) continue;
+    const int pos = qpos[m], off = vcnt[pos];
+    if (dposv[a] == INF && sfirst[a] == pos) {
+      par[a] = -2 - vcre[pos];
+      f.order[off] = a;
+      f.order[off + 1] = b;
+    } else {
+      f.order[off] = b;
+    }
+  }
+  __syncthreads();
+  // pointer jumping, double buffered (par -> par2 -> par ...): a touched peak's parent is itself touched, so a pointer
+  // never lands on -1; <= ceil(log2(depth)) + 1 rounds
+  int* src = par;
+  int* dst = par2;
+  for (int round = 0; round < 32; ++round) {
+    int moved = 0;
+    for (int i = tid; i < P; i += n_threads) {
+      int q = src[i];
+      if (q >= 0) { q = src[q]; moved = 1; }
+      dst[i] = q;
+    }
+    const int any = __syncthreads_or(moved);
+    int* t = src; src = dst; dst = t;
+    if (!any) break;
+  }
+  for (int i = tid; i < P; i += n_threads) {
+    const int q = src[i];  // (src may be f.owner itself: same thread, same index, read before write)
+    f.owner[i] = q <= -2 ? -2 - q : -1;
+    f.id_count[i] = 0;
+  }
+  if (tid == 0) hand->forest = 1;
 }
 
 // CTA-wide finish of assemble_frame_warp (after the id compaction): NaN fill, the rank pass over all connections, the

@@ -327,17 +327,18 @@ def test_fused_pipeline_assembly_paths_vs_oracle(case):
     from sleap_nn_b200 import synthetic
     from sleap_nn_b200.pipeline import BottomUpPostproc
 
-    tree = [(0, 1), (0, 2), (1, 3), (1, 4), (2, 5), (5, 6), (5, 7)]
-    edges = tree + [(3, 7)] if case == "two_parents_all_edges" else tree
-    B, n_inst, Nn, hw, stride = 4, 4, 8, (512, 512), 2
-    poses = synthetic.random_poses(11, B, n_inst, Nn, hw, tree, margin=120.0, step=30.0, min_limb=10.0, min_sep=14.0)
+    # 14 nodes / 13 edges: from 12 visited edges on the tail tries the forest path first
+    tree = [(0, 1), (0, 2), (1, 3), (1, 4), (2, 5), (5, 6), (5, 7), (3, 8), (3, 9), (6, 10), (6, 11), (7, 12), (7, 13)]
+    edges = tree + [(4, 13)] if case == "two_parents_all_edges" else tree
+    B, n_inst, Nn, hw, stride = 4, 4, 14, (512, 512), 2
+    poses = synthetic.random_poses(11, B, n_inst, Nn, hw, tree, margin=140.0, step=26.0, min_limb=10.0, min_sep=14.0)
     dev = torch.device("cuda")
     cms, pafs = synthetic.render_batch(poses, hw, stride, edges, dev, seed=11)
     order = None
     if case == "children_first_order":
         order = tuple(reversed(BottomUpPostproc(Nn, edges, B, (256, 256)).sorted_edge_inds))
     elif case == "two_parents_all_edges":
-        order = tuple(range(len(edges)))  # (5, 7) and (3, 7) are both visited
+        order = tuple(range(len(edges)))  # (7, 13) and (4, 13) are both visited
     pipe = BottomUpPostproc(Nn, edges, B, (256, 256), cms_stride=stride, pafs_stride=stride, sorted_edge_inds=order)
     assert pipe.fused
     res = pipe(cms, pafs)
