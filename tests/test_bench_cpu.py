@@ -36,3 +36,18 @@ def test_reference_arm_line():
 
     assert d["config"] == bench.shared_config(1), "both arms must print the same config object"
     assert "libsleapnn_b200" not in r.stderr, "the reference arm must not map the product's shared library"
+
+
+def test_committed_traffic_record_matches_the_source():
+    """`roofline.traffic` is read from profiles/traffic.json, keyed by kernel + the hash of csrc/peaks.cu at capture time:
+    the committed record must belong to the committed source (re-capture with tools/final_run.sh + tools/ncu_traffic.py
+    after editing the kernel)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for kernel, lo, hi in (("local_peaks_detect_vec<float,4,1,6,1>", 335.5e6, 345e6),
+                           ("local_peaks_detect_vec<__half,2,1,8,1>", 167.7e6, 175e6),
+                           ("local_peaks_detect_vec<__nv_bfloat16,2,1,8,1>", 167.7e6, 175e6)):
+        traffic, rec = bench.recorded_traffic(kernel)
+        assert rec is not None and rec["source_matches"], kernel
+        assert lo <= traffic <= hi, (kernel, traffic)  # = the algorithmic bytes (+ the key / counter writes)
