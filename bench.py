@@ -568,7 +568,8 @@ def run_ours(args, rank: int, world: int):
     # has a free slot (a counter in torch.distributed's store, ~0.1 ms per pull against ~6 ms per batch) - what a
     # multi-GPU predictor fed from host memory does.  On this pool's 8-GPU boxes the GPUs sit behind two host bridges
     # of unequal speed (tools/h2d_scaling_probe.py: 20.8 vs 35.7 GB/s per GPU when all eight copy at once), and a fixed
-    # equal split is paced by the slow group.  --e2e-static keeps the fixed split.
+    # equal split is paced by the slow group.  --e2e-static keeps the fixed split.  (The protocol of
+    # sleap_nn_b200.sharding.SharedBatchQueue, which has its own world-size-2 gloo test, spelled out inline.)
     queue = None
     if world > 1 and not args.e2e_static:
         try:

@@ -91,6 +91,44 @@ def bind_host_to_gpu(device_index: int, min_cpus: int = 2) -> Optional[List[int]
 
 
 # ----------------------------------------------------------------------------- packed results
+class SharedBatchQueue:
+    """One queue of batch indices for all ranks of a job whose inputs live in HOST memory.
+
+    Frames shard with no data-path collective, but a FIXED equal split is paced by the slowest
+    feed: on this pool's 8-GPU boxes the GPUs sit behind two host bridges of unequal speed (20.8 vs 35.7 GB/s per GPU
+    when all eight copy at once, `tools/h2d_scaling_probe.py`), and the ranks behind the fast one finish early.  Here
+    every rank pulls the next batch index when it has a free slot: one atomic `add` on torch.distributed's store per
+    batch (~0.1 ms against ~6 ms for a cfg3 batch over PCIe) - 41.4 k instead of 35.0 k frames/s at N=8
+    (`bench.py`'s e2e leg speaks the same protocol inline).  Without a process group it is a plain counter.
+
+        q = SharedBatchQueue(n_batches)            # collective: every rank constructs it (one barrier)
+        while (k := q.next()) is not None: submit(batch k)
+    """
+
+    def __init__(self, total: int, key: str = "snb_batch_queue", group=None):
+        if total < 0:
+            raise ValueError("total must be >= 0")
+        self.total, self.key, self.taken = int(total), str(key), 0
+        self._store = None
+        self._local = 0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self._store = dist.distributed_c10d._get_default_store()
+            if dist.get_rank(group) == 0:
+                self._store.set(self.key, "0")
+            dist.barrier(group)  # nobody pulls before the counter exists
+
+    def next(self) -> Optional[int]:
+        """The next batch index nobody else has, or None when the queue is empty."""
+        if self._store is None:
+            k, self._local = self._local, self._local + 1
+        else:
+            k = int(self._store.add(self.key, 1)) - 1
+        if k >= self.total:
+            return None
+        self.taken += 1
+        return k
+
+
 @dataclass
 class PackedInstances:
     """Instances of a run of frames in packed form (row i belongs to frame `frame[i]`).

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sleap_nn_b200.sharding import PackedInstances, batch_ranges, frame_shard, gather_packed
+from sleap_nn_b200.sharding import PackedInstances, SharedBatchQueue, batch_ranges, frame_shard, gather_packed
 
 
 @pytest.mark.parametrize("n,world", [(0, 1), (1, 2), (7, 2), (64, 8), (100_000, 8), (100_003, 4), (5, 8)])
@@ -91,6 +91,41 @@ def test_gather_packed_world2_gloo(tmp_path, counts_by_rank):
         np.testing.assert_array_equal(got["val"].numpy(), want.val.numpy())
         np.testing.assert_array_equal(got["score"].numpy(), want.score.numpy())
         assert sorted(got["frame"].tolist()) == got["frame"].tolist()  # global frame order
+
+
+def _queue_worker(rank, world, port, total, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import time
+
+        q = SharedBatchQueue(total)
+        mine = []
+        while (k := q.next()) is not None:
+            mine.append(k)
+            time.sleep(0.002 * (1 + 3 * rank))  # rank 1 is the slow feed: it must end up with fewer batches
+        assert q.next() is None and q.taken == len(mine)
+        torch.save(mine, os.path.join(out_dir, f"q{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [0, 1, 37])
+def test_shared_batch_queue_world2_gloo(tmp_path, total):
+    """Every batch index is handed out exactly once across the ranks, and the faster rank takes more of them."""
+    world = 2
+    mp.spawn(_queue_worker, args=(world, _free_port(), total, str(tmp_path)), nprocs=world, join=True)
+    got = [torch.load(os.path.join(str(tmp_path), f"q{r}.pt")) for r in range(world)]
+    assert sorted(got[0] + got[1]) == list(range(total))
+    assert all(g == sorted(g) for g in got)
+    if total >= 30:
+        assert len(got[0]) > len(got[1]) > 0
+
+
+def test_shared_batch_queue_without_a_process_group():
+    q = SharedBatchQueue(3)
+    assert [q.next(), q.next(), q.next(), q.next(), q.next()] == [0, 1, 2, None, None] and q.taken == 3
 
 
 def test_gather_packed_is_identity_without_a_process_group():
