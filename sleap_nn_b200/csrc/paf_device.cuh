@@ -900,7 +900,7 @@ __device__ __forceinline__ void assemble_forest_cta(const AsmFrame& f, AsmSplit*
     bad |= f.edges[2 * e] == f.edges[2 * e + 1];             // self edge
     atomicMin(&sfirst[a], pos);
     if (atomicMin(&dposv[b], pos) != INF) bad = true;        // a destination twice
-    par[b] = a;
+    else par[b] = a;                                         // (a single writer per peak, also when `bad`)
   }
   __syncthreads();
   for (int m = tid; m < K; m += n_threads) {
