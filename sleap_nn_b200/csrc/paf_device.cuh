@@ -495,7 +495,6 @@ __device__ __forceinline__ void asm_prepass(const AsmFrame& f, int first, int st
 struct AsmSplit {
   int pre;        // assemble_prepass_cta ran: ownership tables initialised, flat tables filled
   int forest;     // assemble_forest_cta produced owner[] / order[] / n_order: the sequential loop is skipped
-  int irregular;  // (scratch of assemble_forest_cta) some connection breaks the forest conditions
   int split, n_inst, n_order, n_vis;
 };
 

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) bottomup_tail_kernel(snb_bottomu
   SNB_STAMP(4);
   // ---- 6. assembly: the sequential part (greedy loop, id compaction) by warp 0, the rest by the whole CTA
   __shared__ AsmSplit s_hand;
-  if (tid == 0) { s_hand.split = 0; s_hand.pre = 0; s_hand.forest = 0; s_hand.irregular = 0; }
+  if (tid == 0) { s_hand.split = 0; s_hand.pre = 0; s_hand.forest = 0; }
   __syncthreads();
   {
     AsmFrame f;
